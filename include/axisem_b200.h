@@ -1,0 +1,227 @@
+/*
+ * axisem_b200.h — C ABI of the B200-native AxiSEM SOLVER time loop.
+ *
+ * Drop-in seam: the single `call time_loop` of the reference
+ * (SOLVER/main.f90:92 -> SOLVER/time_evol_wave.F90:231-245).  Everything above that call
+ * (mesh ingest, pre-computed terms, source/receiver set-up) stays on the host and hands
+ * its module arrays to this library once; `axb_run` then replaces
+ * `sf_time_loop_newmark` (time_evol_wave.F90:264-502) / `symplectic_time_loop`
+ * (:516-741) with device-resident stepping.  INTEGRATION.md shows the Fortran
+ * `iso_c_binding` interface a maintainer would add.
+ *
+ * Conventions (identical to the reference's own C interop, SOLVER/nc_routines.F90:290-300,
+ * SOLVER/pthread.c:44-57):
+ *   - all arrays are caller-owned HOST memory, contiguous, Fortran (column-major) order,
+ *     borrowed for the duration of the call and copied to the device — never retained;
+ *   - `float` = real(kind=realkind)=sp (global_parameters.f90:40), `double` = dp,
+ *     `int32_t` = default integer, logicals are 4-byte integers (0 = .false.);
+ *   - every index stored in an integer map is 1-based, exactly as the Fortran holds it;
+ *     pol indices (ipol, jpol) are 0-based as in the reference (`0:npol`);
+ *   - element-local linear point index: ipt = (iel-1)*25 + jpol*5 + ipol + 1
+ *     (SOLVER/commun.F90:303);
+ *   - every function returns 0 on success; on failure a non-zero code is returned and
+ *     `axb_last_error()` describes it (the reference would `stop`).
+ *   - npol must be 4 (the `_4` routines of the reference).
+ *
+ * The same header is implemented twice with different prefixes:
+ *   libaxisem_b200.so      axb_*   CUDA sm_100a (the product)
+ *   oracle/libaxisem_oracle.so  axo_*   CPU restatement of the reference (test oracle)
+ * AXB_PREFIX selects the prefix; signatures are identical.
+ */
+#ifndef AXISEM_B200_H
+#define AXISEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef AXB_PREFIX
+#define AXB_PREFIX axb_
+#endif
+#define AXB_CAT_(a, b) a##b
+#define AXB_CAT(a, b) AXB_CAT_(a, b)
+#define AXB(name) AXB_CAT(AXB_PREFIX, name)
+
+typedef struct axb_handle_s *axb_handle;
+
+/* src_type(1): monopole / dipole / quadpole (SOLVER/data_source.f90:38) */
+enum { AXB_MONOPOLE = 0, AXB_DIPOLE = 1, AXB_QUADPOLE = 2 };
+
+/* time_scheme (SOLVER/time_evol_wave.F90:237, :760-941) */
+enum {
+    AXB_NEWMARK2 = 0, AXB_SYMPLEC4 = 1, AXB_ML_SO4M5 = 2, AXB_ML_SO6M7 = 3,
+    AXB_KL_O8M17 = 4, AXB_SS_35O10 = 5
+};
+
+/* stf_type for the point-wise STF of the symplectic schemes (SOLVER/source.f90:206-233) */
+enum { AXB_STF_GAUSS_0 = 0, AXB_STF_GAUSS_1 = 1, AXB_STF_GAUSS_2 = 2 };
+
+enum { AXB_DOMAIN_SOLID = 0, AXB_DOMAIN_FLUID = 1 };
+
+/* state arrays for axb_get_state / axb_set_state */
+enum {
+    AXB_F_DISP = 0, AXB_F_VELO = 1, AXB_F_ACC0 = 2, AXB_F_ACC1 = 3,   /* (5,5,nel_solid,3) */
+    AXB_F_CHI = 4, AXB_F_DCHI = 5, AXB_F_DDCHI0 = 6, AXB_F_DDCHI1 = 7, /* (5,5,nel_fluid)   */
+    AXB_F_MEMVAR = 8,       /* (4,6,n_sls,nel_solid) cg4 or (5,5,6,n_sls,nel_solid)          */
+    AXB_F_SRC_DEV_TM1 = 9,  /* (4,6,nel_solid) or (5,5,6,nel_solid)                          */
+    AXB_F_SRC_TR_TM1 = 10   /* (4,nel_solid)   or (5,5,nel_solid)                            */
+};
+
+/* single operators, for per-routine parity tests (each cites the routine it replaces) */
+enum {
+    AXB_OP_SOLID_STIFFNESS = 0,  /* acc1 = K(disp): glob_stiffness_{mono,di,quad}_4           */
+    AXB_OP_ANEL_STIFFNESS = 1,   /* acc1 -= anelastic term: glob_anel_stiffness_*             */
+    AXB_OP_FLUID_STIFFNESS = 2,  /* ddchi1 = K(chi): glob_fluid_stiffness_4                   */
+    AXB_OP_PDISTSUM_SOLID = 3,   /* pdistsum_solid(acc1)  (commun.F90:69-171), all phases     */
+    AXB_OP_PDISTSUM_FLUID = 4,   /* pdistsum_fluid(ddchi1) (commun.F90:180-283)               */
+    AXB_OP_MEMVARS = 5,          /* time_step_memvars(memvar, disp) (attenuation.f90:55-334)  */
+    AXB_OP_BDRY2FLUID = 6,       /* bdry_copy2fluid(ddchi1, disp) (time_evol_wave.F90:1532)   */
+    AXB_OP_BDRY2SOLID = 7        /* bdry_copy2solid(acc1, ddchi1) (time_evol_wave.F90:1577)   */
+};
+
+/* Solid pre-computed planes, SOLVER/data_matr.f90:46-76.  Each non-NULL pointer is a
+ * (0:4,0:4,nel_solid) array; M0_w* are (0:4,nel_solid).  Planes not allocated for the
+ * source order (def_precomp_terms.f90:1216-1284) are NULL. */
+typedef struct {
+    const float *M11s, *M21s, *M41s, *M12s, *M22s, *M32s, *M42s, *M11z, *M21z, *M41z;
+    const float *M13s, *M33s, *M43s;                 /* dipole */
+    const float *M1phi, *M2phi, *M4phi;              /* quadrupole */
+    const float *M_1, *M_2, *M_3, *M_4, *M_5, *M_6, *M_7, *M_8;
+    const float *M_w1, *M_w2, *M_w3, *M_w4, *M_w5;
+    const float *M0_w1, *M0_w2, *M0_w3, *M0_w4, *M0_w5, *M0_w6, *M0_w7, *M0_w8, *M0_w9, *M0_w10;
+} axb_solid_terms;
+
+/* Attenuation inputs: SOLVER/attenuation.f90:38-49, data_matr.f90:95-112,
+ * data_pointwise.f90.  Coarse-grained (`att_coarse_grained`, the default) uses the *_cg4
+ * members (1:4,nel_solid); otherwise the full (0:4,0:4,nel_solid) planes, the axial
+ * (0:4,nel_solid) vectors and inv_s_solid are required.  The SLS fit itself is host
+ * work (attenuation.f90:1183-1339, unseeded RNG); only its results are passed. */
+typedef struct {
+    int32_t coarse_grained;
+    int32_t n_sls;
+    int32_t do_corr_lowq;
+    const double *y_j;              /* (n_sls) */
+    const double *exp_w_j_deltat;   /* (n_sls) */
+    const double *ts_fac_t;         /* (n_sls) */
+    const double *ts_fac_tm1;       /* (n_sls) */
+    const float *Q_mu, *Q_kappa;    /* (nel_solid) */
+    const float *delta_mu_cg4, *delta_kappa_cg4;
+    const float *Y_cg4, *V_s_eta_cg4, *V_s_xi_cg4, *V_z_eta_cg4, *V_z_xi_cg4;
+    const float *DsDeta_over_J_sol_cg4, *DzDeta_over_J_sol_cg4;
+    const float *DsDxi_over_J_sol_cg4, *DzDxi_over_J_sol_cg4;
+    const float *delta_mu, *delta_kappa;
+    const float *Y, *V_s_eta, *V_s_xi, *V_z_eta, *V_z_xi;
+    const float *Y0, *V0_s_eta, *V0_s_xi, *V0_z_eta, *V0_z_xi;
+    const float *DsDeta_over_J_sol, *DzDeta_over_J_sol, *DsDxi_over_J_sol, *DzDxi_over_J_sol;
+    const float *inv_s_solid;       /* (0:4,0:4,nel_solid); needed by both variants */
+} axb_attenuation;
+
+const char *AXB(last_error)(void);
+
+/* mynum, nproc: SOLVER/data_proc.f90.  device = CUDA ordinal (ignored by the oracle). */
+int AXB(create)(axb_handle *h, int32_t device, int32_t rank, int32_t nranks);
+int AXB(destroy)(axb_handle h);
+
+/* data_mesh.f90:58-66 (igloc_*, nglob_*), def_grid.f90:59-77 (axis flags, ax_el_*),
+ * data_spec.f90:38-39 (G0(0:4), G1,G1T,G2,G2T(0:4,0:4)). */
+int AXB(set_mesh)(axb_handle h, int32_t npol, int32_t nel_solid, int32_t nel_fluid,
+                  int32_t nglob_solid, int32_t nglob_fluid,
+                  const int32_t *igloc_solid, const int32_t *igloc_fluid,
+                  const int32_t *axis_solid, const int32_t *axis_fluid,
+                  const int32_t *ax_el_solid, int32_t naxel_solid,
+                  const int32_t *ax_el_fluid, int32_t naxel_fluid,
+                  const float *G0, const float *G1, const float *G1T,
+                  const float *G2, const float *G2T);
+
+int AXB(set_solid_terms)(axb_handle h, int32_t src_order, const axb_solid_terms *t);
+
+/* data_matr.f90:79-82, :37, data_mesh.f90:181.  M_w_fl / M0_w_fl may be NULL for
+ * monopole sources; fluid_free_surface_mask may be NULL (= all ones). */
+int AXB(set_fluid_terms)(axb_handle h, const float *M1chi_fl, const float *M2chi_fl,
+                         const float *M4chi_fl, const float *M_w_fl, const float *M0_w_fl,
+                         const float *inv_mass_fluid, const float *fluid_free_surface_mask);
+
+/* inv_mass_rho(0:4,0:4,nel_solid), data_matr.f90:36 (dipole: 1/2 folded in). */
+int AXB(set_mass)(axb_handle h, const float *inv_mass_rho);
+
+/* {solid,fluid}_absorbing_gamma, data_mesh.f90:185-186; NULL,NULL = have_absorbing_bc false */
+int AXB(set_sponge)(axb_handle h, const float *solid_gamma, const float *fluid_gamma);
+
+/* data_mesh.f90:106-110, data_matr.f90:88: bdry_matr(0:4,nel_bdry,2). */
+int AXB(set_sf_boundary)(axb_handle h, int32_t nel_bdry, const int32_t *bdry_solid_el,
+                         const int32_t *bdry_fluid_el, const int32_t *bdry_jpol_solid,
+                         const int32_t *bdry_jpol_fluid, const float *bdry_matr);
+
+int AXB(set_attenuation)(axb_handle h, const axb_attenuation *a);
+
+/* data_source.f90:38,50-52: source_term_el(0:4,0:4,8,3), ielsrc(8), stf(niter).
+ * fluid_src != 0 passes source_term_fl(0:4,0:4,8) instead. */
+int AXB(set_source)(axb_handle h, int32_t fluid_src, int32_t nelsrc, const int32_t *ielsrc,
+                    const float *source_term, const float *stf, int32_t niter);
+
+/* point-wise STF for the symplectic schemes, compute_stf_t (source.f90:206-233) */
+int AXB(set_stf_params)(axb_handle h, int32_t stf_type, double decay, double t_0,
+                        double shift_fact, double magnitude);
+
+/* recfile_el(num_rec,3) = (iel, ipol, jpol), data_mesh.f90:138 */
+int AXB(set_receivers)(axb_handle h, int32_t num_rec, const int32_t *recfile_el);
+
+/* displ_only wavefield dump (wavefields_io.f90:743-783, 1019-1115; meshes_io.F90:489-640):
+ * kwf_mask, mapping_ijel_ikwf are (0:4,0:4,nel_solid+nel_fluid); the fluid pointwise
+ * planes (data_pointwise.f90) and inv_rho_fluid are (0:4,0:4,nel_fluid). */
+int AXB(set_kwf)(axb_handle h, const int32_t *kwf_mask, const int32_t *mapping_ijel_ikwf,
+                 int32_t npoint_solid_kwf, int32_t npoint_fluid_kwf,
+                 const float *inv_rho_fluid, const float *DsDeta_over_J_flu,
+                 const float *DzDeta_over_J_flu, const float *DsDxi_over_J_flu,
+                 const float *DzDxi_over_J_flu);
+
+/* data_comm.f90:36-71.  glocal_index_msg is (maxmsg, nmsg) Fortran order; send and
+ * receive lists coincide (get_mesh.f90:303-310).  glob2el is (num_comm_gll,3) =
+ * (ipol, jpol, iel). */
+int AXB(set_halo)(axb_handle h, int32_t domain, int32_t nmsg, const int32_t *list_peer,
+                  const int32_t *sizemsg, const int32_t *glocal_index_msg, int32_t maxmsg,
+                  int32_t num_comm_gll, const int32_t *glob2el);
+
+/* data_time.f90: time_scheme, deltat, niter, seis_it, strain_it (0 = no wavefield dump) */
+int AXB(set_time)(axb_handle h, int32_t scheme, double deltat, int32_t niter,
+                  int32_t seis_it, int32_t strain_it);
+
+/* builds the derived (device) structures; must follow all axb_set_* calls */
+int AXB(finalize_setup)(axb_handle h);
+
+/* Multi-rank runs: every rank's handle must be connected to its peers before axb_run.
+ * In-process (oracle, single-process multi-GPU): axb_connect_local with all handles.
+ * One process per GPU: exchange the 64-byte IPC blobs (e.g. over torch.distributed). */
+int AXB(connect_local)(axb_handle *handles, int32_t n);
+int AXB(ipc_export)(axb_handle h, void *blob, int32_t blob_bytes);   /* >= 256 bytes */
+int AXB(ipc_import)(axb_handle h, int32_t peer_rank, const void *blob, int32_t blob_bytes);
+
+/* Advance `nsteps` full time steps (collective over connected handles: every rank
+ * must call it with the same nsteps).  State stays on the device. */
+int AXB(run)(axb_handle h, int32_t nsteps);
+/* in-process lockstep variant for connect_local groups */
+int AXB(run_group)(axb_handle *handles, int32_t n, int32_t nsteps);
+
+int32_t AXB(iter)(axb_handle h);         /* time steps done so far                     */
+int32_t AXB(nseismo)(axb_handle h);      /* seismogram samples recorded so far         */
+int32_t AXB(nstrain)(axb_handle h);      /* wavefield snapshots recorded so far        */
+int64_t AXB(gpu_launches)(axb_handle h); /* kernels launched by this handle (0: oracle) */
+
+/* recdumpvar slice: out(3, num_rec, nsamples) Fortran order, samples first..first+n-1
+ * (0-based; sample 0 is the dump at iter 0).  nc_dump_rec, nc_routines.F90:530-540 */
+int AXB(fetch_seismograms)(axb_handle h, int32_t first, int32_t nsamples, float *out);
+/* oneddumpvar slice: out(npoints, nsnap, 3) with var order (s, p, z); nc_routines.F90:248,275 */
+int AXB(fetch_snapshots)(axb_handle h, int32_t first, int32_t nsnap, float *out);
+
+int AXB(get_state)(axb_handle h, int32_t field, float *out);
+int AXB(set_state)(axb_handle h, int32_t field, const float *in);
+
+/* run one operator of the loop on the current state (testing) */
+int AXB(apply_op)(axb_handle h, int32_t op);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AXISEM_B200_H */

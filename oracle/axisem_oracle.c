@@ -1,0 +1,1599 @@
+/*
+ * axisem_oracle.c — CPU restatement of the AxiSEM SOLVER time loop.  TEST ORACLE ONLY.
+ *
+ * This file is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it.  The product (libaxisem_b200.so)
+ * never links, loads or calls it.
+ *
+ * PARITY UNPINNED: the reference is Fortran 2003 + MPI and cannot be compiled in this
+ * image (no Fortran compiler), and its own tests hold no array-level vectors for this
+ * path — its only golden data are end-to-end, post-processed
+ * miniSEED traces that need the MESHER.  This restatement therefore follows the reference
+ * line by line (citations below), is pinned by the analytic/self-consistency checks the
+ * reference itself uses (tests/test_oracle_physics.py) and by committed fixtures of its
+ * own output (tests/golden/), but not by an execution of the Fortran.
+ *
+ * Arithmetic rules reproduced from the Fortran:
+ *   - fields and pre-computed planes are real(4); `sum(a(i,:)*b(:,j))` is evaluated
+ *     left to right in real(4) (unrolled_loops.f90:164-188); compiled with
+ *     -ffp-contract=off so no FMA contraction happens;
+ *   - expressions containing the real(8) scalars deltat, half_dt, half_dt_sq, two,
+ *     third, coefd/coefv, ts_fac_*, exp_w_j_deltat, a_j_* are promoted to real(8) and
+ *     rounded once on assignment (time_evol_wave.F90:357-364,459,472,477;
+ *     attenuation.f90:144-192);
+ *   - flush-to-zero is on (SOLVER/ftz.c:44-48): axo_run sets MXCSR FTZ|DAZ.
+ *
+ * Layout: exactly the Fortran memory order.  u(0:4,0:4,nel,3) -> u[i + 5*j + 25*e + 25*nel*c].
+ */
+#define AXB_PREFIX axo_
+#include "../include/axisem_b200.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#if defined(__x86_64__)
+#include <xmmintrin.h>
+#include <pmmintrin.h>
+#endif
+
+#define NP 5
+#define NPT 25
+#define MAXMSG 8
+
+typedef struct {
+    int nmsg;
+    int peer[MAXMSG];
+    int size[MAXMSG];
+    int *glocal[MAXMSG];      /* 1-based glocal ids */
+    int ncomm;
+    int *glob2el;             /* (ncomm,3) Fortran order */
+    float *sendbuf[MAXMSG];   /* (size, nc) */
+    float *recvbuf[MAXMSG];
+} halo_t;
+
+struct axb_handle_s {
+    int rank, nranks;
+    int nel_s, nel_f, nglob_s, nglob_f;
+    int *igloc_s, *igloc_f, *axis_s, *axis_f, *ax_el_s, *ax_el_f;
+    int naxel_s, naxel_f;
+    float G0[NP], G1[NPT], G1T[NPT], G2[NPT], G2T[NPT];
+    int src_order;
+    /* solid planes (copies) */
+    float *M11s, *M21s, *M41s, *M12s, *M22s, *M32s, *M42s, *M11z, *M21z, *M41z;
+    float *M13s, *M33s, *M43s, *M1phi, *M2phi, *M4phi;
+    float *M_1, *M_2, *M_3, *M_4, *M_5, *M_6, *M_7, *M_8;
+    float *M_w1, *M_w2, *M_w3, *M_w4, *M_w5;
+    float *M0_w1, *M0_w2, *M0_w3, *M0_w4, *M0_w5, *M0_w6, *M0_w7, *M0_w8, *M0_w9, *M0_w10;
+    /* fluid */
+    float *M1chi, *M2chi, *M4chi, *M_w_fl, *M0_w_fl, *inv_mass_fluid, *fs_mask;
+    float *inv_mass_rho;
+    float *gamma_s, *gamma_f;
+    int have_abc;
+    /* S/F boundary */
+    int nel_bdry;
+    int *bdry_sel, *bdry_fel, *bdry_js, *bdry_jf;
+    float *bdry_matr;
+    /* attenuation */
+    int anel, cg, n_sls, corr_lowq;
+    double *y_j, *exp_w, *ts_t, *ts_tm1;
+    float *Q_mu, *Q_kappa;
+    float *dmu_cg, *dka_cg, *Ycg, *Vse_cg, *Vsx_cg, *Vze_cg, *Vzx_cg;
+    float *Dse_cg, *Dze_cg, *Dsx_cg, *Dzx_cg;
+    float *dmu, *dka, *Y, *Vse, *Vsx, *Vze, *Vzx, *Y0, *V0se, *V0sx, *V0ze, *V0zx;
+    float *Dse, *Dze, *Dsx, *Dzx, *inv_s;
+    /* source */
+    int fluid_src, nelsrc, ielsrc[8], niter_stf;
+    float *src_term;     /* (5,5,8,3) or (5,5,8) */
+    float *stf;
+    int stf_type;
+    double decay, t_0, shift_fact, magnitude;
+    /* receivers */
+    int num_rec;
+    int *recfile_el;     /* (num_rec,3) Fortran order */
+    /* kwf */
+    int have_kwf, npt_s_kwf, npt_f_kwf;
+    int *kwf_mask, *kwf_map;
+    float *inv_rho_fluid, *Dse_f, *Dze_f, *Dsx_f, *Dzx_f;
+    halo_t halo[2];
+    /* time */
+    int scheme, niter, seis_it, strain_it;
+    double deltat, half_dt, half_dt_sq, t;
+    int nstages;
+    double coefd[40], coefv[40], coeff[40];
+    /* state */
+    float *disp, *velo, *acc0, *acc1, *chi, *dchi, *ddchi0, *ddchi1;
+    float *memvar, *src_dev_tm1, *src_tr_tm1;
+    float *gvec_s, *gvec_f;
+    int iter, iseismo, istrain;
+    float *recdump;      /* (3, num_rec, nseismo_max) */
+    int nseismo_max;
+    float *snapdump;     /* (npoints, nstrain_max, 3) */
+    int nstrain_max;
+    int finalized;
+    struct axb_handle_s **group;
+    int ngroup;
+};
+
+typedef struct axb_handle_s axo_t;
+
+static char g_err[512] = "";
+static int fail(const char *msg) { snprintf(g_err, sizeof g_err, "%s", msg); return 1; }
+const char *axo_last_error(void) { return g_err; }
+
+static float *dupf(const float *p, size_t n) {
+    if (!p) return NULL;
+    float *q = (float *)malloc((n ? n : 1) * sizeof(float));
+    memcpy(q, p, n * sizeof(float));
+    return q;
+}
+static int *dupi(const int32_t *p, size_t n) {
+    if (!p) return NULL;
+    int *q = (int *)malloc((n ? n : 1) * sizeof(int));
+    memcpy(q, p, n * sizeof(int));
+    return q;
+}
+static double *dupd(const double *p, size_t n) {
+    if (!p) return NULL;
+    double *q = (double *)malloc((n ? n : 1) * sizeof(double));
+    memcpy(q, p, n * sizeof(double));
+    return q;
+}
+static float *zerosf(size_t n) { return (float *)calloc(n ? n : 1, sizeof(float)); }
+
+int axo_create(axb_handle *h, int32_t device, int32_t rank, int32_t nranks) {
+    (void)device;
+    axo_t *o = (axo_t *)calloc(1, sizeof(axo_t));
+    if (!o) return fail("out of memory");
+    o->rank = rank;
+    o->nranks = nranks;
+    o->seis_it = 1;
+    *h = o;
+    return 0;
+}
+
+int axo_destroy(axb_handle h) {
+    /* test infrastructure: arrays are released with the process; free the big ones */
+    if (!h) return 0;
+    free(h->disp); free(h->velo); free(h->acc0); free(h->acc1);
+    free(h->chi); free(h->dchi); free(h->ddchi0); free(h->ddchi1);
+    free(h->memvar); free(h->src_dev_tm1); free(h->src_tr_tm1);
+    free(h->gvec_s); free(h->gvec_f); free(h->recdump); free(h->snapdump);
+    free(h);
+    return 0;
+}
+
+int axo_set_mesh(axb_handle h, int32_t npol, int32_t nel_solid, int32_t nel_fluid,
+                 int32_t nglob_solid, int32_t nglob_fluid, const int32_t *igloc_solid,
+                 const int32_t *igloc_fluid, const int32_t *axis_solid,
+                 const int32_t *axis_fluid, const int32_t *ax_el_solid, int32_t naxel_solid,
+                 const int32_t *ax_el_fluid, int32_t naxel_fluid, const float *G0,
+                 const float *G1, const float *G1T, const float *G2, const float *G2T) {
+    if (npol != 4) return fail("npol must be 4");
+    h->nel_s = nel_solid; h->nel_f = nel_fluid;
+    h->nglob_s = nglob_solid; h->nglob_f = nglob_fluid;
+    h->igloc_s = dupi(igloc_solid, (size_t)NPT * nel_solid);
+    h->igloc_f = dupi(igloc_fluid, (size_t)NPT * nel_fluid);
+    h->axis_s = dupi(axis_solid, nel_solid);
+    h->axis_f = dupi(axis_fluid, nel_fluid);
+    h->ax_el_s = dupi(ax_el_solid, naxel_solid); h->naxel_s = naxel_solid;
+    h->ax_el_f = dupi(ax_el_fluid, naxel_fluid); h->naxel_f = naxel_fluid;
+    memcpy(h->G0, G0, sizeof h->G0);
+    memcpy(h->G1, G1, sizeof h->G1); memcpy(h->G1T, G1T, sizeof h->G1T);
+    memcpy(h->G2, G2, sizeof h->G2); memcpy(h->G2T, G2T, sizeof h->G2T);
+    return 0;
+}
+
+int axo_set_solid_terms(axb_handle h, int32_t src_order, const axb_solid_terms *t) {
+    size_t n = (size_t)NPT * h->nel_s, n0 = (size_t)NP * h->nel_s;
+    h->src_order = src_order;
+#define CP(x) h->x = dupf(t->x, n)
+#define CP0(x) h->x = dupf(t->x, n0)
+    CP(M11s); CP(M21s); CP(M41s); CP(M12s); CP(M22s); CP(M32s); CP(M42s);
+    CP(M11z); CP(M21z); CP(M41z); CP(M13s); CP(M33s); CP(M43s);
+    CP(M1phi); CP(M2phi); CP(M4phi);
+    CP(M_1); CP(M_2); CP(M_3); CP(M_4); CP(M_5); CP(M_6); CP(M_7); CP(M_8);
+    CP(M_w1); CP(M_w2); CP(M_w3); CP(M_w4); CP(M_w5);
+    CP0(M0_w1); CP0(M0_w2); CP0(M0_w3); CP0(M0_w4); CP0(M0_w5);
+    CP0(M0_w6); CP0(M0_w7); CP0(M0_w8); CP0(M0_w9); CP0(M0_w10);
+#undef CP
+#undef CP0
+    return 0;
+}
+
+int axo_set_fluid_terms(axb_handle h, const float *M1chi_fl, const float *M2chi_fl,
+                        const float *M4chi_fl, const float *M_w_fl, const float *M0_w_fl,
+                        const float *inv_mass_fluid, const float *fluid_free_surface_mask) {
+    size_t n = (size_t)NPT * h->nel_f;
+    h->M1chi = dupf(M1chi_fl, n); h->M2chi = dupf(M2chi_fl, n); h->M4chi = dupf(M4chi_fl, n);
+    h->M_w_fl = dupf(M_w_fl, n); h->M0_w_fl = dupf(M0_w_fl, (size_t)NP * h->nel_f);
+    h->inv_mass_fluid = dupf(inv_mass_fluid, n);
+    h->fs_mask = dupf(fluid_free_surface_mask, n);
+    return 0;
+}
+
+int axo_set_mass(axb_handle h, const float *inv_mass_rho) {
+    h->inv_mass_rho = dupf(inv_mass_rho, (size_t)NPT * h->nel_s);
+    return 0;
+}
+
+int axo_set_sponge(axb_handle h, const float *solid_gamma, const float *fluid_gamma) {
+    h->have_abc = (solid_gamma != NULL) || (fluid_gamma != NULL);
+    h->gamma_s = dupf(solid_gamma, (size_t)NPT * h->nel_s);
+    h->gamma_f = dupf(fluid_gamma, (size_t)NPT * h->nel_f);
+    if (h->have_abc && !h->gamma_s) h->gamma_s = zerosf((size_t)NPT * h->nel_s);
+    if (h->have_abc && !h->gamma_f) h->gamma_f = zerosf((size_t)NPT * h->nel_f);
+    return 0;
+}
+
+int axo_set_sf_boundary(axb_handle h, int32_t nel_bdry, const int32_t *bdry_solid_el,
+                        const int32_t *bdry_fluid_el, const int32_t *bdry_jpol_solid,
+                        const int32_t *bdry_jpol_fluid, const float *bdry_matr) {
+    h->nel_bdry = nel_bdry;
+    h->bdry_sel = dupi(bdry_solid_el, nel_bdry); h->bdry_fel = dupi(bdry_fluid_el, nel_bdry);
+    h->bdry_js = dupi(bdry_jpol_solid, nel_bdry); h->bdry_jf = dupi(bdry_jpol_fluid, nel_bdry);
+    h->bdry_matr = dupf(bdry_matr, (size_t)NP * nel_bdry * 2);
+    return 0;
+}
+
+int axo_set_attenuation(axb_handle h, const axb_attenuation *a) {
+    size_t n4 = (size_t)4 * h->nel_s, n = (size_t)NPT * h->nel_s, n0 = (size_t)NP * h->nel_s;
+    h->anel = 1; h->cg = a->coarse_grained; h->n_sls = a->n_sls; h->corr_lowq = a->do_corr_lowq;
+    h->y_j = dupd(a->y_j, a->n_sls); h->exp_w = dupd(a->exp_w_j_deltat, a->n_sls);
+    h->ts_t = dupd(a->ts_fac_t, a->n_sls); h->ts_tm1 = dupd(a->ts_fac_tm1, a->n_sls);
+    h->Q_mu = dupf(a->Q_mu, h->nel_s); h->Q_kappa = dupf(a->Q_kappa, h->nel_s);
+    h->inv_s = dupf(a->inv_s_solid, n);
+    if (h->cg) {
+        h->dmu_cg = dupf(a->delta_mu_cg4, n4); h->dka_cg = dupf(a->delta_kappa_cg4, n4);
+        h->Ycg = dupf(a->Y_cg4, n4); h->Vse_cg = dupf(a->V_s_eta_cg4, n4);
+        h->Vsx_cg = dupf(a->V_s_xi_cg4, n4); h->Vze_cg = dupf(a->V_z_eta_cg4, n4);
+        h->Vzx_cg = dupf(a->V_z_xi_cg4, n4);
+        h->Dse_cg = dupf(a->DsDeta_over_J_sol_cg4, n4); h->Dze_cg = dupf(a->DzDeta_over_J_sol_cg4, n4);
+        h->Dsx_cg = dupf(a->DsDxi_over_J_sol_cg4, n4); h->Dzx_cg = dupf(a->DzDxi_over_J_sol_cg4, n4);
+        if (!h->dmu_cg || !h->Ycg || !h->Dse_cg || !h->inv_s) return fail("cg4 attenuation arrays missing");
+    } else {
+        h->dmu = dupf(a->delta_mu, n); h->dka = dupf(a->delta_kappa, n);
+        h->Y = dupf(a->Y, n); h->Vse = dupf(a->V_s_eta, n); h->Vsx = dupf(a->V_s_xi, n);
+        h->Vze = dupf(a->V_z_eta, n); h->Vzx = dupf(a->V_z_xi, n);
+        h->Y0 = dupf(a->Y0, n0); h->V0se = dupf(a->V0_s_eta, n0); h->V0sx = dupf(a->V0_s_xi, n0);
+        h->V0ze = dupf(a->V0_z_eta, n0); h->V0zx = dupf(a->V0_z_xi, n0);
+        h->Dse = dupf(a->DsDeta_over_J_sol, n); h->Dze = dupf(a->DzDeta_over_J_sol, n);
+        h->Dsx = dupf(a->DsDxi_over_J_sol, n); h->Dzx = dupf(a->DzDxi_over_J_sol, n);
+        if (!h->dmu || !h->Y || !h->Y0 || !h->Dse || !h->inv_s) return fail("full attenuation arrays missing");
+    }
+    return 0;
+}
+
+int axo_set_source(axb_handle h, int32_t fluid_src, int32_t nelsrc, const int32_t *ielsrc,
+                   const float *source_term, const float *stf, int32_t niter) {
+    if (nelsrc > 8) return fail("nelsrc > 8");
+    h->fluid_src = fluid_src; h->nelsrc = nelsrc;
+    for (int k = 0; k < 8; k++) h->ielsrc[k] = (ielsrc && k < nelsrc) ? ielsrc[k] : 0;
+    h->src_term = dupf(source_term, (size_t)NPT * 8 * (fluid_src ? 1 : 3));
+    h->stf = dupf(stf, niter); h->niter_stf = niter;
+    return 0;
+}
+
+int axo_set_stf_params(axb_handle h, int32_t stf_type, double decay, double t_0,
+                       double shift_fact, double magnitude) {
+    h->stf_type = stf_type; h->decay = decay; h->t_0 = t_0;
+    h->shift_fact = shift_fact; h->magnitude = magnitude;
+    return 0;
+}
+
+int axo_set_receivers(axb_handle h, int32_t num_rec, const int32_t *recfile_el) {
+    h->num_rec = num_rec;
+    h->recfile_el = dupi(recfile_el, (size_t)3 * num_rec);
+    return 0;
+}
+
+int axo_set_kwf(axb_handle h, const int32_t *kwf_mask, const int32_t *mapping_ijel_ikwf,
+                int32_t npoint_solid_kwf, int32_t npoint_fluid_kwf, const float *inv_rho_fluid,
+                const float *DsDeta_over_J_flu, const float *DzDeta_over_J_flu,
+                const float *DsDxi_over_J_flu, const float *DzDxi_over_J_flu) {
+    size_t n = (size_t)NPT * (h->nel_s + h->nel_f), nf = (size_t)NPT * h->nel_f;
+    h->have_kwf = 1; h->npt_s_kwf = npoint_solid_kwf; h->npt_f_kwf = npoint_fluid_kwf;
+    h->kwf_mask = dupi(kwf_mask, n); h->kwf_map = dupi(mapping_ijel_ikwf, n);
+    h->inv_rho_fluid = dupf(inv_rho_fluid, nf);
+    h->Dse_f = dupf(DsDeta_over_J_flu, nf); h->Dze_f = dupf(DzDeta_over_J_flu, nf);
+    h->Dsx_f = dupf(DsDxi_over_J_flu, nf); h->Dzx_f = dupf(DzDxi_over_J_flu, nf);
+    return 0;
+}
+
+int axo_set_halo(axb_handle h, int32_t domain, int32_t nmsg, const int32_t *list_peer,
+                 const int32_t *sizemsg, const int32_t *glocal_index_msg, int32_t maxmsg,
+                 int32_t num_comm_gll, const int32_t *glob2el) {
+    if (nmsg > MAXMSG) return fail("too many neighbours");
+    halo_t *H = &h->halo[domain];
+    int nc = domain == AXB_DOMAIN_SOLID ? 3 : 1;
+    H->nmsg = nmsg;
+    for (int m = 0; m < nmsg; m++) {
+        H->peer[m] = list_peer[m];
+        H->size[m] = sizemsg[m];
+        H->glocal[m] = (int *)malloc(sizeof(int) * (sizemsg[m] ? sizemsg[m] : 1));
+        for (int ip = 0; ip < sizemsg[m]; ip++) H->glocal[m][ip] = glocal_index_msg[ip + (size_t)maxmsg * m];
+        H->sendbuf[m] = zerosf((size_t)sizemsg[m] * nc);
+        H->recvbuf[m] = zerosf((size_t)sizemsg[m] * nc);
+    }
+    H->ncomm = num_comm_gll;
+    H->glob2el = dupi(glob2el, (size_t)3 * num_comm_gll);
+    return 0;
+}
+
+int axo_set_time(axb_handle h, int32_t scheme, double deltat, int32_t niter, int32_t seis_it,
+                 int32_t strain_it) {
+    h->scheme = scheme; h->deltat = deltat; h->niter = niter;
+    h->seis_it = seis_it > 0 ? seis_it : 1; h->strain_it = strain_it;
+    /* parameters.F90:1124-1125 */
+    h->half_dt = 0.5 * deltat;
+    h->half_dt_sq = 0.5 * deltat * deltat;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* symplectic_coefficients, time_evol_wave.F90:749-967; SS_scheme :972-992 (including
+ * the integer division 1/2 == 0 at :981) */
+static void ss_scheme(int n, int nstages, double *a, double *b, const double *g) {
+    double s = 0.0;
+    a[0] = g[0] / 2.0;
+    for (int i = 1; i < n; i++) a[i] = (g[i - 1] + g[i]) / 2.0;
+    for (int i = 0; i < n; i++) s += a[i];
+    a[n] = (double)(1 / 2) - s;                       /* reference quirk: 1/2 == 0 */
+    for (int i = n + 2; i <= 2 * n + 2; i++) a[i - 1] = a[2 * n + 3 - i - 1];
+    for (int i = 0; i < n; i++) b[i] = g[i];
+    s = 0.0;
+    for (int i = 0; i < n; i++) s += g[i];
+    b[n] = 1.0 - 2.0 * s;
+    for (int i = n + 2; i <= 2 * n + 1; i++) b[i - 1] = b[2 * n + 2 - i - 1];
+    (void)nstages;
+}
+
+static int symplectic_coefficients(axo_t *o) {
+    double *d = o->coefd, *v = o->coefv;
+    int n, ns = 0;
+    switch (o->scheme) {
+    case AXB_SYMPLEC4: {
+        /* the reference's literals are default-real (single precision) constants */
+        double zeta = (double)0.1786178958448091f, iota = (double)-0.2123418310626054f,
+               kappa = (double)-0.06626458266981849f;
+        ns = 4;
+        d[0] = zeta; d[1] = kappa; d[2] = 1.0 - 2.0 * (zeta + kappa); d[3] = kappa; d[4] = zeta;
+        v[0] = 0.5 - iota; v[1] = iota; v[2] = iota; v[3] = 0.5 - iota;
+        break; }
+    case AXB_ML_SO4M5: {
+        double rho = (14.0 - sqrt(19.0)) / 108.0, theta = (20.0 - 7.0 * sqrt(19.0)) / 108.0;
+        double nu = 2.0 / 5.0, lambda = -1.0 / 10.0;
+        ns = 5;
+        d[0] = rho; d[1] = theta; d[2] = 0.5 - rho - theta; d[3] = 0.5 - rho - theta;
+        d[4] = theta; d[5] = rho;
+        v[0] = nu; v[1] = lambda; v[2] = 1.0 - 2.0 * (nu + lambda); v[3] = lambda; v[4] = nu;
+        break; }
+    case AXB_ML_SO6M7: {
+        ns = 7;
+        d[0] = (double)-1.01308797891717472981f; d[1] = (double)1.18742957373254270702f;
+        d[2] = (double)-0.01833585209646059034f; d[3] = (double)0.34399425728109261313f;
+        for (int i = 5; i <= 8; i++) d[i - 1] = d[ns + 2 - i - 1];
+        v[0] = (double)0.00016600692650009894f; v[1] = (double)-0.37962421426377360608f;
+        v[2] = (double)0.68913741185181063674f; v[3] = (double)0.38064159097092574080f;
+        for (int i = 5; i <= 7; i++) v[i - 1] = v[ns + 1 - i - 1];
+        break; }
+    case AXB_KL_O8M17: {
+        static const float gf[8] = {0.13020248308889008088f, 0.56116298177510838456f,
+            -0.38947496264484728641f, 0.15884190655515560090f, -0.39590389413323757734f,
+            0.18453964097831570709f, 0.25837438768632204729f, 0.29501172360931029887f};
+        double g[8];
+        n = 8; ns = 2 * n + 1;
+        for (int i = 0; i < n; i++) g[i] = (double)gf[i];
+        ss_scheme(n, ns, d, v, g);
+        break; }
+    case AXB_SS_35O10: {
+        static const float gf[17] = {0.078795722521686419263907679337684f,
+            0.31309610341510852776481247192647f, 0.027918383235078066109520273275299f,
+            -0.22959284159390709415121339679655f, 0.13096206107716486317465685927961f,
+            -0.26973340565451071434460973222411f, 0.074973343155891435666137105641410f,
+            0.11199342399981020488957508073640f, 0.36613344954622675119314812353150f,
+            -0.39910563013603589787862981058340f, 0.10308739852747107731580277001372f,
+            0.41143087395589023782070411897608f, -0.0048663605831352617621956593099771f,
+            -0.39203335370863990644808193642610f, 0.051942502962449647037182904015976f,
+            0.050665090759924496335874344156866f, 0.049674370639729879054568800279461f};
+        double g[17];
+        n = 17; ns = 2 * n + 1;
+        for (int i = 0; i < n; i++) g[i] = (double)gf[i];
+        ss_scheme(n, ns, d, v, g);
+        break; }
+    default:
+        return fail("unknown time scheme");
+    }
+    o->nstages = ns;
+    for (int i = 0; i <= ns; i++) d[i] *= o->deltat;
+    for (int i = 0; i < ns; i++) v[i] *= o->deltat;
+    for (int i = 0; i < ns; i++) {
+        double s = 0.0;
+        for (int k = 0; k <= i; k++) s += d[k];
+        o->coeff[i] = s;
+    }
+    return 0;
+}
+
+int axo_finalize_setup(axb_handle h) {
+    size_t ns = (size_t)NPT * h->nel_s * 3, nf = (size_t)NPT * h->nel_f;
+    h->disp = zerosf(ns); h->velo = zerosf(ns); h->acc0 = zerosf(ns); h->acc1 = zerosf(ns);
+    h->chi = zerosf(nf); h->dchi = zerosf(nf); h->ddchi0 = zerosf(nf); h->ddchi1 = zerosf(nf);
+    h->gvec_s = zerosf((size_t)h->nglob_s * 3); h->gvec_f = zerosf((size_t)h->nglob_f);
+    if (h->anel) {
+        size_t per = h->cg ? 4 : NPT;
+        h->memvar = zerosf(per * 6 * h->n_sls * h->nel_s);
+        h->src_dev_tm1 = zerosf(per * 6 * h->nel_s);
+        h->src_tr_tm1 = zerosf(per * h->nel_s);
+    }
+    if (h->scheme != AXB_NEWMARK2) { if (symplectic_coefficients(h)) return 1; }
+    /* nseismo = floor(niter/seis_it) + 1 (parameters.F90:929) */
+    h->nseismo_max = h->niter / h->seis_it + 1;
+    h->recdump = zerosf((size_t)3 * h->num_rec * h->nseismo_max);
+    if (h->strain_it > 0 && h->have_kwf) {
+        h->nstrain_max = h->niter / h->strain_it + 1;
+        h->snapdump = zerosf((size_t)(h->npt_s_kwf + h->npt_f_kwf) * h->nstrain_max * 3);
+    }
+    h->iter = 0; h->iseismo = 0; h->istrain = 0; h->t = 0.0;
+    h->finalized = 1;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* unrolled_loops.f90:164-188: c(i,j) = sum(a(i,:)*b(:,j)), k ascending, real(4) */
+static void mxm_4(const float *a, const float *b, float *c) {
+    for (int j = 0; j < NP; j++)
+        for (int i = 0; i < NP; i++) {
+            float s = a[i + NP * 0] * b[0 + NP * j];
+            s = s + a[i + NP * 1] * b[1 + NP * j];
+            s = s + a[i + NP * 2] * b[2 + NP * j];
+            s = s + a[i + NP * 3] * b[3 + NP * j];
+            s = s + a[i + NP * 4] * b[4 + NP * j];
+            c[i + NP * j] = s;
+        }
+}
+/* unrolled_loops.f90:194-207 */
+static void vxm_4(const float *a, const float *b, float *c) {
+    for (int j = 0; j < NP; j++) {
+        float s = a[0] * b[0 + NP * j];
+        s = s + a[1] * b[1 + NP * j];
+        s = s + a[2] * b[2 + NP * j];
+        s = s + a[3] * b[3 + NP * j];
+        s = s + a[4] * b[4 + NP * j];
+        c[j] = s;
+    }
+}
+/* unrolled_loops.f90:222-229: outerprod(a,b)(i,j) = a(i)*b(j) */
+static void outerprod_4(const float *a, const float *b, float *c) {
+    for (int j = 0; j < NP; j++)
+        for (int i = 0; i < NP; i++) c[i + NP * j] = a[i] * b[j];
+}
+/* unrolled_loops.f90:76-96 */
+static void mxm_cg4_sparse_a(const float *a, const float *b, float *c) {
+    memset(c, 0, NPT * sizeof(float));
+    for (int j = 0; j < NP; j++) {
+        c[1 + NP * j] = a[0] * b[1 + NP * j] + a[1] * b[3 + NP * j];
+        c[3 + NP * j] = a[2] * b[1 + NP * j] + a[3] * b[3 + NP * j];
+    }
+}
+/* unrolled_loops.f90:100-120 */
+static void mxm_cg4_sparse_b(const float *a, const float *b, float *c) {
+    memset(c, 0, NPT * sizeof(float));
+    for (int i = 0; i < NP; i++) {
+        c[i + NP * 1] = a[i + NP * 1] * b[0] + a[i + NP * 3] * b[2];
+        c[i + NP * 3] = a[i + NP * 1] * b[1] + a[i + NP * 3] * b[3];
+    }
+}
+/* unrolled_loops.f90:124-158 */
+static void mxm_cg4_sparse_c(const float *a, const float *b, float *c) {
+    static const int ii[4] = {1, 1, 3, 3}, jj[4] = {1, 3, 1, 3};
+    for (int q = 0; q < 4; q++) {
+        int i = ii[q], j = jj[q];
+        float s = a[i + NP * 0] * b[0 + NP * j];
+        s = s + a[i + NP * 1] * b[1 + NP * j];
+        s = s + a[i + NP * 2] * b[2 + NP * j];
+        s = s + a[i + NP * 3] * b[3 + NP * j];
+        s = s + a[i + NP * 4] * b[4 + NP * j];
+        c[q] = s;
+    }
+}
+
+#define EL(p, e) ((p) + (size_t)NPT * (e))
+#define EL0(p, e) ((p) + (size_t)NP * (e))
+#define FOR25 for (int q = 0; q < NPT; q++)
+
+/* ------------------------------------------------------------------------------------ */
+/* stiffness_mono.f90:60-157 */
+static void glob_stiffness_mono_4(const axo_t *o, float *glob, const float *u) {
+    const size_t cs = (size_t)NPT * o->nel_s;
+    float us[NPT], uz[NPT], X1[NPT], X2[NPT], X3[NPT], X4[NPT];
+    float S1s[NPT], S2s[NPT], S1z[NPT], S2z[NPT], ls[NPT], lz[NPT], T[NPT];
+    float V1[NP], V2[NP], V3[NP], V4[NP], uz0[NP], W[NP];
+    for (int e = 0; e < o->nel_s; e++) {
+        const float *m_1 = EL(o->M_1, e), *m_2 = EL(o->M_2, e), *m_3 = EL(o->M_3, e), *m_4 = EL(o->M_4, e);
+        const float *m_w1 = EL(o->M_w1, e);
+        const float *m11s = EL(o->M11s, e), *m21s = EL(o->M21s, e), *m41s = EL(o->M41s, e);
+        const float *m12s = EL(o->M12s, e), *m22s = EL(o->M22s, e), *m32s = EL(o->M32s, e), *m42s = EL(o->M42s, e);
+        const float *m11z = EL(o->M11z, e), *m21z = EL(o->M21z, e), *m41z = EL(o->M41z, e);
+        memcpy(us, EL(u, e), sizeof us);
+        memcpy(uz, EL(u + 2 * cs, e), sizeof uz);
+        if (!o->axis_s[e]) { mxm_4(o->G2T, us, X1); mxm_4(o->G2T, uz, X2); }
+        else               { mxm_4(o->G1T, us, X1); mxm_4(o->G1T, uz, X2); }
+        mxm_4(us, o->G2, X3);
+        mxm_4(uz, o->G2, X4);
+        FOR25 {
+            ls[q] = m_4[q] * X4[q] + m_2[q] * X3[q] + m_1[q] * X1[q] + m_3[q] * X2[q] + us[q] * m_w1[q];
+            S1s[q] = m11s[q] * X3[q] + m21s[q] * X1[q] + m12s[q] * X4[q] + m22s[q] * X2[q] + m_1[q] * us[q];
+            S2s[q] = m11s[q] * X1[q] + m41s[q] * X3[q] + m32s[q] * X2[q] + m42s[q] * X4[q] + m_2[q] * us[q];
+            S1z[q] = m11z[q] * X4[q] + m21z[q] * X2[q] + m32s[q] * X3[q] + m22s[q] * X1[q] + m_3[q] * us[q];
+            S2z[q] = m11z[q] * X2[q] + m41z[q] * X4[q] + m12s[q] * X1[q] + m42s[q] * X3[q] + m_4[q] * us[q];
+        }
+        mxm_4(S2s, o->G2T, X2);
+        mxm_4(S2z, o->G2T, X4);
+        if (!o->axis_s[e]) { mxm_4(o->G2, S1s, X1); mxm_4(o->G2, S1z, X3); }
+        else               { mxm_4(o->G1, S1s, X1); mxm_4(o->G1, S1z, X3); }
+        FOR25 { ls[q] = ls[q] + X1[q] + X2[q]; lz[q] = X3[q] + X4[q]; }
+        if (o->axis_s[e]) {
+            const float *m0_w1 = EL0(o->M0_w1, e), *m0_w2 = EL0(o->M0_w2, e), *m0_w3 = EL0(o->M0_w3, e);
+            for (int j = 0; j < NP; j++) uz0[j] = uz[0 + NP * j];
+            vxm_4(o->G0, us, V1);
+            vxm_4(uz0, o->G2, V2);
+            for (int j = 0; j < NP; j++) V4[j] = m0_w1[j] * V1[j] + m0_w3[j] * V2[j];
+            vxm_4(o->G0, uz, V3);
+            for (int j = 0; j < NP; j++) V4[j] = V4[j] + m0_w2[j] * V3[j];
+            for (int j = 0; j < NP; j++) W[j] = m0_w2[j] * V1[j];
+            outerprod_4(o->G0, W, X2);
+            for (int j = 0; j < NP; j++) V2[j] = m0_w3[j] * V1[j];
+            vxm_4(V2, o->G2T, V1);
+            for (int j = 0; j < NP; j++) X2[0 + NP * j] = X2[0 + NP * j] + V1[j];
+            outerprod_4(o->G0, V4, T);
+            FOR25 { ls[q] = ls[q] + T[q]; lz[q] = X2[q] + lz[q]; }
+        }
+        memcpy(EL(glob, e), ls, sizeof ls);
+        memcpy(EL(glob + 2 * cs, e), lz, sizeof lz);
+    }
+}
+
+/* stiffness_di.f90:60-256 */
+static void glob_stiffness_di_4(const axo_t *o, float *glob, const float *u) {
+    const size_t cs = (size_t)NPT * o->nel_s;
+    float u1[NPT], u2[NPT], u3[NPT];
+    float X1[NPT], X2[NPT], X3[NPT], X4[NPT], X5[NPT], X6[NPT], X7[NPT], X8[NPT];
+    float S1p[NPT], S1m[NPT], S2p[NPT], S2m[NPT], S1z[NPT], S2z[NPT];
+    float ls2[NPT], ls3[NPT], l1[NPT], l2[NPT], l3[NPT];
+    float V1[NP], V2[NP], V3[NP], V4[NP], V5[NP], u10[NP], u20[NP], W[NP];
+    for (int e = 0; e < o->nel_s; e++) {
+        const float *m_1 = EL(o->M_1, e), *m_2 = EL(o->M_2, e), *m_3 = EL(o->M_3, e), *m_4 = EL(o->M_4, e);
+        const float *m_5 = EL(o->M_5, e), *m_6 = EL(o->M_6, e), *m_7 = EL(o->M_7, e), *m_8 = EL(o->M_8, e);
+        const float *m_w1 = EL(o->M_w1, e), *m_w2 = EL(o->M_w2, e), *m_w3 = EL(o->M_w3, e);
+        const float *m11s = EL(o->M11s, e), *m21s = EL(o->M21s, e), *m41s = EL(o->M41s, e);
+        const float *m12s = EL(o->M12s, e), *m22s = EL(o->M22s, e), *m42s = EL(o->M42s, e);
+        const float *m13s = EL(o->M13s, e), *m23s = EL(o->M32s, e) /* stiffness_di.f90:128 */;
+        const float *m33s = EL(o->M33s, e), *m43s = EL(o->M43s, e);
+        const float *m11z = EL(o->M11z, e), *m21z = EL(o->M21z, e), *m41z = EL(o->M41z, e);
+        memcpy(u1, EL(u, e), sizeof u1);
+        memcpy(u2, EL(u + cs, e), sizeof u2);
+        memcpy(u3, EL(u + 2 * cs, e), sizeof u3);
+        mxm_4(u1, o->G2, X4); mxm_4(u2, o->G2, X5); mxm_4(u3, o->G2, X6);
+        if (!o->axis_s[e]) { mxm_4(o->G2T, u1, X1); mxm_4(o->G2T, u2, X2); mxm_4(o->G2T, u3, X3); }
+        else               { mxm_4(o->G1T, u1, X1); mxm_4(o->G1T, u2, X2); mxm_4(o->G1T, u3, X3); }
+        FOR25 {
+            float c1, c2, c3;
+            X7[q] = X1[q] + X2[q];
+            X8[q] = X4[q] + X5[q];
+            ls2[q] = m_8[q] * X6[q] + m_7[q] * X3[q] + m_1[q] * X1[q] + m_5[q] * X2[q]
+                   + m_2[q] * X4[q] + m_6[q] * X5[q] + m_w1[q] * u2[q] + m_w2[q] * u3[q];
+            ls3[q] = m_4[q] * X4[q] - m_4[q] * X5[q] + m_3[q] * X1[q] - m_3[q] * X2[q]
+                   + m_w2[q] * u2[q] + m_w3[q] * u3[q];
+            c1 = m13s[q] * X6[q]; c2 = m23s[q] * X3[q]; c3 = m_3[q] * u3[q];
+            S1p[q] = c1 + c2 + c3 + m11s[q] * X4[q] + m21s[q] * X1[q] + m12s[q] * X5[q] + m22s[q] * X2[q] + m_1[q] * u2[q];
+            S1m[q] = c1 + c2 - c3 + m11s[q] * X5[q] + m21s[q] * X2[q] + m12s[q] * X4[q] + m22s[q] * X1[q] + m_5[q] * u2[q];
+            c1 = m33s[q] * X3[q]; c2 = m43s[q] * X6[q]; c3 = m_4[q] * u3[q];
+            S2p[q] = c1 + c2 + c3 + m11s[q] * X1[q] + m41s[q] * X4[q] + m12s[q] * X2[q] + m42s[q] * X5[q] + m_2[q] * u2[q];
+            S2m[q] = c1 + c2 - c3 + m11s[q] * X2[q] + m41s[q] * X5[q] + m12s[q] * X1[q] + m42s[q] * X4[q] + m_6[q] * u2[q];
+            S1z[q] = m33s[q] * X8[q] + m23s[q] * X7[q] + m11z[q] * X6[q] + m21z[q] * X3[q] + m_7[q] * u2[q];
+            S2z[q] = m13s[q] * X7[q] + m43s[q] * X8[q] + m11z[q] * X3[q] + m41z[q] * X6[q] + m_8[q] * u2[q];
+        }
+        if (!o->axis_s[e]) { mxm_4(o->G2, S1p, X1); mxm_4(o->G2, S1m, X3); mxm_4(o->G2, S1z, X5); }
+        else               { mxm_4(o->G1, S1p, X1); mxm_4(o->G1, S1m, X3); mxm_4(o->G1, S1z, X5); }
+        mxm_4(S2p, o->G2T, X2); mxm_4(S2m, o->G2T, X4); mxm_4(S2z, o->G2T, X6);
+        FOR25 {
+            l1[q] = X1[q] + X2[q];
+            l2[q] = X3[q] + X4[q] + ls2[q];
+            l3[q] = X5[q] + X6[q] + ls3[q];
+        }
+        if (o->axis_s[e]) {
+            const float *w1 = EL0(o->M0_w1, e), *w2 = EL0(o->M0_w2, e), *w3 = EL0(o->M0_w3, e);
+            const float *w4 = EL0(o->M0_w4, e), *w6 = EL0(o->M0_w6, e), *w7 = EL0(o->M0_w7, e);
+            const float *w8 = EL0(o->M0_w8, e), *w9 = EL0(o->M0_w9, e), *w10 = EL0(o->M0_w10, e);
+            for (int j = 0; j < NP; j++) { u10[j] = u1[0 + NP * j]; u20[j] = u2[0 + NP * j]; }
+            vxm_4(o->G0, u1, V1); vxm_4(o->G0, u2, V2); vxm_4(o->G0, u3, V3);
+            vxm_4(u10, o->G2, V4); vxm_4(u20, o->G2, V5);
+            for (int j = 0; j < NP; j++) W[j] = w1[j] * V2[j] + w3[j] * V3[j];
+            outerprod_4(o->G0, W, S1p);
+            for (int j = 0; j < NP; j++)
+                W[j] = w1[j] * V1[j] + (w2[j] + w6[j]) * V4[j] + w9[j] * V2[j] + w10[j] * V3[j];
+            outerprod_4(o->G0, W, S1m);
+            for (int j = 0; j < NP; j++)
+                W[j] = w3[j] * V1[j] + (w4[j] + w8[j]) * V4[j] + w7[j] * V3[j] + w10[j] * V2[j];
+            outerprod_4(o->G0, W, S1z);
+            for (int j = 0; j < NP; j++) V4[j] = (w2[j] + w6[j]) * V2[j] + (w4[j] + w8[j]) * V3[j];
+            vxm_4(V4, o->G2T, V1);
+            for (int j = 0; j < NP; j++) S1p[0 + NP * j] = S1p[0 + NP * j] + V1[j];
+            FOR25 { l1[q] = l1[q] + S1p[q]; l2[q] = l2[q] + S1m[q]; l3[q] = l3[q] + S1z[q]; }
+            (void)V5;
+        }
+        memcpy(EL(glob, e), l1, sizeof l1);
+        memcpy(EL(glob + cs, e), l2, sizeof l2);
+        memcpy(EL(glob + 2 * cs, e), l3, sizeof l3);
+    }
+}
+
+/* stiffness_quad.f90:238-412 */
+static void glob_stiffness_quad_4(const axo_t *o, float *glob, const float *u) {
+    const size_t cs = (size_t)NPT * o->nel_s;
+    float us[NPT], up[NPT], uz[NPT];
+    float X1[NPT], X2[NPT], X3[NPT], X4[NPT], X5[NPT], X6[NPT];
+    float S1s[NPT], S2s[NPT], S1p[NPT], S2p[NPT], S1z[NPT], S2z[NPT];
+    float ls[NPT], lp[NPT], lz[NPT];
+    float V1[NP], V2[NP], V3[NP], W[NP];
+    for (int e = 0; e < o->nel_s; e++) {
+        const float *m_1 = EL(o->M_1, e), *m_2 = EL(o->M_2, e), *m_3 = EL(o->M_3, e), *m_4 = EL(o->M_4, e);
+        const float *m_5 = EL(o->M_5, e), *m_6 = EL(o->M_6, e), *m_7 = EL(o->M_7, e), *m_8 = EL(o->M_8, e);
+        const float *m_w1 = EL(o->M_w1, e), *m_w2 = EL(o->M_w2, e), *m_w3 = EL(o->M_w3, e);
+        const float *m_w4 = EL(o->M_w4, e), *m_w5 = EL(o->M_w5, e);
+        const float *m11s = EL(o->M11s, e), *m21s = EL(o->M21s, e), *m41s = EL(o->M41s, e);
+        const float *m12s = EL(o->M12s, e), *m22s = EL(o->M22s, e), *m32s = EL(o->M32s, e), *m42s = EL(o->M42s, e);
+        const float *m11z = EL(o->M11z, e), *m21z = EL(o->M21z, e), *m41z = EL(o->M41z, e);
+        const float *m1phi = EL(o->M1phi, e), *m2phi = EL(o->M2phi, e), *m4phi = EL(o->M4phi, e);
+        memcpy(us, EL(u, e), sizeof us);
+        memcpy(up, EL(u + cs, e), sizeof up);
+        memcpy(uz, EL(u + 2 * cs, e), sizeof uz);
+        if (!o->axis_s[e]) { mxm_4(o->G2T, us, X1); mxm_4(o->G2T, up, X2); mxm_4(o->G2T, uz, X3); }
+        else               { mxm_4(o->G1T, us, X1); mxm_4(o->G1T, up, X2); mxm_4(o->G1T, uz, X3); }
+        mxm_4(us, o->G2, X4); mxm_4(up, o->G2, X5); mxm_4(uz, o->G2, X6);
+        FOR25 {
+            float c1 = m_2[q] * X4[q], c2 = m_1[q] * X1[q], c3 = m_6[q] * X5[q];
+            float c4 = m_5[q] * X2[q], c5 = m_4[q] * X6[q], c6 = m_3[q] * X3[q];
+            ls[q] = c1 + c2 + 2 * (c3 + c4) + c5 + c6 + m_w1[q] * us[q] + m_w2[q] * up[q] + 2 * m_w3[q] * uz[q];
+            lp[q] = -2 * (c1 + c2 + c5 + c6) - (c3 + c4) + m_w2[q] * us[q] + m_w4[q] * up[q] - m_w3[q] * uz[q];
+            lz[q] = 2 * (m_8[q] * X5[q] + m_7[q] * X2[q]) + m_w3[q] * (2 * us[q] - up[q]) + m_w5[q] * uz[q];
+            S1s[q] = m11s[q] * X4[q] + m21s[q] * X1[q] + m12s[q] * X6[q] + m22s[q] * X3[q] + m_1[q] * (us[q] - 2 * up[q]);
+            S2s[q] = m11s[q] * X1[q] + m41s[q] * X4[q] + m32s[q] * X3[q] + m42s[q] * X6[q] + m_2[q] * (us[q] - 2 * up[q]);
+            S1z[q] = m11z[q] * X6[q] + m21z[q] * X3[q] + m32s[q] * X4[q] + m22s[q] * X1[q] + m_3[q] * (us[q] - 2 * up[q]);
+            S2z[q] = m11z[q] * X3[q] + m41z[q] * X6[q] + m12s[q] * X1[q] + m42s[q] * X4[q] + m_4[q] * (us[q] - 2 * up[q]);
+            S1p[q] = m1phi[q] * X5[q] + m2phi[q] * X2[q] + m_5[q] * (2 * us[q] - up[q]) + 2 * m_7[q] * uz[q];
+            S2p[q] = m1phi[q] * X2[q] + m4phi[q] * X5[q] + m_6[q] * (2 * us[q] - up[q]) + 2 * m_8[q] * uz[q];
+        }
+        mxm_4(S2s, o->G2T, X2); mxm_4(S2p, o->G2T, X4); mxm_4(S2z, o->G2T, X6);
+        if (!o->axis_s[e]) { mxm_4(o->G2, S1s, X1); mxm_4(o->G2, S1p, X3); mxm_4(o->G2, S1z, X5); }
+        else               { mxm_4(o->G1, S1s, X1); mxm_4(o->G1, S1p, X3); mxm_4(o->G1, S1z, X5); }
+        FOR25 {
+            ls[q] = ls[q] + X1[q] + X2[q];
+            lp[q] = lp[q] + X3[q] + X4[q];
+            lz[q] = lz[q] + X5[q] + X6[q];
+        }
+        if (o->axis_s[e]) {
+            const float *w1 = EL0(o->M0_w1, e), *w2 = EL0(o->M0_w2, e), *w3 = EL0(o->M0_w3, e);
+            const float *w4 = EL0(o->M0_w4, e), *w5 = EL0(o->M0_w5, e), *w6 = EL0(o->M0_w6, e);
+            vxm_4(o->G0, us, V1); vxm_4(o->G0, up, V2); vxm_4(o->G0, uz, V3);
+            for (int j = 0; j < NP; j++) W[j] = w1[j] * V1[j] + w2[j] * V2[j] + w3[j] * V3[j];
+            outerprod_4(o->G0, W, S1s);
+            for (int j = 0; j < NP; j++) W[j] = w2[j] * V1[j] + w4[j] * V2[j] + w5[j] * V3[j];
+            outerprod_4(o->G0, W, S1p);
+            for (int j = 0; j < NP; j++) W[j] = w3[j] * V1[j] + w5[j] * V2[j] + w6[j] * V3[j];
+            outerprod_4(o->G0, W, S1z);
+            FOR25 { ls[q] = ls[q] + S1s[q]; lp[q] = lp[q] + S1p[q]; lz[q] = lz[q] + S1z[q]; }
+        }
+        memcpy(EL(glob, e), ls, sizeof ls);
+        memcpy(EL(glob + cs, e), lp, sizeof lp);
+        memcpy(EL(glob + 2 * cs, e), lz, sizeof lz);
+    }
+}
+
+/* stiffness_fluid.f90:139-216 */
+static void glob_fluid_stiffness_4(const axo_t *o, float *glob, const float *chi) {
+    float c[NPT], X1[NPT], X2[NPT], S1[NPT], S2[NPT], l[NPT], T[NPT], V1[NP], W[NP];
+    for (int e = 0; e < o->nel_f; e++) {
+        const float *m1 = EL(o->M1chi, e), *m2 = EL(o->M2chi, e), *m4 = EL(o->M4chi, e);
+        memcpy(c, EL(chi, e), sizeof c);
+        if (o->axis_f[e]) mxm_4(o->G1T, c, X1); else mxm_4(o->G2T, c, X1);
+        mxm_4(c, o->G2, X2);
+        FOR25 { S1[q] = m1[q] * X2[q] + m2[q] * X1[q]; S2[q] = m1[q] * X1[q] + m4[q] * X2[q]; }
+        if (o->axis_f[e]) mxm_4(o->G1, S1, X1); else mxm_4(o->G2, S1, X1);
+        mxm_4(S2, o->G2T, X2);
+        FOR25 l[q] = X1[q] + X2[q];
+        if (o->src_order != AXB_MONOPOLE) {
+            const float *mw = EL(o->M_w_fl, e);
+            FOR25 l[q] = l[q] + mw[q] * c[q];
+            if (o->axis_f[e]) {
+                const float *m0 = EL0(o->M0_w_fl, e);
+                vxm_4(o->G0, c, V1);
+                for (int j = 0; j < NP; j++) W[j] = m0[j] * V1[j];
+                outerprod_4(o->G0, W, T);
+                FOR25 l[q] = l[q] + T[q];
+            }
+        }
+        memcpy(EL(glob, e), l, sizeof l);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* anelastic stiffness: stiffness_mono.f90:409-589, stiffness_di.f90:604-825,
+ * stiffness_quad.f90:555-774 */
+#define MV_CG(R, k, v, j, e) (R)[(k) + 4 * ((v) + 6 * ((j) + (size_t)o->n_sls * (e)))]
+#define MV_FULL(R, q, v, j, e) (R)[(q) + NPT * ((v) + 6 * ((j) + (size_t)o->n_sls * (e)))]
+
+static void glob_anel_stiffness_cg4(const axo_t *o, float *glob, const float *R) {
+    const size_t cs = (size_t)NPT * o->nel_s;
+    static const int pidx[4] = {1 + NP * 1, 1 + NP * 3, 3 + NP * 1, 3 + NP * 3}; /* (1,1),(1,3),(3,1),(3,3) */
+    float X1[NPT], X2[NPT], X3[NPT], X4[NPT], X5[NPT], X6[NPT];
+    for (int e = 0; e < o->nel_s; e++) {
+        const float *yl = o->Ycg + 4 * (size_t)e, *vse = o->Vse_cg + 4 * (size_t)e, *vsx = o->Vsx_cg + 4 * (size_t)e;
+        const float *vze = o->Vze_cg + 4 * (size_t)e, *vzx = o->Vzx_cg + 4 * (size_t)e;
+        float r[6][4];
+        const float *GA = o->axis_s[e] ? o->G1 : o->G2;
+        for (int v = 0; v < 6; v++) for (int k = 0; k < 4; k++) r[v][k] = 0.0f;
+        for (int j = 0; j < o->n_sls; j++)
+            for (int v = 0; v < 6; v++) {
+                if (o->src_order == AXB_MONOPOLE && (v == 3 || v == 5)) continue;
+                for (int k = 0; k < 4; k++) r[v][k] = r[v][k] + MV_CG(R, k, v, j, e);
+            }
+        const float *r1 = r[0], *r2 = r[1], *r3 = r[2], *r4 = r[3], *r5 = r[4], *r6 = r[5];
+        float S1a[4], S2a[4], S1b[4], S2b[4], S1z[4], S2z[4];
+        float *g1 = EL(glob, e), *g2 = EL(glob + cs, e), *g3 = EL(glob + 2 * cs, e);
+        if (o->src_order == AXB_MONOPOLE) {
+            for (int k = 0; k < 4; k++) {
+                S1a[k] = vze[k] * r1[k] + vse[k] * r5[k];
+                S2a[k] = vzx[k] * r1[k] + vsx[k] * r5[k];
+                S1z[k] = vze[k] * r5[k] + vse[k] * r3[k];
+                S2z[k] = vzx[k] * r5[k] + vsx[k] * r3[k];
+            }
+            mxm_cg4_sparse_b(GA, S1a, X1); mxm_cg4_sparse_b(GA, S1z, X3);
+            mxm_cg4_sparse_a(S2a, o->G2T, X2); mxm_cg4_sparse_a(S2z, o->G2T, X4);
+            float ls[NPT], lz[NPT];
+            FOR25 { ls[q] = X1[q] + X2[q]; lz[q] = X3[q] + X4[q]; }
+            for (int k = 0; k < 4; k++) ls[pidx[k]] = ls[pidx[k]] + yl[k] * r2[k];
+            FOR25 { g1[q] = g1[q] - ls[q]; g3[q] = g3[q] - lz[q]; }
+        } else if (o->src_order == AXB_DIPOLE) {
+            for (int k = 0; k < 4; k++) {
+                S1a[k] = vze[k] * (r1[k] - r6[k]) + vse[k] * (r5[k] - r4[k]);
+                S2a[k] = vzx[k] * (r1[k] - r6[k]) + vsx[k] * (r5[k] - r4[k]);
+                S1b[k] = vze[k] * (r1[k] + r6[k]) + vse[k] * (r5[k] + r4[k]);
+                S2b[k] = vzx[k] * (r1[k] + r6[k]) + vsx[k] * (r5[k] + r4[k]);
+                S1z[k] = vze[k] * r5[k] + vse[k] * r3[k];
+                S2z[k] = vzx[k] * r5[k] + vsx[k] * r3[k];
+            }
+            mxm_cg4_sparse_b(GA, S1a, X1); mxm_cg4_sparse_b(GA, S1b, X3); mxm_cg4_sparse_b(GA, S1z, X5);
+            mxm_cg4_sparse_a(S2a, o->G2T, X2); mxm_cg4_sparse_a(S2b, o->G2T, X4); mxm_cg4_sparse_a(S2z, o->G2T, X6);
+            float lp[NPT], lm[NPT], lz[NPT];
+            FOR25 { lp[q] = X1[q] + X2[q]; lm[q] = X3[q] + X4[q]; lz[q] = X5[q] + X6[q]; }
+            for (int k = 0; k < 4; k++) {
+                lm[pidx[k]] = lm[pidx[k]] + 2 * yl[k] * (r2[k] - r6[k]);
+                lz[pidx[k]] = lz[pidx[k]] - yl[k] * r4[k];
+            }
+            FOR25 { g1[q] = g1[q] - lp[q]; g2[q] = g2[q] - lm[q]; g3[q] = g3[q] - lz[q]; }
+        } else {
+            for (int k = 0; k < 4; k++) {
+                S1a[k] = vze[k] * r1[k] + vse[k] * r5[k];
+                S2a[k] = vzx[k] * r1[k] + vsx[k] * r5[k];
+                S1b[k] = vze[k] * r6[k] + vse[k] * r4[k];
+                S2b[k] = vzx[k] * r6[k] + vsx[k] * r4[k];
+                S1z[k] = vze[k] * r5[k] + vse[k] * r3[k];
+                S2z[k] = vzx[k] * r5[k] + vsx[k] * r3[k];
+            }
+            mxm_cg4_sparse_b(GA, S1a, X1); mxm_cg4_sparse_b(GA, S1b, X3); mxm_cg4_sparse_b(GA, S1z, X5);
+            mxm_cg4_sparse_a(S2a, o->G2T, X2); mxm_cg4_sparse_a(S2b, o->G2T, X4); mxm_cg4_sparse_a(S2z, o->G2T, X6);
+            float ls[NPT], lp[NPT], lz[NPT];
+            FOR25 { ls[q] = X1[q] + X2[q]; lp[q] = -X3[q] - X4[q]; lz[q] = X5[q] + X6[q]; }
+            for (int k = 0; k < 4; k++) {
+                ls[pidx[k]] = ls[pidx[k]] + yl[k] * (r2[k] - 2 * r6[k]);
+                lp[pidx[k]] = lp[pidx[k]] + yl[k] * (r6[k] - 2 * r2[k]);
+                lz[pidx[k]] = lz[pidx[k]] - 2 * yl[k] * r4[k];
+            }
+            FOR25 { g1[q] = g1[q] - ls[q]; g2[q] = g2[q] - lp[q]; g3[q] = g3[q] - lz[q]; }
+        }
+    }
+}
+
+static void glob_anel_stiffness_4(const axo_t *o, float *glob, const float *R) {
+    const size_t cs = (size_t)NPT * o->nel_s;
+    float r[6][NPT], X1[NPT], X2[NPT], X3[NPT], X4[NPT], X5[NPT], X6[NPT];
+    float S1a[NPT], S2a[NPT], S1b[NPT], S2b[NPT], S1z[NPT], S2z[NPT], T[NPT];
+    float V1[NP], V2[NP], V3[NP], V4[NP];
+    for (int e = 0; e < o->nel_s; e++) {
+        const float *yl = EL(o->Y, e), *vse = EL(o->Vse, e), *vsx = EL(o->Vsx, e);
+        const float *vze = EL(o->Vze, e), *vzx = EL(o->Vzx, e);
+        const float *GA = o->axis_s[e] ? o->G1 : o->G2;
+        for (int v = 0; v < 6; v++) FOR25 r[v][q] = 0.0f;
+        for (int j = 0; j < o->n_sls; j++)
+            for (int v = 0; v < 6; v++) {
+                if (o->src_order == AXB_MONOPOLE && (v == 3 || v == 5)) continue;
+                FOR25 r[v][q] = r[v][q] + MV_FULL(R, q, v, j, e);
+            }
+        const float *r1 = r[0], *r2 = r[1], *r3 = r[2], *r4 = r[3], *r5 = r[4], *r6 = r[5];
+        float *g1 = EL(glob, e), *g2 = EL(glob + cs, e), *g3 = EL(glob + 2 * cs, e);
+        const float *y0 = EL0(o->Y0, e), *v0se = EL0(o->V0se, e), *v0sx = EL0(o->V0sx, e);
+        const float *v0ze = EL0(o->V0ze, e), *v0zx = EL0(o->V0zx, e);
+#define R0(a, j) (a)[0 + NP * (j)]
+        if (o->src_order == AXB_MONOPOLE) {
+            float ls[NPT], lz[NPT];
+            FOR25 {
+                S1a[q] = vze[q] * r1[q] + vse[q] * r5[q];
+                S2a[q] = vzx[q] * r1[q] + vsx[q] * r5[q];
+                S1z[q] = vze[q] * r5[q] + vse[q] * r3[q];
+                S2z[q] = vzx[q] * r5[q] + vsx[q] * r3[q];
+            }
+            mxm_4(GA, S1a, X1); mxm_4(GA, S1z, X3);
+            mxm_4(S2a, o->G2T, X2); mxm_4(S2z, o->G2T, X4);
+            FOR25 { ls[q] = X1[q] + X2[q] + yl[q] * r2[q]; lz[q] = X3[q] + X4[q]; }
+            if (o->axis_s[e]) {
+                for (int j = 0; j < NP; j++)
+                    V1[j] = v0ze[j] * R0(r1, j) + v0se[j] * R0(r5, j) + y0[j] * R0(r2, j);
+                outerprod_4(o->G0, V1, T);
+                FOR25 ls[q] = ls[q] + T[q];
+                for (int j = 0; j < NP; j++) {
+                    V2[j] = v0ze[j] * R0(r5, j) + v0se[j] * R0(r3, j);
+                    V3[j] = v0zx[j] * R0(r5, j) + v0sx[j] * R0(r3, j);
+                }
+                vxm_4(V3, o->G2T, V4);
+                outerprod_4(o->G0, V2, T);
+                FOR25 lz[q] = lz[q] + T[q];
+                for (int j = 0; j < NP; j++) lz[0 + NP * j] = lz[0 + NP * j] + V4[j];
+            }
+            FOR25 { g1[q] = g1[q] - ls[q]; g3[q] = g3[q] - lz[q]; }
+        } else if (o->src_order == AXB_DIPOLE) {
+            float lp[NPT], lm[NPT], lz[NPT];
+            FOR25 {
+                S1a[q] = vze[q] * (r1[q] - r6[q]) + vse[q] * (r5[q] - r4[q]);
+                S2a[q] = vzx[q] * (r1[q] - r6[q]) + vsx[q] * (r5[q] - r4[q]);
+                S1b[q] = vze[q] * (r1[q] + r6[q]) + vse[q] * (r5[q] + r4[q]);
+                S2b[q] = vzx[q] * (r1[q] + r6[q]) + vsx[q] * (r5[q] + r4[q]);
+                S1z[q] = vze[q] * r5[q] + vse[q] * r3[q];
+                S2z[q] = vzx[q] * r5[q] + vsx[q] * r3[q];
+            }
+            mxm_4(GA, S1a, X1); mxm_4(GA, S1b, X3); mxm_4(GA, S1z, X5);
+            mxm_4(S2a, o->G2T, X2); mxm_4(S2b, o->G2T, X4); mxm_4(S2z, o->G2T, X6);
+            FOR25 {
+                lp[q] = X1[q] + X2[q];
+                lm[q] = X3[q] + X4[q] + 2 * yl[q] * (r2[q] - r6[q]);
+                lz[q] = X5[q] + X6[q] - yl[q] * r4[q];
+            }
+            if (o->axis_s[e]) {
+                for (int j = 0; j < NP; j++) {
+                    V1[j] = v0ze[j] * (R0(r1, j) - R0(r6, j)) + v0se[j] * (R0(r5, j) - R0(r4, j));
+                    V2[j] = v0zx[j] * (R0(r1, j) - R0(r6, j)) + v0sx[j] * (R0(r5, j) - R0(r4, j));
+                }
+                vxm_4(V2, o->G2T, V3);
+                outerprod_4(o->G0, V1, T);
+                FOR25 lp[q] = lp[q] + T[q];
+                for (int j = 0; j < NP; j++) lp[0 + NP * j] = lp[0 + NP * j] + V3[j];
+                for (int j = 0; j < NP; j++)
+                    V1[j] = v0ze[j] * (R0(r1, j) + R0(r6, j)) + v0se[j] * (R0(r5, j) + R0(r4, j))
+                          + y0[j] * 2 * (R0(r2, j) - R0(r6, j));
+                outerprod_4(o->G0, V1, T);
+                FOR25 lm[q] = lm[q] + T[q];
+                /* reference quirk (stiffness_di.f90:710-711): V1 is computed but V2 is added */
+                outerprod_4(o->G0, V2, T);
+                FOR25 lz[q] = lz[q] + T[q];
+            }
+            FOR25 { g1[q] = g1[q] - lp[q]; g2[q] = g2[q] - lm[q]; g3[q] = g3[q] - lz[q]; }
+        } else {
+            float ls[NPT], lp[NPT], lz[NPT];
+            FOR25 {
+                S1a[q] = vze[q] * r1[q] + vse[q] * r5[q];
+                S2a[q] = vzx[q] * r1[q] + vsx[q] * r5[q];
+                S1b[q] = vze[q] * r6[q] + vse[q] * r4[q];
+                S2b[q] = vzx[q] * r6[q] + vsx[q] * r4[q];
+                S1z[q] = vze[q] * r5[q] + vse[q] * r3[q];
+                S2z[q] = vzx[q] * r5[q] + vsx[q] * r3[q];
+            }
+            mxm_4(GA, S1a, X1); mxm_4(GA, S1b, X3); mxm_4(GA, S1z, X5);
+            mxm_4(S2a, o->G2T, X2); mxm_4(S2b, o->G2T, X4); mxm_4(S2z, o->G2T, X6);
+            FOR25 {
+                ls[q] = X1[q] + X2[q] + yl[q] * (r2[q] - 2 * r6[q]);
+                lp[q] = -X3[q] - X4[q] + yl[q] * (r6[q] - 2 * r2[q]);
+                lz[q] = X5[q] + X6[q] - 2 * yl[q] * r4[q];
+            }
+            if (o->axis_s[e]) {
+                for (int j = 0; j < NP; j++) V1[j] = v0ze[j] * R0(r1, j) + y0[j] * (R0(r2, j) - 2 * R0(r6, j));
+                outerprod_4(o->G0, V1, T);
+                FOR25 ls[q] = ls[q] + T[q];
+                for (int j = 0; j < NP; j++) V1[j] = -v0ze[j] * R0(r6, j) + y0[j] * (R0(r6, j) - 2 * R0(r2, j));
+                outerprod_4(o->G0, V1, T);
+                FOR25 lp[q] = lp[q] + T[q];
+                for (int j = 0; j < NP; j++) V1[j] = v0se[j] * R0(r3, j);
+                outerprod_4(o->G0, V1, T);
+                FOR25 lz[q] = lz[q] + T[q];
+            }
+            FOR25 { g1[q] = g1[q] - ls[q]; g2[q] = g2[q] - lp[q]; g3[q] = g3[q] - lz[q]; }
+        }
+#undef R0
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* attenuation.f90:1139-1155 */
+static void fast_correct(int n, const double *y, double *yp) {
+    double dy[32];
+    dy[0] = 1 + .5 * y[0];
+    for (int k = 1; k < n; k++) dy[k] = dy[k - 1] + (dy[k - 1] - .5) * y[k - 1] + .5 * y[k];
+    for (int k = 0; k < n; k++) yp[k] = y[k] * dy[k];
+}
+static void a_j_of_Q(const axo_t *o, float Q, double *a_j) {
+    double yq[32], yp[32], s = 0.0;
+    for (int k = 0; k < o->n_sls; k++) yq[k] = o->y_j[k] / Q;
+    if (o->corr_lowq) fast_correct(o->n_sls, yq, yp);
+    else memcpy(yp, yq, sizeof(double) * o->n_sls);
+    for (int k = 0; k < o->n_sls; k++) s += yp[k];
+    for (int k = 0; k < o->n_sls; k++) a_j[k] = yp[k] / s;
+}
+
+/* pointwise_derivatives.f90:216-248 */
+static void gradient_cg4(const axo_t *o, const float *f, float *ds, float *dz, int e) {
+    float m1[4], m2[4];
+    const float *dzdeta = o->Dze_cg + 4 * (size_t)e, *dzdxi = o->Dzx_cg + 4 * (size_t)e;
+    const float *dsdeta = o->Dse_cg + 4 * (size_t)e, *dsdxi = o->Dsx_cg + 4 * (size_t)e;
+    mxm_cg4_sparse_c(o->axis_s[e] ? o->G1T : o->G2T, f, m1);
+    mxm_cg4_sparse_c(f, o->G2, m2);
+    for (int k = 0; k < 4; k++) {
+        ds[k] = dzdeta[k] * m1[k] + dzdxi[k] * m2[k];
+        dz[k] = dsdeta[k] * m1[k] + dsdxi[k] * m2[k];
+    }
+}
+/* pointwise_derivatives.f90:55-73 */
+static void f_over_s_cg4(const axo_t *o, const float *f, float *out, int e) {
+    const float *is = EL(o->inv_s, e);
+    out[0] = is[1 + NP * 1] * f[1 + NP * 1];
+    out[1] = is[1 + NP * 3] * f[1 + NP * 3];
+    out[2] = is[3 + NP * 1] * f[3 + NP * 1];
+    out[3] = is[3 + NP * 3] * f[3 + NP * 3];
+}
+
+/* attenuation.f90:471-535 */
+static void compute_strain_att_el_cg4(const axo_t *o, const float *u1, const float *u2,
+                                      const float *u3, float g[6][4], int e) {
+    float b1s[4], b1z[4], b2s[4], b2z[4], T[NPT], fs[4], fs2[4];
+    for (int v = 0; v < 6; v++) for (int k = 0; k < 4; k++) g[v][k] = 0.0f;
+    if (o->src_order == AXB_DIPOLE) { FOR25 T[q] = u1[q] + u2[q]; gradient_cg4(o, T, b1s, b1z, e); }
+    else gradient_cg4(o, u1, b1s, b1z, e);
+    gradient_cg4(o, u3, b2s, b2z, e);
+    for (int k = 0; k < 4; k++) { g[0][k] = b1s[k]; g[2][k] = b2z[k]; g[4][k] = b1z[k] + b2s[k]; }
+    if (o->src_order == AXB_MONOPOLE) {
+        f_over_s_cg4(o, u1, fs, e);
+        for (int k = 0; k < 4; k++) g[1][k] = fs[k];
+    } else if (o->src_order == AXB_DIPOLE) {
+        f_over_s_cg4(o, u2, fs, e);
+        for (int k = 0; k < 4; k++) g[1][k] = 2 * fs[k];
+        FOR25 T[q] = u1[q] - u2[q];
+        gradient_cg4(o, T, b1s, b1z, e);
+        f_over_s_cg4(o, u3, fs, e);
+        for (int k = 0; k < 4; k++) { g[3][k] = -fs[k] - b1z[k]; g[5][k] = -g[1][k] - b1s[k]; }
+    } else {
+        FOR25 T[q] = u1[q] - 2 * u2[q];
+        f_over_s_cg4(o, T, fs, e);
+        for (int k = 0; k < 4; k++) g[1][k] = fs[k];
+        gradient_cg4(o, u2, b1s, b1z, e);
+        f_over_s_cg4(o, u3, fs, e);
+        FOR25 T[q] = u2[q] - 2 * u1[q];
+        f_over_s_cg4(o, T, fs2, e);
+        for (int k = 0; k < 4; k++) { g[3][k] = -2 * fs[k] - b1z[k]; g[5][k] = fs2[k] - b1s[k]; }
+    }
+}
+
+/* pointwise_derivatives.f90:252-286 */
+static void gradient_4(const axo_t *o, const float *f, float *ds, float *dz, int e) {
+    float m1[NPT], m2[NPT];
+    const float *dzdeta = EL(o->Dze, e), *dzdxi = EL(o->Dzx, e);
+    const float *dsdeta = EL(o->Dse, e), *dsdxi = EL(o->Dsx, e);
+    mxm_4(o->axis_s[e] ? o->G1T : o->G2T, f, m1);
+    mxm_4(f, o->G2, m2);
+    FOR25 {
+        ds[q] = dzdeta[q] * m1[q] + dzdxi[q] * m2[q];
+        dz[q] = dsdeta[q] * m1[q] + dsdxi[q] * m2[q];
+    }
+}
+/* pointwise_derivatives.f90:104-126 (+ dsdf_elem_solid :419-446) */
+static void f_over_s_4(const axo_t *o, const float *f, float *out, int e) {
+    const float *is = EL(o->inv_s, e);
+    FOR25 out[q] = is[q] * f[q];
+    if (o->axis_s[e]) {
+        float ds[NPT], dz[NPT];
+        gradient_4(o, f, ds, dz, e);
+        for (int j = 0; j < NP; j++) out[0 + NP * j] = ds[0 + NP * j];
+    }
+}
+/* attenuation.f90:542-606 */
+static void compute_strain_att_el_4(const axo_t *o, const float *u1, const float *u2,
+                                    const float *u3, float g[6][NPT], int e) {
+    float b1s[NPT], b1z[NPT], b2s[NPT], b2z[NPT], T[NPT], fs[NPT], fs2[NPT];
+    for (int v = 0; v < 6; v++) FOR25 g[v][q] = 0.0f;
+    if (o->src_order == AXB_DIPOLE) { FOR25 T[q] = u1[q] + u2[q]; gradient_4(o, T, b1s, b1z, e); }
+    else gradient_4(o, u1, b1s, b1z, e);
+    gradient_4(o, u3, b2s, b2z, e);
+    FOR25 { g[0][q] = b1s[q]; g[2][q] = b2z[q]; g[4][q] = b1z[q] + b2s[q]; }
+    if (o->src_order == AXB_MONOPOLE) {
+        f_over_s_4(o, u1, fs, e);
+        FOR25 g[1][q] = fs[q];
+    } else if (o->src_order == AXB_DIPOLE) {
+        f_over_s_4(o, u2, fs, e);
+        FOR25 g[1][q] = 2 * fs[q];
+        FOR25 T[q] = u1[q] - u2[q];
+        gradient_4(o, T, b1s, b1z, e);
+        f_over_s_4(o, u3, fs, e);
+        FOR25 { g[3][q] = -fs[q] - b1z[q]; g[5][q] = -g[1][q] - b1s[q]; }
+    } else {
+        FOR25 T[q] = u1[q] - 2 * u2[q];
+        f_over_s_4(o, T, fs, e);
+        FOR25 g[1][q] = fs[q];
+        gradient_4(o, u2, b1s, b1z, e);
+        f_over_s_4(o, u3, fs, e);
+        FOR25 T[q] = u2[q] - 2 * u1[q];
+        f_over_s_4(o, T, fs2, e);
+        FOR25 { g[3][q] = -2 * fs[q] - b1z[q]; g[5][q] = fs2[q] - b1s[q]; }
+    }
+}
+
+/* attenuation.f90:81-202 (cg4) and :210-334 (_4): the two differ only in the number of
+ * points per element (np = 4 or 25). */
+static void time_step_memvars(axo_t *o) {
+    const size_t cs = (size_t)NPT * o->nel_s;
+    const double third = 1.0 / 3.0;
+    double a_mu[32], a_ka[32];
+    float Qmu_last = -1.0f, Qka_last = -1.0f;   /* cg4 leaves them uninitialised; treat as -1 */
+    const int np = o->cg ? 4 : NPT;
+    for (int e = 0; e < o->nel_s; e++) {
+        const float *u1 = EL(o->disp, e), *u2 = EL(o->disp + cs, e), *u3 = EL(o->disp + 2 * cs, e);
+        float gr[6][NPT];
+        if (o->cg) {
+            float g4[6][4];
+            compute_strain_att_el_cg4(o, u1, u2, u3, g4, e);
+            for (int v = 0; v < 6; v++) for (int k = 0; k < 4; k++) gr[v][k] = g4[v][k];
+        } else {
+            compute_strain_att_el_4(o, u1, u2, u3, gr, e);
+        }
+        if (o->Q_mu[e] != Qmu_last) { Qmu_last = o->Q_mu[e]; a_j_of_Q(o, Qmu_last, a_mu); }
+        if (o->Q_kappa[e] != Qka_last) { Qka_last = o->Q_kappa[e]; a_j_of_Q(o, Qka_last, a_ka); }
+        const float *dmu = o->cg ? o->dmu_cg + 4 * (size_t)e : EL(o->dmu, e);
+        const float *dka = o->cg ? o->dka_cg + 4 * (size_t)e : EL(o->dka, e);
+        float *tr_tm1 = o->src_tr_tm1 + (size_t)np * e;
+        float *dev_tm1 = o->src_dev_tm1 + (size_t)np * 6 * e;
+        for (int k = 0; k < np; k++) {
+            /* trace: sum(grad(:,1:3), dim=2) in real(4), left to right */
+            float trace = gr[0][k] + gr[1][k];
+            trace = trace + gr[2][k];
+            float src_tr_t = dka[k] * trace;
+            float src_dev_t[6] = {0, 0, 0, 0, 0, 0};
+            for (int v = 0; v < 3; v++)
+                src_dev_t[v] = (float)((double)(dmu[k] * 2) * ((double)gr[v][k] - (double)trace * third));
+            src_dev_t[4] = dmu[k] * gr[4][k];
+            if (o->src_order != AXB_MONOPOLE) {
+                src_dev_t[3] = dmu[k] * gr[3][k];
+                src_dev_t[5] = dmu[k] * gr[5][k];
+            }
+            float s_tr_tm1 = tr_tm1[k];
+            float s_dev_tm1[6];
+            for (int v = 0; v < 6; v++) s_dev_tm1[v] = dev_tm1[k + np * v];
+            for (int j = 0; j < o->n_sls; j++) {
+                float tr_buf = (float)(o->ts_t[j] * a_ka[j] * (double)src_tr_t
+                                       + o->ts_tm1[j] * a_ka[j] * (double)s_tr_tm1);
+                float dev_buf[6];
+                for (int v = 0; v < 6; v++)
+                    dev_buf[v] = (float)(o->ts_t[j] * a_mu[j] * (double)src_dev_t[v]
+                                         + o->ts_tm1[j] * a_mu[j] * (double)s_dev_tm1[v]);
+                size_t base = (size_t)np * 6 * ((size_t)j + (size_t)o->n_sls * e);
+                float *mv = o->memvar + base;
+                for (int v = 0; v < 3; v++)
+                    mv[k + np * v] = (float)(o->exp_w[j] * (double)mv[k + np * v]
+                                             + (double)dev_buf[v] + (double)tr_buf);
+                mv[k + np * 4] = (float)(o->exp_w[j] * (double)mv[k + np * 4] + (double)dev_buf[4]);
+                if (o->src_order != AXB_MONOPOLE) {
+                    mv[k + np * 3] = (float)(o->exp_w[j] * (double)mv[k + np * 3] + (double)dev_buf[3]);
+                    mv[k + np * 5] = (float)(o->exp_w[j] * (double)mv[k + np * 5] + (double)dev_buf[5]);
+                }
+            }
+            tr_tm1[k] = src_tr_t;
+            for (int v = 0; v < 6; v++) dev_tm1[k + np * v] = src_dev_t[v];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* apply_masks.f90:40-100 */
+static void axis_mask(float *u, size_t cs, const int *ax, int nax, int c_lo, int c_hi) {
+    for (int a = 0; a < nax; a++)
+        for (int c = c_lo; c <= c_hi; c++)
+            for (int j = 0; j < NP; j++) u[0 + NP * j + (size_t)NPT * (ax[a] - 1) + cs * c] = 0.0f;
+}
+static void mask_solid(const axo_t *o, float *u) {
+    size_t cs = (size_t)NPT * o->nel_s;
+    if (o->src_order == AXB_MONOPOLE) axis_mask(u, cs, o->ax_el_s, o->naxel_s, 0, 0);
+    else if (o->src_order == AXB_DIPOLE) axis_mask(u, cs, o->ax_el_s, o->naxel_s, 1, 2);
+    else axis_mask(u, cs, o->ax_el_s, o->naxel_s, 0, 2);
+}
+
+/* time_evol_wave.F90:1532-1571 */
+static void bdry_copy2fluid(const axo_t *o, float *uflu, const float *usol) {
+    size_t cs = (size_t)NPT * o->nel_s;
+    for (int b = 0; b < o->nel_bdry; b++) {
+        int js = o->bdry_js[b], jf = o->bdry_jf[b], es = o->bdry_sel[b] - 1, ef = o->bdry_fel[b] - 1;
+        const float *B1 = o->bdry_matr + (size_t)NP * b, *B2 = o->bdry_matr + (size_t)NP * (b + o->nel_bdry);
+        for (int i = 0; i < NP; i++) {
+            size_t ps = i + NP * js + (size_t)NPT * es, pf = i + NP * jf + (size_t)NPT * ef;
+            if (o->src_order == AXB_DIPOLE)
+                uflu[pf] = uflu[pf] - B1[i] * (usol[ps] + usol[ps + cs]) - B2[i] * usol[ps + 2 * cs];
+            else
+                uflu[pf] = uflu[pf] - B1[i] * usol[ps] - B2[i] * usol[ps + 2 * cs];
+        }
+    }
+}
+/* time_evol_wave.F90:1577-1611 */
+static void bdry_copy2solid(const axo_t *o, float *usol, const float *uflu) {
+    size_t cs = (size_t)NPT * o->nel_s;
+    for (int b = 0; b < o->nel_bdry; b++) {
+        int js = o->bdry_js[b], jf = o->bdry_jf[b], es = o->bdry_sel[b] - 1, ef = o->bdry_fel[b] - 1;
+        const float *B1 = o->bdry_matr + (size_t)NP * b, *B2 = o->bdry_matr + (size_t)NP * (b + o->nel_bdry);
+        for (int i = 0; i < NP; i++) {
+            size_t ps = i + NP * js + (size_t)NPT * es, pf = i + NP * jf + (size_t)NPT * ef;
+            usol[ps] = usol[ps] + B1[i] * uflu[pf];
+            if (o->src_order == AXB_DIPOLE) usol[ps + cs] = usol[ps + cs] + B1[i] * uflu[pf];
+            usol[ps + 2 * cs] = usol[ps + 2 * cs] + B2[i] * uflu[pf];
+        }
+    }
+}
+
+/* time_evol_wave.F90:1062-1097 */
+static void add_source_el(const axo_t *o, float *acc, float stf1) {
+    size_t cs = (size_t)NPT * o->nel_s;
+    if (stf1 == 0.0f) return;
+    for (int k = 0; k < o->nelsrc; k++)
+        for (int c = 0; c < 3; c++)
+            FOR25 {
+                size_t p = q + (size_t)NPT * (o->ielsrc[k] - 1) + cs * c;
+                acc[p] = acc[p] - o->src_term[q + NPT * (k + 8 * c)] * stf1;
+            }
+}
+static void add_source_fl(const axo_t *o, float *ddchi, float stf1) {
+    if (stf1 == 0.0f) return;
+    for (int k = 0; k < o->nelsrc; k++)
+        FOR25 {
+            size_t p = q + (size_t)NPT * (o->ielsrc[k] - 1);
+            ddchi[p] = ddchi[p] - o->src_term[q + NPT * k] * stf1;
+        }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* commun.F90:69-283 + commpi.F90:371-637.  nc = 3 for the solid (the time loop always
+ * passes the 3-wide array: size(vec,dim=4)), 1 for the fluid. */
+static const int edge_q[16] = {0, 1, 2, 3, 4, 5, 9, 10, 14, 15, 19, 20, 21, 22, 23, 24};
+
+static void feed_buffer(axo_t *o, int dom, const float *vec) {
+    halo_t *H = &o->halo[dom];
+    int nc = dom == AXB_DOMAIN_SOLID ? 3 : 1;
+    int nel = dom == AXB_DOMAIN_SOLID ? o->nel_s : o->nel_f;
+    int nglob = dom == AXB_DOMAIN_SOLID ? o->nglob_s : o->nglob_f;
+    const int *igloc = dom == AXB_DOMAIN_SOLID ? o->igloc_s : o->igloc_f;
+    float *gvec = dom == AXB_DOMAIN_SOLID ? o->gvec_s : o->gvec_f;
+    size_t cs = (size_t)NPT * nel;
+    memset(gvec, 0, sizeof(float) * (size_t)nglob * nc);
+    for (int ip = 0; ip < H->ncomm; ip++) {
+        int ipol = H->glob2el[ip], jpol = H->glob2el[ip + H->ncomm], iel = H->glob2el[ip + 2 * H->ncomm];
+        size_t ipt = (size_t)(iel - 1) * NPT + jpol * NP + ipol;
+        int ipg = igloc[ipt] - 1;
+        for (int c = 0; c < nc; c++)
+            gvec[ipg + (size_t)nglob * c] = gvec[ipg + (size_t)nglob * c] + vec[ipt + cs * c];
+    }
+    for (int m = 0; m < H->nmsg; m++)
+        for (int ip = 0; ip < H->size[m]; ip++) {
+            int ipg = H->glocal[m][ip] - 1;
+            for (int c = 0; c < nc; c++)
+                H->sendbuf[m][ip + (size_t)H->size[m] * c] = gvec[ipg + (size_t)nglob * c];
+        }
+}
+
+static void gather_scatter(axo_t *o, int dom, float *vec) {
+    int nc = dom == AXB_DOMAIN_SOLID ? 3 : 1;
+    int nel = dom == AXB_DOMAIN_SOLID ? o->nel_s : o->nel_f;
+    int nglob = dom == AXB_DOMAIN_SOLID ? o->nglob_s : o->nglob_f;
+    const int *igloc = dom == AXB_DOMAIN_SOLID ? o->igloc_s : o->igloc_f;
+    float *gvec = dom == AXB_DOMAIN_SOLID ? o->gvec_s : o->gvec_f;
+    size_t cs = (size_t)NPT * nel;
+    memset(gvec, 0, sizeof(float) * (size_t)nglob * nc);
+    for (int e = 0; e < nel; e++)
+        for (int k = 0; k < 16; k++) {
+            size_t ipt = (size_t)e * NPT + edge_q[k];
+            int id = igloc[ipt] - 1;
+            for (int c = 0; c < nc; c++)
+                gvec[id + (size_t)nglob * c] = gvec[id + (size_t)nglob * c] + vec[ipt + cs * c];
+        }
+    for (int e = 0; e < nel; e++)
+        for (int k = 0; k < 16; k++) {
+            size_t ipt = (size_t)e * NPT + edge_q[k];
+            int id = igloc[ipt] - 1;
+            for (int c = 0; c < nc; c++) vec[ipt + cs * c] = gvec[id + (size_t)nglob * c];
+        }
+}
+
+/* "MPI": copy my send buffers into the peers' receive buffers (message m of the peer
+ * that lists me as its neighbour) */
+static int exchange(axo_t *o, int dom) {
+    halo_t *H = &o->halo[dom];
+    int nc = dom == AXB_DOMAIN_SOLID ? 3 : 1;
+    for (int m = 0; m < H->nmsg; m++) {
+        axo_t *p = NULL;
+        for (int g = 0; g < o->ngroup; g++) if (o->group[g]->rank == H->peer[m]) p = o->group[g];
+        if (!p) return fail("halo peer not connected");
+        halo_t *Hp = &p->halo[dom];
+        int mm = -1;
+        for (int q = 0; q < Hp->nmsg; q++) if (Hp->peer[q] == o->rank) mm = q;
+        if (mm < 0 || Hp->size[mm] != H->size[m]) return fail("halo lists inconsistent");
+        memcpy(Hp->recvbuf[mm], H->sendbuf[m], sizeof(float) * (size_t)H->size[m] * nc);
+    }
+    return 0;
+}
+
+static void extract_from_buffer(axo_t *o, int dom, float *vec) {
+    halo_t *H = &o->halo[dom];
+    int nc = dom == AXB_DOMAIN_SOLID ? 3 : 1;
+    int nel = dom == AXB_DOMAIN_SOLID ? o->nel_s : o->nel_f;
+    int nglob = dom == AXB_DOMAIN_SOLID ? o->nglob_s : o->nglob_f;
+    const int *igloc = dom == AXB_DOMAIN_SOLID ? o->igloc_s : o->igloc_f;
+    float *gvec = dom == AXB_DOMAIN_SOLID ? o->gvec_s : o->gvec_f;
+    size_t cs = (size_t)NPT * nel;
+    for (int m = 0; m < H->nmsg; m++)
+        for (int ip = 0; ip < H->size[m]; ip++) {
+            int ipg = H->glocal[m][ip] - 1;
+            for (int c = 0; c < nc; c++)
+                gvec[ipg + (size_t)nglob * c] = gvec[ipg + (size_t)nglob * c]
+                                                + H->recvbuf[m][ip + (size_t)H->size[m] * c];
+        }
+    for (int ip = 0; ip < H->ncomm; ip++) {
+        int ipol = H->glob2el[ip], jpol = H->glob2el[ip + H->ncomm], iel = H->glob2el[ip + 2 * H->ncomm];
+        size_t ipt = (size_t)(iel - 1) * NPT + jpol * NP + ipol;
+        int ipg = igloc[ipt] - 1;
+        for (int c = 0; c < nc; c++) vec[ipt + cs * c] = gvec[ipg + (size_t)nglob * c];
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* seismograms.f90:783-820 */
+static void sample_receivers(axo_t *o) {
+    size_t cs = (size_t)NPT * o->nel_s;
+    float *out = o->recdump + (size_t)3 * o->num_rec * o->iseismo;
+    for (int r = 0; r < o->num_rec; r++) {
+        int iel = o->recfile_el[r], ip = o->recfile_el[r + o->num_rec], jp = o->recfile_el[r + 2 * o->num_rec];
+        size_t p = ip + NP * jp + (size_t)NPT * (iel - 1);
+        float d1 = o->disp[p], d2 = o->disp[p + cs], d3 = o->disp[p + 2 * cs];
+        if (o->src_order == AXB_MONOPOLE)      { out[3 * r] = d1; out[3 * r + 1] = 0.0f; out[3 * r + 2] = d3; }
+        else if (o->src_order == AXB_DIPOLE)   { out[3 * r] = d1 + d2; out[3 * r + 1] = d1 - d2; out[3 * r + 2] = d3; }
+        else                                   { out[3 * r] = d1; out[3 * r + 1] = d2; out[3 * r + 2] = d3; }
+    }
+    o->iseismo++;
+}
+
+/* wavefields_io.f90:1019-1115 (displ_only + netcdf branch), :743-783 */
+static void dump_disp_global(axo_t *o) {
+    size_t cs = (size_t)NPT * o->nel_s;
+    size_t npts = (size_t)o->npt_s_kwf + o->npt_f_kwf;
+    size_t vs = npts * o->nstrain_max;
+    float *base = o->snapdump + npts * o->istrain;
+    for (int e = 0; e < o->nel_s; e++)
+        FOR25 {
+            size_t p = q + (size_t)NPT * e;
+            if (!o->kwf_mask[p]) continue;
+            int ct = o->kwf_map[p] - 1;
+            float u1 = o->disp[p], u2 = o->disp[p + cs], u3 = o->disp[p + 2 * cs];
+            float f1, f2;
+            if (o->src_order == AXB_DIPOLE) { f1 = u1 + u2; f2 = u1 - u2; } else { f1 = u1; f2 = u2; }
+            base[ct] = f1;
+            if (o->src_order != AXB_MONOPOLE) base[ct + vs] = f2;
+            base[ct + 2 * vs] = u3;
+        }
+    for (int e = 0; e < o->nel_f; e++) {
+        float m1[NPT], m2[NPT];
+        const float *f = EL(o->chi, e);
+        mxm_4(o->axis_f[e] ? o->G1T : o->G2T, f, m1);
+        mxm_4(f, o->G2, m2);
+        FOR25 {
+            size_t p = q + (size_t)NPT * e, pk = p + cs;
+            if (!o->kwf_mask[pk]) continue;
+            int ct = o->kwf_map[pk] - 1;   /* 1-based into [solid | fluid] */
+            float dsdf = o->Dze_f[p] * m1[q] + o->Dzx_f[p] * m2[q];
+            float dzdf = o->Dse_f[p] * m1[q] + o->Dsx_f[p] * m2[q];
+            base[ct] = o->inv_rho_fluid[p] * dsdf;
+            if (o->src_order != AXB_MONOPOLE) base[ct + vs] = 0.0f;   /* wavefields_io.f90:1080 */
+            base[ct + 2 * vs] = o->inv_rho_fluid[p] * dzdf;
+        }
+    }
+    o->istrain++;
+}
+
+/* time_evol_wave.F90:1104-1251, the parts on the hot path */
+static void dump_stuff(axo_t *o, int iter) {
+    if (o->num_rec > 0 && iter % o->seis_it == 0 && o->iseismo < o->nseismo_max) sample_receivers(o);
+    if (o->strain_it > 0 && o->have_kwf && iter % o->strain_it == 0 && o->istrain < o->nstrain_max)
+        dump_disp_global(o);
+}
+
+/* ------------------------------------------------------------------------------------ */
+static void solid_stiffness(axo_t *o, float *acc, const float *u) {
+    if (o->src_order == AXB_MONOPOLE) glob_stiffness_mono_4(o, acc, u);
+    else if (o->src_order == AXB_DIPOLE) glob_stiffness_di_4(o, acc, u);
+    else glob_stiffness_quad_4(o, acc, u);
+}
+static void anel_stiffness(axo_t *o, float *acc) {
+    if (o->cg) glob_anel_stiffness_cg4(o, acc, o->memvar);
+    else glob_anel_stiffness_4(o, acc, o->memvar);
+}
+
+/* the loop body is split at the two MPI phases so that a group of in-process ranks can
+ * be advanced in lockstep; the order of operations inside is the reference's. */
+typedef struct { int stage; double cd, cv; float stf; } stage_t;
+
+static void newmark_part1(axo_t *o) {
+    const size_t ns = (size_t)NPT * o->nel_s, nf = (size_t)NPT * o->nel_f;
+    const double dt = o->deltat, hsq = o->half_dt_sq;
+    o->t += dt;
+    for (size_t p = 0; p < nf; p++)
+        o->chi[p] = (float)((double)o->chi[p] + dt * (double)o->dchi[p] + hsq * (double)o->ddchi0[p]);
+    for (int c = 0; c < 3; c++) {
+        if (c == 1 && o->src_order == AXB_MONOPOLE) continue;
+        float *d = o->disp + ns * c; const float *v = o->velo + ns * c, *a = o->acc0 + ns * c;
+        for (size_t p = 0; p < ns; p++)
+            d[p] = (float)((double)d[p] + dt * (double)v[p] + hsq * (double)a[p]);
+    }
+    if (o->src_order != AXB_MONOPOLE) axis_mask(o->chi, 0, o->ax_el_f, o->naxel_f, 0, 0);
+    glob_fluid_stiffness_4(o, o->ddchi1, o->chi);
+    if (o->fluid_src) add_source_fl(o, o->ddchi1, o->stf[o->iter]);
+    bdry_copy2fluid(o, o->ddchi1, o->disp);
+    if (o->src_order != AXB_MONOPOLE) axis_mask(o->ddchi1, 0, o->ax_el_f, o->naxel_f, 0, 0);
+    if (o->fs_mask) for (size_t p = 0; p < nf; p++) o->ddchi1[p] = o->ddchi1[p] * o->fs_mask[p];
+    feed_buffer(o, AXB_DOMAIN_FLUID, o->ddchi1);            /* pdistsum_fluid phase 1 */
+}
+static void fluid_local_and_solid_stiffness(axo_t *o, float *ddchi, float *acc) {
+    gather_scatter(o, AXB_DOMAIN_FLUID, ddchi);
+    mask_solid(o, o->disp);
+    solid_stiffness(o, acc, o->disp);
+    if (o->anel) anel_stiffness(o, acc);
+}
+static void newmark_part2(axo_t *o) {
+    const size_t nf = (size_t)NPT * o->nel_f;
+    fluid_local_and_solid_stiffness(o, o->ddchi1, o->acc1);
+    extract_from_buffer(o, AXB_DOMAIN_FLUID, o->ddchi1);    /* pdistsum_fluid phase 2 */
+    for (size_t p = 0; p < nf; p++) o->ddchi1[p] = -o->inv_mass_fluid[p] * o->ddchi1[p];
+    if (o->have_abc)
+        for (size_t p = 0; p < nf; p++)
+            o->ddchi1[p] = o->ddchi1[p] - 2 * o->gamma_f[p] * o->dchi[p]
+                           - (o->gamma_f[p] * o->gamma_f[p]) * o->chi[p];
+    bdry_copy2solid(o, o->acc1, o->ddchi1);
+    mask_solid(o, o->acc1);
+    feed_buffer(o, AXB_DOMAIN_SOLID, o->acc1);              /* pdistsum_solid phase 1 */
+}
+static void newmark_part3(axo_t *o) {
+    const size_t ns = (size_t)NPT * o->nel_s, nf = (size_t)NPT * o->nel_f;
+    const double hdt = o->half_dt;
+    gather_scatter(o, AXB_DOMAIN_SOLID, o->acc1);
+    if (o->anel) time_step_memvars(o);
+    for (size_t p = 0; p < nf; p++) {
+        o->dchi[p] = (float)((double)o->dchi[p] + hdt * (double)(o->ddchi0[p] + o->ddchi1[p]));
+        o->ddchi0[p] = o->ddchi1[p];
+    }
+    extract_from_buffer(o, AXB_DOMAIN_SOLID, o->acc1);      /* pdistsum_solid phase 2 */
+    if (!o->fluid_src) add_source_el(o, o->acc1, o->stf[o->iter]);
+    for (int c = 0; c < 3; c++) {
+        if (c == 1 && o->src_order == AXB_MONOPOLE) continue;
+        float *a1 = o->acc1 + ns * c, *a0 = o->acc0 + ns * c, *v = o->velo + ns * c;
+        const float *d = o->disp + ns * c;
+        for (size_t e = 0, p = 0; p < ns; p++) {
+            (void)e;
+            float im = o->inv_mass_rho[p];
+            if (c == 2 && o->src_order == AXB_DIPOLE) a1[p] = (float)(-2.0 * (double)im * (double)a1[p]);
+            else a1[p] = -im * a1[p];
+            if (o->have_abc)
+                a1[p] = a1[p] - 2 * o->gamma_s[p] * v[p] - (o->gamma_s[p] * o->gamma_s[p]) * d[p];
+            v[p] = (float)((double)v[p] + hdt * (double)(a0[p] + a1[p]));
+            a0[p] = a1[p];
+        }
+    }
+    o->iter++;
+    dump_stuff(o, o->iter);
+}
+
+/* source.f90:206-233 + gauss_t etc.: point-wise STF */
+static double stf_t(const axo_t *o, double t) {
+    double a = o->decay / o->t_0, x = a * (t - o->shift_fact);
+    const double pi = 3.1415926535898;
+    switch (o->stf_type) {
+    case AXB_STF_GAUSS_0: return exp(-(x * x)) * o->magnitude * a / sqrt(pi);
+    case AXB_STF_GAUSS_1: return -2.0 * a * a * (t - o->shift_fact) * exp(-(x * x))
+                                 / (a * sqrt(2.0) * exp(-0.5)) * o->magnitude;
+    default: return a * a * (2.0 * a * a * (t - o->shift_fact) * (t - o->shift_fact) - 1.0)
+                    * exp(-(x * x)) / (2.0 * a * a * exp(-1.5)) * o->magnitude;
+    }
+}
+
+/* time_evol_wave.F90:584-739 */
+static void symp_drift(axo_t *o, double cd) {
+    const size_t ns = (size_t)NPT * o->nel_s, nf = (size_t)NPT * o->nel_f;
+    for (size_t p = 0; p < nf; p++) o->chi[p] = (float)((double)o->chi[p] + (double)o->dchi[p] * cd);
+    for (int c = 0; c < 3; c++) {
+        if (c == 1 && o->src_order == AXB_MONOPOLE) continue;
+        float *d = o->disp + ns * c; const float *v = o->velo + ns * c;
+        for (size_t p = 0; p < ns; p++) d[p] = (float)((double)d[p] + (double)v[p] * cd);
+    }
+}
+static void symp_part1(axo_t *o, int i) {
+    symp_drift(o, o->coefd[i]);
+    if (o->src_order != AXB_MONOPOLE) axis_mask(o->chi, 0, o->ax_el_f, o->naxel_f, 0, 0);
+    glob_fluid_stiffness_4(o, o->ddchi1, o->chi);
+    bdry_copy2fluid(o, o->ddchi1, o->disp);
+    if (o->src_order != AXB_MONOPOLE) axis_mask(o->ddchi1, 0, o->ax_el_f, o->naxel_f, 0, 0);
+    feed_buffer(o, AXB_DOMAIN_FLUID, o->ddchi1);
+}
+static void symp_part2(axo_t *o) {
+    const size_t nf = (size_t)NPT * o->nel_f;
+    fluid_local_and_solid_stiffness(o, o->ddchi1, o->acc1);
+    extract_from_buffer(o, AXB_DOMAIN_FLUID, o->ddchi1);
+    for (size_t p = 0; p < nf; p++) o->ddchi1[p] = -o->ddchi1[p] * o->inv_mass_fluid[p];
+    if (o->have_abc)
+        for (size_t p = 0; p < nf; p++)
+            o->ddchi1[p] = o->ddchi1[p] - 2 * o->gamma_f[p] * o->dchi[p]
+                           - (o->gamma_f[p] * o->gamma_f[p]) * o->chi[p];
+    bdry_copy2solid(o, o->acc1, o->ddchi1);
+    mask_solid(o, o->acc1);
+    feed_buffer(o, AXB_DOMAIN_SOLID, o->acc1);
+}
+static void symp_part3(axo_t *o, int i, double stf_i) {
+    const size_t ns = (size_t)NPT * o->nel_s, nf = (size_t)NPT * o->nel_f;
+    const double cv = o->coefv[i];
+    gather_scatter(o, AXB_DOMAIN_SOLID, o->acc1);
+    for (size_t p = 0; p < nf; p++) o->dchi[p] = (float)((double)o->dchi[p] + cv * (double)o->ddchi1[p]);
+    extract_from_buffer(o, AXB_DOMAIN_SOLID, o->acc1);
+    add_source_el(o, o->acc1, (float)stf_i);
+    for (int c = 0; c < 3; c++) {
+        if (c == 1 && o->src_order == AXB_MONOPOLE) continue;
+        float *a = o->acc1 + ns * c, *v = o->velo + ns * c; const float *d = o->disp + ns * c;
+        for (size_t p = 0; p < ns; p++) {
+            a[p] = -o->inv_mass_rho[p] * a[p];
+            if (o->have_abc)
+                a[p] = a[p] - 2 * o->gamma_s[p] * v[p] - (o->gamma_s[p] * o->gamma_s[p]) * d[p];
+            if (c == 2 && o->src_order == AXB_DIPOLE) v[p] = (float)((double)v[p] + 2.0 * (double)a[p] * cv);
+            else v[p] = (float)((double)v[p] + (double)a[p] * cv);
+        }
+    }
+}
+static void symp_finish(axo_t *o) {
+    symp_drift(o, o->coefd[o->nstages]);
+    if (o->anel) time_step_memvars(o);
+    o->iter++;
+    dump_stuff(o, o->iter);
+}
+
+static void set_ftz(void) {
+#if defined(__x86_64__)
+    _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);        /* SOLVER/ftz.c:44-48 */
+    _MM_SET_DENORMALS_ZERO_MODE(_MM_DENORMALS_ZERO_ON);
+#endif
+}
+
+int axo_connect_local(axb_handle *handles, int32_t n) {
+    axo_t **g = (axo_t **)malloc(sizeof(axo_t *) * n);
+    for (int i = 0; i < n; i++) g[i] = handles[i];
+    for (int i = 0; i < n; i++) { handles[i]->group = g; handles[i]->ngroup = n; }
+    return 0;
+}
+int axo_ipc_export(axb_handle h, void *blob, int32_t n) { (void)h; (void)blob; (void)n; return fail("oracle: in-process only"); }
+int axo_ipc_import(axb_handle h, int32_t p, const void *blob, int32_t n) { (void)h; (void)p; (void)blob; (void)n; return fail("oracle: in-process only"); }
+
+int axo_run_group(axb_handle *hs, int32_t n, int32_t nsteps) {
+    set_ftz();
+    for (int i = 0; i < n; i++) {
+        if (!hs[i]->finalized) return fail("finalize_setup not called");
+        if (n > 1 && hs[i]->ngroup != n) return fail("group not connected");
+        if (hs[i]->iter + nsteps > hs[i]->niter) return fail("run beyond niter");
+    }
+    for (int i = 0; i < n; i++)
+        if (hs[i]->iter == 0 && hs[i]->iseismo == 0 && hs[i]->istrain == 0)
+            dump_stuff(hs[i], 0);                          /* time_evol_wave.F90:350 */
+    for (int s = 0; s < nsteps; s++) {
+        if (hs[0]->scheme == AXB_NEWMARK2) {
+            for (int i = 0; i < n; i++) newmark_part1(hs[i]);
+            for (int i = 0; i < n; i++) if (exchange(hs[i], AXB_DOMAIN_FLUID)) return 1;
+            for (int i = 0; i < n; i++) newmark_part2(hs[i]);
+            for (int i = 0; i < n; i++) if (exchange(hs[i], AXB_DOMAIN_SOLID)) return 1;
+            for (int i = 0; i < n; i++) newmark_part3(hs[i]);
+        } else {
+            double stf_symp[40];
+            for (int i = 0; i < n; i++) hs[i]->t += hs[i]->deltat;
+            for (int k = 0; k < hs[0]->nstages; k++)
+                stf_symp[k] = stf_t(hs[0], hs[0]->t - hs[0]->deltat + hs[0]->coeff[k]);
+            for (int k = 0; k < hs[0]->nstages; k++) {
+                for (int i = 0; i < n; i++) symp_part1(hs[i], k);
+                for (int i = 0; i < n; i++) if (exchange(hs[i], AXB_DOMAIN_FLUID)) return 1;
+                for (int i = 0; i < n; i++) symp_part2(hs[i]);
+                for (int i = 0; i < n; i++) if (exchange(hs[i], AXB_DOMAIN_SOLID)) return 1;
+                for (int i = 0; i < n; i++) symp_part3(hs[i], k, stf_symp[k]);
+            }
+            for (int i = 0; i < n; i++) symp_finish(hs[i]);
+        }
+    }
+    return 0;
+}
+
+int axo_run(axb_handle h, int32_t nsteps) {
+    if (h->nranks > 1 && h->ngroup > 1) return fail("use run_group for in-process groups");
+    axb_handle one[1] = {h};
+    if (h->ngroup == 0) { h->group = (axo_t **)malloc(sizeof(axo_t *)); h->group[0] = h; h->ngroup = 1; }
+    return axo_run_group(one, 1, nsteps);
+}
+
+int32_t axo_iter(axb_handle h) { return h->iter; }
+int32_t axo_nseismo(axb_handle h) { return h->iseismo; }
+int32_t axo_nstrain(axb_handle h) { return h->istrain; }
+int64_t axo_gpu_launches(axb_handle h) { (void)h; return 0; }
+
+int axo_fetch_seismograms(axb_handle h, int32_t first, int32_t nsamples, float *out) {
+    if (first < 0 || first + nsamples > h->iseismo) return fail("seismogram range");
+    memcpy(out, h->recdump + (size_t)3 * h->num_rec * first, sizeof(float) * 3 * h->num_rec * nsamples);
+    return 0;
+}
+int axo_fetch_snapshots(axb_handle h, int32_t first, int32_t nsnap, float *out) {
+    size_t npts = (size_t)h->npt_s_kwf + h->npt_f_kwf;
+    if (first < 0 || first + nsnap > h->istrain) return fail("snapshot range");
+    for (int v = 0; v < 3; v++)
+        for (int s = 0; s < nsnap; s++)
+            memcpy(out + npts * (s + (size_t)nsnap * v),
+                   h->snapdump + npts * ((first + s) + (size_t)h->nstrain_max * v), sizeof(float) * npts);
+    return 0;
+}
+
+static float *field_ptr(axo_t *o, int f, size_t *n) {
+    size_t ns = (size_t)NPT * o->nel_s * 3, nf = (size_t)NPT * o->nel_f;
+    size_t per = o->cg ? 4 : NPT;
+    switch (f) {
+    case AXB_F_DISP: *n = ns; return o->disp;
+    case AXB_F_VELO: *n = ns; return o->velo;
+    case AXB_F_ACC0: *n = ns; return o->acc0;
+    case AXB_F_ACC1: *n = ns; return o->acc1;
+    case AXB_F_CHI: *n = nf; return o->chi;
+    case AXB_F_DCHI: *n = nf; return o->dchi;
+    case AXB_F_DDCHI0: *n = nf; return o->ddchi0;
+    case AXB_F_DDCHI1: *n = nf; return o->ddchi1;
+    case AXB_F_MEMVAR: *n = per * 6 * o->n_sls * o->nel_s; return o->memvar;
+    case AXB_F_SRC_DEV_TM1: *n = per * 6 * o->nel_s; return o->src_dev_tm1;
+    case AXB_F_SRC_TR_TM1: *n = per * o->nel_s; return o->src_tr_tm1;
+    }
+    return NULL;
+}
+int axo_get_state(axb_handle h, int32_t field, float *out) {
+    size_t n; float *p = field_ptr(h, field, &n);
+    if (!p) return fail("no such field");
+    memcpy(out, p, n * sizeof(float));
+    return 0;
+}
+int axo_set_state(axb_handle h, int32_t field, const float *in) {
+    size_t n; float *p = field_ptr(h, field, &n);
+    if (!p) return fail("no such field");
+    memcpy(p, in, n * sizeof(float));
+    return 0;
+}
+
+int axo_apply_op(axb_handle h, int32_t op) {
+    set_ftz();
+    if (!h->finalized) return fail("finalize_setup not called");
+    switch (op) {
+    case AXB_OP_SOLID_STIFFNESS: solid_stiffness(h, h->acc1, h->disp); return 0;
+    case AXB_OP_ANEL_STIFFNESS: if (!h->anel) return fail("no attenuation"); anel_stiffness(h, h->acc1); return 0;
+    case AXB_OP_FLUID_STIFFNESS: glob_fluid_stiffness_4(h, h->ddchi1, h->chi); return 0;
+    case AXB_OP_PDISTSUM_SOLID:
+        if (h->halo[0].nmsg) return fail("apply_op(pdistsum) is single-rank only");
+        gather_scatter(h, AXB_DOMAIN_SOLID, h->acc1); return 0;
+    case AXB_OP_PDISTSUM_FLUID:
+        if (h->halo[1].nmsg) return fail("apply_op(pdistsum) is single-rank only");
+        gather_scatter(h, AXB_DOMAIN_FLUID, h->ddchi1); return 0;
+    case AXB_OP_MEMVARS: if (!h->anel) return fail("no attenuation"); time_step_memvars(h); return 0;
+    case AXB_OP_BDRY2FLUID: bdry_copy2fluid(h, h->ddchi1, h->disp); return 0;
+    case AXB_OP_BDRY2SOLID: bdry_copy2solid(h, h->acc1, h->ddchi1); return 0;
+    }
+    return fail("unknown op");
+}
