@@ -61,7 +61,7 @@ OPS = {"solid_stiffness": 0, "anel_stiffness": 1, "fluid_stiffness": 2, "pdistsu
 SYMBOLS = ["last_error", "create", "destroy", "set_mesh", "set_solid_terms", "set_fluid_terms",
            "set_mass", "set_sponge", "set_sf_boundary", "set_attenuation", "set_source",
            "set_stf_params", "set_receivers", "set_kwf", "set_halo", "set_time",
-           "finalize_setup", "connect_local", "ipc_export", "ipc_import", "run", "run_group",
+           "finalize_setup", "set_stream", "synchronize", "connect_local", "ipc_export", "ipc_import", "run", "run_group",
            "iter", "nseismo", "nstrain", "gpu_launches", "fetch_seismograms",
            "fetch_snapshots", "get_state", "set_state", "apply_op"]
 
@@ -105,7 +105,7 @@ class Library:
     def __init__(self, path: str, prefix: str):
         self.path = path
         self.prefix = prefix
-        self.lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        self.lib = C.CDLL(path, mode=C.RTLD_LOCAL)
         missing = [s for s in SYMBOLS if not hasattr(self.lib, prefix + s)]
         if missing:
             raise AxbError(f"{path}: missing symbols {missing}")
@@ -223,8 +223,17 @@ class TimeLoop:
         self._keep.clear()          # arrays were copied by the library
 
     # ------------------------------------------------------------------------------
-    def run(self, nsteps: int):
+    def run(self, nsteps: int, sync: bool = True):
+        """Advance nsteps; kernels are enqueued asynchronously, `sync` waits for them."""
         self.lib.check(self.lib.fn["run"](self.h, C.c_int32(nsteps)))
+        if sync:
+            self.synchronize()
+
+    def synchronize(self):
+        self.lib.check(self.lib.fn["synchronize"](self.h))
+
+    def set_stream(self, cuda_stream: int):
+        self.lib.check(self.lib.fn["set_stream"](self.h, C.c_void_p(cuda_stream)))
 
     @property
     def iter(self) -> int:

@@ -1,0 +1,1180 @@
+// axb_api.cu — C ABI (include/axisem_b200.h) of the device-resident AxiSEM time loop.
+//
+// Set-up calls copy the host's module arrays to HBM once; axb_run only enqueues kernels on
+// the handle's stream (no host round trip per step: iteration counter, STF sample index
+// and seismogram cursor live on the device).  There is no CPU fallback: every entry point
+// either runs on the GPU or fails with an error.
+#pragma GCC visibility push(default)
+#include "../../include/axisem_b200.h"
+#pragma GCC visibility pop
+#include "axb_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace axb;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string &m) { g_err = m; return 1; }
+
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t _e = (call);                                                         \
+        if (_e != cudaSuccess)                                                           \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(_e));             \
+    } while (0)
+
+constexpr int MAXMSG = 8;
+
+struct Halo {
+    int nmsg = 0, nc = 1;
+    int peer[MAXMSG] = {0}, size[MAXMSG] = {0}, offset[MAXMSG] = {0};
+    std::vector<std::vector<int>> glocal;     // per message, 1-based glocal ids
+    int ncomm = 0;
+    std::vector<int> glob2el;                 // (ncomm,3) Fortran order
+    int nslots = 0;                           // sum of sizes
+    // device
+    int nentries = 0;
+    int *d_start = nullptr, *d_addr = nullptr, *d_dst_msg = nullptr, *d_dst_slot = nullptr;
+    // receive slab (owned): [parity 2][nc][nslots] floats, then flags
+    float *recv = nullptr;
+    int *flags = nullptr;                     // [MAXMSG] one per message (written by the peer)
+    // where my messages go (peer memory)
+    float *peer_recv[MAXMSG] = {nullptr};
+    int peer_nslots[MAXMSG] = {0}, peer_offset[MAXMSG] = {0};
+    int *peer_flag[MAXMSG] = {nullptr};
+    int seq = 0;                              // exchanges done
+};
+
+}  // namespace
+
+struct axb_handle_s {
+    int device = 0, rank = 0, nranks = 1;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int nel_s = 0, nel_f = 0, nglob_s = 0, nglob_f = 0;
+    std::vector<int> igloc_s, igloc_f, axis_s_h;
+    int *d_axis_s = nullptr, *d_axis_f = nullptr;
+    GMat G;
+    int order = 0;
+    SolidPlanes P;
+    std::vector<void *> allocs;
+    // fluid
+    float *M1chi = nullptr, *M2chi = nullptr, *M4chi = nullptr, *M_w_fl = nullptr, *M0_w_fl = nullptr;
+    float *inv_mass_fluid = nullptr, *fs_mask = nullptr;
+    float *inv_mass_rho = nullptr, *gamma_s = nullptr, *gamma_f = nullptr;
+    // boundary
+    int nel_bdry = 0;
+    std::vector<int> bdry_fel_h, bdry_jf_h;
+    int *d_bsel = nullptr, *d_bfel = nullptr, *d_bjs = nullptr, *d_bjf = nullptr;
+    float *d_bmatr = nullptr;
+    int2 *d_bdry_of_el = nullptr;
+    // attenuation
+    bool anel = false, cg = true;
+    AttCg A;
+    std::vector<float> Qmu_h, Qka_h;
+    std::vector<double> y_j;
+    int corr_lowq = 0;
+    // source
+    int fluid_src = 0, nelsrc = 0, ielsrc[8] = {0}, niter_stf = 0;
+    float *d_src_term = nullptr, *d_stf = nullptr;
+    int stf_type = 0;
+    double decay = 0, t_0 = 1, shift = 0, magnitude = 0;
+    // receivers / dump
+    int num_rec = 0;
+    int *d_recfile = nullptr;
+    float *d_recdump = nullptr;
+    int nseismo_max = 0;
+    bool have_kwf = false;
+    int npt_s_kwf = 0, npt_f_kwf = 0, nstrain_max = 0;
+    int *d_kwf_mask = nullptr, *d_kwf_map = nullptr;
+    float *d_inv_rho = nullptr, *d_Dse_f = nullptr, *d_Dze_f = nullptr, *d_Dsx_f = nullptr, *d_Dzx_f = nullptr;
+    float *d_snap = nullptr;
+    Halo halo[2];
+    // time
+    int scheme = 0, niter = 0, seis_it = 1, strain_it = 0, nstages = 0;
+    double deltat = 0, half_dt = 0, half_dt_sq = 0;
+    double coefd[40], coefv[40], coeff[40];
+    float *d_stf_symp = nullptr;
+    // state
+    float *disp = nullptr, *velo = nullptr, *acc0 = nullptr, *acc1 = nullptr;
+    float *chi = nullptr, *dchi = nullptr, *ddchi0 = nullptr, *ddchi1 = nullptr;
+    int *d_asm_gid_s = nullptr, *d_asm_grp_s = nullptr, *d_asm_gid_f = nullptr, *d_asm_grp_f = nullptr;
+    int *d_counters = nullptr;
+    int iter = 0, iseismo = 0, istrain = 0;
+    bool acc1_is_acc0 = false;     // after a full step acc1/ddchi1 == acc0/ddchi0 in the reference
+    bool finalized = false;
+    int64_t launches = 0;
+    int grid_s = 0, grid_f = 0;
+    std::vector<axb_handle_s *> group;
+};
+
+namespace {
+
+template <class T>
+int upload(axb_handle_s *h, T *&dst, const T *src, size_t n) {
+    dst = nullptr;
+    if (!src) return 0;
+    CK(cudaMalloc((void **)&dst, std::max<size_t>(n, 1) * sizeof(T)));
+    h->allocs.push_back(dst);
+    if (n) CK(cudaMemcpy(dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+template <class T>
+int dzeros(axb_handle_s *h, T *&dst, size_t n) {
+    CK(cudaMalloc((void **)&dst, std::max<size_t>(n, 1) * sizeof(T)));
+    h->allocs.push_back(dst);
+    CK(cudaMemset(dst, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    return 0;
+}
+int use(axb_handle_s *h) {
+    CK(cudaSetDevice(h->device));
+    return 0;
+}
+#define UP(dst, src, n) do { if (upload(h, dst, src, (size_t)(n))) return 1; } while (0)
+#define UPC(dst, src, n) do { float *_t; if (upload(h, _t, src, (size_t)(n))) return 1; dst = _t; } while (0)
+
+// symplectic_coefficients / SS_scheme: time_evol_wave.F90:749-992 (incl. 1/2 == 0 at :981)
+void ss_scheme(int n, double *a, double *b, const double *g) {
+    double s = 0.0;
+    a[0] = g[0] / 2.0;
+    for (int i = 1; i < n; i++) a[i] = (g[i - 1] + g[i]) / 2.0;
+    for (int i = 0; i < n; i++) s += a[i];
+    a[n] = (double)(1 / 2) - s;
+    for (int i = n + 2; i <= 2 * n + 2; i++) a[i - 1] = a[2 * n + 3 - i - 1];
+    for (int i = 0; i < n; i++) b[i] = g[i];
+    s = 0.0;
+    for (int i = 0; i < n; i++) s += g[i];
+    b[n] = 1.0 - 2.0 * s;
+    for (int i = n + 2; i <= 2 * n + 1; i++) b[i - 1] = b[2 * n + 2 - i - 1];
+}
+
+int symplectic_coefficients(axb_handle_s *o) {
+    double *d = o->coefd, *v = o->coefv;
+    int n, ns = 0;
+    switch (o->scheme) {
+    case AXB_SYMPLEC4: {
+        // default-real literals in the Fortran source -> single-precision values
+        double zeta = (double)0.1786178958448091f, iota = (double)-0.2123418310626054f,
+               kappa = (double)-0.06626458266981849f;
+        ns = 4;
+        d[0] = zeta; d[1] = kappa; d[2] = 1.0 - 2.0 * (zeta + kappa); d[3] = kappa; d[4] = zeta;
+        v[0] = 0.5 - iota; v[1] = iota; v[2] = iota; v[3] = 0.5 - iota;
+        break; }
+    case AXB_ML_SO4M5: {
+        double rho = (14.0 - std::sqrt(19.0)) / 108.0, theta = (20.0 - 7.0 * std::sqrt(19.0)) / 108.0;
+        double nu = 2.0 / 5.0, lambda = -1.0 / 10.0;
+        ns = 5;
+        d[0] = rho; d[1] = theta; d[2] = 0.5 - rho - theta; d[3] = 0.5 - rho - theta;
+        d[4] = theta; d[5] = rho;
+        v[0] = nu; v[1] = lambda; v[2] = 1.0 - 2.0 * (nu + lambda); v[3] = lambda; v[4] = nu;
+        break; }
+    case AXB_ML_SO6M7: {
+        ns = 7;
+        d[0] = (double)-1.01308797891717472981f; d[1] = (double)1.18742957373254270702f;
+        d[2] = (double)-0.01833585209646059034f; d[3] = (double)0.34399425728109261313f;
+        for (int i = 5; i <= 8; i++) d[i - 1] = d[ns + 2 - i - 1];
+        v[0] = (double)0.00016600692650009894f; v[1] = (double)-0.37962421426377360608f;
+        v[2] = (double)0.68913741185181063674f; v[3] = (double)0.38064159097092574080f;
+        for (int i = 5; i <= 7; i++) v[i - 1] = v[ns + 1 - i - 1];
+        break; }
+    case AXB_KL_O8M17: {
+        static const float gf[8] = {0.13020248308889008088f, 0.56116298177510838456f,
+            -0.38947496264484728641f, 0.15884190655515560090f, -0.39590389413323757734f,
+            0.18453964097831570709f, 0.25837438768632204729f, 0.29501172360931029887f};
+        double g[8];
+        n = 8; ns = 2 * n + 1;
+        for (int i = 0; i < n; i++) g[i] = (double)gf[i];
+        ss_scheme(n, d, v, g);
+        break; }
+    case AXB_SS_35O10: {
+        static const float gf[17] = {0.078795722521686419263907679337684f,
+            0.31309610341510852776481247192647f, 0.027918383235078066109520273275299f,
+            -0.22959284159390709415121339679655f, 0.13096206107716486317465685927961f,
+            -0.26973340565451071434460973222411f, 0.074973343155891435666137105641410f,
+            0.11199342399981020488957508073640f, 0.36613344954622675119314812353150f,
+            -0.39910563013603589787862981058340f, 0.10308739852747107731580277001372f,
+            0.41143087395589023782070411897608f, -0.0048663605831352617621956593099771f,
+            -0.39203335370863990644808193642610f, 0.051942502962449647037182904015976f,
+            0.050665090759924496335874344156866f, 0.049674370639729879054568800279461f};
+        double g[17];
+        n = 17; ns = 2 * n + 1;
+        for (int i = 0; i < n; i++) g[i] = (double)gf[i];
+        ss_scheme(n, d, v, g);
+        break; }
+    default:
+        return fail("unknown time scheme");
+    }
+    o->nstages = ns;
+    for (int i = 0; i <= ns; i++) d[i] *= o->deltat;
+    for (int i = 0; i < ns; i++) v[i] *= o->deltat;
+    for (int i = 0; i < ns; i++) {
+        double s = 0.0;
+        for (int k = 0; k <= i; k++) s += d[k];
+        o->coeff[i] = s;
+    }
+    return 0;
+}
+
+// compute_stf_t (source.f90:206-233)
+double stf_t(const axb_handle_s *o, double t) {
+    const double a = o->decay / o->t_0, x = a * (t - o->shift);
+    const double pi = 3.1415926535898;
+    switch (o->stf_type) {
+    case AXB_STF_GAUSS_0: return std::exp(-(x * x)) * o->magnitude * a / std::sqrt(pi);
+    case AXB_STF_GAUSS_1: return -2.0 * a * a * (t - o->shift) * std::exp(-(x * x))
+                                 / (a * std::sqrt(2.0) * std::exp(-0.5)) * o->magnitude;
+    default: return a * a * (2.0 * a * a * (t - o->shift) * (t - o->shift) - 1.0)
+                    * std::exp(-(x * x)) / (2.0 * a * a * std::exp(-1.5)) * o->magnitude;
+    }
+}
+
+void fast_correct(int n, const double *y, double *yp) {      // attenuation.f90:1139-1155
+    double dy[32];
+    dy[0] = 1 + .5 * y[0];
+    for (int k = 1; k < n; k++) dy[k] = dy[k - 1] + (dy[k - 1] - .5) * y[k - 1] + .5 * y[k];
+    for (int k = 0; k < n; k++) yp[k] = y[k] * dy[k];
+}
+void a_j_of_Q(const axb_handle_s *o, float Q, double *a_j) { // attenuation.f90:116-134
+    const int n = o->A.n_sls;
+    double yq[32], yp[32], s = 0.0;
+    for (int k = 0; k < n; k++) yq[k] = o->y_j[k] / Q;
+    if (o->corr_lowq) fast_correct(n, yq, yp);
+    else std::memcpy(yp, yq, sizeof(double) * n);
+    for (int k = 0; k < n; k++) s += yp[k];
+    for (int k = 0; k < n; k++) a_j[k] = yp[k] / s;
+}
+
+// Pull-style assembly table (see AsmTable).  Only the 16 edge points of an element take
+// part (commun.F90:110-120); members are listed in ascending element order.
+int build_asm(axb_handle_s *h, int nel, int nglob, const std::vector<int> &igloc, Halo &H,
+              int *&d_gid, int *&d_grp) {
+    static const int edge_q[16] = {0, 1, 2, 3, 4, 5, 9, 10, 14, 15, 19, 20, 21, 22, 23, 24};
+    const size_t npts = (size_t)NPT * nel;
+    std::vector<int> count(nglob + 1, 0);
+    for (int e = 0; e < nel; e++)
+        for (int k = 0; k < 16; k++) count[igloc[(size_t)e * NPT + edge_q[k]] - 1 + 1]++;
+    // remote contributions per glocal id: slots in message order
+    std::vector<int> rcount(nglob, 0);
+    for (int m = 0; m < H.nmsg; m++)
+        for (int ip = 0; ip < H.size[m]; ip++) rcount[H.glocal[m][ip] - 1]++;
+    std::vector<int64_t> start(nglob + 1, 0);
+    for (int g = 0; g < nglob; g++) start[g + 1] = start[g] + count[g + 1];
+    std::vector<int> members(start[nglob]);
+    std::vector<int64_t> fill(start.begin(), start.end() - 1);
+    for (int e = 0; e < nel; e++)
+        for (int k = 0; k < 16; k++) {
+            const size_t p = (size_t)e * NPT + edge_q[k];
+            members[fill[igloc[p] - 1]++] = (int)p;
+        }
+    // group offsets
+    std::vector<int64_t> goff(nglob, -1);
+    int64_t total = 0;
+    for (int g = 0; g < nglob; g++) {
+        const int nloc = count[g + 1];
+        if (nloc + rcount[g] >= 2 && nloc >= 1) { goff[g] = total; total += 2 + nloc + rcount[g]; }
+    }
+    if (total > 0x7fffffffLL) return fail("assembly table too large for 32-bit offsets");
+    std::vector<int> grp(std::max<int64_t>(total, 1), 0);
+    std::vector<int> rfill(nglob, 0);
+    for (int g = 0; g < nglob; g++) {
+        if (goff[g] < 0) continue;
+        const int nloc = count[g + 1];
+        grp[goff[g]] = nloc;
+        grp[goff[g] + 1] = rcount[g];
+        for (int m = 0; m < nloc; m++) grp[goff[g] + 2 + m] = members[start[g] + m];
+    }
+    for (int m = 0; m < H.nmsg; m++)
+        for (int ip = 0; ip < H.size[m]; ip++) {
+            const int g = H.glocal[m][ip] - 1;
+            if (goff[g] < 0) return fail("halo point without a local edge copy");
+            grp[goff[g] + 2 + count[g + 1] + rfill[g]++] = H.offset[m] + ip;
+        }
+    std::vector<int> gid(std::max<size_t>(npts, 1), -1);
+    for (int e = 0; e < nel; e++)
+        for (int k = 0; k < 16; k++) {
+            const size_t p = (size_t)e * NPT + edge_q[k];
+            const int64_t o = goff[igloc[p] - 1];
+            gid[p] = o < 0 ? -1 : (int)o;
+        }
+    if (upload(h, d_gid, gid.data(), gid.size())) return 1;
+    if (upload(h, d_grp, grp.data(), grp.size())) return 1;
+    return 0;
+}
+
+// Halo send side: CSR of local copies per send entry in glob2el order (commpi.F90:383-391)
+int build_halo_send(axb_handle_s *h, int nel, int nglob, const std::vector<int> &igloc, Halo &H) {
+    if (H.nmsg == 0) return 0;
+    std::vector<std::vector<int>> mem(nglob);
+    for (int ip = 0; ip < H.ncomm; ip++) {
+        const int ipol = H.glob2el[ip], jpol = H.glob2el[ip + H.ncomm], iel = H.glob2el[ip + 2 * H.ncomm];
+        const size_t ipt = (size_t)(iel - 1) * NPT + jpol * NP + ipol;
+        mem[igloc[ipt] - 1].push_back((int)ipt);
+    }
+    std::vector<int> start(1, 0), addr, dmsg, dslot;
+    for (int m = 0; m < H.nmsg; m++)
+        for (int ip = 0; ip < H.size[m]; ip++) {
+            const auto &v = mem[H.glocal[m][ip] - 1];
+            addr.insert(addr.end(), v.begin(), v.end());
+            start.push_back((int)addr.size());
+            dmsg.push_back(m);
+            dslot.push_back(ip);           // + peer offset, added at connect time
+        }
+    H.nentries = (int)dmsg.size();
+    if (addr.empty()) addr.push_back(0);
+    if (upload(h, H.d_start, start.data(), start.size())) return 1;
+    if (upload(h, H.d_addr, addr.data(), addr.size())) return 1;
+    if (upload(h, H.d_dst_msg, dmsg.data(), dmsg.size())) return 1;
+    if (upload(h, H.d_dst_slot, dslot.data(), dslot.size())) return 1;
+    (void)nel;
+    return 0;
+}
+
+inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+}  // namespace
+
+// ======================================================================================
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char *axb_last_error(void) { return g_err.c_str(); }
+
+int axb_create(axb_handle *out, int32_t device, int32_t rank, int32_t nranks) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(std::string("axisem_b200: no CUDA device (") + cudaGetErrorString(e) +
+                    "); this library has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("axb_create: bad device ordinal");
+    axb_handle_s *h = new axb_handle_s();
+    h->device = device; h->rank = rank; h->nranks = nranks;
+    std::memset(&h->P, 0, sizeof h->P);
+    std::memset(&h->A, 0, sizeof h->A);
+    if (use(h)) { delete h; return 1; }
+    cudaError_t se = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) { delete h; return fail(cudaGetErrorString(se)); }
+    h->own_stream = true;
+    *out = h;
+    return 0;
+}
+
+int axb_destroy(axb_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int axb_set_stream(axb_handle h, void *cuda_stream) {
+    if (use(h)) return 1;
+    if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    h->stream = (cudaStream_t)cuda_stream;
+    h->own_stream = false;
+    return 0;
+}
+
+int axb_set_mesh(axb_handle h, int32_t npol, int32_t nel_solid, int32_t nel_fluid,
+                 int32_t nglob_solid, int32_t nglob_fluid, const int32_t *igloc_solid,
+                 const int32_t *igloc_fluid, const int32_t *axis_solid,
+                 const int32_t *axis_fluid, const int32_t *ax_el_solid, int32_t naxel_solid,
+                 const int32_t *ax_el_fluid, int32_t naxel_fluid, const float *G0,
+                 const float *G1, const float *G1T, const float *G2, const float *G2T) {
+    if (npol != 4) return fail("axb_set_mesh: npol must be 4");
+    if (use(h)) return 1;
+    h->nel_s = nel_solid; h->nel_f = nel_fluid; h->nglob_s = nglob_solid; h->nglob_f = nglob_fluid;
+    h->igloc_s.assign(igloc_solid, igloc_solid + (size_t)NPT * nel_solid);
+    if (nel_fluid) h->igloc_f.assign(igloc_fluid, igloc_fluid + (size_t)NPT * nel_fluid);
+    for (size_t p = 0; p < h->igloc_s.size(); p++)
+        if (h->igloc_s[p] < 1 || h->igloc_s[p] > nglob_solid) return fail("igloc_solid out of range");
+    for (size_t p = 0; p < h->igloc_f.size(); p++)
+        if (h->igloc_f[p] < 1 || h->igloc_f[p] > nglob_fluid) return fail("igloc_fluid out of range");
+    // the axial element lists must agree with the logical flags (def_grid.f90:59-77)
+    {
+        int n = 0;
+        for (int e = 0; e < nel_solid; e++) n += axis_solid[e] != 0;
+        if (n != naxel_solid) return fail("axis_solid / ax_el_solid mismatch");
+        for (int a = 0; a < naxel_solid; a++)
+            if (ax_el_solid[a] < 1 || ax_el_solid[a] > nel_solid || !axis_solid[ax_el_solid[a] - 1])
+                return fail("ax_el_solid inconsistent with axis_solid");
+        n = 0;
+        for (int e = 0; e < nel_fluid; e++) n += axis_fluid[e] != 0;
+        if (n != naxel_fluid) return fail("axis_fluid / ax_el_fluid mismatch");
+        for (int a = 0; a < naxel_fluid; a++)
+            if (ax_el_fluid[a] < 1 || ax_el_fluid[a] > nel_fluid || !axis_fluid[ax_el_fluid[a] - 1])
+                return fail("ax_el_fluid inconsistent with axis_fluid");
+    }
+    h->axis_s_h.assign(axis_solid, axis_solid + nel_solid);
+    UP(h->d_axis_s, (const int *)axis_solid, nel_solid);
+    UP(h->d_axis_f, (const int *)axis_fluid, nel_fluid);
+    std::memcpy(h->G.G0, G0, sizeof h->G.G0);
+    std::memcpy(h->G.G1, G1, sizeof h->G.G1); std::memcpy(h->G.G1T, G1T, sizeof h->G.G1T);
+    std::memcpy(h->G.G2, G2, sizeof h->G.G2); std::memcpy(h->G.G2T, G2T, sizeof h->G.G2T);
+    return 0;
+}
+
+int axb_set_solid_terms(axb_handle h, int32_t src_order, const axb_solid_terms *t) {
+    if (use(h)) return 1;
+    if (src_order < 0 || src_order > 2) return fail("bad src_order");
+    h->order = src_order;
+    const size_t n = (size_t)NPT * h->nel_s, n0 = (size_t)NP * h->nel_s;
+#define CP(x) UPC(h->P.x, t->x, n)
+#define CP0(x) UPC(h->P.x, t->x, n0)
+    CP(M11s); CP(M21s); CP(M41s); CP(M12s); CP(M22s); CP(M32s); CP(M42s);
+    CP(M11z); CP(M21z); CP(M41z); CP(M13s); CP(M33s); CP(M43s);
+    CP(M1phi); CP(M2phi); CP(M4phi);
+    CP(M_1); CP(M_2); CP(M_3); CP(M_4); CP(M_5); CP(M_6); CP(M_7); CP(M_8);
+    CP(M_w1); CP(M_w2); CP(M_w3); CP(M_w4); CP(M_w5);
+    CP0(M0_w1); CP0(M0_w2); CP0(M0_w3); CP0(M0_w4); CP0(M0_w5);
+    CP0(M0_w6); CP0(M0_w7); CP0(M0_w8); CP0(M0_w9); CP0(M0_w10);
+#undef CP
+#undef CP0
+    const SolidPlanes &P = h->P;
+    bool ok = P.M11s && P.M21s && P.M41s && P.M12s && P.M22s && P.M32s && P.M42s && P.M11z &&
+              P.M21z && P.M41z && P.M_1 && P.M_2 && P.M_3 && P.M_4 && P.M_w1 && P.M0_w1 &&
+              P.M0_w2 && P.M0_w3;
+    if (src_order == AXB_DIPOLE)
+        ok = ok && P.M13s && P.M33s && P.M43s && P.M_5 && P.M_6 && P.M_7 && P.M_8 && P.M_w2 &&
+             P.M_w3 && P.M0_w4 && P.M0_w6 && P.M0_w7 && P.M0_w8 && P.M0_w9 && P.M0_w10;
+    if (src_order == AXB_QUADPOLE)
+        ok = ok && P.M1phi && P.M2phi && P.M4phi && P.M_5 && P.M_6 && P.M_7 && P.M_8 && P.M_w2 &&
+             P.M_w3 && P.M_w4 && P.M_w5 && P.M0_w4 && P.M0_w5 && P.M0_w6;
+    if (!ok && h->nel_s > 0) return fail("axb_set_solid_terms: a plane required for this source order is NULL");
+    return 0;
+}
+
+int axb_set_fluid_terms(axb_handle h, const float *M1chi_fl, const float *M2chi_fl,
+                        const float *M4chi_fl, const float *M_w_fl, const float *M0_w_fl,
+                        const float *inv_mass_fluid, const float *fluid_free_surface_mask) {
+    if (use(h)) return 1;
+    const size_t n = (size_t)NPT * h->nel_f;
+    UP(h->M1chi, M1chi_fl, n); UP(h->M2chi, M2chi_fl, n); UP(h->M4chi, M4chi_fl, n);
+    UP(h->M_w_fl, M_w_fl, n); UP(h->M0_w_fl, M0_w_fl, (size_t)NP * h->nel_f);
+    UP(h->inv_mass_fluid, inv_mass_fluid, n);
+    UP(h->fs_mask, fluid_free_surface_mask, n);
+    if (h->nel_f && (!h->M1chi || !h->M2chi || !h->M4chi || !h->inv_mass_fluid))
+        return fail("axb_set_fluid_terms: NULL plane");
+    return 0;
+}
+
+int axb_set_mass(axb_handle h, const float *inv_mass_rho) {
+    if (use(h)) return 1;
+    UP(h->inv_mass_rho, inv_mass_rho, (size_t)NPT * h->nel_s);
+    return 0;
+}
+
+int axb_set_sponge(axb_handle h, const float *solid_gamma, const float *fluid_gamma) {
+    if (use(h)) return 1;
+    if (!solid_gamma && !fluid_gamma) return 0;
+    if (solid_gamma) UP(h->gamma_s, solid_gamma, (size_t)NPT * h->nel_s);
+    else if (dzeros(h, h->gamma_s, (size_t)NPT * h->nel_s)) return 1;
+    if (fluid_gamma) UP(h->gamma_f, fluid_gamma, (size_t)NPT * h->nel_f);
+    else if (dzeros(h, h->gamma_f, (size_t)NPT * h->nel_f)) return 1;
+    return 0;
+}
+
+int axb_set_sf_boundary(axb_handle h, int32_t nel_bdry, const int32_t *bdry_solid_el,
+                        const int32_t *bdry_fluid_el, const int32_t *bdry_jpol_solid,
+                        const int32_t *bdry_jpol_fluid, const float *bdry_matr) {
+    if (use(h)) return 1;
+    for (int b = 0; b < nel_bdry; b++) {
+        if (bdry_solid_el[b] < 1 || bdry_solid_el[b] > h->nel_s || bdry_fluid_el[b] < 1 ||
+            bdry_fluid_el[b] > h->nel_f)
+            return fail("S/F boundary element out of range");
+        if ((bdry_jpol_solid[b] != 0 && bdry_jpol_solid[b] != 4) ||
+            (bdry_jpol_fluid[b] != 0 && bdry_jpol_fluid[b] != 4))
+            return fail("S/F boundary jpol must be 0 or npol");
+    }
+    h->nel_bdry = nel_bdry;
+    h->bdry_fel_h.assign(bdry_fluid_el, bdry_fluid_el + nel_bdry);
+    h->bdry_jf_h.assign(bdry_jpol_fluid, bdry_jpol_fluid + nel_bdry);
+    UP(h->d_bsel, (const int *)bdry_solid_el, nel_bdry); UP(h->d_bfel, (const int *)bdry_fluid_el, nel_bdry);
+    UP(h->d_bjs, (const int *)bdry_jpol_solid, nel_bdry); UP(h->d_bjf, (const int *)bdry_jpol_fluid, nel_bdry);
+    UP(h->d_bmatr, bdry_matr, (size_t)NP * nel_bdry * 2);
+    return 0;
+}
+
+int axb_set_attenuation(axb_handle h, const axb_attenuation *a) {
+    if (use(h)) return 1;
+    if (a->n_sls < 1 || a->n_sls > 8) return fail("n_sls must be in 1..8");
+    if (!a->coarse_grained)
+        return fail("axb_set_attenuation: only COARSE_GRAINED true (the reference default) is "
+                    "implemented on the device in this round");
+    const size_t n4 = (size_t)4 * h->nel_s, n = (size_t)NPT * h->nel_s;
+    h->anel = true; h->cg = true; h->corr_lowq = a->do_corr_lowq;
+    AttCg &A = h->A;
+    A.n_sls = a->n_sls;
+    h->y_j.assign(a->y_j, a->y_j + a->n_sls);
+    { double *t; UP(t, a->exp_w_j_deltat, a->n_sls); A.exp_w = t; }
+    { double *t; UP(t, a->ts_fac_t, a->n_sls); A.ts_t = t; }
+    { double *t; UP(t, a->ts_fac_tm1, a->n_sls); A.ts_tm1 = t; }
+    h->Qmu_h.assign(a->Q_mu, a->Q_mu + h->nel_s);
+    h->Qka_h.assign(a->Q_kappa, a->Q_kappa + h->nel_s);
+    UPC(A.Ycg, a->Y_cg4, n4); UPC(A.Vse, a->V_s_eta_cg4, n4); UPC(A.Vsx, a->V_s_xi_cg4, n4);
+    UPC(A.Vze, a->V_z_eta_cg4, n4); UPC(A.Vzx, a->V_z_xi_cg4, n4);
+    UPC(A.Dse, a->DsDeta_over_J_sol_cg4, n4); UPC(A.Dze, a->DzDeta_over_J_sol_cg4, n4);
+    UPC(A.Dsx, a->DsDxi_over_J_sol_cg4, n4); UPC(A.Dzx, a->DzDxi_over_J_sol_cg4, n4);
+    UPC(A.dmu, a->delta_mu_cg4, n4); UPC(A.dka, a->delta_kappa_cg4, n4);
+    UPC(A.inv_s, a->inv_s_solid, n);
+    if (!A.Ycg || !A.Vse || !A.Vsx || !A.Vze || !A.Vzx || !A.Dse || !A.Dze || !A.Dsx || !A.Dzx ||
+        !A.dmu || !A.dka || !A.inv_s)
+        return fail("axb_set_attenuation: NULL cg4 array");
+    return 0;
+}
+
+int axb_set_source(axb_handle h, int32_t fluid_src, int32_t nelsrc, const int32_t *ielsrc,
+                   const float *source_term, const float *stf, int32_t niter) {
+    if (use(h)) return 1;
+    if (nelsrc < 0 || nelsrc > 8) return fail("nelsrc must be in 0..8");
+    h->fluid_src = fluid_src; h->nelsrc = nelsrc;
+    for (int k = 0; k < 8; k++) h->ielsrc[k] = (k < nelsrc) ? ielsrc[k] : 0;
+    for (int k = 0; k < nelsrc; k++)
+        if (ielsrc[k] < 1 || ielsrc[k] > (fluid_src ? h->nel_f : h->nel_s)) return fail("ielsrc out of range");
+    UP(h->d_src_term, source_term, (size_t)NPT * 8 * (fluid_src ? 1 : 3));
+    UP(h->d_stf, stf, niter);
+    h->niter_stf = niter;
+    return 0;
+}
+
+int axb_set_stf_params(axb_handle h, int32_t stf_type, double decay, double t_0,
+                       double shift_fact, double magnitude) {
+    h->stf_type = stf_type; h->decay = decay; h->t_0 = t_0; h->shift = shift_fact;
+    h->magnitude = magnitude;
+    return 0;
+}
+
+int axb_set_receivers(axb_handle h, int32_t num_rec, const int32_t *recfile_el) {
+    if (use(h)) return 1;
+    for (int r = 0; r < num_rec; r++) {
+        const int iel = recfile_el[r], ip = recfile_el[r + num_rec], jp = recfile_el[r + 2 * num_rec];
+        if (iel < 1 || iel > h->nel_s || ip < 0 || ip > 4 || jp < 0 || jp > 4)
+            return fail("recfile_el out of range");
+    }
+    h->num_rec = num_rec;
+    UP(h->d_recfile, (const int *)recfile_el, (size_t)3 * num_rec);
+    return 0;
+}
+
+int axb_set_kwf(axb_handle h, const int32_t *kwf_mask, const int32_t *mapping_ijel_ikwf,
+                int32_t npoint_solid_kwf, int32_t npoint_fluid_kwf, const float *inv_rho_fluid,
+                const float *DsDeta_over_J_flu, const float *DzDeta_over_J_flu,
+                const float *DsDxi_over_J_flu, const float *DzDxi_over_J_flu) {
+    if (use(h)) return 1;
+    const size_t n = (size_t)NPT * (h->nel_s + h->nel_f), nf = (size_t)NPT * h->nel_f;
+    const int npts = npoint_solid_kwf + npoint_fluid_kwf;
+    for (size_t p = 0; p < n; p++)
+        if (kwf_mask[p] && (mapping_ijel_ikwf[p] < 1 || mapping_ijel_ikwf[p] > npts))
+            return fail("mapping_ijel_ikwf out of range");
+    h->have_kwf = true; h->npt_s_kwf = npoint_solid_kwf; h->npt_f_kwf = npoint_fluid_kwf;
+    UP(h->d_kwf_mask, (const int *)kwf_mask, n); UP(h->d_kwf_map, (const int *)mapping_ijel_ikwf, n);
+    UP(h->d_inv_rho, inv_rho_fluid, nf);
+    UP(h->d_Dse_f, DsDeta_over_J_flu, nf); UP(h->d_Dze_f, DzDeta_over_J_flu, nf);
+    UP(h->d_Dsx_f, DsDxi_over_J_flu, nf); UP(h->d_Dzx_f, DzDxi_over_J_flu, nf);
+    if (h->nel_f && (!h->d_inv_rho || !h->d_Dse_f || !h->d_Dze_f || !h->d_Dsx_f || !h->d_Dzx_f))
+        return fail("axb_set_kwf: NULL fluid plane");
+    return 0;
+}
+
+int axb_set_halo(axb_handle h, int32_t domain, int32_t nmsg, const int32_t *list_peer,
+                 const int32_t *sizemsg, const int32_t *glocal_index_msg, int32_t maxmsg,
+                 int32_t num_comm_gll, const int32_t *glob2el) {
+    if (domain != AXB_DOMAIN_SOLID && domain != AXB_DOMAIN_FLUID) return fail("bad domain");
+    if (nmsg > MAXMSG) return fail("too many neighbours (max 8)");
+    Halo &H = h->halo[domain];
+    const int nglob = domain == AXB_DOMAIN_SOLID ? h->nglob_s : h->nglob_f;
+    const int nel = domain == AXB_DOMAIN_SOLID ? h->nel_s : h->nel_f;
+    H.nmsg = nmsg;
+    H.nc = domain == AXB_DOMAIN_SOLID ? 3 : 1;
+    H.glocal.assign(nmsg, {});
+    int off = 0;
+    for (int m = 0; m < nmsg; m++) {
+        H.peer[m] = list_peer[m]; H.size[m] = sizemsg[m]; H.offset[m] = off;
+        off += sizemsg[m];
+        H.glocal[m].resize(sizemsg[m]);
+        for (int ip = 0; ip < sizemsg[m]; ip++) {
+            const int g = glocal_index_msg[ip + (size_t)maxmsg * m];
+            if (g < 1 || g > nglob) return fail("glocal_index_msg out of range");
+            H.glocal[m][ip] = g;
+        }
+    }
+    H.nslots = off;
+    H.ncomm = num_comm_gll;
+    H.glob2el.assign(glob2el, glob2el + (size_t)3 * num_comm_gll);
+    for (int ip = 0; ip < num_comm_gll; ip++) {
+        const int ipol = glob2el[ip], jpol = glob2el[ip + num_comm_gll], iel = glob2el[ip + 2 * num_comm_gll];
+        if (ipol < 0 || ipol > 4 || jpol < 0 || jpol > 4 || iel < 1 || iel > nel) return fail("glob2el out of range");
+    }
+    return 0;
+}
+
+int axb_set_time(axb_handle h, int32_t scheme, double deltat, int32_t niter, int32_t seis_it,
+                 int32_t strain_it) {
+    if (scheme < 0 || scheme > AXB_SS_35O10) return fail("unknown time scheme");
+    if (!(deltat > 0)) return fail("deltat must be positive");
+    h->scheme = scheme; h->deltat = deltat; h->niter = niter;
+    h->seis_it = seis_it > 0 ? seis_it : 1; h->strain_it = strain_it;
+    h->half_dt = 0.5 * deltat;                 // parameters.F90:1124-1125
+    h->half_dt_sq = 0.5 * deltat * deltat;
+    return 0;
+}
+
+int axb_finalize_setup(axb_handle h) {
+    if (use(h)) return 1;
+    if (h->nel_s > 0 && !h->inv_mass_rho) return fail("axb_set_mass not called");
+    const size_t ns = (size_t)NPT * h->nel_s * 3, nf = (size_t)NPT * h->nel_f;
+    if ((size_t)NPT * h->nel_s * 3 > 0x7fffffffULL) return fail("too many solid points for 32-bit point addresses");
+    if (dzeros(h, h->disp, ns) || dzeros(h, h->velo, ns) || dzeros(h, h->acc0, ns) || dzeros(h, h->acc1, ns)) return 1;
+    if (dzeros(h, h->chi, nf) || dzeros(h, h->dchi, nf) || dzeros(h, h->ddchi0, nf) || dzeros(h, h->ddchi1, nf)) return 1;
+    // halo slabs first (assembly tables reference slot numbers)
+    for (int d = 0; d < 2; d++) {
+        Halo &H = h->halo[d];
+        if (H.nmsg == 0) continue;
+        if (dzeros(h, H.recv, (size_t)2 * H.nc * H.nslots)) return 1;
+        if (dzeros(h, H.flags, MAXMSG)) return 1;
+    }
+    if (build_asm(h, h->nel_s, h->nglob_s, h->igloc_s, h->halo[0], h->d_asm_gid_s, h->d_asm_grp_s)) return 1;
+    if (build_asm(h, h->nel_f, h->nglob_f, h->igloc_f, h->halo[1], h->d_asm_gid_f, h->d_asm_grp_f)) return 1;
+    if (build_halo_send(h, h->nel_s, h->nglob_s, h->igloc_s, h->halo[0])) return 1;
+    if (build_halo_send(h, h->nel_f, h->nglob_f, h->igloc_f, h->halo[1])) return 1;
+    // S/F boundary seen from the fluid elements
+    if (h->nel_f) {
+        std::vector<int2> bo(h->nel_f, make_int2(0, 0));
+        for (int b = 0; b < h->nel_bdry; b++) {
+            int2 &r = bo[h->bdry_fel_h[b] - 1];
+            int &slot = (h->bdry_jf_h[b] == 0) ? r.x : r.y;
+            if (slot != 0) return fail("two S/F boundary entries on the same fluid edge");
+            slot = b + 1;
+        }
+        UP(h->d_bdry_of_el, bo.data(), bo.size());
+    }
+    if (h->anel) {
+        // a_j tables per distinct Q (time_step_memvars_cg4 recomputes them whenever Q changes)
+        std::map<float, int> idx_mu, idx_ka;
+        std::vector<int> qi_mu(h->nel_s), qi_ka(h->nel_s);
+        std::vector<double> tab_mu, tab_ka;
+        double aj[32];
+        for (int e = 0; e < h->nel_s; e++) {
+            auto it = idx_mu.find(h->Qmu_h[e]);
+            if (it == idx_mu.end()) {
+                it = idx_mu.emplace(h->Qmu_h[e], (int)idx_mu.size()).first;
+                a_j_of_Q(h, h->Qmu_h[e], aj);
+                tab_mu.insert(tab_mu.end(), aj, aj + h->A.n_sls);
+            }
+            qi_mu[e] = it->second;
+            auto ik = idx_ka.find(h->Qka_h[e]);
+            if (ik == idx_ka.end()) {
+                ik = idx_ka.emplace(h->Qka_h[e], (int)idx_ka.size()).first;
+                a_j_of_Q(h, h->Qka_h[e], aj);
+                tab_ka.insert(tab_ka.end(), aj, aj + h->A.n_sls);
+            }
+            qi_ka[e] = ik->second;
+        }
+        { int *t; UP(t, qi_mu.data(), qi_mu.size()); h->A.qidx_mu = t; }
+        { int *t; UP(t, qi_ka.data(), qi_ka.size()); h->A.qidx_ka = t; }
+        { double *t; UP(t, tab_mu.data(), tab_mu.size()); h->A.a_mu_tab = t; }
+        { double *t; UP(t, tab_ka.data(), tab_ka.size()); h->A.a_ka_tab = t; }
+        if (dzeros(h, h->A.memvar, (size_t)24 * h->A.n_sls * h->nel_s)) return 1;
+        if (dzeros(h, h->A.src_dev_tm1, (size_t)24 * h->nel_s)) return 1;
+        if (dzeros(h, h->A.src_tr_tm1, (size_t)4 * h->nel_s)) return 1;
+    }
+    if (h->scheme != AXB_NEWMARK2) {
+        if (symplectic_coefficients(h)) return 1;
+        // stf at the sub-stage times of every step: subdt = t - deltat + coeff
+        // (time_evol_wave.F90:592-593, :689), t accumulated as in :586
+        std::vector<float> tab((size_t)h->nstages * std::max(h->niter, 1));
+        double t = 0.0;
+        for (int it = 0; it < h->niter; it++) {
+            t += h->deltat;
+            for (int k = 0; k < h->nstages; k++)
+                tab[(size_t)it * h->nstages + k] = (float)stf_t(h, t - h->deltat + h->coeff[k]);
+        }
+        UP(h->d_stf_symp, tab.data(), tab.size());
+    } else if (h->nelsrc > 0 && (!h->d_stf || h->niter_stf < h->niter)) {
+        return fail("stf(niter) missing or shorter than niter");
+    }
+    h->nseismo_max = h->niter / h->seis_it + 1;          // parameters.F90:929
+    if (dzeros(h, h->d_recdump, (size_t)3 * std::max(h->num_rec, 1) * h->nseismo_max)) return 1;
+    if (h->strain_it > 0 && h->have_kwf) {
+        h->nstrain_max = h->niter / h->strain_it + 1;
+        if (dzeros(h, h->d_snap, (size_t)(h->npt_s_kwf + h->npt_f_kwf) * h->nstrain_max * 3)) return 1;
+    }
+    if (dzeros(h, h->d_counters, 4)) return 1;
+    // persistent grids: whole multiples of the SM count
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    const int sms = prop.multiProcessorCount;
+    h->grid_s = std::max(1, std::min(cdiv(h->nel_s, 8), sms * 8));
+    h->grid_f = std::max(1, std::min(cdiv(h->nel_f, 8), sms * 8));
+    h->iter = h->iseismo = h->istrain = 0;
+    h->finalized = true;
+    CK(cudaDeviceSynchronize());
+    // host copies no longer needed
+    std::vector<int>().swap(h->igloc_s);
+    std::vector<int>().swap(h->igloc_f);
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// halo wiring
+static int wire(axb_handle_s *me, int d, int m, float *peer_recv, int *peer_flags, int peer_nslots,
+                int peer_offset, int peer_msg_index) {
+    Halo &H = me->halo[d];
+    H.peer_recv[m] = peer_recv;
+    H.peer_nslots[m] = peer_nslots;
+    H.peer_offset[m] = peer_offset;
+    H.peer_flag[m] = peer_flags + peer_msg_index;
+    return 0;
+}
+
+int axb_connect_local(axb_handle *hs, int32_t n) {
+    for (int a = 0; a < n; a++) {
+        if (!hs[a]->finalized) return fail("connect_local before finalize_setup");
+        hs[a]->group.assign(hs, hs + n);
+    }
+    for (int a = 0; a < n; a++)
+        for (int b = 0; b < n; b++) {
+            if (a == b || hs[a]->device == hs[b]->device) continue;
+            if (use(hs[a])) return 1;
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, hs[a]->device, hs[b]->device));
+            if (!can) return fail("GPUs are not peer-accessible");
+            cudaError_t e = cudaDeviceEnablePeerAccess(hs[b]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    for (int a = 0; a < n; a++)
+        for (int d = 0; d < 2; d++) {
+            Halo &H = hs[a]->halo[d];
+            for (int m = 0; m < H.nmsg; m++) {
+                axb_handle_s *p = nullptr;
+                for (int b = 0; b < n; b++) if (hs[b]->rank == H.peer[m]) p = hs[b];
+                if (!p) return fail("halo peer not in the group");
+                Halo &Hp = p->halo[d];
+                int mm = -1;
+                for (int q = 0; q < Hp.nmsg; q++) if (Hp.peer[q] == hs[a]->rank) mm = q;
+                if (mm < 0 || Hp.size[mm] != H.size[m]) return fail("halo lists inconsistent between ranks");
+                wire(hs[a], d, m, Hp.recv, Hp.flags, Hp.nslots, Hp.offset[mm], mm);
+            }
+        }
+    return 0;
+}
+
+// IPC blob: [0..63] memhandle solid slab, [64..127] flags solid, [128..191] fluid slab,
+// [192..255] flags fluid, then per domain: nmsg, nslots, (peer, size, offset) x MAXMSG
+struct IpcBlob {
+    cudaIpcMemHandle_t recv[2], flags[2];
+    int rank, nmsg[2], nslots[2];
+    int peer[2][MAXMSG], size[2][MAXMSG], offset[2][MAXMSG];
+};
+
+int axb_ipc_export(axb_handle h, void *blob, int32_t blob_bytes) {
+    if (use(h)) return 1;
+    if ((size_t)blob_bytes < sizeof(IpcBlob)) return fail("ipc blob too small");
+    if (!h->finalized) return fail("ipc_export before finalize_setup");
+    IpcBlob b;
+    std::memset(&b, 0, sizeof b);
+    b.rank = h->rank;
+    for (int d = 0; d < 2; d++) {
+        Halo &H = h->halo[d];
+        b.nmsg[d] = H.nmsg; b.nslots[d] = H.nslots;
+        for (int m = 0; m < H.nmsg; m++) { b.peer[d][m] = H.peer[m]; b.size[d][m] = H.size[m]; b.offset[d][m] = H.offset[m]; }
+        if (H.nmsg) {
+            CK(cudaIpcGetMemHandle(&b.recv[d], H.recv));
+            CK(cudaIpcGetMemHandle(&b.flags[d], H.flags));
+        }
+    }
+    std::memcpy(blob, &b, sizeof b);
+    return 0;
+}
+
+int axb_ipc_import(axb_handle h, int32_t peer_rank, const void *blob, int32_t blob_bytes) {
+    if (use(h)) return 1;
+    if ((size_t)blob_bytes < sizeof(IpcBlob)) return fail("ipc blob too small");
+    IpcBlob b;
+    std::memcpy(&b, blob, sizeof b);
+    if (b.rank != peer_rank) return fail("ipc blob does not belong to that rank");
+    for (int d = 0; d < 2; d++) {
+        Halo &H = h->halo[d];
+        for (int m = 0; m < H.nmsg; m++) {
+            if (H.peer[m] != peer_rank) continue;
+            int mm = -1;
+            for (int q = 0; q < b.nmsg[d]; q++) if (b.peer[d][q] == h->rank) mm = q;
+            if (mm < 0 || b.size[d][mm] != H.size[m]) return fail("halo lists inconsistent between ranks");
+            void *pr = nullptr, *pf = nullptr;
+            CK(cudaIpcOpenMemHandle(&pr, b.recv[d], cudaIpcMemLazyEnablePeerAccess));
+            CK(cudaIpcOpenMemHandle(&pf, b.flags[d], cudaIpcMemLazyEnablePeerAccess));
+            wire(h, d, m, (float *)pr, (int *)pf, b.nslots[d], b.offset[d][mm], mm);
+        }
+    }
+    return 0;
+}
+
+// --------------------------------------------------------------------------------------
+// kernel launches
+#define LAUNCH(h, kern, grid, block, ...)                                                \
+    do {                                                                                 \
+        kern<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);                         \
+        (h)->launches++;                                                                 \
+    } while (0)
+
+static SolidStepArgs solid_args(axb_handle_s *h, int mode, double c0, double c1, int anel, int do_stiff) {
+    SolidStepArgs a;
+    a.nel = h->nel_s; a.mode = mode; a.dt = c0; a.half_dt_sq = c1;
+    a.disp = h->disp; a.velo = h->velo; a.acc0 = h->acc0; a.acc1 = h->acc1;
+    a.axis = h->d_axis_s; a.anel = anel; a.do_stiff = do_stiff;
+    return a;
+}
+static void launch_solid_element(axb_handle_s *h, const SolidStepArgs &a) {
+    if (h->nel_s == 0) return;
+    if (h->order == 0) LAUNCH(h, k_solid_element<0>, h->grid_s, 256, h->G, h->P, h->A, a);
+    else if (h->order == 1) LAUNCH(h, k_solid_element<1>, h->grid_s, 256, h->G, h->P, h->A, a);
+    else LAUNCH(h, k_solid_element<2>, h->grid_s, 256, h->G, h->P, h->A, a);
+}
+static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1, int full, int use_mask) {
+    if (h->nel_f == 0) return;
+    FluidStepArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.nel = h->nel_f; a.mode = mode; a.order = h->order; a.full = full; a.dt = c0; a.half_dt_sq = c1;
+    a.chi = h->chi; a.ddchi1 = h->ddchi1; a.dchi = h->dchi; a.ddchi0 = h->ddchi0; a.axis = h->d_axis_f;
+    a.M1chi = h->M1chi; a.M2chi = h->M2chi; a.M4chi = h->M4chi; a.M_w_fl = h->M_w_fl; a.M0_w_fl = h->M0_w_fl;
+    a.fs_mask = h->fs_mask; a.bdry_of_el = h->d_bdry_of_el; a.bdry_sel = h->d_bsel; a.bdry_js = h->d_bjs;
+    a.bdry_matr = h->d_bmatr; a.nel_bdry = h->nel_bdry; a.disp = h->disp; a.cs_solid = (size_t)NPT * h->nel_s;
+    a.nelsrc = h->fluid_src ? h->nelsrc : 0;
+    for (int k = 0; k < 8; k++) a.ielsrc[k] = h->ielsrc[k];
+    a.src_term = h->d_src_term; a.stf = h->d_stf; a.iter = h->d_counters; a.use_mask = use_mask;
+    LAUNCH(h, k_fluid_element, h->grid_f, 256, h->G, a);
+}
+static void launch_fluid_corr(axb_handle_s *h, int mode, double c, int assemble_only) {
+    if (h->nel_f == 0) return;
+    FluidCorrArgs a;
+    a.npts = NPT * h->nel_f; a.mode = mode; a.half_dt = c;
+    a.ddchi1 = h->ddchi1; a.ddchi0 = h->ddchi0; a.dchi = h->dchi; a.chi = h->chi;
+    a.inv_mass_fluid = h->inv_mass_fluid; a.gamma = h->gamma_f;
+    a.T.gid = h->d_asm_gid_f; a.T.grp = h->d_asm_grp_f;
+    Halo &H = h->halo[1];
+    a.recv = H.recv ? H.recv + (size_t)((H.seq + 1) & 1) * H.nc * H.nslots : nullptr;
+    a.recv_cs = H.nslots; a.assemble_only = assemble_only;
+    LAUNCH(h, k_fluid_corrector, cdiv(a.npts, 256), 256, a);
+}
+static void launch_solid_corr(axb_handle_s *h, int mode, double c, int stf_stride, int stf_off, int assemble_only) {
+    if (h->nel_s == 0) return;
+    SolidCorrArgs a;
+    a.npts = NPT * h->nel_s; a.order = h->order; a.mode = mode; a.half_dt = c;
+    a.acc1 = h->acc1; a.acc0 = h->acc0; a.velo = h->velo; a.disp = h->disp;
+    a.inv_mass_rho = h->inv_mass_rho; a.gamma = h->gamma_s;
+    a.T.gid = h->d_asm_gid_s; a.T.grp = h->d_asm_grp_s;
+    Halo &H = h->halo[0];
+    a.recv = H.recv ? H.recv + (size_t)((H.seq + 1) & 1) * H.nc * H.nslots : nullptr;
+    a.recv_cs = H.nslots;
+    a.nelsrc = h->fluid_src ? 0 : h->nelsrc;
+    for (int k = 0; k < 8; k++) a.ielsrc[k] = h->ielsrc[k];
+    a.src_term = h->d_src_term;
+    a.stf = (mode == 0) ? h->d_stf : h->d_stf_symp;
+    a.iter = h->d_counters; a.stf_stride = stf_stride; a.stf_off = stf_off;
+    a.assemble_only = assemble_only;
+    const int grid = cdiv(a.npts, 256);
+    if (h->order == 0) LAUNCH(h, k_solid_corrector<0>, grid, 256, a);
+    else if (h->order == 1) LAUNCH(h, k_solid_corrector<1>, grid, 256, a);
+    else LAUNCH(h, k_solid_corrector<2>, grid, 256, a);
+}
+static void launch_bdry2solid(axb_handle_s *h) {
+    if (h->nel_bdry == 0) return;
+    BdrySolidArgs a;
+    a.nel_bdry = h->nel_bdry; a.order = h->order; a.bdry_sel = h->d_bsel; a.bdry_fel = h->d_bfel;
+    a.bdry_js = h->d_bjs; a.bdry_jf = h->d_bjf; a.bdry_matr = h->d_bmatr; a.axis_solid = h->d_axis_s;
+    a.uflu = h->ddchi0; a.acc1 = h->acc1; a.cs = (size_t)NPT * h->nel_s;
+    LAUNCH(h, k_bdry2solid, cdiv(h->nel_bdry * NP, 128), 128, a);
+}
+// phase 1 of pdistsum_*: pack partial sums into the neighbours' slabs and raise their flags
+static int halo_send(axb_handle_s *h, int d, const float *vec, size_t cs) {
+    Halo &H = h->halo[d];
+    if (H.nmsg == 0) return 0;
+    const int parity = H.seq & 1;
+    PackArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.nentries = H.nentries; a.nc = H.nc; a.start = H.d_start; a.addr = H.d_addr; a.vec = vec; a.cs = cs;
+    a.dst_msg = H.d_dst_msg; a.dst_slot = H.d_dst_slot;
+    FlagArgs f;
+    std::memset(&f, 0, sizeof f);
+    f.n = H.nmsg; f.value = H.seq + 1;
+    for (int m = 0; m < H.nmsg; m++) {
+        if (!H.peer_recv[m]) return fail("halo peers not connected (axb_connect_local / axb_ipc_import)");
+        a.dst_base[m] = H.peer_recv[m] + (size_t)parity * H.nc * H.peer_nslots[m] + H.peer_offset[m];
+        a.dst_cs[m] = H.peer_nslots[m];
+        f.flag[m] = H.peer_flag[m];
+    }
+    LAUNCH(h, k_halo_pack, cdiv((long long)a.nentries * a.nc, 128), 128, a);
+    LAUNCH(h, k_halo_signal, 1, 32, f);
+    H.seq++;
+    return 0;
+}
+// phase 2: wait until every neighbour's message of this exchange has landed
+static void halo_wait(axb_handle_s *h, int d) {
+    Halo &H = h->halo[d];
+    if (H.nmsg == 0) return;
+    FlagArgs f;
+    std::memset(&f, 0, sizeof f);
+    f.n = H.nmsg; f.value = H.seq;
+    for (int m = 0; m < H.nmsg; m++) f.flag[m] = H.flags + m;
+    LAUNCH(h, k_halo_wait, 1, 32, f);
+}
+static void launch_dumps(axb_handle_s *h) {
+    // dump_stuff (time_evol_wave.F90:1104-1251): receivers every seis_it, wavefield every strain_it
+    bool any = false;
+    if (h->num_rec > 0 && h->iter % h->seis_it == 0 && h->iseismo < h->nseismo_max) {
+        RecArgs a;
+        a.num_rec = h->num_rec; a.order = h->order; a.seis_it = h->seis_it; a.nseismo_max = h->nseismo_max;
+        a.recfile_el = h->d_recfile; a.disp = h->disp; a.cs = (size_t)NPT * h->nel_s;
+        a.recdump = h->d_recdump; a.counters = h->d_counters;
+        LAUNCH(h, k_sample_receivers, cdiv(h->num_rec, 128), 128, a);
+        h->iseismo++; any = true;
+    }
+    if (h->have_kwf && h->strain_it > 0 && h->iter % h->strain_it == 0 && h->istrain < h->nstrain_max) {
+        DumpArgs a;
+        a.nel_s = h->nel_s; a.nel_f = h->nel_f; a.order = h->order; a.strain_it = h->strain_it;
+        a.nstrain_max = h->nstrain_max; a.kwf_mask = h->d_kwf_mask; a.kwf_map = h->d_kwf_map;
+        a.disp = h->disp; a.chi = h->chi; a.cs = (size_t)NPT * h->nel_s; a.axis_f = h->d_axis_f;
+        a.inv_rho = h->d_inv_rho; a.Dse = h->d_Dse_f; a.Dze = h->d_Dze_f; a.Dsx = h->d_Dsx_f; a.Dzx = h->d_Dzx_f;
+        a.snap = h->d_snap; a.npts = (size_t)h->npt_s_kwf + h->npt_f_kwf; a.counters = h->d_counters;
+        if (h->nel_s) LAUNCH(h, k_dump_solid, cdiv((long long)NPT * h->nel_s, 256), 256, a);
+        if (h->nel_f) LAUNCH(h, k_dump_fluid, h->grid_f, 256, h->G, a);
+        h->istrain++; any = true;
+    }
+    if (any)
+        LAUNCH(h, k_advance, 1, 32, h->d_counters, h->seis_it, h->strain_it, h->num_rec,
+               (int)h->have_kwf, h->nseismo_max, h->nstrain_max, 1);
+}
+
+// One Newmark step, split at the two exchange points so that in-process groups can be
+// enqueued rank by rank (every send is enqueued before the matching wait of any rank).
+static int newmark_a(axb_handle_s *h) {
+    const size_t css = (size_t)NPT * h->nel_s;
+    // S_A first: the fluid needs the *predicted* solid displacement on the S/F boundary
+    launch_solid_element(h, solid_args(h, 0, h->deltat, h->half_dt_sq, h->anel ? 2 : 0, 1));
+    launch_fluid_element(h, 0, h->deltat, h->half_dt_sq, 1, 1);
+    if (halo_send(h, 1, h->ddchi1, (size_t)NPT * h->nel_f)) return 1;
+    (void)css;
+    return 0;
+}
+static int newmark_b(axb_handle_s *h) {
+    halo_wait(h, 1);
+    launch_fluid_corr(h, 0, h->half_dt, 0);
+    launch_bdry2solid(h);
+    if (halo_send(h, 0, h->acc1, (size_t)NPT * h->nel_s)) return 1;
+    return 0;
+}
+static int newmark_c(axb_handle_s *h) {
+    halo_wait(h, 0);
+    launch_solid_corr(h, 0, h->half_dt, 1, 0, 0);
+    LAUNCH(h, k_next_iter, 1, 32, h->d_counters);
+    h->iter++;
+    launch_dumps(h);
+    return 0;
+}
+static int symp_a(axb_handle_s *h, int k) {
+    launch_solid_element(h, solid_args(h, 1, h->coefd[k], 0.0, h->anel ? 1 : 0, 1));
+    launch_fluid_element(h, 1, h->coefd[k], 0.0, 1, 0);
+    return halo_send(h, 1, h->ddchi1, (size_t)NPT * h->nel_f);
+}
+static int symp_b(axb_handle_s *h, int k) {
+    halo_wait(h, 1);
+    launch_fluid_corr(h, 1, h->coefv[k], 0);
+    launch_bdry2solid(h);
+    return halo_send(h, 0, h->acc1, (size_t)NPT * h->nel_s);
+}
+static int symp_c(axb_handle_s *h, int k) {
+    halo_wait(h, 0);
+    launch_solid_corr(h, 1, h->coefv[k], h->nstages, k, 0);
+    return 0;
+}
+static int symp_finish(axb_handle_s *h) {
+    const double cd = h->coefd[h->nstages];
+    const int nf = NPT * h->nel_f;
+    const size_t cs = (size_t)NPT * h->nel_s;
+    if (nf) LAUNCH(h, k_drift, cdiv(nf, 256), 256, nf, h->chi, h->dchi, cd);
+    if (h->nel_s) {
+        if (h->order == 0) {
+            LAUNCH(h, k_drift, cdiv(cs, 256), 256, (int)cs, h->disp, h->velo, cd);
+            LAUNCH(h, k_drift, cdiv(cs, 256), 256, (int)cs, h->disp + 2 * cs, h->velo + 2 * cs, cd);
+        } else {
+            LAUNCH(h, k_drift, cdiv(3 * cs, 256), 256, (int)(3 * cs), h->disp, h->velo, cd);
+        }
+    }
+    if (h->anel) launch_solid_element(h, solid_args(h, 2, 0.0, 0.0, 3, 0));
+    LAUNCH(h, k_next_iter, 1, 32, h->d_counters);
+    h->iter++;
+    launch_dumps(h);
+    return 0;
+}
+
+int axb_run_group(axb_handle *hs, int32_t n, int32_t nsteps) {
+    for (int i = 0; i < n; i++) {
+        if (!hs[i]->finalized) return fail("axb_run before axb_finalize_setup");
+        if (hs[i]->iter + nsteps > hs[i]->niter) return fail("axb_run beyond niter");
+    }
+    for (int i = 0; i < n; i++) {
+        if (use(hs[i])) return 1;
+        if (hs[i]->iter == 0 && hs[i]->iseismo == 0 && hs[i]->istrain == 0) launch_dumps(hs[i]);
+        hs[i]->acc1_is_acc0 = true;
+    }
+    for (int s = 0; s < nsteps; s++) {
+        if (hs[0]->scheme == AXB_NEWMARK2) {
+            for (int i = 0; i < n; i++) { if (use(hs[i]) || newmark_a(hs[i])) return 1; }
+            for (int i = 0; i < n; i++) { if (use(hs[i]) || newmark_b(hs[i])) return 1; }
+            for (int i = 0; i < n; i++) { if (use(hs[i]) || newmark_c(hs[i])) return 1; }
+        } else {
+            for (int k = 0; k < hs[0]->nstages; k++) {
+                for (int i = 0; i < n; i++) { if (use(hs[i]) || symp_a(hs[i], k)) return 1; }
+                for (int i = 0; i < n; i++) { if (use(hs[i]) || symp_b(hs[i], k)) return 1; }
+                for (int i = 0; i < n; i++) { if (use(hs[i]) || symp_c(hs[i], k)) return 1; }
+            }
+            for (int i = 0; i < n; i++) { if (use(hs[i]) || symp_finish(hs[i])) return 1; }
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        if (use(hs[i])) return 1;
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+int axb_run(axb_handle h, int32_t nsteps) {
+    axb_handle one[1] = {h};
+    return axb_run_group(one, 1, nsteps);
+}
+
+int axb_synchronize(axb_handle h) {
+    if (use(h)) return 1;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int32_t axb_iter(axb_handle h) { return h->iter; }
+int32_t axb_nseismo(axb_handle h) { return h->iseismo; }
+int32_t axb_nstrain(axb_handle h) { return h->istrain; }
+int64_t axb_gpu_launches(axb_handle h) { return h->launches; }
+
+int axb_fetch_seismograms(axb_handle h, int32_t first, int32_t nsamples, float *out) {
+    if (use(h)) return 1;
+    if (first < 0 || nsamples < 0 || first + nsamples > h->iseismo) return fail("seismogram range");
+    CK(cudaMemcpyAsync(out, h->d_recdump + (size_t)3 * h->num_rec * first,
+                       sizeof(float) * 3 * h->num_rec * nsamples, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int axb_fetch_snapshots(axb_handle h, int32_t first, int32_t nsnap, float *out) {
+    if (use(h)) return 1;
+    const size_t npts = (size_t)h->npt_s_kwf + h->npt_f_kwf;
+    if (first < 0 || nsnap < 0 || first + nsnap > h->istrain) return fail("snapshot range");
+    for (int v = 0; v < 3; v++)
+        CK(cudaMemcpyAsync(out + npts * (size_t)nsnap * v,
+                           h->d_snap + npts * (first + (size_t)h->nstrain_max * v),
+                           sizeof(float) * npts * nsnap, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static float *field_ptr(axb_handle_s *o, int f, size_t *n, bool reading) {
+    const size_t ns = (size_t)NPT * o->nel_s * 3, nf = (size_t)NPT * o->nel_f;
+    switch (f) {
+    case AXB_F_DISP: *n = ns; return o->disp;
+    case AXB_F_VELO: *n = ns; return o->velo;
+    case AXB_F_ACC0: *n = ns; return o->acc0;
+    case AXB_F_ACC1: *n = ns; return (reading && o->acc1_is_acc0) ? o->acc0 : o->acc1;
+    case AXB_F_CHI: *n = nf; return o->chi;
+    case AXB_F_DCHI: *n = nf; return o->dchi;
+    case AXB_F_DDCHI0: *n = nf; return o->ddchi0;
+    case AXB_F_DDCHI1: *n = nf; return (reading && o->acc1_is_acc0) ? o->ddchi0 : o->ddchi1;
+    case AXB_F_MEMVAR: if (!o->anel) return nullptr; *n = (size_t)24 * o->A.n_sls * o->nel_s; return o->A.memvar;
+    case AXB_F_SRC_DEV_TM1: if (!o->anel) return nullptr; *n = (size_t)24 * o->nel_s; return o->A.src_dev_tm1;
+    case AXB_F_SRC_TR_TM1: if (!o->anel) return nullptr; *n = (size_t)4 * o->nel_s; return o->A.src_tr_tm1;
+    }
+    return nullptr;
+}
+int axb_get_state(axb_handle h, int32_t field, float *out) {
+    if (use(h)) return 1;
+    if (!h->finalized) return fail("get_state before finalize_setup");
+    size_t n = 0; float *p = field_ptr(h, field, &n, true);
+    if (!p) return fail("no such field");
+    CK(cudaMemcpyAsync(out, p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+int axb_set_state(axb_handle h, int32_t field, const float *in) {
+    if (use(h)) return 1;
+    if (!h->finalized) return fail("set_state before finalize_setup");
+    if (field == AXB_F_ACC1 || field == AXB_F_DDCHI1) h->acc1_is_acc0 = false;
+    size_t n = 0; float *p = field_ptr(h, field, &n, false);
+    if (!p) return fail("no such field");
+    CK(cudaMemcpyAsync(p, in, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int axb_apply_op(axb_handle h, int32_t op) {
+    if (use(h)) return 1;
+    if (!h->finalized) return fail("apply_op before finalize_setup");
+    h->acc1_is_acc0 = false;
+    const size_t css = (size_t)NPT * h->nel_s;
+    switch (op) {
+    case AXB_OP_SOLID_STIFFNESS: launch_solid_element(h, solid_args(h, 2, 0, 0, 0, 1)); break;
+    case AXB_OP_ANEL_STIFFNESS:
+        if (!h->anel) return fail("no attenuation");
+        launch_solid_element(h, solid_args(h, 2, 0, 0, 1, 0)); break;
+    case AXB_OP_FLUID_STIFFNESS: launch_fluid_element(h, 2, 0, 0, 0, 0); break;
+    case AXB_OP_PDISTSUM_SOLID:
+        if (h->halo[0].nmsg) return fail("apply_op(pdistsum) is single-rank only");
+        launch_solid_corr(h, 0, 0, 1, 0, 1);
+        CK(cudaMemcpyAsync(h->acc1, h->acc0, css * 3 * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        break;
+    case AXB_OP_PDISTSUM_FLUID:
+        if (h->halo[1].nmsg) return fail("apply_op(pdistsum) is single-rank only");
+        launch_fluid_corr(h, 0, 0, 1);
+        CK(cudaMemcpyAsync(h->ddchi1, h->ddchi0, (size_t)NPT * h->nel_f * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+        break;
+    case AXB_OP_MEMVARS:
+        if (!h->anel) return fail("no attenuation");
+        launch_solid_element(h, solid_args(h, 2, 0, 0, 3, 0)); break;
+    case AXB_OP_BDRY2FLUID:
+        if (h->nel_bdry)
+            LAUNCH(h, k_bdry2fluid, cdiv(h->nel_bdry * NP, 128), 128, h->nel_bdry, h->order, h->d_bsel,
+                   h->d_bfel, h->d_bjs, h->d_bjf, h->d_bmatr, h->disp, css, h->ddchi1);
+        break;
+    case AXB_OP_BDRY2SOLID: {
+        if (!h->nel_bdry) break;
+        BdrySolidArgs a;
+        a.nel_bdry = h->nel_bdry; a.order = h->order; a.bdry_sel = h->d_bsel; a.bdry_fel = h->d_bfel;
+        a.bdry_js = h->d_bjs; a.bdry_jf = h->d_bjf; a.bdry_matr = h->d_bmatr;
+        a.axis_solid = nullptr; a.uflu = h->ddchi1; a.acc1 = h->acc1; a.cs = css;
+        // stand-alone operator: no axis mask (bdry_copy2solid itself has none)
+        std::vector<int> z(std::max(h->nel_s, 1), 0);
+        int *dz = nullptr;
+        CK(cudaMalloc((void **)&dz, z.size() * sizeof(int)));
+        CK(cudaMemcpy(dz, z.data(), z.size() * sizeof(int), cudaMemcpyHostToDevice));
+        a.axis_solid = dz;
+        LAUNCH(h, k_bdry2solid, cdiv(h->nel_bdry * NP, 128), 128, a);
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(dz);
+        break; }
+    default: return fail("unknown op");
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

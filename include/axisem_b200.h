@@ -198,6 +198,12 @@ int AXB(connect_local)(axb_handle *handles, int32_t n);
 int AXB(ipc_export)(axb_handle h, void *blob, int32_t blob_bytes);   /* >= 256 bytes */
 int AXB(ipc_import)(axb_handle h, int32_t peer_rank, const void *blob, int32_t blob_bytes);
 
+/* Launch on an existing CUDA stream (a cudaStream_t, e.g. torch's current stream) instead
+ * of the handle's own; kernels are only enqueued by axb_run — axb_synchronize (or any
+ * fetch/get call) waits for them.  No-ops in the oracle. */
+int AXB(set_stream)(axb_handle h, void *cuda_stream);
+int AXB(synchronize)(axb_handle h);
+
 /* Advance `nsteps` full time steps (collective over connected handles: every rank
  * must call it with the same nsteps).  State stays on the device. */
 int AXB(run)(axb_handle h, int32_t nsteps);

@@ -1527,6 +1527,9 @@ int axo_run(axb_handle h, int32_t nsteps) {
     return axo_run_group(one, 1, nsteps);
 }
 
+int axo_set_stream(axb_handle h, void *s) { (void)h; (void)s; return 0; }
+int axo_synchronize(axb_handle h) { (void)h; return 0; }
+
 int32_t axo_iter(axb_handle h) { return h->iter; }
 int32_t axo_nseismo(axb_handle h) { return h->iseismo; }
 int32_t axo_nstrain(axb_handle h) { return h->istrain; }
