@@ -60,9 +60,9 @@ OPS = {"solid_stiffness": 0, "anel_stiffness": 1, "fluid_stiffness": 2, "pdistsu
 # every symbol include/axisem_b200.h declares
 SYMBOLS = ["last_error", "create", "destroy", "set_mesh", "set_solid_terms", "set_fluid_terms",
            "set_mass", "set_sponge", "set_sf_boundary", "set_attenuation", "set_source",
-           "set_stf_params", "set_receivers", "set_kwf", "set_halo", "set_time",
+           "set_stf_values", "set_stf_params", "set_receivers", "set_kwf", "set_halo", "set_time",
            "finalize_setup", "set_stream", "synchronize", "connect_local", "ipc_export", "ipc_import", "run", "run_group",
-           "iter", "nseismo", "nstrain", "gpu_launches", "fetch_seismograms",
+           "profile", "get_profile", "iter", "nseismo", "nstrain", "gpu_launches", "fetch_seismograms",
            "fetch_snapshots", "get_state", "set_state", "apply_op"]
 
 
@@ -231,6 +231,21 @@ class TimeLoop:
 
     def synchronize(self):
         self.lib.check(self.lib.fn["synchronize"](self.h))
+
+    def profile(self, enable: bool = True):
+        self.lib.check(self.lib.fn["profile"](self.h, C.c_int32(int(enable))))
+
+    def get_profile(self):
+        """(ms[8], launches[8]) per kernel class, see include/axisem_b200.h."""
+        ms = (C.c_double * 8)()
+        n = (C.c_int64 * 8)()
+        self.lib.check(self.lib.fn["get_profile"](self.h, ms, n))
+        return list(ms), list(n)
+
+    def set_stf_values(self, first_iter: int, values: np.ndarray):
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        self.lib.check(self.lib.fn["set_stf_values"](self.h, C.c_int32(first_iter),
+                                                     C.c_int32(v.size), v.ctypes.data_as(_F)))
 
     def set_stream(self, cuda_stream: int):
         self.lib.check(self.lib.fn["set_stream"](self.h, C.c_void_p(cuda_stream)))

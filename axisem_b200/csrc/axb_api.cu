@@ -114,6 +114,14 @@ struct axb_handle_s {
     bool finalized = false;
     int64_t launches = 0;
     int grid_s = 0, grid_f = 0;
+    // per-kernel event timing (axb_profile)
+    bool prof = false;
+    int prof_cls = 7;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_cls;              // class of each (start, stop) pair
+    size_t ev_used = 0;
+    double prof_ms[8] = {0};
+    int64_t prof_n[8] = {0};
     std::vector<axb_handle_s *> group;
 };
 
@@ -372,6 +380,7 @@ int axb_destroy(axb_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (void *p : h->allocs) cudaFree(p);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -822,11 +831,24 @@ int axb_ipc_import(axb_handle h, int32_t peer_rank, const void *blob, int32_t bl
 
 // --------------------------------------------------------------------------------------
 // kernel launches
+static void prof_mark(axb_handle_s *h, bool begin) {
+    if (!h->prof) return;
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->ev_pool.push_back(e);
+    }
+    cudaEventRecord(h->ev_pool[h->ev_used++], h->stream);
+    if (begin) h->ev_cls.push_back(h->prof_cls);
+}
 #define LAUNCH(h, kern, grid, block, ...)                                                \
     do {                                                                                 \
+        prof_mark((h), true);                                                            \
         kern<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);                         \
+        prof_mark((h), false);                                                           \
         (h)->launches++;                                                                 \
     } while (0)
+#define CLS(h, c) (h)->prof_cls = (c)
 
 static SolidStepArgs solid_args(axb_handle_s *h, int mode, double c0, double c1, int anel, int do_stiff) {
     SolidStepArgs a;
@@ -837,12 +859,14 @@ static SolidStepArgs solid_args(axb_handle_s *h, int mode, double c0, double c1,
 }
 static void launch_solid_element(axb_handle_s *h, const SolidStepArgs &a) {
     if (h->nel_s == 0) return;
+    CLS(h, 0);
     if (h->order == 0) LAUNCH(h, k_solid_element<0>, h->grid_s, 256, h->G, h->P, h->A, a);
     else if (h->order == 1) LAUNCH(h, k_solid_element<1>, h->grid_s, 256, h->G, h->P, h->A, a);
     else LAUNCH(h, k_solid_element<2>, h->grid_s, 256, h->G, h->P, h->A, a);
 }
 static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1, int full, int use_mask) {
     if (h->nel_f == 0) return;
+    CLS(h, 1);
     FluidStepArgs a;
     std::memset(&a, 0, sizeof a);
     a.nel = h->nel_f; a.mode = mode; a.order = h->order; a.full = full; a.dt = c0; a.half_dt_sq = c1;
@@ -857,6 +881,7 @@ static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1
 }
 static void launch_fluid_corr(axb_handle_s *h, int mode, double c, int assemble_only) {
     if (h->nel_f == 0) return;
+    CLS(h, 2);
     FluidCorrArgs a;
     a.npts = NPT * h->nel_f; a.mode = mode; a.half_dt = c;
     a.ddchi1 = h->ddchi1; a.ddchi0 = h->ddchi0; a.dchi = h->dchi; a.chi = h->chi;
@@ -869,6 +894,7 @@ static void launch_fluid_corr(axb_handle_s *h, int mode, double c, int assemble_
 }
 static void launch_solid_corr(axb_handle_s *h, int mode, double c, int stf_stride, int stf_off, int assemble_only) {
     if (h->nel_s == 0) return;
+    CLS(h, 4);
     SolidCorrArgs a;
     a.npts = NPT * h->nel_s; a.order = h->order; a.mode = mode; a.half_dt = c;
     a.acc1 = h->acc1; a.acc0 = h->acc0; a.velo = h->velo; a.disp = h->disp;
@@ -890,6 +916,7 @@ static void launch_solid_corr(axb_handle_s *h, int mode, double c, int stf_strid
 }
 static void launch_bdry2solid(axb_handle_s *h) {
     if (h->nel_bdry == 0) return;
+    CLS(h, 3);
     BdrySolidArgs a;
     a.nel_bdry = h->nel_bdry; a.order = h->order; a.bdry_sel = h->d_bsel; a.bdry_fel = h->d_bfel;
     a.bdry_js = h->d_bjs; a.bdry_jf = h->d_bjf; a.bdry_matr = h->d_bmatr; a.axis_solid = h->d_axis_s;
@@ -900,6 +927,7 @@ static void launch_bdry2solid(axb_handle_s *h) {
 static int halo_send(axb_handle_s *h, int d, const float *vec, size_t cs) {
     Halo &H = h->halo[d];
     if (H.nmsg == 0) return 0;
+    CLS(h, 5);
     const int parity = H.seq & 1;
     PackArgs a;
     std::memset(&a, 0, sizeof a);
@@ -923,6 +951,7 @@ static int halo_send(axb_handle_s *h, int d, const float *vec, size_t cs) {
 static void halo_wait(axb_handle_s *h, int d) {
     Halo &H = h->halo[d];
     if (H.nmsg == 0) return;
+    CLS(h, 5);
     FlagArgs f;
     std::memset(&f, 0, sizeof f);
     f.n = H.nmsg; f.value = H.seq;
@@ -932,6 +961,7 @@ static void halo_wait(axb_handle_s *h, int d) {
 static void launch_dumps(axb_handle_s *h) {
     // dump_stuff (time_evol_wave.F90:1104-1251): receivers every seis_it, wavefield every strain_it
     bool any = false;
+    CLS(h, 6);
     if (h->num_rec > 0 && h->iter % h->seis_it == 0 && h->iseismo < h->nseismo_max) {
         RecArgs a;
         a.num_rec = h->num_rec; a.order = h->order; a.seis_it = h->seis_it; a.nseismo_max = h->nseismo_max;
@@ -977,6 +1007,7 @@ static int newmark_b(axb_handle_s *h) {
 static int newmark_c(axb_handle_s *h) {
     halo_wait(h, 0);
     launch_solid_corr(h, 0, h->half_dt, 1, 0, 0);
+    CLS(h, 7);
     LAUNCH(h, k_next_iter, 1, 32, h->d_counters);
     h->iter++;
     launch_dumps(h);
@@ -1002,6 +1033,7 @@ static int symp_finish(axb_handle_s *h) {
     const double cd = h->coefd[h->nstages];
     const int nf = NPT * h->nel_f;
     const size_t cs = (size_t)NPT * h->nel_s;
+    CLS(h, 7);
     if (nf) LAUNCH(h, k_drift, cdiv(nf, 256), 256, nf, h->chi, h->dchi, cd);
     if (h->nel_s) {
         if (h->order == 0) {
@@ -1012,6 +1044,7 @@ static int symp_finish(axb_handle_s *h) {
         }
     }
     if (h->anel) launch_solid_element(h, solid_args(h, 2, 0.0, 0.0, 3, 0));
+    CLS(h, 7);
     LAUNCH(h, k_next_iter, 1, 32, h->d_counters);
     h->iter++;
     launch_dumps(h);
@@ -1058,6 +1091,35 @@ int axb_synchronize(axb_handle h) {
     if (use(h)) return 1;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
+    return 0;
+}
+
+int axb_profile(axb_handle h, int32_t enable) {
+    if (use(h)) return 1;
+    CK(cudaStreamSynchronize(h->stream));
+    h->prof = enable != 0;
+    h->ev_used = 0; h->ev_cls.clear();
+    for (int i = 0; i < 8; i++) { h->prof_ms[i] = 0.0; h->prof_n[i] = 0; }
+    return 0;
+}
+int axb_get_profile(axb_handle h, double *ms, int64_t *launches) {
+    if (use(h)) return 1;
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t k = 0; k < h->ev_cls.size(); k++) {
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, h->ev_pool[2 * k], h->ev_pool[2 * k + 1]));
+        h->prof_ms[h->ev_cls[k]] += t;
+        h->prof_n[h->ev_cls[k]] += 1;
+    }
+    for (int i = 0; i < 8; i++) { ms[i] = h->prof_ms[i]; launches[i] = h->prof_n[i]; h->prof_ms[i] = 0.0; h->prof_n[i] = 0; }
+    h->ev_used = 0; h->ev_cls.clear();
+    return 0;
+}
+
+int axb_set_stf_values(axb_handle h, int32_t first_iter, int32_t n, const float *values) {
+    if (use(h)) return 1;
+    if (!h->d_stf || first_iter < 0 || n < 0 || first_iter + n > h->niter_stf) return fail("stf range");
+    CK(cudaMemcpyAsync(h->d_stf + first_iter, values, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
     return 0;
 }
 

@@ -114,21 +114,55 @@ def material(spec: MeshSpec, es: ElementSet, g: Geometry):
     return rho, lam, mu, xi_a, phi_a, eta_a, vp, qmu, qka
 
 
-def c_ijkl_ani(lam, mu, xi_ani, phi_ani, eta_ani, sin_fa, cos_fa, i, j, k, l):
+def c_ijkl_ani(lam, mu, xi_ani, phi_ani, eta_ani, sin_fa, cos_fa, i, j, k, l, _cache=None):
     """def_precomp_terms.f90:2284-2332 with fast axis s=(sin th, 0, cos th) (radial TI:
-    get_model.F90:185-186)."""
-    s = (sin_fa, 0.0 * sin_fa, cos_fa)
+    get_model.F90:185-186).  Terms whose Kronecker/fast-axis factor vanishes identically
+    are skipped (they contribute exact zeros in the reference)."""
     d = lambda a, b: 1.0 if a == b else 0.0
     i, j, k, l = i - 1, j - 1, k - 1, l - 1
-    c = lam * d(i, j) * d(k, l)
-    c = c + mu * (d(i, k) * d(j, l) + d(i, l) * d(j, k))
-    c = c + ((eta_ani - 1.0) * lam + 2.0 * eta_ani * mu * (1.0 - 1.0 / xi_ani)) \
-        * (d(i, j) * s[k] * s[l] + d(k, l) * s[i] * s[j])
-    c = c + mu * (1.0 / xi_ani - 1.0) \
-        * (d(i, k) * s[j] * s[l] + d(i, l) * s[j] * s[k]
-           + d(j, k) * s[i] * s[l] + d(j, l) * s[i] * s[k])
-    c = c + ((1.0 - 2.0 * eta_ani + phi_ani) * (lam + 2.0 * mu)
-             + (4.0 * eta_ani - 4.0) * mu / xi_ani) * (s[i] * s[j] * s[k] * s[l])
+    c = 0.0
+    f = d(i, j) * d(k, l)
+    if f:
+        c = c + lam * f
+    f = d(i, k) * d(j, l) + d(i, l) * d(j, k)
+    if f:
+        c = c + mu * f
+    if _cache is not None and _cache.get("iso", False):
+        return c + 0.0 * lam if np.isscalar(c) else c
+    s = (sin_fa, None, cos_fa)           # s[1] == 0
+
+    def ss(a, b):
+        if a == 1 or b == 1:
+            return None
+        return s[a] * s[b]
+
+    if _cache is None:
+        _cache = {}
+    if "A" not in _cache:
+        _cache["A"] = (eta_ani - 1.0) * lam + 2.0 * eta_ani * mu * (1.0 - 1.0 / xi_ani)
+        _cache["B"] = mu * (1.0 / xi_ani - 1.0)
+        _cache["C"] = ((1.0 - 2.0 * eta_ani + phi_ani) * (lam + 2.0 * mu)
+                       + (4.0 * eta_ani - 4.0) * mu / xi_ani)
+    t = None
+    for (dd, a, b) in ((d(i, j), k, l), (d(k, l), i, j)):
+        if dd:
+            v = ss(a, b)
+            if v is not None:
+                t = v * dd if t is None else t + v * dd
+    if t is not None:
+        c = c + _cache["A"] * t
+    t = None
+    for (dd, a, b) in ((d(i, k), j, l), (d(i, l), j, k), (d(j, k), i, l), (d(j, l), i, k)):
+        if dd:
+            v = ss(a, b)
+            if v is not None:
+                t = v * dd if t is None else t + v * dd
+    if t is not None:
+        c = c + _cache["B"] * t
+    if 1 not in (i, j, k, l):
+        c = c + _cache["C"] * (s[i] * s[j] * s[k] * s[l])
+    if np.isscalar(c):
+        c = c + 0.0 * lam
     return c
 
 
@@ -163,7 +197,9 @@ def solid_stiffness_terms(src_type: str, es: ElementSet, g: Geometry, lam, mu, x
 
     ST = np.broadcast_to(g.sin_t[:, None, :], lam.shape)
     CT = np.broadcast_to(g.cos_t[:, None, :], lam.shape)
-    C = lambda a, b, c, d: c_ijkl_ani(lam, mu, xi_a, phi_a, eta_a, ST, CT, a, b, c, d)
+    iso = bool(np.all(xi_a == 1.0) and np.all(phi_a == 1.0) and np.all(eta_a == 1.0))
+    cc = {"iso": iso}
+    C = lambda a, b, c, d: c_ijkl_ani(lam, mu, xi_a, phi_a, eta_a, ST, CT, a, b, c, d, cc)
     C11, C12, C13, C15 = C(1, 1, 1, 1), C(1, 1, 2, 2), C(1, 1, 3, 3), C(1, 1, 3, 1)
     C22, C23, C25 = C(2, 2, 2, 2), C(2, 2, 3, 3), C(2, 2, 3, 1)
     C33, C35 = C(3, 3, 3, 3), C(3, 3, 3, 1)
@@ -346,35 +382,34 @@ def pointwise_derivative_terms(es: ElementSet, g: Geometry) -> Dict[str, np.ndar
             "inv_s": _f32(inv_s)}
 
 
-def sf_boundary_terms(mesh: LocalMesh, gs: Geometry) -> np.ndarray:
+def sf_boundary_terms(mesh: LocalMesh, gs: Geometry, es: ElementSet) -> np.ndarray:
     """bdry_matr(0:4, nel_bdry, 2) — def_precomp_terms.f90:2503-2712 — returned as a
-    numpy array of shape (2, nel_bdry, 5) (Fortran memory order)."""
+    numpy array of shape (2, nel_bdry, 5) (Fortran memory order).  `es`/`gs` describe the
+    solid element of every boundary entry (same order as mesh.bdry_solid_el)."""
     b = mesh.basis
     nb = mesh.nel_bdry
     out = np.zeros((2, nb, 5))
-    es = mesh.solid
-    for k in range(nb):
-        e = mesh.bdry_solid_el[k] - 1
-        j = mesh.bdry_jpol_solid[k]
-        th = gs.th[e, :]
-        r = gs.r[e, j]
-        delta_th = 0.5 * abs(th[4] - th[0])
-        if es.axis[e]:
-            w = b.wt_axial_k
-            opx = 1.0 + b.xi_k
-            for i in range(1, 5):
-                out[0, k, i] = delta_th * w[i] * np.sin(th[i]) / opx[i] * np.sin(th[i])
-                out[1, k, i] = delta_th * w[i] * np.sin(th[i]) / opx[i] * np.cos(th[i])
-            out[0, k, 0] = 0.0
-            # note: the reference uses cos(0)=1 here also at the southern axis (:2603)
-            out[1, k, 0] = 1.0 / r * delta_th * w[0] * gs.dsdxi[e, j, 0]
-        else:
-            w = b.wt
-            out[0, k, :] = delta_th * w * np.sin(th) * np.sin(th)
-            out[1, k, :] = delta_th * w * np.sin(th) * np.cos(th)
-        if not mesh.bdry_above[k]:
-            out[:, k, :] *= -1.0
-        out[:, k, :] *= r * r
+    jj = mesh.bdry_jpol_solid
+    k = np.arange(nb)
+    th = gs.th                                   # (nb, 5)
+    r = gs.r[k, jj]                              # (nb,)
+    delta_th = 0.5 * np.abs(th[:, 4] - th[:, 0])
+    ax = es.axis
+    # non-axial
+    out[0] = (delta_th[:, None] * b.wt[None, :]) * np.sin(th) * np.sin(th)
+    out[1] = (delta_th[:, None] * b.wt[None, :]) * np.sin(th) * np.cos(th)
+    if ax.any():
+        w = b.wt_axial_k
+        opx = 1.0 + b.xi_k
+        a = np.nonzero(ax)[0]
+        for i in range(1, 5):
+            out[0, a, i] = delta_th[a] * w[i] * np.sin(th[a, i]) / opx[i] * np.sin(th[a, i])
+            out[1, a, i] = delta_th[a] * w[i] * np.sin(th[a, i]) / opx[i] * np.cos(th[a, i])
+        out[0, a, 0] = 0.0
+        # note: the reference uses cos(0)=1 here also at the southern axis (:2603)
+        out[1, a, 0] = 1.0 / r[a] * delta_th[a] * w[0] * gs.dsdxi[a, jj[a], 0]
+    sign = np.where(mesh.bdry_above, 1.0, -1.0)
+    out *= (sign * r * r)[None, :, None]
     return _f32(out)
 
 

@@ -8,6 +8,8 @@ benchmark, so parity tests compare like with like.
 """
 from __future__ import annotations
 
+import os
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -80,42 +82,117 @@ class Problem:
         return int(self.recfile_el.shape[0])
 
 
-def _assembled_mass(spec: MeshSpec, basis: SpectralBasis, own: ElementSet, it0: int, it1: int,
-                    fluid: bool, own_val: np.ndarray, valfun) -> np.ndarray:
+def _subset(es: ElementSet, idx) -> ElementSet:
+    return ElementSet(es.it[idx], es.ir[idx], es.th_a[idx], es.th_b[idx], es.r_a[idx],
+                      es.r_b[idx], es.axis[idx], es.north[idx], es.layer[idx])
+
+
+def _assemble_columns(spec: MeshSpec, it0: int, it1: int, fluid: bool, own_val: np.ndarray,
+                      ghost_val) -> np.ndarray:
     """Direct-stiffness-sum a per-point quantity over the *whole* mesh and return it on
-    this rank's elements (def_mass_matrix_k calls pdistsum_* once, :756, :820).  Ghost
-    columns of the neighbouring slices supply the cross-rank contributions."""
-    nrn = spec.nrnode_fluid if fluid else spec.nrnode_solid
-    if own.nel == 0:
+    this rank's elements (def_mass_matrix_k calls pdistsum_* once, :756, :820).
+    `own_val` is (ncol*nrd, 5, 5) in (it, ir) order; `ghost_val(c)` returns the values of
+    the elements of column c (a neighbouring slice) for the cross-rank contributions."""
+    irs = np.nonzero(spec.fluid_ir == fluid)[0]
+    nrd = irs.size
+    if nrd == 0 or own_val.shape[0] == 0:
         return own_val
+    nrn = spec.nrnode_fluid if fluid else spec.nrnode_solid
     lo = max(it0 - 1, 0)
     hi = min(it1 + 1, spec.ntheta)
-    ghost_cols = [c for c in (it0 - 1, it1) if 0 <= c < spec.ntheta and not (it0 <= c < it1)]
-    sets = [(own, own_val)]
-    for c in ghost_cols:
-        irs = np.nonzero(spec.fluid_ir == fluid)[0]
-        es = make_elements(spec, np.full(irs.size, c), irs)
-        sets.append((es, valfun(es)))
-    dense = np.zeros(((hi - lo) * 4 + 1, nrn), dtype=np.float32)
-    idx = []
-    i = np.arange(5)
-    for es, val in sets:
-        ip = np.where(es.north[:, None], i[None, :], 4 - i[None, :])
-        tn = 4 * (es.it[:, None] - lo) + ip
-        rn = spec.rbase[es.ir][:, None] + ip
-        T = np.broadcast_to(tn[:, None, :], val.shape)
-        Rn = np.broadcast_to(rn[:, :, None], val.shape)
-        np.add.at(dense, (T.reshape(-1), Rn.reshape(-1)), val.astype(np.float32).reshape(-1))
-        idx.append((T, Rn))
-    T, Rn = idx[0]
-    return dense[T, Rn]
+    dense = np.zeros(((hi - lo) * 4 + 1, nrn), dtype=np.float64)   # order-independent sums
+    rb = spec.rbase[irs]
+    half = spec.ntheta // 2
+
+    def scatter(cols, val):          # cols: array of it, val: (ncols, nrd, 5, 5) float32
+        for north in (True, False):
+            m = (cols < half) == north
+            if not m.any():
+                continue
+            c = cols[m] - lo
+            v = val[m]
+            for j in range(5):
+                for i in range(5):
+                    ip, jp = (i, j) if north else (4 - i, 4 - j)
+                    dense[(4 * c + ip)[:, None], (rb + jp)[None, :]] += v[:, :, j, i]
+
+    def gather(cols):
+        out = np.empty((cols.size, nrd, 5, 5), dtype=np.float64)
+        for north in (True, False):
+            m = (cols < half) == north
+            if not m.any():
+                continue
+            c = cols[m] - lo
+            for j in range(5):
+                for i in range(5):
+                    ip, jp = (i, j) if north else (4 - i, 4 - j)
+                    out[np.nonzero(m)[0][:, None], np.arange(nrd)[None, :], j, i] = \
+                        dense[(4 * c + ip)[:, None], (rb + jp)[None, :]]
+        return out
+
+    cols = np.arange(it0, it1)
+    scatter(cols, own_val.astype(np.float32).reshape(cols.size, nrd, 5, 5))
+    for c in (it0 - 1, it1):
+        if 0 <= c < spec.ntheta:
+            scatter(np.array([c]), ghost_val(c).astype(np.float32).reshape(1, nrd, 5, 5))
+    return gather(cols).reshape(-1, 5, 5)
+
+
+def _element_arrays(spec: MeshSpec, basis: SpectralBasis, cols: np.ndarray, src_type: str,
+                    anel: bool, att: Optional[AttenuationModel], deltat: float) -> Dict:
+    """Every per-element array of the elements in theta columns `cols` (both domains)."""
+    IT, IR = np.meshgrid(cols, np.arange(spec.nr), indexing="ij")
+    IT = IT.reshape(-1)
+    IR = IR.reshape(-1)
+    fl = spec.fluid_ir[IR]
+    es_s = make_elements(spec, IT[~fl], IR[~fl])
+    es_f = make_elements(spec, IT[fl], IR[fl])
+    out: Dict = {}
+    gs = geometry(es_s, basis)
+    rho_s, lam_s, mu_s, xi_s, phi_s, eta_s, _, qmu, qka = material(spec, es_s, gs)
+    out["mass_s"] = _f32(rho_s * gs.massmat_k)
+    out["pw_s"] = pointwise_derivative_terms(es_s, gs)
+    if anel:
+        att_d, lam_s, mu_s = attenuation_terms(att, deltat, es_s, gs, lam_s, mu_s, qmu, qka)
+        for n in ("DsDeta_over_J", "DzDeta_over_J", "DsDxi_over_J", "DzDxi_over_J"):
+            att_d[n + "_cg4"] = _f32(cg4(out["pw_s"][n]))
+        out["att"] = att_d
+    out["solid"] = solid_stiffness_terms(src_type, es_s, gs, lam_s, mu_s, xi_s, phi_s, eta_s,
+                                         anel, basis)
+    if es_f.nel:
+        gf = geometry(es_f, basis)
+        rho_f, lam_f, *_ = material(spec, es_f, gf)
+        out["mass_f"] = _f32(gf.massmat_k / lam_f)
+        out["inv_rho_fluid"] = _f32(1.0 / rho_f)
+        out["pw_f"] = pointwise_derivative_terms(es_f, gf)
+        out["fluid"] = fluid_stiffness_terms(src_type, es_f, gf, rho_f, basis)
+        fsm = np.ones((es_f.nel, 5, 5), dtype=np.float32)
+        rr = np.broadcast_to(gf.r[:, :, None], fsm.shape)
+        fsm[rr > spec.router - 1.0] = 0.0                     # time_evol_wave.F90:1615-1630
+        out["fsm"] = fsm
+    return out
+
+
+def _concat(parts, key):
+    if isinstance(parts[0][key], dict):
+        keys = parts[0][key].keys()
+        res = {}
+        for k in keys:
+            v0 = parts[0][key][k]
+            if isinstance(v0, np.ndarray) and v0.ndim >= 1 and v0.dtype == np.float32:
+                res[k] = np.concatenate([p[key][k] for p in parts], axis=0)
+            else:
+                res[k] = v0          # rank-independent scalars / small vectors
+        return res
+    return np.concatenate([p[key] for p in parts], axis=0)
 
 
 def build_problem(spec: MeshSpec, source: Optional[SourceParams] = None, *, rank: int = 0,
                   nranks: int = 1, anel: bool = False, att: Optional[AttenuationModel] = None,
                   time_scheme: str = "newmark2", niter: int = 100, seis_it: int = 1,
                   strain_it: int = 0, courant: float = 0.6, deltat: Optional[float] = None,
-                  rec_colat_deg=None, dump: bool = False) -> Problem:
+                  rec_colat_deg=None, dump: bool = False, chunk_cols: int = 32,
+                  threads: Optional[int] = None) -> Problem:
     assert time_scheme in TIME_SCHEMES
     source = source or SourceParams()
     src_type = source.src_type1
@@ -125,59 +202,65 @@ def build_problem(spec: MeshSpec, source: Optional[SourceParams] = None, *, rank
         deltat = stable_timestep(spec, basis, courant)
         if time_scheme != "newmark2":
             deltat *= 1.5                      # time_evol_wave.F90:511
-    gs = geometry(mesh.solid, basis)
-    gf = geometry(mesh.fluid, basis)
-    rho_s, lam_s, mu_s, xi_s, phi_s, eta_s, _, qmu, qka = material(spec, mesh.solid, gs)
-    rho_f, lam_f, mu_f, *_ = material(spec, mesh.fluid, gf)
-
-    # ---- mass matrices (before attenuation changes the moduli, as in the reference) ---
-    def rho_mass(es):
-        g = geometry(es, basis)
-        rho = material(spec, es, g)[0]
-        return rho * g.massmat_k
-
-    def lam_mass(es):
-        g = geometry(es, basis)
-        lam = material(spec, es, g)[1]
-        return g.massmat_k / lam
-
-    m_s = _assembled_mass(spec, basis, mesh.solid, mesh.it0, mesh.it1, False,
-                          rho_s * gs.massmat_k, rho_mass)
-    inv_mass_rho = (1.0 / m_s.astype(np.float64)) if mesh.nel_solid else m_s
-    if src_type == "dipole":
-        inv_mass_rho = 0.5 * inv_mass_rho                 # def_precomp_terms.f90:773
-    if mesh.nel_fluid:
-        m_f = _assembled_mass(spec, basis, mesh.fluid, mesh.it0, mesh.it1, True,
-                              gf.massmat_k / lam_f, lam_mass)
-        inv_mass_fluid = 1.0 / m_f.astype(np.float64)
-        inv_rho_fluid = 1.0 / rho_f
-    else:
-        inv_mass_fluid = np.zeros((0, 5, 5))
-        inv_rho_fluid = np.zeros((0, 5, 5))
-
-    pw_s = pointwise_derivative_terms(mesh.solid, gs)
-    pw_f = pointwise_derivative_terms(mesh.fluid, gf)
-
-    att_d = None
     if anel:
         att = att or AttenuationModel()
-        att_d, lam_s, mu_s = attenuation_terms(att, deltat, mesh.solid, gs, lam_s, mu_s, qmu, qka)
-        for n in ("DsDeta_over_J", "DzDeta_over_J", "DsDxi_over_J", "DzDxi_over_J"):
-            att_d[n + "_cg4"] = _f32(cg4(pw_s[n]))
+
+    # ---- per-element arrays, built in chunks of theta columns on a thread pool ---------
+    cols = np.arange(mesh.it0, mesh.it1)
+    chunks = [cols[k:k + chunk_cols] for k in range(0, cols.size, chunk_cols)]
+    work = lambda c: _element_arrays(spec, basis, c, src_type, anel, att, deltat)
+    nthr = threads if threads is not None else min(len(chunks), os.cpu_count() or 1)
+    if nthr > 1:
+        with ThreadPoolExecutor(max_workers=nthr) as ex:
+            parts = list(ex.map(work, chunks))
+    else:
+        parts = [work(c) for c in chunks]
+    has_fluid = mesh.nel_fluid > 0
+    solid = _concat(parts, "solid")
+    pw_s = _concat(parts, "pw_s")
+    att_d = None
+    if anel:
+        att_d = _concat(parts, "att")
         att_d["coarse_grained"] = att.coarse_grained
         att_d["do_corr_lowq"] = att.do_corr_lowq
         att_d["n_sls"] = att.n_sls
+    if has_fluid:
+        fluid = _concat(parts, "fluid")
+        pw_f = _concat(parts, "pw_f")
+        inv_rho_fluid = _concat(parts, "inv_rho_fluid")
+        fsm = _concat(parts, "fsm")
+    else:
+        fluid, pw_f = {}, {k: np.zeros((0, 5, 5), np.float32) for k in pw_s}
+        inv_rho_fluid = np.zeros((0, 5, 5), np.float32)
+        fsm = np.zeros((0, 5, 5), np.float32)
 
-    solid = solid_stiffness_terms(src_type, mesh.solid, gs, lam_s, mu_s, xi_s, phi_s, eta_s,
-                                  anel, basis)
-    fluid = fluid_stiffness_terms(src_type, mesh.fluid, gf, rho_f, basis) if mesh.nel_fluid else {}
-    bdry = sf_boundary_terms(mesh, gs) if mesh.nel_bdry else np.zeros((2, 0, 5), np.float32)
+    # ---- mass matrices (before attenuation changes the moduli, as in the reference) ---
+    def ghost(fluidflag):
+        def f(c):
+            irs = np.nonzero(spec.fluid_ir == fluidflag)[0]
+            es = make_elements(spec, np.full(irs.size, c), irs)
+            g = geometry(es, basis)
+            m = material(spec, es, g)
+            return (g.massmat_k / m[1]) if fluidflag else (m[0] * g.massmat_k)
+        return f
 
-    # free-surface mask (time_evol_wave.F90:1615-1630)
-    fsm = np.ones((mesh.nel_fluid, 5, 5), dtype=np.float32)
-    if mesh.nel_fluid:
-        rr = np.broadcast_to(gf.r[:, :, None], fsm.shape)
-        fsm[rr > spec.router - 1.0] = 0.0
+    m_s = _assemble_columns(spec, mesh.it0, mesh.it1, False, _concat(parts, "mass_s"), ghost(False))
+    inv_mass_rho = (1.0 / m_s.astype(np.float64))
+    if src_type == "dipole":
+        inv_mass_rho = 0.5 * inv_mass_rho                 # def_precomp_terms.f90:773
+    if has_fluid:
+        m_f = _assemble_columns(spec, mesh.it0, mesh.it1, True, _concat(parts, "mass_f"), ghost(True))
+        inv_mass_fluid = 1.0 / m_f.astype(np.float64)
+    else:
+        inv_mass_fluid = np.zeros((0, 5, 5))
+    del parts
+
+    if mesh.nel_bdry:
+        bidx = mesh.bdry_solid_el - 1
+        sub = _subset(mesh.solid, bidx)
+        bdry = sf_boundary_terms(mesh, geometry(sub, basis), sub)
+    else:
+        bdry = np.zeros((2, 0, 5), np.float32)
 
     nelsrc, ielsrc, st = compute_source_terms(mesh, source, pw_s)
     if time_scheme == "newmark2":
@@ -194,7 +277,7 @@ def build_problem(spec: MeshSpec, source: Optional[SourceParams] = None, *, rank
         deltat=float(deltat), niter=int(niter), seis_it=int(seis_it), strain_it=int(strain_it),
         anel=anel, solid=solid, fluid=fluid, inv_mass_rho=_f32(inv_mass_rho),
         inv_mass_fluid=_f32(inv_mass_fluid), fluid_free_surface_mask=fsm,
-        inv_rho_fluid=_f32(inv_rho_fluid), pw_solid=pw_s, pw_fluid=pw_f, bdry_matr=bdry,
+        inv_rho_fluid=inv_rho_fluid, pw_solid=pw_s, pw_fluid=pw_f, bdry_matr=bdry,
         att=att_d, att_model=att if anel else None, source=source, nelsrc=nelsrc,
         ielsrc=ielsrc, source_term_el=st, stf=stf, recfile_el=rec["recfile_el"],
         rec_index=rec["index"])

@@ -161,6 +161,10 @@ int AXB(set_attenuation)(axb_handle h, const axb_attenuation *a);
 int AXB(set_source)(axb_handle h, int32_t fluid_src, int32_t nelsrc, const int32_t *ielsrc,
                     const float *source_term, const float *stf, int32_t niter);
 
+/* overwrite stf(first_iter+1 : first_iter+n) (0-based first_iter) — lets a host stream the
+ * source time function while the loop runs (Newmark only) */
+int AXB(set_stf_values)(axb_handle h, int32_t first_iter, int32_t n, const float *values);
+
 /* point-wise STF for the symplectic schemes, compute_stf_t (source.f90:206-233) */
 int AXB(set_stf_params)(axb_handle h, int32_t stf_type, double decay, double t_0,
                         double shift_fact, double magnitude);
@@ -209,6 +213,14 @@ int AXB(synchronize)(axb_handle h);
 int AXB(run)(axb_handle h, int32_t nsteps);
 /* in-process lockstep variant for connect_local groups */
 int AXB(run_group)(axb_handle *handles, int32_t n, int32_t nsteps);
+
+/* Per-kernel device timing with CUDA events on the launching stream (off by default).
+ * Classes: 0 solid element kernel (S_A), 1 fluid element kernel (F_A), 2 fluid corrector
+ * (F_B), 3 S/F coupling, 4 solid corrector (S_B), 5 halo pack/signal/wait, 6 sampling and
+ * dumps, 7 other.  get_profile synchronises, returns accumulated milliseconds and launch
+ * counts per class (arrays of 8) and resets the accumulators. */
+int AXB(profile)(axb_handle h, int32_t enable);
+int AXB(get_profile)(axb_handle h, double *ms, int64_t *launches);
 
 int32_t AXB(iter)(axb_handle h);         /* time steps done so far                     */
 int32_t AXB(nseismo)(axb_handle h);      /* seismogram samples recorded so far         */

@@ -29,6 +29,7 @@
 #include "../include/axisem_b200.h"
 
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1469,6 +1470,8 @@ static void symp_finish(axo_t *o) {
     dump_stuff(o, o->iter);
 }
 
+#define PAR_RANKS
+
 static void set_ftz(void) {
 #if defined(__x86_64__)
     _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);        /* SOLVER/ftz.c:44-48 */
@@ -1485,6 +1488,62 @@ int axo_connect_local(axb_handle *handles, int32_t n) {
 int axo_ipc_export(axb_handle h, void *blob, int32_t n) { (void)h; (void)blob; (void)n; return fail("oracle: in-process only"); }
 int axo_ipc_import(axb_handle h, int32_t p, const void *blob, int32_t n) { (void)h; (void)p; (void)blob; (void)n; return fail("oracle: in-process only"); }
 
+/* One thread per rank (= one MPI rank per core in the reference); barriers stand where
+ * the reference has its MPI_WAITALLs. */
+typedef struct { axo_t **hs; int n, i, nsteps; pthread_barrier_t *bar; int err; } worker_t;
+
+static void *rank_worker(void *arg) {
+    worker_t *w = (worker_t *)arg;
+    axo_t *o = w->hs[w->i];
+    set_ftz();
+    for (int s = 0; s < w->nsteps; s++) {
+        if (o->scheme == AXB_NEWMARK2) {
+            newmark_part1(o);
+            pthread_barrier_wait(w->bar);
+            if (exchange(o, AXB_DOMAIN_FLUID)) w->err = 1;
+            pthread_barrier_wait(w->bar);
+            newmark_part2(o);
+            pthread_barrier_wait(w->bar);
+            if (exchange(o, AXB_DOMAIN_SOLID)) w->err = 1;
+            pthread_barrier_wait(w->bar);
+            newmark_part3(o);
+        } else {
+            double stf_symp[40];
+            o->t += o->deltat;
+            for (int k = 0; k < o->nstages; k++) stf_symp[k] = stf_t(o, o->t - o->deltat + o->coeff[k]);
+            for (int k = 0; k < o->nstages; k++) {
+                symp_part1(o, k);
+                pthread_barrier_wait(w->bar);
+                if (exchange(o, AXB_DOMAIN_FLUID)) w->err = 1;
+                pthread_barrier_wait(w->bar);
+                symp_part2(o);
+                pthread_barrier_wait(w->bar);
+                if (exchange(o, AXB_DOMAIN_SOLID)) w->err = 1;
+                pthread_barrier_wait(w->bar);
+                symp_part3(o, k, stf_symp[k]);
+            }
+            symp_finish(o);
+        }
+    }
+    return NULL;
+}
+
+static int run_group_threaded(axb_handle *hs, int n, int nsteps) {
+    pthread_barrier_t bar;
+    pthread_t th[64];
+    worker_t w[64];
+    if (n > 64) return fail("too many ranks");
+    pthread_barrier_init(&bar, NULL, n);
+    for (int i = 0; i < n; i++) {
+        w[i].hs = hs; w[i].n = n; w[i].i = i; w[i].nsteps = nsteps; w[i].bar = &bar; w[i].err = 0;
+        pthread_create(&th[i], NULL, rank_worker, &w[i]);
+    }
+    int err = 0;
+    for (int i = 0; i < n; i++) { pthread_join(th[i], NULL); err |= w[i].err; }
+    pthread_barrier_destroy(&bar);
+    return err;
+}
+
 int axo_run_group(axb_handle *hs, int32_t n, int32_t nsteps) {
     set_ftz();
     for (int i = 0; i < n; i++) {
@@ -1495,26 +1554,29 @@ int axo_run_group(axb_handle *hs, int32_t n, int32_t nsteps) {
     for (int i = 0; i < n; i++)
         if (hs[i]->iter == 0 && hs[i]->iseismo == 0 && hs[i]->istrain == 0)
             dump_stuff(hs[i], 0);                          /* time_evol_wave.F90:350 */
+    if (n > 1) return run_group_threaded(hs, n, nsteps);
     for (int s = 0; s < nsteps; s++) {
         if (hs[0]->scheme == AXB_NEWMARK2) {
-            for (int i = 0; i < n; i++) newmark_part1(hs[i]);
+            /* one thread per rank (= one MPI rank per core in the reference); the end of
+             * each parallel loop is the barrier at which the "messages" are exchanged */
+            PAR_RANKS for (int i = 0; i < n; i++) { set_ftz(); newmark_part1(hs[i]); }
             for (int i = 0; i < n; i++) if (exchange(hs[i], AXB_DOMAIN_FLUID)) return 1;
-            for (int i = 0; i < n; i++) newmark_part2(hs[i]);
+            PAR_RANKS for (int i = 0; i < n; i++) { set_ftz(); newmark_part2(hs[i]); }
             for (int i = 0; i < n; i++) if (exchange(hs[i], AXB_DOMAIN_SOLID)) return 1;
-            for (int i = 0; i < n; i++) newmark_part3(hs[i]);
+            PAR_RANKS for (int i = 0; i < n; i++) { set_ftz(); newmark_part3(hs[i]); }
         } else {
             double stf_symp[40];
             for (int i = 0; i < n; i++) hs[i]->t += hs[i]->deltat;
             for (int k = 0; k < hs[0]->nstages; k++)
                 stf_symp[k] = stf_t(hs[0], hs[0]->t - hs[0]->deltat + hs[0]->coeff[k]);
             for (int k = 0; k < hs[0]->nstages; k++) {
-                for (int i = 0; i < n; i++) symp_part1(hs[i], k);
+                PAR_RANKS for (int i = 0; i < n; i++) { set_ftz(); symp_part1(hs[i], k); }
                 for (int i = 0; i < n; i++) if (exchange(hs[i], AXB_DOMAIN_FLUID)) return 1;
-                for (int i = 0; i < n; i++) symp_part2(hs[i]);
+                PAR_RANKS for (int i = 0; i < n; i++) { set_ftz(); symp_part2(hs[i]); }
                 for (int i = 0; i < n; i++) if (exchange(hs[i], AXB_DOMAIN_SOLID)) return 1;
-                for (int i = 0; i < n; i++) symp_part3(hs[i], k, stf_symp[k]);
+                PAR_RANKS for (int i = 0; i < n; i++) { set_ftz(); symp_part3(hs[i], k, stf_symp[k]); }
             }
-            for (int i = 0; i < n; i++) symp_finish(hs[i]);
+            PAR_RANKS for (int i = 0; i < n; i++) { set_ftz(); symp_finish(hs[i]); }
         }
     }
     return 0;
@@ -1527,6 +1589,15 @@ int axo_run(axb_handle h, int32_t nsteps) {
     return axo_run_group(one, 1, nsteps);
 }
 
+int axo_set_stf_values(axb_handle h, int32_t first, int32_t n, const float *v) {
+    if (first < 0 || first + n > h->niter_stf) return fail("stf range");
+    memcpy(h->stf + first, v, sizeof(float) * n);
+    return 0;
+}
+int axo_profile(axb_handle h, int32_t e) { (void)h; (void)e; return 0; }
+int axo_get_profile(axb_handle h, double *ms, int64_t *n) {
+    (void)h; for (int i = 0; i < 8; i++) { ms[i] = 0.0; n[i] = 0; } return 0;
+}
 int axo_set_stream(axb_handle h, void *s) { (void)h; (void)s; return 0; }
 int axo_synchronize(axb_handle h) { (void)h; return 0; }
 
