@@ -65,7 +65,15 @@ struct axb_handle_s {
     int *d_axis_s = nullptr, *d_axis_f = nullptr;
     GMat G;
     int order = 0;
-    SolidPlanes P;
+    // solid element kernel inputs in their device layout (axb_solid_tile.cuh)
+    int nel_pad_s = 0;             // nel_s rounded up to whole tiles
+    size_t css = 0;                // component stride of disp/velo/acc* = 25 * nel_pad_s
+    float *d_coef = nullptr;       // [tile][plane][TP]
+    int *d_meta = nullptr;         // [tile][3][TE]: axis, qidx_mu, qidx_ka
+    float *d_M0_w[10] = {nullptr};
+    bool have_solid_terms = false;
+    int nst = 0;                   // ring depth of k_solid_tile
+    size_t smem_solid = 0;
     std::vector<void *> allocs;
     // fluid
     float *M1chi = nullptr, *M2chi = nullptr, *M4chi = nullptr, *M_w_fl = nullptr, *M0_w_fl = nullptr;
@@ -79,7 +87,11 @@ struct axb_handle_s {
     int2 *d_bdry_of_el = nullptr;
     // attenuation
     bool anel = false, cg = true;
-    AttCg A;
+    int n_sls = 0;
+    float *d_cg = nullptr;         // [tile][NCG][TE*4]
+    float *d_inv_s = nullptr;      // (25 * nel_pad_s)
+    double *d_a_mu_tab = nullptr, *d_a_ka_tab = nullptr, *d_exp_w = nullptr, *d_ts_t = nullptr, *d_ts_tm1 = nullptr;
+    float *memvar = nullptr, *src_dev_tm1 = nullptr, *src_tr_tm1 = nullptr;
     std::vector<float> Qmu_h, Qka_h;
     std::vector<double> y_j;
     int corr_lowq = 0;
@@ -113,7 +125,7 @@ struct axb_handle_s {
     bool acc1_is_acc0 = false;     // after a full step acc1/ddchi1 == acc0/ddchi0 in the reference
     bool finalized = false;
     int64_t launches = 0;
-    int grid_s = 0, grid_f = 0;
+    int grid_s = 0, grid_f = 0, sms = 0;
     // per-kernel event timing (axb_profile)
     bool prof = false;
     int prof_cls = 7;
@@ -141,6 +153,17 @@ int dzeros(axb_handle_s *h, T *&dst, size_t n) {
     CK(cudaMalloc((void **)&dst, std::max<size_t>(n, 1) * sizeof(T)));
     h->allocs.push_back(dst);
     CK(cudaMemset(dst, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    return 0;
+}
+// upload n values into a zero-filled allocation of npad values
+template <class T>
+int upload_padded(axb_handle_s *h, T *&dst, const T *src, size_t n, size_t npad) {
+    dst = nullptr;
+    if (!src) return 0;
+    CK(cudaMalloc((void **)&dst, std::max<size_t>(npad, 1) * sizeof(T)));
+    h->allocs.push_back(dst);
+    CK(cudaMemset(dst, 0, std::max<size_t>(npad, 1) * sizeof(T)));
+    if (n) CK(cudaMemcpy(dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
     return 0;
 }
 int use(axb_handle_s *h) {
@@ -252,7 +275,7 @@ void fast_correct(int n, const double *y, double *yp) {      // attenuation.f90:
     for (int k = 0; k < n; k++) yp[k] = y[k] * dy[k];
 }
 void a_j_of_Q(const axb_handle_s *o, float Q, double *a_j) { // attenuation.f90:116-134
-    const int n = o->A.n_sls;
+    const int n = o->n_sls;
     double yq[32], yp[32], s = 0.0;
     for (int k = 0; k < n; k++) yq[k] = o->y_j[k] / Q;
     if (o->corr_lowq) fast_correct(n, yq, yp);
@@ -365,8 +388,6 @@ int axb_create(axb_handle *out, int32_t device, int32_t rank, int32_t nranks) {
     if (device < 0 || device >= ndev) return fail("axb_create: bad device ordinal");
     axb_handle_s *h = new axb_handle_s();
     h->device = device; h->rank = rank; h->nranks = nranks;
-    std::memset(&h->P, 0, sizeof h->P);
-    std::memset(&h->A, 0, sizeof h->A);
     if (use(h)) { delete h; return 1; }
     cudaError_t se = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (se != cudaSuccess) { delete h; return fail(cudaGetErrorString(se)); }
@@ -403,6 +424,8 @@ int axb_set_mesh(axb_handle h, int32_t npol, int32_t nel_solid, int32_t nel_flui
     if (npol != 4) return fail("axb_set_mesh: npol must be 4");
     if (use(h)) return 1;
     h->nel_s = nel_solid; h->nel_f = nel_fluid; h->nglob_s = nglob_solid; h->nglob_f = nglob_fluid;
+    h->nel_pad_s = (nel_solid + TE - 1) / TE * TE;
+    h->css = (size_t)NPT * h->nel_pad_s;
     h->igloc_s.assign(igloc_solid, igloc_solid + (size_t)NPT * nel_solid);
     if (nel_fluid) h->igloc_f.assign(igloc_fluid, igloc_fluid + (size_t)NPT * nel_fluid);
     for (size_t p = 0; p < h->igloc_s.size(); p++)
@@ -433,33 +456,51 @@ int axb_set_mesh(axb_handle h, int32_t npol, int32_t nel_solid, int32_t nel_flui
     return 0;
 }
 
+// planes (0:4,0:4,nel_solid) -> one coefficient slab [tile][plane][TP] (axb_solid_tile.cuh)
+static int plane_to_slab(axb_handle_s *h, const float *host_plane, float *d_tmp, int pl, int npl) {
+    const size_t n = (size_t)NPT * h->nel_s;
+    if (n == 0) return 0;
+    CK(cudaMemcpy(d_tmp, host_plane, n * sizeof(float), cudaMemcpyHostToDevice));
+    k_plane_to_slab<<<(unsigned)((n + 255) / 256), 256>>>(d_tmp, h->d_coef, pl, npl, h->nel_s);
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int axb_set_solid_terms(axb_handle h, int32_t src_order, const axb_solid_terms *t) {
     if (use(h)) return 1;
     if (src_order < 0 || src_order > 2) return fail("bad src_order");
     h->order = src_order;
-    const size_t n = (size_t)NPT * h->nel_s, n0 = (size_t)NP * h->nel_s;
-#define CP(x) UPC(h->P.x, t->x, n)
-#define CP0(x) UPC(h->P.x, t->x, n0)
-    CP(M11s); CP(M21s); CP(M41s); CP(M12s); CP(M22s); CP(M32s); CP(M42s);
-    CP(M11z); CP(M21z); CP(M41z); CP(M13s); CP(M33s); CP(M43s);
-    CP(M1phi); CP(M2phi); CP(M4phi);
-    CP(M_1); CP(M_2); CP(M_3); CP(M_4); CP(M_5); CP(M_6); CP(M_7); CP(M_8);
-    CP(M_w1); CP(M_w2); CP(M_w3); CP(M_w4); CP(M_w5);
-    CP0(M0_w1); CP0(M0_w2); CP0(M0_w3); CP0(M0_w4); CP0(M0_w5);
-    CP0(M0_w6); CP0(M0_w7); CP0(M0_w8); CP0(M0_w9); CP0(M0_w10);
-#undef CP
-#undef CP0
-    const SolidPlanes &P = h->P;
-    bool ok = P.M11s && P.M21s && P.M41s && P.M12s && P.M22s && P.M32s && P.M42s && P.M11z &&
-              P.M21z && P.M41z && P.M_1 && P.M_2 && P.M_3 && P.M_4 && P.M_w1 && P.M0_w1 &&
-              P.M0_w2 && P.M0_w3;
-    if (src_order == AXB_DIPOLE)
-        ok = ok && P.M13s && P.M33s && P.M43s && P.M_5 && P.M_6 && P.M_7 && P.M_8 && P.M_w2 &&
-             P.M_w3 && P.M0_w4 && P.M0_w6 && P.M0_w7 && P.M0_w8 && P.M0_w9 && P.M0_w10;
-    if (src_order == AXB_QUADPOLE)
-        ok = ok && P.M1phi && P.M2phi && P.M4phi && P.M_5 && P.M_6 && P.M_7 && P.M_8 && P.M_w2 &&
-             P.M_w3 && P.M_w4 && P.M_w5 && P.M0_w4 && P.M0_w5 && P.M0_w6;
-    if (!ok && h->nel_s > 0) return fail("axb_set_solid_terms: a plane required for this source order is NULL");
+    if (h->nel_s == 0) { h->have_solid_terms = true; return 0; }
+    // slab plane order: the enum in axb_solid_tile.cuh
+    std::vector<const float *> pl = {t->M11s, t->M21s, t->M41s, t->M12s, t->M22s, t->M32s, t->M42s,
+                                     t->M11z, t->M21z, t->M41z, t->M_1, t->M_2, t->M_3, t->M_4, t->M_w1};
+    std::vector<const float *> w0 = {t->M0_w1, t->M0_w2, t->M0_w3, t->M0_w4, t->M0_w5,
+                                     t->M0_w6, t->M0_w7, t->M0_w8, t->M0_w9, t->M0_w10};
+    bool ok0 = t->M0_w1 && t->M0_w2 && t->M0_w3;
+    if (src_order == AXB_DIPOLE) {
+        for (const float *q : {t->M13s, t->M33s, t->M43s, t->M_5, t->M_6, t->M_7, t->M_8, t->M_w2, t->M_w3}) pl.push_back(q);
+        ok0 = ok0 && t->M0_w4 && t->M0_w6 && t->M0_w7 && t->M0_w8 && t->M0_w9 && t->M0_w10;
+    } else if (src_order == AXB_QUADPOLE) {
+        for (const float *q : {t->M1phi, t->M2phi, t->M4phi, t->M_5, t->M_6, t->M_7, t->M_8, t->M_w2, t->M_w3,
+                               t->M_w4, t->M_w5}) pl.push_back(q);
+        ok0 = ok0 && t->M0_w4 && t->M0_w5 && t->M0_w6;
+    }
+    const int npl = solid_nplanes(src_order);
+    if ((int)pl.size() != npl) return fail("internal: plane list");
+    for (const float *q : pl)
+        if (!q) return fail("axb_set_solid_terms: a plane required for this source order is NULL");
+    if (!ok0) return fail("axb_set_solid_terms: an axial vector required for this source order is NULL");
+    const size_t ntiles = h->nel_pad_s / TE;
+    if (dzeros(h, h->d_coef, ntiles * npl * TP)) return 1;
+    float *d_tmp = nullptr;
+    CK(cudaMalloc((void **)&d_tmp, (size_t)NPT * h->nel_s * sizeof(float)));
+    for (int k = 0; k < npl; k++)
+        if (plane_to_slab(h, pl[k], d_tmp, k, npl)) { cudaFree(d_tmp); return 1; }
+    CK(cudaDeviceSynchronize());
+    cudaFree(d_tmp);
+    for (int k = 0; k < 10; k++)
+        if (upload_padded(h, h->d_M0_w[k], w0[k], (size_t)NP * h->nel_s, (size_t)NP * h->nel_pad_s)) return 1;
+    h->have_solid_terms = true;
     return 0;
 }
 
@@ -522,23 +563,36 @@ int axb_set_attenuation(axb_handle h, const axb_attenuation *a) {
                     "implemented on the device in this round");
     const size_t n4 = (size_t)4 * h->nel_s, n = (size_t)NPT * h->nel_s;
     h->anel = true; h->cg = true; h->corr_lowq = a->do_corr_lowq;
-    AttCg &A = h->A;
-    A.n_sls = a->n_sls;
+    h->n_sls = a->n_sls;
     h->y_j.assign(a->y_j, a->y_j + a->n_sls);
-    { double *t; UP(t, a->exp_w_j_deltat, a->n_sls); A.exp_w = t; }
-    { double *t; UP(t, a->ts_fac_t, a->n_sls); A.ts_t = t; }
-    { double *t; UP(t, a->ts_fac_tm1, a->n_sls); A.ts_tm1 = t; }
+    UP(h->d_exp_w, a->exp_w_j_deltat, a->n_sls);
+    UP(h->d_ts_t, a->ts_fac_t, a->n_sls);
+    UP(h->d_ts_tm1, a->ts_fac_tm1, a->n_sls);
+    if (!a->Q_mu || !a->Q_kappa) return fail("axb_set_attenuation: NULL Q array");
     h->Qmu_h.assign(a->Q_mu, a->Q_mu + h->nel_s);
     h->Qka_h.assign(a->Q_kappa, a->Q_kappa + h->nel_s);
-    UPC(A.Ycg, a->Y_cg4, n4); UPC(A.Vse, a->V_s_eta_cg4, n4); UPC(A.Vsx, a->V_s_xi_cg4, n4);
-    UPC(A.Vze, a->V_z_eta_cg4, n4); UPC(A.Vzx, a->V_z_xi_cg4, n4);
-    UPC(A.Dse, a->DsDeta_over_J_sol_cg4, n4); UPC(A.Dze, a->DzDeta_over_J_sol_cg4, n4);
-    UPC(A.Dsx, a->DsDxi_over_J_sol_cg4, n4); UPC(A.Dzx, a->DzDxi_over_J_sol_cg4, n4);
-    UPC(A.dmu, a->delta_mu_cg4, n4); UPC(A.dka, a->delta_kappa_cg4, n4);
-    UPC(A.inv_s, a->inv_s_solid, n);
-    if (!A.Ycg || !A.Vse || !A.Vsx || !A.Vze || !A.Vzx || !A.Dse || !A.Dze || !A.Dsx || !A.Dzx ||
-        !A.dmu || !A.dka || !A.inv_s)
-        return fail("axb_set_attenuation: NULL cg4 array");
+    // slab plane order: enum G_* in axb_solid_tile.cuh
+    const float *cgp[NCG] = {a->Y_cg4, a->V_s_eta_cg4, a->V_s_xi_cg4, a->V_z_eta_cg4, a->V_z_xi_cg4,
+                             a->DsDeta_over_J_sol_cg4, a->DzDeta_over_J_sol_cg4,
+                             a->DsDxi_over_J_sol_cg4, a->DzDxi_over_J_sol_cg4,
+                             a->delta_mu_cg4, a->delta_kappa_cg4};
+    for (int k = 0; k < NCG; k++)
+        if (!cgp[k]) return fail("axb_set_attenuation: NULL cg4 array");
+    if (!a->inv_s_solid) return fail("axb_set_attenuation: NULL inv_s_solid");
+    const size_t ntiles = h->nel_pad_s / TE;
+    if (dzeros(h, h->d_cg, ntiles * NCG * TE * 4)) return 1;
+    if (n4) {
+        float *d_tmp = nullptr;
+        CK(cudaMalloc((void **)&d_tmp, n4 * sizeof(float)));
+        for (int k = 0; k < NCG; k++) {
+            CK(cudaMemcpy(d_tmp, cgp[k], n4 * sizeof(float), cudaMemcpyHostToDevice));
+            k_cg_to_slab<<<(unsigned)((n4 + 255) / 256), 256>>>(d_tmp, h->d_cg, k, h->nel_s);
+            CK(cudaGetLastError());
+        }
+        CK(cudaDeviceSynchronize());
+        cudaFree(d_tmp);
+    }
+    if (upload_padded(h, h->d_inv_s, a->inv_s_solid, n, h->css)) return 1;
     return 0;
 }
 
@@ -641,8 +695,9 @@ int axb_set_time(axb_handle h, int32_t scheme, double deltat, int32_t niter, int
 int axb_finalize_setup(axb_handle h) {
     if (use(h)) return 1;
     if (h->nel_s > 0 && !h->inv_mass_rho) return fail("axb_set_mass not called");
-    const size_t ns = (size_t)NPT * h->nel_s * 3, nf = (size_t)NPT * h->nel_f;
-    if ((size_t)NPT * h->nel_s * 3 > 0x7fffffffULL) return fail("too many solid points for 32-bit point addresses");
+    if (h->nel_s > 0 && !h->have_solid_terms) return fail("axb_set_solid_terms not called");
+    const size_t ns = h->css * 3, nf = (size_t)NPT * h->nel_f;
+    if (ns > 0x7fffffffULL) return fail("too many solid points for 32-bit point addresses");
     if (dzeros(h, h->disp, ns) || dzeros(h, h->velo, ns) || dzeros(h, h->acc0, ns) || dzeros(h, h->acc1, ns)) return 1;
     if (dzeros(h, h->chi, nf) || dzeros(h, h->dchi, nf) || dzeros(h, h->ddchi0, nf) || dzeros(h, h->ddchi1, nf)) return 1;
     // halo slabs first (assembly tables reference slot numbers)
@@ -667,10 +722,13 @@ int axb_finalize_setup(axb_handle h) {
         }
         UP(h->d_bdry_of_el, bo.data(), bo.size());
     }
+    // per-tile element metadata of the solid kernel: axis flag, a_j table rows
+    std::vector<int> meta((size_t)std::max(h->nel_pad_s, TE) * 3, 0);
+    auto meta_at = [&](int e, int row) -> int & { return meta[((size_t)(e / TE) * 3 + row) * TE + e % TE]; };
+    for (int e = 0; e < h->nel_s; e++) meta_at(e, 0) = h->axis_s_h[e] != 0;
     if (h->anel) {
         // a_j tables per distinct Q (time_step_memvars_cg4 recomputes them whenever Q changes)
         std::map<float, int> idx_mu, idx_ka;
-        std::vector<int> qi_mu(h->nel_s), qi_ka(h->nel_s);
         std::vector<double> tab_mu, tab_ka;
         double aj[32];
         for (int e = 0; e < h->nel_s; e++) {
@@ -678,25 +736,25 @@ int axb_finalize_setup(axb_handle h) {
             if (it == idx_mu.end()) {
                 it = idx_mu.emplace(h->Qmu_h[e], (int)idx_mu.size()).first;
                 a_j_of_Q(h, h->Qmu_h[e], aj);
-                tab_mu.insert(tab_mu.end(), aj, aj + h->A.n_sls);
+                tab_mu.insert(tab_mu.end(), aj, aj + h->n_sls);
             }
-            qi_mu[e] = it->second;
+            meta_at(e, 1) = it->second;
             auto ik = idx_ka.find(h->Qka_h[e]);
             if (ik == idx_ka.end()) {
                 ik = idx_ka.emplace(h->Qka_h[e], (int)idx_ka.size()).first;
                 a_j_of_Q(h, h->Qka_h[e], aj);
-                tab_ka.insert(tab_ka.end(), aj, aj + h->A.n_sls);
+                tab_ka.insert(tab_ka.end(), aj, aj + h->n_sls);
             }
-            qi_ka[e] = ik->second;
+            meta_at(e, 2) = ik->second;
         }
-        { int *t; UP(t, qi_mu.data(), qi_mu.size()); h->A.qidx_mu = t; }
-        { int *t; UP(t, qi_ka.data(), qi_ka.size()); h->A.qidx_ka = t; }
-        { double *t; UP(t, tab_mu.data(), tab_mu.size()); h->A.a_mu_tab = t; }
-        { double *t; UP(t, tab_ka.data(), tab_ka.size()); h->A.a_ka_tab = t; }
-        if (dzeros(h, h->A.memvar, (size_t)24 * h->A.n_sls * h->nel_s)) return 1;
-        if (dzeros(h, h->A.src_dev_tm1, (size_t)24 * h->nel_s)) return 1;
-        if (dzeros(h, h->A.src_tr_tm1, (size_t)4 * h->nel_s)) return 1;
+        if (tab_mu.empty()) { tab_mu.assign(h->n_sls, 0.0); tab_ka.assign(h->n_sls, 0.0); }
+        UP(h->d_a_mu_tab, tab_mu.data(), tab_mu.size());
+        UP(h->d_a_ka_tab, tab_ka.data(), tab_ka.size());
+        if (dzeros(h, h->memvar, (size_t)24 * h->n_sls * h->nel_pad_s)) return 1;
+        if (dzeros(h, h->src_dev_tm1, (size_t)24 * h->nel_pad_s)) return 1;
+        if (dzeros(h, h->src_tr_tm1, (size_t)4 * h->nel_pad_s)) return 1;
     }
+    UP(h->d_meta, meta.data(), meta.size());
     if (h->scheme != AXB_NEWMARK2) {
         if (symplectic_coefficients(h)) return 1;
         // stf at the sub-stage times of every step: subdt = t - deltat + coeff
@@ -723,8 +781,22 @@ int axb_finalize_setup(axb_handle h) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
     const int sms = prop.multiProcessorCount;
-    h->grid_s = std::max(1, std::min(cdiv(h->nel_s, 8), sms * 8));
+    h->sms = sms;
     h->grid_f = std::max(1, std::min(cdiv(h->nel_f, 8), sms * 8));
+    if (h->nel_s > 0) {
+        // S_A: one persistent CTA per SM; the ring takes all the shared memory it can get
+        const SolidTileLayout Ly = solid_tile_layout(h->order, h->anel, h->n_sls);
+        const size_t cap = prop.sharedMemPerBlockOptin;
+        if (cap < Ly.hdr_bytes + 2 * Ly.stage_bytes) return fail("not enough shared memory for the solid tile ring");
+        int nst = (int)std::min<size_t>(MAX_STAGES, (cap - Ly.hdr_bytes) / Ly.stage_bytes);
+        if (const char *ev = getenv("AXB_SOLID_STAGES")) nst = std::max(2, std::min(nst, atoi(ev)));
+        h->nst = nst;
+        h->smem_solid = Ly.hdr_bytes + (size_t)nst * Ly.stage_bytes;
+        h->grid_s = std::max(1, std::min(h->nel_pad_s / TE, sms));
+        CK(cudaFuncSetAttribute(k_solid_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+        CK(cudaFuncSetAttribute(k_solid_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+        CK(cudaFuncSetAttribute(k_solid_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    }
     h->iter = h->iseismo = h->istrain = 0;
     h->finalized = true;
     CK(cudaDeviceSynchronize());
@@ -850,19 +922,33 @@ static void prof_mark(axb_handle_s *h, bool begin) {
     } while (0)
 #define CLS(h, c) (h)->prof_cls = (c)
 
-static SolidStepArgs solid_args(axb_handle_s *h, int mode, double c0, double c1, int anel, int do_stiff) {
-    SolidStepArgs a;
-    a.nel = h->nel_s; a.mode = mode; a.dt = c0; a.half_dt_sq = c1;
-    a.disp = h->disp; a.velo = h->velo; a.acc0 = h->acc0; a.acc1 = h->acc1;
-    a.axis = h->d_axis_s; a.anel = anel; a.do_stiff = do_stiff;
+static SolidTileArgs solid_args(axb_handle_s *h, int mode, double c0, double c1, int anel, int do_stiff) {
+    SolidTileArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.ntiles = h->nel_pad_s / TE; a.mode = mode; a.do_stiff = do_stiff; a.anel = anel;
+    a.nst = h->nst; a.n_sls = h->n_sls; a.dt = c0; a.half_dt_sq = c1;
+    a.disp = h->disp; a.velo = h->velo; a.acc0 = h->acc0; a.acc1 = h->acc1; a.cs = h->css;
+    a.coef = h->d_coef; a.meta = h->d_meta;
+    for (int k = 0; k < 10; k++) a.M0_w[k] = h->d_M0_w[k];
+    a.cg = h->d_cg; a.inv_s = h->d_inv_s;
+    a.a_mu_tab = h->d_a_mu_tab; a.a_ka_tab = h->d_a_ka_tab;
+    a.exp_w = h->d_exp_w; a.ts_t = h->d_ts_t; a.ts_tm1 = h->d_ts_tm1;
+    a.memvar = h->memvar; a.src_dev_tm1 = h->src_dev_tm1; a.src_tr_tm1 = h->src_tr_tm1;
     return a;
 }
-static void launch_solid_element(axb_handle_s *h, const SolidStepArgs &a) {
+#define LAUNCH_SMEM(h, kern, grid, block, smem, ...)                                     \
+    do {                                                                                 \
+        prof_mark((h), true);                                                            \
+        kern<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);                    \
+        prof_mark((h), false);                                                           \
+        (h)->launches++;                                                                 \
+    } while (0)
+static void launch_solid_element(axb_handle_s *h, const SolidTileArgs &a) {
     if (h->nel_s == 0) return;
     CLS(h, 0);
-    if (h->order == 0) LAUNCH(h, k_solid_element<0>, h->grid_s, 256, h->G, h->P, h->A, a);
-    else if (h->order == 1) LAUNCH(h, k_solid_element<1>, h->grid_s, 256, h->G, h->P, h->A, a);
-    else LAUNCH(h, k_solid_element<2>, h->grid_s, 256, h->G, h->P, h->A, a);
+    if (h->order == 0) LAUNCH_SMEM(h, k_solid_tile<0>, h->grid_s, SOLID_THREADS, h->smem_solid, h->G, a);
+    else if (h->order == 1) LAUNCH_SMEM(h, k_solid_tile<1>, h->grid_s, SOLID_THREADS, h->smem_solid, h->G, a);
+    else LAUNCH_SMEM(h, k_solid_tile<2>, h->grid_s, SOLID_THREADS, h->smem_solid, h->G, a);
 }
 static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1, int full, int use_mask) {
     if (h->nel_f == 0) return;
@@ -873,7 +959,7 @@ static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1
     a.chi = h->chi; a.ddchi1 = h->ddchi1; a.dchi = h->dchi; a.ddchi0 = h->ddchi0; a.axis = h->d_axis_f;
     a.M1chi = h->M1chi; a.M2chi = h->M2chi; a.M4chi = h->M4chi; a.M_w_fl = h->M_w_fl; a.M0_w_fl = h->M0_w_fl;
     a.fs_mask = h->fs_mask; a.bdry_of_el = h->d_bdry_of_el; a.bdry_sel = h->d_bsel; a.bdry_js = h->d_bjs;
-    a.bdry_matr = h->d_bmatr; a.nel_bdry = h->nel_bdry; a.disp = h->disp; a.cs_solid = (size_t)NPT * h->nel_s;
+    a.bdry_matr = h->d_bmatr; a.nel_bdry = h->nel_bdry; a.disp = h->disp; a.cs_solid = h->css;
     a.nelsrc = h->fluid_src ? h->nelsrc : 0;
     for (int k = 0; k < 8; k++) a.ielsrc[k] = h->ielsrc[k];
     a.src_term = h->d_src_term; a.stf = h->d_stf; a.iter = h->d_counters; a.use_mask = use_mask;
@@ -896,7 +982,7 @@ static void launch_solid_corr(axb_handle_s *h, int mode, double c, int stf_strid
     if (h->nel_s == 0) return;
     CLS(h, 4);
     SolidCorrArgs a;
-    a.npts = NPT * h->nel_s; a.order = h->order; a.mode = mode; a.half_dt = c;
+    a.npts = NPT * h->nel_s; a.cs = h->css; a.order = h->order; a.mode = mode; a.half_dt = c;
     a.acc1 = h->acc1; a.acc0 = h->acc0; a.velo = h->velo; a.disp = h->disp;
     a.inv_mass_rho = h->inv_mass_rho; a.gamma = h->gamma_s;
     a.T.gid = h->d_asm_gid_s; a.T.grp = h->d_asm_grp_s;
@@ -920,7 +1006,7 @@ static void launch_bdry2solid(axb_handle_s *h) {
     BdrySolidArgs a;
     a.nel_bdry = h->nel_bdry; a.order = h->order; a.bdry_sel = h->d_bsel; a.bdry_fel = h->d_bfel;
     a.bdry_js = h->d_bjs; a.bdry_jf = h->d_bjf; a.bdry_matr = h->d_bmatr; a.axis_solid = h->d_axis_s;
-    a.uflu = h->ddchi0; a.acc1 = h->acc1; a.cs = (size_t)NPT * h->nel_s;
+    a.uflu = h->ddchi0; a.acc1 = h->acc1; a.cs = h->css;
     LAUNCH(h, k_bdry2solid, cdiv(h->nel_bdry * NP, 128), 128, a);
 }
 // phase 1 of pdistsum_*: pack partial sums into the neighbours' slabs and raise their flags
@@ -965,7 +1051,7 @@ static void launch_dumps(axb_handle_s *h) {
     if (h->num_rec > 0 && h->iter % h->seis_it == 0 && h->iseismo < h->nseismo_max) {
         RecArgs a;
         a.num_rec = h->num_rec; a.order = h->order; a.seis_it = h->seis_it; a.nseismo_max = h->nseismo_max;
-        a.recfile_el = h->d_recfile; a.disp = h->disp; a.cs = (size_t)NPT * h->nel_s;
+        a.recfile_el = h->d_recfile; a.disp = h->disp; a.cs = h->css;
         a.recdump = h->d_recdump; a.counters = h->d_counters;
         LAUNCH(h, k_sample_receivers, cdiv(h->num_rec, 128), 128, a);
         h->iseismo++; any = true;
@@ -974,7 +1060,7 @@ static void launch_dumps(axb_handle_s *h) {
         DumpArgs a;
         a.nel_s = h->nel_s; a.nel_f = h->nel_f; a.order = h->order; a.strain_it = h->strain_it;
         a.nstrain_max = h->nstrain_max; a.kwf_mask = h->d_kwf_mask; a.kwf_map = h->d_kwf_map;
-        a.disp = h->disp; a.chi = h->chi; a.cs = (size_t)NPT * h->nel_s; a.axis_f = h->d_axis_f;
+        a.disp = h->disp; a.chi = h->chi; a.cs = h->css; a.axis_f = h->d_axis_f;
         a.inv_rho = h->d_inv_rho; a.Dse = h->d_Dse_f; a.Dze = h->d_Dze_f; a.Dsx = h->d_Dsx_f; a.Dzx = h->d_Dzx_f;
         a.snap = h->d_snap; a.npts = (size_t)h->npt_s_kwf + h->npt_f_kwf; a.counters = h->d_counters;
         if (h->nel_s) LAUNCH(h, k_dump_solid, cdiv((long long)NPT * h->nel_s, 256), 256, a);
@@ -989,19 +1075,17 @@ static void launch_dumps(axb_handle_s *h) {
 // One Newmark step, split at the two exchange points so that in-process groups can be
 // enqueued rank by rank (every send is enqueued before the matching wait of any rank).
 static int newmark_a(axb_handle_s *h) {
-    const size_t css = (size_t)NPT * h->nel_s;
     // S_A first: the fluid needs the *predicted* solid displacement on the S/F boundary
     launch_solid_element(h, solid_args(h, 0, h->deltat, h->half_dt_sq, h->anel ? 2 : 0, 1));
     launch_fluid_element(h, 0, h->deltat, h->half_dt_sq, 1, 1);
     if (halo_send(h, 1, h->ddchi1, (size_t)NPT * h->nel_f)) return 1;
-    (void)css;
     return 0;
 }
 static int newmark_b(axb_handle_s *h) {
     halo_wait(h, 1);
     launch_fluid_corr(h, 0, h->half_dt, 0);
     launch_bdry2solid(h);
-    if (halo_send(h, 0, h->acc1, (size_t)NPT * h->nel_s)) return 1;
+    if (halo_send(h, 0, h->acc1, h->css)) return 1;
     return 0;
 }
 static int newmark_c(axb_handle_s *h) {
@@ -1022,7 +1106,7 @@ static int symp_b(axb_handle_s *h, int k) {
     halo_wait(h, 1);
     launch_fluid_corr(h, 1, h->coefv[k], 0);
     launch_bdry2solid(h);
-    return halo_send(h, 0, h->acc1, (size_t)NPT * h->nel_s);
+    return halo_send(h, 0, h->acc1, h->css);
 }
 static int symp_c(axb_handle_s *h, int k) {
     halo_wait(h, 0);
@@ -1032,7 +1116,7 @@ static int symp_c(axb_handle_s *h, int k) {
 static int symp_finish(axb_handle_s *h) {
     const double cd = h->coefd[h->nstages];
     const int nf = NPT * h->nel_f;
-    const size_t cs = (size_t)NPT * h->nel_s;
+    const size_t cs = h->css;
     CLS(h, 7);
     if (nf) LAUNCH(h, k_drift, cdiv(nf, 256), 256, nf, h->chi, h->dchi, cd);
     if (h->nel_s) {
@@ -1149,29 +1233,37 @@ int axb_fetch_snapshots(axb_handle h, int32_t first, int32_t nsnap, float *out) 
     return 0;
 }
 
-static float *field_ptr(axb_handle_s *o, int f, size_t *n, bool reading) {
-    const size_t ns = (size_t)NPT * o->nel_s * 3, nf = (size_t)NPT * o->nel_f;
+// Solid fields are (5,5,nel_solid,3) on the host and 3 planes of pitch css on the device.
+static float *field_ptr(axb_handle_s *o, int f, size_t *n, bool *planes, bool reading) {
+    const size_t ns = (size_t)NPT * o->nel_s, nf = (size_t)NPT * o->nel_f;
+    *planes = false;
     switch (f) {
-    case AXB_F_DISP: *n = ns; return o->disp;
-    case AXB_F_VELO: *n = ns; return o->velo;
-    case AXB_F_ACC0: *n = ns; return o->acc0;
-    case AXB_F_ACC1: *n = ns; return (reading && o->acc1_is_acc0) ? o->acc0 : o->acc1;
+    case AXB_F_DISP: *n = ns; *planes = true; return o->disp;
+    case AXB_F_VELO: *n = ns; *planes = true; return o->velo;
+    case AXB_F_ACC0: *n = ns; *planes = true; return o->acc0;
+    case AXB_F_ACC1: *n = ns; *planes = true; return (reading && o->acc1_is_acc0) ? o->acc0 : o->acc1;
     case AXB_F_CHI: *n = nf; return o->chi;
     case AXB_F_DCHI: *n = nf; return o->dchi;
     case AXB_F_DDCHI0: *n = nf; return o->ddchi0;
     case AXB_F_DDCHI1: *n = nf; return (reading && o->acc1_is_acc0) ? o->ddchi0 : o->ddchi1;
-    case AXB_F_MEMVAR: if (!o->anel) return nullptr; *n = (size_t)24 * o->A.n_sls * o->nel_s; return o->A.memvar;
-    case AXB_F_SRC_DEV_TM1: if (!o->anel) return nullptr; *n = (size_t)24 * o->nel_s; return o->A.src_dev_tm1;
-    case AXB_F_SRC_TR_TM1: if (!o->anel) return nullptr; *n = (size_t)4 * o->nel_s; return o->A.src_tr_tm1;
+    case AXB_F_MEMVAR: if (!o->anel) return nullptr; *n = (size_t)24 * o->n_sls * o->nel_s; return o->memvar;
+    case AXB_F_SRC_DEV_TM1: if (!o->anel) return nullptr; *n = (size_t)24 * o->nel_s; return o->src_dev_tm1;
+    case AXB_F_SRC_TR_TM1: if (!o->anel) return nullptr; *n = (size_t)4 * o->nel_s; return o->src_tr_tm1;
     }
     return nullptr;
 }
 int axb_get_state(axb_handle h, int32_t field, float *out) {
     if (use(h)) return 1;
     if (!h->finalized) return fail("get_state before finalize_setup");
-    size_t n = 0; float *p = field_ptr(h, field, &n, true);
+    size_t n = 0; bool planes = false;
+    float *p = field_ptr(h, field, &n, &planes, true);
     if (!p) return fail("no such field");
-    CK(cudaMemcpyAsync(out, p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (n == 0) return 0;
+    if (planes)
+        CK(cudaMemcpy2DAsync(out, n * sizeof(float), p, h->css * sizeof(float), n * sizeof(float), 3,
+                             cudaMemcpyDeviceToHost, h->stream));
+    else
+        CK(cudaMemcpyAsync(out, p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1179,9 +1271,15 @@ int axb_set_state(axb_handle h, int32_t field, const float *in) {
     if (use(h)) return 1;
     if (!h->finalized) return fail("set_state before finalize_setup");
     if (field == AXB_F_ACC1 || field == AXB_F_DDCHI1) h->acc1_is_acc0 = false;
-    size_t n = 0; float *p = field_ptr(h, field, &n, false);
+    size_t n = 0; bool planes = false;
+    float *p = field_ptr(h, field, &n, &planes, false);
     if (!p) return fail("no such field");
-    CK(cudaMemcpyAsync(p, in, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    if (n == 0) return 0;
+    if (planes)
+        CK(cudaMemcpy2DAsync(p, h->css * sizeof(float), in, n * sizeof(float), n * sizeof(float), 3,
+                             cudaMemcpyHostToDevice, h->stream));
+    else
+        CK(cudaMemcpyAsync(p, in, n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1190,7 +1288,7 @@ int axb_apply_op(axb_handle h, int32_t op) {
     if (use(h)) return 1;
     if (!h->finalized) return fail("apply_op before finalize_setup");
     h->acc1_is_acc0 = false;
-    const size_t css = (size_t)NPT * h->nel_s;
+    const size_t css = h->css;
     switch (op) {
     case AXB_OP_SOLID_STIFFNESS: launch_solid_element(h, solid_args(h, 2, 0, 0, 0, 1)); break;
     case AXB_OP_ANEL_STIFFNESS:
