@@ -33,6 +33,7 @@ int fail(const std::string &m) { g_err = m; return 1; }
     } while (0)
 
 constexpr int MAXMSG = 8;
+typedef void (*solid_kernel_t)(GMat, SolidTileArgs);
 
 struct Halo {
     int nmsg = 0, nc = 1;
@@ -72,6 +73,7 @@ struct axb_handle_s {
     int *d_meta = nullptr;         // [tile][3][TE]: axis, qidx_mu, qidx_ka
     float *d_M0_w[10] = {nullptr};
     bool have_solid_terms = false;
+    void (*solid_kernel)(GMat, SolidTileArgs) = nullptr;
     int nst = 0;                   // ring depth of k_solid_tile
     size_t smem_solid = 0;
     std::vector<void *> allocs;
@@ -90,7 +92,9 @@ struct axb_handle_s {
     int n_sls = 0;
     float *d_cg = nullptr;         // [tile][NCG][TE*4]
     float *d_inv_s = nullptr;      // (25 * nel_pad_s)
-    double *d_a_mu_tab = nullptr, *d_a_ka_tab = nullptr, *d_exp_w = nullptr, *d_ts_t = nullptr, *d_ts_tm1 = nullptr;
+    double2 *d_c_mu_tab = nullptr, *d_c_ka_tab = nullptr;
+    double *d_exp_w = nullptr;
+    std::vector<double> ts_t_h, ts_tm1_h;
     float *memvar = nullptr, *src_dev_tm1 = nullptr, *src_tr_tm1 = nullptr;
     std::vector<float> Qmu_h, Qka_h;
     std::vector<double> y_j;
@@ -566,8 +570,8 @@ int axb_set_attenuation(axb_handle h, const axb_attenuation *a) {
     h->n_sls = a->n_sls;
     h->y_j.assign(a->y_j, a->y_j + a->n_sls);
     UP(h->d_exp_w, a->exp_w_j_deltat, a->n_sls);
-    UP(h->d_ts_t, a->ts_fac_t, a->n_sls);
-    UP(h->d_ts_tm1, a->ts_fac_tm1, a->n_sls);
+    h->ts_t_h.assign(a->ts_fac_t, a->ts_fac_t + a->n_sls);
+    h->ts_tm1_h.assign(a->ts_fac_tm1, a->ts_fac_tm1 + a->n_sls);
     if (!a->Q_mu || !a->Q_kappa) return fail("axb_set_attenuation: NULL Q array");
     h->Qmu_h.assign(a->Q_mu, a->Q_mu + h->nel_s);
     h->Qka_h.assign(a->Q_kappa, a->Q_kappa + h->nel_s);
@@ -729,27 +733,31 @@ int axb_finalize_setup(axb_handle h) {
     if (h->anel) {
         // a_j tables per distinct Q (time_step_memvars_cg4 recomputes them whenever Q changes)
         std::map<float, int> idx_mu, idx_ka;
-        std::vector<double> tab_mu, tab_ka;
+        std::vector<double2> tab_mu, tab_ka;
         double aj[32];
+        auto push = [&](std::vector<double2> &tab) {
+            for (int k = 0; k < h->n_sls; k++)
+                tab.push_back(make_double2(h->ts_t_h[k] * aj[k], h->ts_tm1_h[k] * aj[k]));
+        };
         for (int e = 0; e < h->nel_s; e++) {
             auto it = idx_mu.find(h->Qmu_h[e]);
             if (it == idx_mu.end()) {
                 it = idx_mu.emplace(h->Qmu_h[e], (int)idx_mu.size()).first;
                 a_j_of_Q(h, h->Qmu_h[e], aj);
-                tab_mu.insert(tab_mu.end(), aj, aj + h->n_sls);
+                push(tab_mu);
             }
             meta_at(e, 1) = it->second;
             auto ik = idx_ka.find(h->Qka_h[e]);
             if (ik == idx_ka.end()) {
                 ik = idx_ka.emplace(h->Qka_h[e], (int)idx_ka.size()).first;
                 a_j_of_Q(h, h->Qka_h[e], aj);
-                tab_ka.insert(tab_ka.end(), aj, aj + h->n_sls);
+                push(tab_ka);
             }
             meta_at(e, 2) = ik->second;
         }
-        if (tab_mu.empty()) { tab_mu.assign(h->n_sls, 0.0); tab_ka.assign(h->n_sls, 0.0); }
-        UP(h->d_a_mu_tab, tab_mu.data(), tab_mu.size());
-        UP(h->d_a_ka_tab, tab_ka.data(), tab_ka.size());
+        if (tab_mu.empty()) { tab_mu.assign(h->n_sls, make_double2(0, 0)); tab_ka.assign(h->n_sls, make_double2(0, 0)); }
+        UP(h->d_c_mu_tab, tab_mu.data(), tab_mu.size());
+        UP(h->d_c_ka_tab, tab_ka.data(), tab_ka.size());
         if (dzeros(h, h->memvar, (size_t)24 * h->n_sls * h->nel_pad_s)) return 1;
         if (dzeros(h, h->src_dev_tm1, (size_t)24 * h->nel_pad_s)) return 1;
         if (dzeros(h, h->src_tr_tm1, (size_t)4 * h->nel_pad_s)) return 1;
@@ -793,9 +801,14 @@ int axb_finalize_setup(axb_handle h) {
         h->nst = nst;
         h->smem_solid = Ly.hdr_bytes + (size_t)nst * Ly.stage_bytes;
         h->grid_s = std::max(1, std::min(h->nel_pad_s / TE, sms));
-        CK(cudaFuncSetAttribute(k_solid_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
-        CK(cudaFuncSetAttribute(k_solid_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
-        CK(cudaFuncSetAttribute(k_solid_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+        // compiled variants: elastic, the reference default NR_LIN_SOLIDS 5, any other n_sls
+        const int v = !h->anel ? 0 : (h->n_sls == 5 ? 1 : 2);
+        static solid_kernel_t const table[3][3] = {
+            {k_solid_tile<0, 0>, k_solid_tile<0, 5>, k_solid_tile<0, -1>},
+            {k_solid_tile<1, 0>, k_solid_tile<1, 5>, k_solid_tile<1, -1>},
+            {k_solid_tile<2, 0>, k_solid_tile<2, 5>, k_solid_tile<2, -1>}};
+        h->solid_kernel = table[h->order][v];
+        CK(cudaFuncSetAttribute(h->solid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
     }
     h->iter = h->iseismo = h->istrain = 0;
     h->finalized = true;
@@ -931,8 +944,7 @@ static SolidTileArgs solid_args(axb_handle_s *h, int mode, double c0, double c1,
     a.coef = h->d_coef; a.meta = h->d_meta;
     for (int k = 0; k < 10; k++) a.M0_w[k] = h->d_M0_w[k];
     a.cg = h->d_cg; a.inv_s = h->d_inv_s;
-    a.a_mu_tab = h->d_a_mu_tab; a.a_ka_tab = h->d_a_ka_tab;
-    a.exp_w = h->d_exp_w; a.ts_t = h->d_ts_t; a.ts_tm1 = h->d_ts_tm1;
+    a.c_mu_tab = h->d_c_mu_tab; a.c_ka_tab = h->d_c_ka_tab; a.exp_w = h->d_exp_w;
     a.memvar = h->memvar; a.src_dev_tm1 = h->src_dev_tm1; a.src_tr_tm1 = h->src_tr_tm1;
     return a;
 }
@@ -946,9 +958,7 @@ static SolidTileArgs solid_args(axb_handle_s *h, int mode, double c0, double c1,
 static void launch_solid_element(axb_handle_s *h, const SolidTileArgs &a) {
     if (h->nel_s == 0) return;
     CLS(h, 0);
-    if (h->order == 0) LAUNCH_SMEM(h, k_solid_tile<0>, h->grid_s, SOLID_THREADS, h->smem_solid, h->G, a);
-    else if (h->order == 1) LAUNCH_SMEM(h, k_solid_tile<1>, h->grid_s, SOLID_THREADS, h->smem_solid, h->G, a);
-    else LAUNCH_SMEM(h, k_solid_tile<2>, h->grid_s, SOLID_THREADS, h->smem_solid, h->G, a);
+    LAUNCH_SMEM(h, h->solid_kernel, h->grid_s, SOLID_THREADS, h->smem_solid, h->G, a);
 }
 static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1, int full, int use_mask) {
     if (h->nel_f == 0) return;

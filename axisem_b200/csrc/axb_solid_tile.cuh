@@ -57,8 +57,8 @@ struct SolidTileLayout {
     int u, coef, meta, cg, invs, sdev, str, mv, floats;
     size_t stage_bytes, hdr_bytes;
 };
-__host__ __device__ inline SolidTileLayout solid_tile_layout(int order, bool anel, int n_sls) {
-    SolidTileLayout L;
+__host__ __device__ constexpr SolidTileLayout solid_tile_layout(int order, bool anel, int n_sls) {
+    SolidTileLayout L{};
     int o = 0;
     L.u = o; o += solid_ncomp(order) * 3 * TP;       // [comp][disp|velo|acc0][TP]
     L.coef = o; o += solid_nplanes(order) * TP;
@@ -92,7 +92,10 @@ struct SolidTileArgs {
     const float *M0_w[10];    // axial vectors (5, nel_pad); index = number - 1
     const float *cg;          // [tile][NCG][TE*4]
     const float *inv_s;       // (25 * nel_pad)
-    const double *a_mu_tab, *a_ka_tab, *exp_w, *ts_t, *ts_tm1;
+    // per distinct Q and SLS: {ts_fac_t * a_j, ts_fac_tm1 * a_j} (attenuation.f90:162-175 evaluates
+    // ts_fac_t(j) * a_j_mu(j) * src left to right, so the first product can be formed once)
+    const double2 *c_mu_tab, *c_ka_tab;
+    const double *exp_w;
     float *memvar, *src_dev_tm1, *src_tr_tm1;
 };
 
@@ -174,11 +177,14 @@ __device__ __forceinline__ void axial_rows(const GMat &sG, int i, float (&g1t_ro
 }
 
 // =======================================================================================
-template <int ORDER>
+// NSLS: number of standard linear solids compiled in (0: elastic, -1: run-time a.n_sls)
+template <int ORDER, int NSLS>
 __global__ void __launch_bounds__(SOLID_THREADS, 1)
 k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileArgs a) {
     constexpr int NC = solid_ncomp(ORDER);
     constexpr int NPL = solid_nplanes(ORDER);
+    const int n_sls = NSLS >= 0 ? NSLS : a.n_sls;
+    const int anel = NSLS == 0 ? 0 : a.anel;
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + MAX_STAGES;
@@ -186,7 +192,7 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
     float *x_rsum = reinterpret_cast<float *>(smem + 640);     // [TE][24]
     float *x_anS = x_rsum + TE * 24;                            // [TE][36]
     float *x_src = x_anS + TE * 36;                             // [TE][28]
-    const SolidTileLayout Ly = solid_tile_layout(ORDER, a.anel != 0, a.n_sls);
+    const SolidTileLayout Ly = solid_tile_layout(ORDER, NSLS != 0, n_sls);
     unsigned char *ring = smem + Ly.hdr_bytes;
 
     const int t = threadIdx.x;
@@ -202,8 +208,8 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
     }
     __syncthreads();
 
-    const bool anel_stiff = a.anel == 1 || a.anel == 2;
-    const bool anel_update = a.anel >= 2;
+    const bool anel_stiff = anel == 1 || anel == 2;
+    const bool anel_update = anel >= 2;
 
     // ---------------------------------------------------------------- producer warp ----
     if (warp == NCW) {
@@ -213,8 +219,8 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
             const uint32_t plane_b = TP * 4;
             uint32_t bytes = NC * plane_b * (a.mode == 0 ? 3 : (a.mode == 1 ? 2 : 1)) + 3 * TE * 4;
             if (a.do_stiff) bytes += NPL * plane_b;
-            if (a.anel) {
-                bytes += NCG * TE * 16 + TE * 96 * a.n_sls;
+            if (anel) {
+                bytes += NCG * TE * 16 + TE * 96 * n_sls;
                 if (anel_update) bytes += plane_b + TE * 96 + TE * 16;
             }
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
@@ -233,9 +239,9 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                 }
                 if (a.do_stiff) bulk_g2s(S + Ly.coef, a.coef + (size_t)tile * NPL * TP, NPL * plane_b, bar);
                 bulk_g2s(S + Ly.meta, a.meta + (size_t)tile * 3 * TE, 3 * TE * 4, bar);
-                if (a.anel) {
+                if (anel) {
                     bulk_g2s(S + Ly.cg, a.cg + (size_t)tile * NCG * TE * 4, NCG * TE * 16, bar);
-                    bulk_g2s(S + Ly.mv, a.memvar + (size_t)tile * TE * 24 * a.n_sls, TE * 96 * a.n_sls, bar);
+                    bulk_g2s(S + Ly.mv, a.memvar + (size_t)tile * TE * 24 * n_sls, TE * 96 * n_sls, bar);
                     if (anel_update) {
                         bulk_g2s(S + Ly.invs, a.inv_s + pg, plane_b, bar);
                         bulk_g2s(S + Ly.sdev, a.src_dev_tm1 + (size_t)tile * TE * 24, TE * 96, bar);
@@ -315,12 +321,13 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                 }
             }
         }
-        if (a.anel && mvt) {
+        if (anel && mvt) {
             // r(v)(k) = sum over the standard linear solids (stiffness_mono.f90:545-549)
             float rsum = 0.0f;
             if (mv_lane) {
-                const float *mv = S + Ly.mv + mel * 24 * a.n_sls + ml;
-                for (int sl = 0; sl < a.n_sls; sl++) rsum = rsum + mv[24 * sl];
+                const float *mv = S + Ly.mv + mel * 24 * n_sls + ml;
+#pragma unroll
+                for (int sl = 0; sl < n_sls; sl++) rsum = rsum + mv[24 * sl];
             }
             x_rsum[t] = rsum;
         }
@@ -647,19 +654,21 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
             const float s_dev_tm1 = S[Ly.sdev + t];
             const size_t meg = (size_t)tile * TE + mel;
             if (mv_lane) {
-                const float src_tr_t = x_src[mel * 28 + 24 + mv_k];
-                const float s_tr_tm1 = S[Ly.str + mel * 4 + mv_k];
-                const double *a_mu = a.a_mu_tab + (size_t)a.n_sls * meta[TE + mel];
-                const double *a_ka = a.a_ka_tab + (size_t)a.n_sls * meta[2 * TE + mel];
-                const float *mv = S + Ly.mv + mel * 24 * a.n_sls + ml;
-                float *out = a.memvar + meg * 24 * a.n_sls + ml;
-                for (int sl = 0; sl < a.n_sls; sl++) {
-                    const float dev_buf = (float)(a.ts_t[sl] * a_mu[sl] * (double)src_dev_t
-                                                  + a.ts_tm1[sl] * a_mu[sl] * (double)s_dev_tm1);
+                const double src_tr_t = (double)x_src[mel * 28 + 24 + mv_k];
+                const double s_tr_tm1 = (double)S[Ly.str + mel * 4 + mv_k];
+                const double dsrc_t = (double)src_dev_t, dsrc_tm1 = (double)s_dev_tm1;
+                const double2 *c_mu = a.c_mu_tab + (size_t)n_sls * meta[TE + mel];
+                const double2 *c_ka = a.c_ka_tab + (size_t)n_sls * meta[2 * TE + mel];
+                const float *mv = S + Ly.mv + mel * 24 * n_sls + ml;
+                float *out = a.memvar + meg * 24 * n_sls + ml;
+#pragma unroll
+                for (int sl = 0; sl < n_sls; sl++) {
+                    const double2 cm = c_mu[sl];
+                    const float dev_buf = (float)(cm.x * dsrc_t + cm.y * dsrc_tm1);
                     float nv;
                     if (mv_v < 3) {
-                        const float tr_buf = (float)(a.ts_t[sl] * a_ka[sl] * (double)src_tr_t
-                                                     + a.ts_tm1[sl] * a_ka[sl] * (double)s_tr_tm1);
+                        const double2 ck = c_ka[sl];
+                        const float tr_buf = (float)(ck.x * src_tr_t + ck.y * s_tr_tm1);
                         nv = (float)(a.exp_w[sl] * (double)mv[24 * sl] + (double)dev_buf + (double)tr_buf);
                     } else {
                         nv = (float)(a.exp_w[sl] * (double)mv[24 * sl] + (double)dev_buf);

@@ -25,6 +25,8 @@ def load_library(strict: bool = False) -> Library:
     """Load the product library (`strict=True`: the -fmad=false build whose results are
     bit-identical to the oracle; used by the parity tests)."""
     path = LIB_STRICT if strict else LIB_FAST
+    if not strict and os.environ.get("AXB_LIBRARY"):
+        path = os.environ["AXB_LIBRARY"]       # developer override: a differently tuned build
     if path not in _libs:
         if not os.path.exists(path):
             raise AxbError(
