@@ -4,8 +4,9 @@ The same binding drives two implementations of the header:
 
   * ``libaxisem_b200.so``  (prefix ``axb_``) — the CUDA sm_100a product, loaded by
     :mod:`axisem_b200.solver`;
-  * ``oracle/libaxisem_oracle.so`` (prefix ``axo_``) — the CPU oracle, loaded only by the
-    tests / smoke / bench baseline through ``oracle/oracle.py``.
+  * the CPU test oracle, a second implementation of the same header under another symbol
+    prefix; it lives outside this package and is loaded only by the tests / smoke /
+    bench baseline through its own loader, never from here.
 
 `TimeLoop` is the host-side mirror of the reference's `time_loop` seam
 (SOLVER/time_evol_wave.F90:231): hand over the module arrays once, `run`, fetch the

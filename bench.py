@@ -212,17 +212,8 @@ def main():
         loop.set(f, (rng.standard_normal(shp, dtype=np.float32) * np.float32(1e-6)))
 
     if world > 1:
-        blob = bytearray(1024)
-        import ctypes as C
-        buf = (C.c_char * 1024).from_buffer(blob)
-        loop.lib.check(loop.lib.fn["ipc_export"](loop.h, buf, C.c_int32(1024)))
-        blobs = [None] * world
-        dist.all_gather_object(blobs, bytes(blob), group=gloo)
-        for peer in (rank - 1, rank + 1):
-            if 0 <= peer < world:
-                pb = (C.c_char * 1024).from_buffer_copy(blobs[peer])
-                loop.lib.check(loop.lib.fn["ipc_import"](loop.h, C.c_int32(peer), pb, C.c_int32(1024)))
-        dist.barrier()
+        from axisem_b200.dist import connect_ranks
+        connect_ranks(loop, rank, world, group=gloo)
 
     def sync_all():
         torch.cuda.synchronize()

@@ -28,8 +28,12 @@
 #define AXB_PREFIX axo_
 #include "../include/axisem_b200.h"
 
+#include <fcntl.h>
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -51,6 +55,11 @@ typedef struct {
     int *glob2el;             /* (ncomm,3) Fortran order */
     float *sendbuf[MAXMSG];   /* (size, nc) */
     float *recvbuf[MAXMSG];
+    /* one-process-per-rank mode (axo_ipc_*): receive slabs live in POSIX shared memory */
+    float *shm_recv[2][MAXMSG];    /* [parity][msg] in my segment */
+    float *peer_recv[2][MAXMSG];   /* where my message m goes (peer's segment) */
+    volatile int *my_flag[MAXMSG], *peer_flag[MAXMSG];
+    int seq;
 } halo_t;
 
 struct axb_handle_s {
@@ -114,6 +123,11 @@ struct axb_handle_s {
     int finalized;
     struct axb_handle_s **group;
     int ngroup;
+    /* shared-memory segment of this rank (one-process-per-rank mode) */
+    char shm_name[64];
+    void *shm_base;
+    size_t shm_bytes;
+    int ipc_mode;
 };
 
 typedef struct axb_handle_s axo_t;
@@ -160,6 +174,7 @@ int axo_destroy(axb_handle h) {
     free(h->chi); free(h->dchi); free(h->ddchi0); free(h->ddchi1);
     free(h->memvar); free(h->src_dev_tm1); free(h->src_tr_tm1);
     free(h->gvec_s); free(h->gvec_f); free(h->recdump); free(h->snapdump);
+    if (h->shm_base) { munmap(h->shm_base, h->shm_bytes); shm_unlink(h->shm_name); }
     free(h);
     return 0;
 }
@@ -1485,8 +1500,133 @@ int axo_connect_local(axb_handle *handles, int32_t n) {
     for (int i = 0; i < n; i++) { handles[i]->group = g; handles[i]->ngroup = n; }
     return 0;
 }
-int axo_ipc_export(axb_handle h, void *blob, int32_t n) { (void)h; (void)blob; (void)n; return fail("oracle: in-process only"); }
-int axo_ipc_import(axb_handle h, int32_t p, const void *blob, int32_t n) { (void)h; (void)p; (void)blob; (void)n; return fail("oracle: in-process only"); }
+/* ---- one process per rank: the "MPI" of the oracle is a POSIX shared-memory segment per
+ * rank holding its receive slabs [domain][parity][message] and one arrival counter per
+ * message; peers write straight into it (commpi.F90:408-449 ISEND/IRECV) and the owner
+ * spins on the counters (MPI_WAITALL, :453, :587).  Blob = segment name + slab layout. */
+typedef struct {
+    int rank;
+    char name[64];
+    int nmsg[2], peer[2][MAXMSG], size[2][MAXMSG];
+    long off[2][2][MAXMSG];       /* float offset of [dom][parity][msg] */
+    long bytes;
+} ipc_blob_t;
+
+static void ipc_layout(const axo_t *o, ipc_blob_t *b) {
+    memset(b, 0, sizeof *b);
+    b->rank = o->rank;
+    long off = 1024;              /* first 4 KiB: counters, int[2][MAXMSG] */
+    for (int d = 0; d < 2; d++) {
+        const halo_t *H = &o->halo[d];
+        int nc = d == AXB_DOMAIN_SOLID ? 3 : 1;
+        b->nmsg[d] = H->nmsg;
+        for (int m = 0; m < H->nmsg; m++) { b->peer[d][m] = H->peer[m]; b->size[d][m] = H->size[m]; }
+        for (int par = 0; par < 2; par++)
+            for (int m = 0; m < H->nmsg; m++) { b->off[d][par][m] = off; off += (long)H->size[m] * nc; }
+    }
+    b->bytes = off * (long)sizeof(float);
+}
+
+int axo_ipc_export(axb_handle h, void *blob, int32_t n) {
+    static int counter = 0;
+    ipc_blob_t b;
+    if ((size_t)n < sizeof b) return fail("ipc blob too small");
+    if (!h->finalized) return fail("ipc_export before finalize_setup");
+    ipc_layout(h, &b);
+    if (!h->shm_base) {
+        snprintf(h->shm_name, sizeof h->shm_name, "/axo_%d_%d_%d", (int)getpid(), h->rank, counter++);
+        int fd = shm_open(h->shm_name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd < 0) return fail("shm_open failed");
+        if (ftruncate(fd, b.bytes) != 0) { close(fd); return fail("ftruncate failed"); }
+        h->shm_base = mmap(NULL, b.bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+        if (h->shm_base == MAP_FAILED) { h->shm_base = NULL; return fail("mmap failed"); }
+        h->shm_bytes = b.bytes;
+        memset(h->shm_base, 0, b.bytes);
+        for (int d = 0; d < 2; d++)
+            for (int m = 0; m < h->halo[d].nmsg; m++) {
+                h->halo[d].my_flag[m] = (volatile int *)h->shm_base + d * MAXMSG + m;
+                for (int par = 0; par < 2; par++)
+                    h->halo[d].shm_recv[par][m] = (float *)h->shm_base + b.off[d][par][m];
+            }
+    }
+    snprintf(b.name, sizeof b.name, "%s", h->shm_name);
+    memcpy(blob, &b, sizeof b);
+    h->ipc_mode = 1;
+    return 0;
+}
+
+int axo_ipc_import(axb_handle h, int32_t peer_rank, const void *blob, int32_t n) {
+    ipc_blob_t b;
+    if ((size_t)n < sizeof b) return fail("ipc blob too small");
+    memcpy(&b, blob, sizeof b);
+    if (b.rank != peer_rank) return fail("ipc blob does not belong to that rank");
+    int fd = shm_open(b.name, O_RDWR, 0600);
+    if (fd < 0) return fail("shm_open(peer) failed");
+    void *base = mmap(NULL, b.bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (base == MAP_FAILED) return fail("mmap(peer) failed");
+    for (int d = 0; d < 2; d++) {
+        halo_t *H = &h->halo[d];
+        for (int m = 0; m < H->nmsg; m++) {
+            if (H->peer[m] != peer_rank) continue;
+            int mm = -1;
+            for (int q = 0; q < b.nmsg[d]; q++) if (b.peer[d][q] == h->rank) mm = q;
+            if (mm < 0 || b.size[d][mm] != H->size[m]) return fail("halo lists inconsistent between ranks");
+            for (int par = 0; par < 2; par++) H->peer_recv[par][m] = (float *)base + b.off[d][par][mm];
+            H->peer_flag[m] = (volatile int *)base + d * MAXMSG + mm;
+        }
+    }
+    h->ipc_mode = 1;
+    return 0;
+}
+
+/* send_recv_buffers + MPI_WAITALL between processes */
+static int exchange_ipc(axo_t *o, int dom) {
+    halo_t *H = &o->halo[dom];
+    int nc = dom == AXB_DOMAIN_SOLID ? 3 : 1;
+    int par = H->seq & 1;
+    for (int m = 0; m < H->nmsg; m++) {
+        if (!H->peer_recv[par][m]) return fail("halo peers not connected (axo_ipc_import)");
+        memcpy(H->peer_recv[par][m], H->sendbuf[m], sizeof(float) * (size_t)H->size[m] * nc);
+        __atomic_store_n((int *)H->peer_flag[m], H->seq + 1, __ATOMIC_RELEASE);
+    }
+    for (int m = 0; m < H->nmsg; m++) {
+        long spins = 0;
+        while (__atomic_load_n((int *)H->my_flag[m], __ATOMIC_ACQUIRE) < H->seq + 1) {
+            if (++spins > 2000000000L) return fail("halo exchange timed out");
+            if ((spins & 1023) == 0) sched_yield();
+        }
+        H->recvbuf[m] = H->shm_recv[par][m];
+    }
+    H->seq++;
+    return 0;
+}
+
+static int run_ipc(axo_t *o, int nsteps) {
+    for (int s = 0; s < nsteps; s++) {
+        if (o->scheme == AXB_NEWMARK2) {
+            newmark_part1(o);
+            if (exchange_ipc(o, AXB_DOMAIN_FLUID)) return 1;
+            newmark_part2(o);
+            if (exchange_ipc(o, AXB_DOMAIN_SOLID)) return 1;
+            newmark_part3(o);
+        } else {
+            double stf_symp[40];
+            o->t += o->deltat;
+            for (int k = 0; k < o->nstages; k++) stf_symp[k] = stf_t(o, o->t - o->deltat + o->coeff[k]);
+            for (int k = 0; k < o->nstages; k++) {
+                symp_part1(o, k);
+                if (exchange_ipc(o, AXB_DOMAIN_FLUID)) return 1;
+                symp_part2(o);
+                if (exchange_ipc(o, AXB_DOMAIN_SOLID)) return 1;
+                symp_part3(o, k, stf_symp[k]);
+            }
+            symp_finish(o);
+        }
+    }
+    return 0;
+}
 
 /* One thread per rank (= one MPI rank per core in the reference); barriers stand where
  * the reference has its MPI_WAITALLs. */
@@ -1583,6 +1723,13 @@ int axo_run_group(axb_handle *hs, int32_t n, int32_t nsteps) {
 }
 
 int axo_run(axb_handle h, int32_t nsteps) {
+    if (h->ipc_mode) {
+        set_ftz();
+        if (!h->finalized) return fail("finalize_setup not called");
+        if (h->iter + nsteps > h->niter) return fail("run beyond niter");
+        if (h->iter == 0 && h->iseismo == 0 && h->istrain == 0) dump_stuff(h, 0);
+        return run_ipc(h, nsteps);
+    }
     if (h->nranks > 1 && h->ngroup > 1) return fail("use run_group for in-process groups");
     axb_handle one[1] = {h};
     if (h->ngroup == 0) { h->group = (axo_t **)malloc(sizeof(axo_t *)); h->group[0] = h; h->ngroup = 1; }
