@@ -62,7 +62,7 @@ struct axb_handle_s {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int nel_s = 0, nel_f = 0, nglob_s = 0, nglob_f = 0;
-    std::vector<int> igloc_s, igloc_f, axis_s_h;
+    std::vector<int> igloc_s, igloc_f, axis_s_h, axis_f_h;
     int *d_axis_s = nullptr, *d_axis_f = nullptr;
     GMat G;
     int order = 0;
@@ -78,15 +78,20 @@ struct axb_handle_s {
     size_t smem_solid = 0;
     std::vector<void *> allocs;
     // fluid
-    float *M1chi = nullptr, *M2chi = nullptr, *M4chi = nullptr, *M_w_fl = nullptr, *M0_w_fl = nullptr;
-    float *inv_mass_fluid = nullptr, *fs_mask = nullptr;
+    int nel_pad_f = 0;
+    float *d_coef_f = nullptr;     // [tile][npl_f][TP]: M1chi, M2chi, M4chi [, M_w_fl] [, fs_mask]
+    int npl_f = 0, mask_plane_f = -1;
+    int *d_meta_f = nullptr;       // [tile][3][TE]
+    float *M0_w_fl = nullptr;
+    float *inv_mass_fluid = nullptr;
+    int nst_f = 0;
+    size_t smem_fluid = 0;
     float *inv_mass_rho = nullptr, *gamma_s = nullptr, *gamma_f = nullptr;
     // boundary
     int nel_bdry = 0;
     std::vector<int> bdry_fel_h, bdry_jf_h;
     int *d_bsel = nullptr, *d_bfel = nullptr, *d_bjs = nullptr, *d_bjf = nullptr;
     float *d_bmatr = nullptr;
-    int2 *d_bdry_of_el = nullptr;
     // attenuation
     bool anel = false, cg = true;
     int n_sls = 0;
@@ -129,7 +134,7 @@ struct axb_handle_s {
     bool acc1_is_acc0 = false;     // after a full step acc1/ddchi1 == acc0/ddchi0 in the reference
     bool finalized = false;
     int64_t launches = 0;
-    int grid_s = 0, grid_f = 0, sms = 0;
+    int grid_s = 0, grid_f = 0, grid_ft = 0, sms = 0;
     // per-kernel event timing (axb_profile)
     bool prof = false;
     int prof_cls = 7;
@@ -429,6 +434,7 @@ int axb_set_mesh(axb_handle h, int32_t npol, int32_t nel_solid, int32_t nel_flui
     if (use(h)) return 1;
     h->nel_s = nel_solid; h->nel_f = nel_fluid; h->nglob_s = nglob_solid; h->nglob_f = nglob_fluid;
     h->nel_pad_s = (nel_solid + TE - 1) / TE * TE;
+    h->nel_pad_f = (nel_fluid + TE - 1) / TE * TE;
     h->css = (size_t)NPT * h->nel_pad_s;
     h->igloc_s.assign(igloc_solid, igloc_solid + (size_t)NPT * nel_solid);
     if (nel_fluid) h->igloc_f.assign(igloc_fluid, igloc_fluid + (size_t)NPT * nel_fluid);
@@ -452,6 +458,7 @@ int axb_set_mesh(axb_handle h, int32_t npol, int32_t nel_solid, int32_t nel_flui
                 return fail("ax_el_fluid inconsistent with axis_fluid");
     }
     h->axis_s_h.assign(axis_solid, axis_solid + nel_solid);
+    h->axis_f_h.assign(axis_fluid, axis_fluid + nel_fluid);
     UP(h->d_axis_s, (const int *)axis_solid, nel_solid);
     UP(h->d_axis_f, (const int *)axis_fluid, nel_fluid);
     std::memcpy(h->G.G0, G0, sizeof h->G.G0);
@@ -513,12 +520,31 @@ int axb_set_fluid_terms(axb_handle h, const float *M1chi_fl, const float *M2chi_
                         const float *inv_mass_fluid, const float *fluid_free_surface_mask) {
     if (use(h)) return 1;
     const size_t n = (size_t)NPT * h->nel_f;
-    UP(h->M1chi, M1chi_fl, n); UP(h->M2chi, M2chi_fl, n); UP(h->M4chi, M4chi_fl, n);
-    UP(h->M_w_fl, M_w_fl, n); UP(h->M0_w_fl, M0_w_fl, (size_t)NP * h->nel_f);
+    if (h->nel_f == 0) return 0;
+    if (!M1chi_fl || !M2chi_fl || !M4chi_fl || !inv_mass_fluid) return fail("axb_set_fluid_terms: NULL plane");
+    // the free-surface mask is all ones unless the fluid reaches the surface: skip the plane then
+    bool mask_needed = false;
+    if (fluid_free_surface_mask)
+        for (size_t p = 0; p < n; p++) if (fluid_free_surface_mask[p] != 1.0f) { mask_needed = true; break; }
+    std::vector<const float *> pl = {M1chi_fl, M2chi_fl, M4chi_fl};
+    // slot 3 is always M_w_fl for non-monopole sources (axb_fluid_tile.cuh reads it there)
+    if (M_w_fl) pl.push_back(M_w_fl);
+    h->mask_plane_f = -1;
+    if (mask_needed) { h->mask_plane_f = (int)pl.size(); pl.push_back(fluid_free_surface_mask); }
+    h->npl_f = (int)pl.size();
+    const size_t ntiles = h->nel_pad_f / TE;
+    if (dzeros(h, h->d_coef_f, ntiles * h->npl_f * TP)) return 1;
+    float *d_tmp = nullptr;
+    CK(cudaMalloc((void **)&d_tmp, n * sizeof(float)));
+    for (int k = 0; k < h->npl_f; k++) {
+        CK(cudaMemcpy(d_tmp, pl[k], n * sizeof(float), cudaMemcpyHostToDevice));
+        k_plane_to_slab<<<(unsigned)((n + 255) / 256), 256>>>(d_tmp, h->d_coef_f, k, h->npl_f, h->nel_f);
+        CK(cudaGetLastError());
+    }
+    CK(cudaDeviceSynchronize());
+    cudaFree(d_tmp);
+    if (upload_padded(h, h->M0_w_fl, M0_w_fl, (size_t)NP * h->nel_f, (size_t)NP * h->nel_pad_f)) return 1;
     UP(h->inv_mass_fluid, inv_mass_fluid, n);
-    UP(h->fs_mask, fluid_free_surface_mask, n);
-    if (h->nel_f && (!h->M1chi || !h->M2chi || !h->M4chi || !h->inv_mass_fluid))
-        return fail("axb_set_fluid_terms: NULL plane");
     return 0;
 }
 
@@ -700,7 +726,10 @@ int axb_finalize_setup(axb_handle h) {
     if (use(h)) return 1;
     if (h->nel_s > 0 && !h->inv_mass_rho) return fail("axb_set_mass not called");
     if (h->nel_s > 0 && !h->have_solid_terms) return fail("axb_set_solid_terms not called");
-    const size_t ns = h->css * 3, nf = (size_t)NPT * h->nel_f;
+    if (h->nel_f > 0 && !h->d_coef_f) return fail("axb_set_fluid_terms not called");
+    if (h->nel_f > 0 && h->order != 0 && h->npl_f < 4) return fail("axb_set_fluid_terms: M_w_fl is required for dipole/quadrupole sources");
+    if (h->nel_f > 0 && h->order != 0 && !h->M0_w_fl) return fail("axb_set_fluid_terms: M0_w_fl is required for dipole/quadrupole sources");
+    const size_t ns = h->css * 3, nf = (size_t)NPT * h->nel_pad_f;
     if (ns > 0x7fffffffULL) return fail("too many solid points for 32-bit point addresses");
     if (dzeros(h, h->disp, ns) || dzeros(h, h->velo, ns) || dzeros(h, h->acc0, ns) || dzeros(h, h->acc1, ns)) return 1;
     if (dzeros(h, h->chi, nf) || dzeros(h, h->dchi, nf) || dzeros(h, h->ddchi0, nf) || dzeros(h, h->ddchi1, nf)) return 1;
@@ -715,16 +744,18 @@ int axb_finalize_setup(axb_handle h) {
     if (build_asm(h, h->nel_f, h->nglob_f, h->igloc_f, h->halo[1], h->d_asm_gid_f, h->d_asm_grp_f)) return 1;
     if (build_halo_send(h, h->nel_s, h->nglob_s, h->igloc_s, h->halo[0])) return 1;
     if (build_halo_send(h, h->nel_f, h->nglob_f, h->igloc_f, h->halo[1])) return 1;
-    // S/F boundary seen from the fluid elements
+    // per-tile element metadata of the fluid kernel: axis flag, S/F boundary entry (1-based)
+    // of the jpol=0 row and of the jpol=npol row
     if (h->nel_f) {
-        std::vector<int2> bo(h->nel_f, make_int2(0, 0));
+        std::vector<int> mf((size_t)h->nel_pad_f * 3, 0);
+        auto at = [&](int e, int row) -> int & { return mf[((size_t)(e / TE) * 3 + row) * TE + e % TE]; };
+        for (int e = 0; e < h->nel_f; e++) at(e, 0) = h->axis_f_h[e] != 0;
         for (int b = 0; b < h->nel_bdry; b++) {
-            int2 &r = bo[h->bdry_fel_h[b] - 1];
-            int &slot = (h->bdry_jf_h[b] == 0) ? r.x : r.y;
+            int &slot = at(h->bdry_fel_h[b] - 1, h->bdry_jf_h[b] == 0 ? 1 : 2);
             if (slot != 0) return fail("two S/F boundary entries on the same fluid edge");
             slot = b + 1;
         }
-        UP(h->d_bdry_of_el, bo.data(), bo.size());
+        UP(h->d_meta_f, mf.data(), mf.size());
     }
     // per-tile element metadata of the solid kernel: axis flag, a_j table rows
     std::vector<int> meta((size_t)std::max(h->nel_pad_s, TE) * 3, 0);
@@ -790,17 +821,32 @@ int axb_finalize_setup(axb_handle h) {
     CK(cudaGetDeviceProperties(&prop, h->device));
     const int sms = prop.multiProcessorCount;
     h->sms = sms;
-    h->grid_f = std::max(1, std::min(cdiv(h->nel_f, 8), sms * 8));
+    h->grid_f = std::max(1, std::min(cdiv(h->nel_f, 8), sms * 8));     // k_dump_fluid
+    if (h->nel_f > 0) {
+        // F_A: two persistent CTAs per SM, each with its own ring
+        const size_t cap = std::min<size_t>(prop.sharedMemPerBlockOptin, prop.sharedMemPerMultiprocessor / 2 - 1024);
+        const size_t sb = fluid_stage_bytes(h->npl_f);
+        int nst = (int)std::min<size_t>(FLUID_MAX_STAGES, (cap - FLUID_HDR_BYTES) / sb);
+        if (nst < 2) return fail("not enough shared memory for the fluid tile ring");
+        h->nst_f = nst;
+        h->smem_fluid = FLUID_HDR_BYTES + (size_t)nst * sb;
+        h->grid_ft = std::max(1, std::min(h->nel_pad_f / TE, 2 * sms));
+        CK(cudaFuncSetAttribute(k_fluid_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fluid));
+    }
     if (h->nel_s > 0) {
         // S_A: one persistent CTA per SM; the ring takes all the shared memory it can get
         const SolidTileLayout Ly = solid_tile_layout(h->order, h->anel, h->n_sls);
-        const size_t cap = prop.sharedMemPerBlockOptin;
+        // shared memory per CTA: the opt-in maximum, or an equal share of the SM (minus the
+        // 1 KiB the driver reserves per CTA) when several CTAs are resident
+        const size_t cap = SOLID_CTAS_PER_SM == 1 ? prop.sharedMemPerBlockOptin
+                         : std::min<size_t>(prop.sharedMemPerBlockOptin,
+                                            prop.sharedMemPerMultiprocessor / SOLID_CTAS_PER_SM - 1024);
         if (cap < Ly.hdr_bytes + 2 * Ly.stage_bytes) return fail("not enough shared memory for the solid tile ring");
         int nst = (int)std::min<size_t>(MAX_STAGES, (cap - Ly.hdr_bytes) / Ly.stage_bytes);
         if (const char *ev = getenv("AXB_SOLID_STAGES")) nst = std::max(2, std::min(nst, atoi(ev)));
         h->nst = nst;
         h->smem_solid = Ly.hdr_bytes + (size_t)nst * Ly.stage_bytes;
-        h->grid_s = std::max(1, std::min(h->nel_pad_s / TE, sms));
+        h->grid_s = std::max(1, std::min(h->nel_pad_s / TE, sms * SOLID_CTAS_PER_SM));
         // compiled variants: elastic, the reference default NR_LIN_SOLIDS 5, any other n_sls
         const int v = !h->anel ? 0 : (h->n_sls == 5 ? 1 : 2);
         static solid_kernel_t const table[3][3] = {
@@ -808,7 +854,7 @@ int axb_finalize_setup(axb_handle h) {
             {k_solid_tile<1, 0>, k_solid_tile<1, 5>, k_solid_tile<1, -1>},
             {k_solid_tile<2, 0>, k_solid_tile<2, 5>, k_solid_tile<2, -1>}};
         h->solid_kernel = table[h->order][v];
-        CK(cudaFuncSetAttribute(h->solid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+        CK(cudaFuncSetAttribute(h->solid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_solid));
     }
     h->iter = h->iseismo = h->istrain = 0;
     h->finalized = true;
@@ -963,17 +1009,18 @@ static void launch_solid_element(axb_handle_s *h, const SolidTileArgs &a) {
 static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1, int full, int use_mask) {
     if (h->nel_f == 0) return;
     CLS(h, 1);
-    FluidStepArgs a;
+    FluidTileArgs a;
     std::memset(&a, 0, sizeof a);
-    a.nel = h->nel_f; a.mode = mode; a.order = h->order; a.full = full; a.dt = c0; a.half_dt_sq = c1;
-    a.chi = h->chi; a.ddchi1 = h->ddchi1; a.dchi = h->dchi; a.ddchi0 = h->ddchi0; a.axis = h->d_axis_f;
-    a.M1chi = h->M1chi; a.M2chi = h->M2chi; a.M4chi = h->M4chi; a.M_w_fl = h->M_w_fl; a.M0_w_fl = h->M0_w_fl;
-    a.fs_mask = h->fs_mask; a.bdry_of_el = h->d_bdry_of_el; a.bdry_sel = h->d_bsel; a.bdry_js = h->d_bjs;
-    a.bdry_matr = h->d_bmatr; a.nel_bdry = h->nel_bdry; a.disp = h->disp; a.cs_solid = h->css;
+    a.ntiles = h->nel_pad_f / TE; a.mode = mode; a.order = h->order; a.full = full;
+    a.npl = h->npl_f; a.mask_plane = h->mask_plane_f; a.nst = h->nst_f; a.dt = c0; a.half_dt_sq = c1;
+    a.chi = h->chi; a.ddchi1 = h->ddchi1; a.dchi = h->dchi; a.ddchi0 = h->ddchi0;
+    a.coef = h->d_coef_f; a.meta = h->d_meta_f; a.M0_w_fl = h->M0_w_fl;
+    a.bdry_sel = h->d_bsel; a.bdry_js = h->d_bjs; a.bdry_matr = h->d_bmatr; a.nel_bdry = h->nel_bdry;
+    a.disp = h->disp; a.cs_solid = h->css;
     a.nelsrc = h->fluid_src ? h->nelsrc : 0;
     for (int k = 0; k < 8; k++) a.ielsrc[k] = h->ielsrc[k];
     a.src_term = h->d_src_term; a.stf = h->d_stf; a.iter = h->d_counters; a.use_mask = use_mask;
-    LAUNCH(h, k_fluid_element, h->grid_f, 256, h->G, a);
+    LAUNCH_SMEM(h, k_fluid_tile, h->grid_ft, SOLID_THREADS, h->smem_fluid, h->G, a);
 }
 static void launch_fluid_corr(axb_handle_s *h, int mode, double c, int assemble_only) {
     if (h->nel_f == 0) return;

@@ -1,9 +1,9 @@
 // axb_kernels.cuh — sm_100a kernels of the AxiSEM time loop.
 //
 // Solid elements (S_A): TMA-bulk ring + thread-per-point tiles, see axb_solid_tile.cuh.
-// Fluid elements (F_A): one warp per spectral element, lane q = ipol + 5*jpol (< 25) owns
-// one GLL point; the 5x5 contractions of unrolled_loops.f90:164-188 are done with warp
-// shuffles.  Pointwise kernels (correctors with assembly) are one thread per GLL point.
+// Fluid elements (F_A): the same design, axb_fluid_tile.cuh.  The wavefield-dump kernel of
+// the fluid keeps the warp-per-element mapping with shuffle contractions.  Pointwise kernels
+// (correctors with assembly) are one thread per GLL point.
 //
 // Arithmetic mirrors oracle/axisem_oracle.c statement by statement (same association,
 // real(8) promotion where the Fortran promotes).  Built with -fmad=false the results are
@@ -93,109 +93,8 @@ __device__ __forceinline__ void load_lane_g(const GMat &G, int i, int j, LaneG &
 
 }  // namespace axb
 #include "axb_solid_tile.cuh"
+#include "axb_fluid_tile.cuh"
 namespace axb {
-
-// ---------------------------------------------------------------------------------------
-struct FluidStepArgs {
-    int nel;
-    int mode;                 // 0 Newmark, 1 symplectic drift, 2 none (op test)
-    int order;                // source order (monopole: no M_w term / no axis masks)
-    int full;                 // 1: apply source, S/F coupling and masks (time loop); 0: bare stiffness
-    double dt, half_dt_sq;
-    float *chi, *ddchi1;
-    const float *dchi, *ddchi0;
-    const int *axis;
-    const float *M1chi, *M2chi, *M4chi, *M_w_fl, *M0_w_fl;
-    const float *fs_mask;     // may be null
-    // S/F coupling seen from the fluid: per fluid element the boundary index (1-based, 0 =
-    // none) of its jpol=0 row and of its jpol=4 row
-    const int2 *bdry_of_el;
-    const int *bdry_sel, *bdry_js;
-    const float *bdry_matr;   // (5, nel_bdry, 2)
-    int nel_bdry;
-    const float *disp;        // solid displacement (already predicted)
-    size_t cs_solid;
-    // fluid source
-    int nelsrc;
-    int ielsrc[8];
-    const float *src_term;    // (5,5,8)
-    const float *stf;         // stf(niter) ; index *iter
-    const int *iter;
-    int use_mask;             // Newmark multiplies by the free-surface mask, symplectic does not
-};
-
-// F_A: fluid predictor + stiffness + source + S/F term + masks.
-// Replaces time_evol_wave.F90:357, 366-383 / :597, 604-614 and stiffness_fluid.f90:139-216.
-__global__ void __launch_bounds__(256)
-k_fluid_element(const __grid_constant__ GMat G, const __grid_constant__ FluidStepArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int warps_per_block = blockDim.x >> 5;
-    const bool active = lane < NPT;
-    const int q = active ? lane : 0;
-    const int i = q % NP, j = q / NP, j5 = 5 * j;
-    __shared__ GMat sG;
-    stage_g(G, sG);
-    LaneG L;
-    load_lane_g(sG, i, j, L);
-    for (int e = blockIdx.x * warps_per_block + wib; e < a.nel; e += gridDim.x * warps_per_block) {
-        const size_t pe = (size_t)NPT * e + q;
-        const bool ax = a.axis[e] != 0;
-        float c = 0.f;
-        if (active) {
-            c = a.chi[pe];
-            if (a.mode == 0)
-                c = (float)((double)c + a.dt * (double)a.dchi[pe] + a.half_dt_sq * (double)a.ddchi0[pe]);
-            else if (a.mode == 1)
-                c = (float)((double)c + (double)a.dchi[pe] * a.dt);
-            if (a.full && a.order != 0 && ax && i == 0) c = 0.f;     // apply_axis_mask_scal(chi)
-            if (a.mode != 2) a.chi[pe] = c;
-        }
-        float X1 = ax ? contract_xi(c, L.g1t_row, j5) : contract_xi(c, L.g2t_row, j5);
-        float X2 = contract_eta(c, L.g2_col, i);
-        float m1 = 0.f, m2 = 0.f, m4 = 0.f;
-        if (active) { m1 = a.M1chi[pe]; m2 = a.M2chi[pe]; m4 = a.M4chi[pe]; }
-        float S1 = m1 * X2 + m2 * X1;
-        float S2 = m1 * X1 + m4 * X2;
-        X1 = ax ? contract_xi(S1, L.g1_row, j5) : contract_xi(S1, L.g2_row, j5);
-        X2 = contract_eta(S2, L.g2t_col, i);
-        float l = X1 + X2;
-        if (a.order != 0) {
-            const float mw = active ? a.M_w_fl[pe] : 0.f;
-            l = l + mw * c;
-            if (ax) {
-                const float m0 = a.M0_w_fl[j + NP * (size_t)e];
-                float V1 = contract_vec(c, j5, 1, L.g0);
-                l = l + L.g0_i * (m0 * V1);
-            }
-        }
-        if (a.full && active) {
-            // add_source_fl (time_evol_wave.F90:1062-1076)
-            if (a.nelsrc > 0) {
-                const float stf1 = a.stf[*a.iter];
-                if (stf1 != 0.f)
-                    for (int k = 0; k < a.nelsrc; k++)
-                        if (a.ielsrc[k] - 1 == e) l = l - a.src_term[q + NPT * k] * stf1;
-            }
-            // bdry_copy2fluid (time_evol_wave.F90:1532-1571)
-            if (a.nel_bdry > 0 && (j == 0 || j == 4)) {
-                const int2 bd = a.bdry_of_el[e];
-                const int b = (j == 0 ? bd.x : bd.y) - 1;
-                if (b >= 0) {
-                    const size_t ps = i + NP * a.bdry_js[b] + (size_t)NPT * (a.bdry_sel[b] - 1);
-                    const float B1 = a.bdry_matr[i + NP * (size_t)b];
-                    const float B2 = a.bdry_matr[i + NP * ((size_t)b + a.nel_bdry)];
-                    const float us = a.disp[ps], uz = a.disp[ps + 2 * a.cs_solid];
-                    if (a.order == 1) l = l - B1 * (us + a.disp[ps + a.cs_solid]) - B2 * uz;
-                    else l = l - B1 * us - B2 * uz;
-                }
-            }
-            if (a.order != 0 && ax && i == 0) l = 0.f;                // apply_axis_mask_scal(ddchi1)
-            if (a.use_mask && a.fs_mask) l = l * a.fs_mask[pe];
-        }
-        if (active) a.ddchi1[pe] = l;
-    }
-}
 
 // ---------------------------------------------------------------------------------------
 // Assembly group table (pull-style direct stiffness summation):

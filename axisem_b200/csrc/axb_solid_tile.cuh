@@ -34,6 +34,10 @@ constexpr int NCW = (TP + 31) / 32;      // consumer warps
 constexpr int NCT = NCW * 32;            // consumer threads
 constexpr int SOLID_THREADS = NCT + 32;  // + one producer warp
 constexpr int MAX_STAGES = 8;
+#ifndef AXB_SOLID_CTAS
+#define AXB_SOLID_CTAS 1
+#endif
+constexpr int SOLID_CTAS_PER_SM = AXB_SOLID_CTAS;   // resident CTAs per SM the ring is sized for
 constexpr int NCG = 11;                  // planes of the coarse-grained attenuation slab
 static_assert(TE % 4 == 0, "tile must be a multiple of 4 elements");
 
@@ -179,7 +183,7 @@ __device__ __forceinline__ void axial_rows(const GMat &sG, int i, float (&g1t_ro
 // =======================================================================================
 // NSLS: number of standard linear solids compiled in (0: elastic, -1: run-time a.n_sls)
 template <int ORDER, int NSLS>
-__global__ void __launch_bounds__(SOLID_THREADS, 1)
+__global__ void __launch_bounds__(SOLID_THREADS, SOLID_CTAS_PER_SM)
 k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileArgs a) {
     constexpr int NC = solid_ncomp(ORDER);
     constexpr int NPL = solid_nplanes(ORDER);
