@@ -128,7 +128,8 @@ struct axb_handle_s {
     // state
     float *disp = nullptr, *velo = nullptr, *acc0 = nullptr, *acc1 = nullptr;
     float *chi = nullptr, *dchi = nullptr, *ddchi0 = nullptr, *ddchi1 = nullptr;
-    int *d_asm_gid_s = nullptr, *d_asm_grp_s = nullptr, *d_asm_gid_f = nullptr, *d_asm_grp_f = nullptr;
+    int4 *d_asm_cp_s = nullptr, *d_asm_cp_f = nullptr;
+    int *d_asm_grp_s = nullptr, *d_asm_grp_f = nullptr;
     int *d_counters = nullptr;
     int iter = 0, iseismo = 0, istrain = 0;
     bool acc1_is_acc0 = false;     // after a full step acc1/ddchi1 == acc0/ddchi0 in the reference
@@ -296,7 +297,7 @@ void a_j_of_Q(const axb_handle_s *o, float Q, double *a_j) { // attenuation.f90:
 // Pull-style assembly table (see AsmTable).  Only the 16 edge points of an element take
 // part (commun.F90:110-120); members are listed in ascending element order.
 int build_asm(axb_handle_s *h, int nel, int nglob, const std::vector<int> &igloc, Halo &H,
-              int *&d_gid, int *&d_grp) {
+              int4 *&d_cp, int *&d_grp) {
     static const int edge_q[16] = {0, 1, 2, 3, 4, 5, 9, 10, 14, 15, 19, 20, 21, 22, 23, 24};
     const size_t npts = (size_t)NPT * nel;
     std::vector<int> count(nglob + 1, 0);
@@ -338,15 +339,27 @@ int build_asm(axb_handle_s *h, int nel, int nglob, const std::vector<int> &igloc
             if (goff[g] < 0) return fail("halo point without a local edge copy");
             grp[goff[g] + 2 + count[g + 1] + rfill[g]++] = H.offset[m] + ip;
         }
-    std::vector<int> gid(std::max<size_t>(npts, 1), -1);
+    // per edge point: the int4 fast entry (see AsmTable)
+    std::vector<int4> cp((size_t)std::max(nel, 1) * 16, make_int4(-1, -1, -1, -1));
     for (int e = 0; e < nel; e++)
         for (int k = 0; k < 16; k++) {
             const size_t p = (size_t)e * NPT + edge_q[k];
-            const int64_t o = goff[igloc[p] - 1];
-            gid[p] = o < 0 ? -1 : (int)o;
+            const int g = igloc[p] - 1;
+            const int64_t o = goff[g];
+            if (o < 0) continue;
+            const int nloc = count[g + 1];
+            int4 &c = cp[(size_t)e * 16 + k];
+            if (rcount[g] == 0 && nloc <= 4) {
+                int m[4] = {-1, -1, -1, -1};
+                for (int t = 0; t < nloc; t++) m[t] = members[start[g] + t];
+                c = make_int4(m[0], m[1], m[2], m[3]);
+            } else {
+                c = make_int4(-2, (int)o, 0, 0);
+            }
         }
-    if (upload(h, d_gid, gid.data(), gid.size())) return 1;
+    if (upload(h, d_cp, cp.data(), cp.size())) return 1;
     if (upload(h, d_grp, grp.data(), grp.size())) return 1;
+    (void)npts;
     return 0;
 }
 
@@ -740,8 +753,8 @@ int axb_finalize_setup(axb_handle h) {
         if (dzeros(h, H.recv, (size_t)2 * H.nc * H.nslots)) return 1;
         if (dzeros(h, H.flags, MAXMSG)) return 1;
     }
-    if (build_asm(h, h->nel_s, h->nglob_s, h->igloc_s, h->halo[0], h->d_asm_gid_s, h->d_asm_grp_s)) return 1;
-    if (build_asm(h, h->nel_f, h->nglob_f, h->igloc_f, h->halo[1], h->d_asm_gid_f, h->d_asm_grp_f)) return 1;
+    if (build_asm(h, h->nel_s, h->nglob_s, h->igloc_s, h->halo[0], h->d_asm_cp_s, h->d_asm_grp_s)) return 1;
+    if (build_asm(h, h->nel_f, h->nglob_f, h->igloc_f, h->halo[1], h->d_asm_cp_f, h->d_asm_grp_f)) return 1;
     if (build_halo_send(h, h->nel_s, h->nglob_s, h->igloc_s, h->halo[0])) return 1;
     if (build_halo_send(h, h->nel_f, h->nglob_f, h->igloc_f, h->halo[1])) return 1;
     // per-tile element metadata of the fluid kernel: axis flag, S/F boundary entry (1-based)
@@ -1029,7 +1042,7 @@ static void launch_fluid_corr(axb_handle_s *h, int mode, double c, int assemble_
     a.npts = NPT * h->nel_f; a.mode = mode; a.half_dt = c;
     a.ddchi1 = h->ddchi1; a.ddchi0 = h->ddchi0; a.dchi = h->dchi; a.chi = h->chi;
     a.inv_mass_fluid = h->inv_mass_fluid; a.gamma = h->gamma_f;
-    a.T.gid = h->d_asm_gid_f; a.T.grp = h->d_asm_grp_f;
+    a.T.cp = h->d_asm_cp_f; a.T.grp = h->d_asm_grp_f;
     Halo &H = h->halo[1];
     a.recv = H.recv ? H.recv + (size_t)((H.seq + 1) & 1) * H.nc * H.nslots : nullptr;
     a.recv_cs = H.nslots; a.assemble_only = assemble_only;
@@ -1042,7 +1055,7 @@ static void launch_solid_corr(axb_handle_s *h, int mode, double c, int stf_strid
     a.npts = NPT * h->nel_s; a.cs = h->css; a.order = h->order; a.mode = mode; a.half_dt = c;
     a.acc1 = h->acc1; a.acc0 = h->acc0; a.velo = h->velo; a.disp = h->disp;
     a.inv_mass_rho = h->inv_mass_rho; a.gamma = h->gamma_s;
-    a.T.gid = h->d_asm_gid_s; a.T.grp = h->d_asm_grp_s;
+    a.T.cp = h->d_asm_cp_s; a.T.grp = h->d_asm_grp_s;
     Halo &H = h->halo[0];
     a.recv = H.recv ? H.recv + (size_t)((H.seq + 1) & 1) * H.nc * H.nslots : nullptr;
     a.recv_cs = H.nslots;

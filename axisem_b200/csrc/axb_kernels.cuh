@@ -97,23 +97,29 @@ __device__ __forceinline__ void load_lane_g(const GMat &G, int i, int j, LaneG &
 namespace axb {
 
 // ---------------------------------------------------------------------------------------
-// Assembly group table (pull-style direct stiffness summation):
-// for every element-local point p, gid[p] < 0  -> not shared;
-// else grp[gid[p]] = nloc, grp[..+1] = nrem, then nloc local point addresses in ascending
-// element order (commun.F90:101-128), then nrem receive-slab slots in message order
-// (commpi.F90:469-477).
+// Assembly tables (pull-style direct stiffness summation).  Only the 16
+// edge points of an element can be shared (commun.F90:110-120); each has one int4 entry
+// cp[16*e + slot]:
+//   x == -1        not shared: the point keeps its own value;
+//   x >= 0         2..4 local copies and no remote ones: x,y,z,w (-1 padded) are their point
+//                  addresses in ascending element order — the order commun.F90:101-128 sums in;
+//   x == -2        general group (more copies, or halo partners): grp[y] = nloc, grp[y+1] =
+//                  nrem, then nloc local addresses, then nrem receive-slab slots in message
+//                  order (commpi.F90:469-477).
+// One coalesced 16-byte load then tells a thread everything, and the value loads that
+// follow are independent of each other.
 struct AsmTable {
-    const int *gid;
+    const int4 *cp;
     const int *grp;
 };
-
-__device__ __forceinline__ float assembled(const float *vec, const AsmTable &T, int g,
-                                           const float *recv, size_t recv_cs, int c) {
-    const int nloc = T.grp[g], nrem = T.grp[g + 1];
-    float s = 0.0f;
-    for (int m = 0; m < nloc; m++) s = s + vec[T.grp[g + 2 + m]];
-    for (int m = 0; m < nrem; m++) s = s + recv[T.grp[g + 2 + nloc + m] + recv_cs * c];
-    return s;
+// slot of element-local point q among the 16 edge points (-1: interior)
+__device__ __forceinline__ int edge_slot(int q) {
+    const int j = q / NP, i = q - NP * j;
+    if (j == 0) return i;
+    if (j == NP - 1) return 11 + i;
+    if (i == 0) return 3 + 2 * j;
+    if (i == NP - 1) return 4 + 2 * j;
+    return -1;
 }
 
 struct FluidCorrArgs {
@@ -134,8 +140,25 @@ __global__ void __launch_bounds__(256) k_fluid_corrector(const __grid_constant__
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.npts) return;
     float v = a.ddchi1[p];
-    const int g = a.T.gid[p];
-    if (g >= 0) v = assembled(a.ddchi1, a.T, g, a.recv, a.recv_cs, 0);
+    const int e = p / NPT, slot = edge_slot(p - e * NPT);
+    if (slot >= 0) {
+        const int4 c = a.T.cp[16 * (size_t)e + slot];
+        if (c.x >= 0) {
+            float s = 0.0f;
+            s = s + a.ddchi1[c.x];
+            s = s + a.ddchi1[c.y];
+            if (c.z >= 0) s = s + a.ddchi1[c.z];
+            if (c.w >= 0) s = s + a.ddchi1[c.w];
+            v = s;
+        } else if (c.x == -2) {
+            const int g = c.y;
+            const int nloc = a.T.grp[g], nrem = a.T.grp[g + 1];
+            float s = 0.0f;
+            for (int m = 0; m < nloc; m++) s = s + a.ddchi1[a.T.grp[g + 2 + m]];
+            for (int m = 0; m < nrem; m++) s = s + a.recv[a.T.grp[g + 2 + nloc + m]];
+            v = s;
+        }
+    }
     if (a.assemble_only) { a.ddchi0[p] = v; return; }   // op test: result staged in ddchi0
     if (a.mode == 0) v = -a.inv_mass_fluid[p] * v;
     else v = -v * a.inv_mass_fluid[p];
@@ -223,30 +246,46 @@ __global__ void __launch_bounds__(256) k_solid_corrector(const __grid_constant__
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.npts) return;
     const size_t cs = a.cs;
-    const int g = a.T.gid[p];
+    const int e = p / NPT, q = p - e * NPT, slot = edge_slot(q);
     float v[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         if (ORDER == 0 && c == 1) { v[c] = 0.f; continue; }
         v[c] = a.acc1[p + cs * c];
     }
-    if (g >= 0) {
-        const int nloc = a.T.grp[g], nrem = a.T.grp[g + 1];
-        float s[3] = {0.f, 0.f, 0.f};
-        for (int m = 0; m < nloc; m++) {
-            const int ad = a.T.grp[g + 2 + m];
+    if (slot >= 0) {
+        const int4 cp = a.T.cp[16 * (size_t)e + slot];
+        if (cp.x >= 0) {
 #pragma unroll
-            for (int c = 0; c < 3; c++)
-                if (!(ORDER == 0 && c == 1)) s[c] = s[c] + a.acc1[ad + cs * c];
+            for (int c = 0; c < 3; c++) {
+                if (ORDER == 0 && c == 1) continue;
+                const float *vec = a.acc1 + cs * c;
+                float s = 0.0f;
+                s = s + vec[cp.x];
+                s = s + vec[cp.y];
+                if (cp.z >= 0) s = s + vec[cp.z];
+                if (cp.w >= 0) s = s + vec[cp.w];
+                v[c] = s;
+            }
+        } else if (cp.x == -2) {
+            const int g = cp.y;
+            const int nloc = a.T.grp[g], nrem = a.T.grp[g + 1];
+            float s[3] = {0.f, 0.f, 0.f};
+            for (int m = 0; m < nloc; m++) {
+                const int ad = a.T.grp[g + 2 + m];
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    if (!(ORDER == 0 && c == 1)) s[c] = s[c] + a.acc1[ad + cs * c];
+            }
+            for (int m = 0; m < nrem; m++) {
+                const int sl = a.T.grp[g + 2 + nloc + m];
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    if (!(ORDER == 0 && c == 1)) s[c] = s[c] + a.recv[sl + a.recv_cs * c];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; c++) v[c] = s[c];
         }
-        for (int m = 0; m < nrem; m++) {
-            const int sl = a.T.grp[g + 2 + nloc + m];
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-                if (!(ORDER == 0 && c == 1)) s[c] = s[c] + a.recv[sl + a.recv_cs * c];
-        }
-#pragma unroll
-        for (int c = 0; c < 3; c++) v[c] = s[c];
     }
     if (a.assemble_only) {
         // op test: stage the assembled field in acc0 (acc1 must stay intact while other
@@ -259,7 +298,6 @@ __global__ void __launch_bounds__(256) k_solid_corrector(const __grid_constant__
     if (a.nelsrc > 0) {
         const float stf1 = a.stf[(size_t)(*a.iter) * a.stf_stride + a.stf_off];
         if (stf1 != 0.f) {
-            const int e = p / NPT, q = p - e * NPT;
             for (int k = 0; k < a.nelsrc; k++)
                 if (a.ielsrc[k] - 1 == e) {
 #pragma unroll
