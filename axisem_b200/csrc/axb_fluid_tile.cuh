@@ -124,9 +124,9 @@ k_fluid_tile(const __grid_constant__ GMat G, const __grid_constant__ FluidTileAr
         if (pt) {
             c = S[t];
             if (a.mode == 0)
-                c = (float)((double)c + a.dt * (double)S[TP + t] + a.half_dt_sq * (double)S[2 * TP + t]);
+                c = d2f(f2d(c) + a.dt * f2d(S[TP + t]) + a.half_dt_sq * f2d(S[2 * TP + t]));
             else if (a.mode == 1)
-                c = (float)((double)c + (double)S[TP + t] * a.dt);
+                c = d2f(f2d(c) + f2d(S[TP + t]) * a.dt);
             if (a.full && a.order != 0 && ax && i == 0) c = 0.f;     // apply_axis_mask_scal(chi)
             if (a.mode != 2) { S[t] = c; a.chi[pg] = c; }
         }

@@ -19,6 +19,18 @@ constexpr int NP = 5;
 constexpr int NPT = 25;
 constexpr unsigned FULL = 0xffffffffu;
 
+// real(4) <-> real(8) conversions.  The reference runs with flush-to-zero (SOLVER/ftz.c:44-48)
+// and --ftz=true makes nvcc emulate that on conversions as well, at three instructions each
+// on sm_100a.  The bit-exact build (-DAXB_STRICT) keeps that; the product build converts with
+// a plain cvt, which is identical unless a value is subnormal (below 1.2e-38).
+#ifdef AXB_STRICT
+__device__ __forceinline__ double f2d(float x) { return (double)x; }
+__device__ __forceinline__ float d2f(double x) { return (float)x; }
+#else
+__device__ __forceinline__ double f2d(float x) { double d; asm("cvt.f64.f32 %0, %1;" : "=d"(d) : "f"(x)); return d; }
+__device__ __forceinline__ float d2f(double x) { float f; asm("cvt.rn.f32.f64 %0, %1;" : "=f"(f) : "d"(x)); return f; }
+#endif
+
 struct GMat {            // Fortran order: G(i,j) at [i + 5*j]
     float G0[NP];
     float G1[NPT], G1T[NPT], G2[NPT], G2T[NPT];
@@ -141,6 +153,9 @@ __global__ void __launch_bounds__(256) k_fluid_corrector(const __grid_constant__
     if (p >= a.npts) return;
     float v = a.ddchi1[p];
     const int e = p / NPT, slot = edge_slot(p - e * NPT);
+    const float imf = a.assemble_only ? 0.f : a.inv_mass_fluid[p];
+    const float dc = a.assemble_only ? 0.f : a.dchi[p];
+    const float dd0 = (a.assemble_only || a.mode != 0) ? 0.f : a.ddchi0[p];
     if (slot >= 0) {
         const int4 c = a.T.cp[16 * (size_t)e + slot];
         if (c.x >= 0) {
@@ -160,17 +175,16 @@ __global__ void __launch_bounds__(256) k_fluid_corrector(const __grid_constant__
         }
     }
     if (a.assemble_only) { a.ddchi0[p] = v; return; }   // op test: result staged in ddchi0
-    if (a.mode == 0) v = -a.inv_mass_fluid[p] * v;
-    else v = -v * a.inv_mass_fluid[p];
-    const float dc = a.dchi[p];
+    if (a.mode == 0) v = -imf * v;
+    else v = -v * imf;
     if (a.gamma) {
         const float gm = a.gamma[p];
         v = v - 2 * gm * dc - (gm * gm) * a.chi[p];
     }
     if (a.mode == 0) {
-        a.dchi[p] = (float)((double)dc + a.half_dt * (double)(a.ddchi0[p] + v));
+        a.dchi[p] = d2f(f2d(dc) + a.half_dt * f2d(dd0 + v));
     } else {
-        a.dchi[p] = (float)((double)dc + a.half_dt * (double)v);
+        a.dchi[p] = d2f(f2d(dc) + a.half_dt * f2d(v));
     }
     a.ddchi0[p] = v;          // ddchi0 = ddchi1 (Newmark); also where S_bdry reads it
 }
@@ -247,11 +261,21 @@ __global__ void __launch_bounds__(256) k_solid_corrector(const __grid_constant__
     if (p >= a.npts) return;
     const size_t cs = a.cs;
     const int e = p / NPT, q = p - e * NPT, slot = edge_slot(q);
-    float v[3];
+    // every input of this point is requested up front (the stores below would otherwise
+    // order the per-component loads behind them)
+    float v[3], vel[3], a0[3], dsp[3];
+    const float im = a.assemble_only ? 0.f : a.inv_mass_rho[p];
+    const float gm = (a.gamma && !a.assemble_only) ? a.gamma[p] : 0.f;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-        if (ORDER == 0 && c == 1) { v[c] = 0.f; continue; }
+        v[c] = vel[c] = a0[c] = dsp[c] = 0.f;
+        if (ORDER == 0 && c == 1) continue;
         v[c] = a.acc1[p + cs * c];
+        if (!a.assemble_only) {
+            vel[c] = a.velo[p + cs * c];
+            if (a.mode == 0) a0[c] = a.acc0[p + cs * c];
+            if (a.gamma) dsp[c] = a.disp[p + cs * c];
+        }
     }
     if (slot >= 0) {
         const int4 cp = a.T.cp[16 * (size_t)e + slot];
@@ -306,24 +330,21 @@ __global__ void __launch_bounds__(256) k_solid_corrector(const __grid_constant__
                 }
         }
     }
-    const float im = a.inv_mass_rho[p];
-    const float gm = a.gamma ? a.gamma[p] : 0.f;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         if (ORDER == 0 && c == 1) continue;
         float x = v[c];
-        const float vel = a.velo[p + cs * c];
         if (a.mode == 0) {
-            if (ORDER == 1 && c == 2) x = (float)(-2.0 * (double)im * (double)x);
+            if (ORDER == 1 && c == 2) x = d2f(-2.0 * f2d(im) * f2d(x));
             else x = -im * x;
-            if (a.gamma) x = x - 2 * gm * vel - (gm * gm) * a.disp[p + cs * c];
-            a.velo[p + cs * c] = (float)((double)vel + a.half_dt * (double)(a.acc0[p + cs * c] + x));
+            if (a.gamma) x = x - 2 * gm * vel[c] - (gm * gm) * dsp[c];
+            a.velo[p + cs * c] = d2f(f2d(vel[c]) + a.half_dt * f2d(a0[c] + x));
             a.acc0[p + cs * c] = x;
         } else {
             x = -im * x;
-            if (a.gamma) x = x - 2 * gm * vel - (gm * gm) * a.disp[p + cs * c];
-            if (ORDER == 1 && c == 2) a.velo[p + cs * c] = (float)((double)vel + 2.0 * (double)x * a.half_dt);
-            else a.velo[p + cs * c] = (float)((double)vel + (double)x * a.half_dt);
+            if (a.gamma) x = x - 2 * gm * vel[c] - (gm * gm) * dsp[c];
+            if (ORDER == 1 && c == 2) a.velo[p + cs * c] = d2f(f2d(vel[c]) + 2.0 * f2d(x) * a.half_dt);
+            else a.velo[p + cs * c] = d2f(f2d(vel[c]) + f2d(x) * a.half_dt);
             a.acc0[p + cs * c] = x;     // keeps the reference's `acc` available to get_state
         }
     }
@@ -332,7 +353,7 @@ __global__ void __launch_bounds__(256) k_solid_corrector(const __grid_constant__
 // final drift of a symplectic step (time_evol_wave.F90:720-725)
 __global__ void k_drift(int n, float *x, const float *v, double cd) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < n) x[p] = (float)((double)x[p] + (double)v[p] * cd);
+    if (p < n) x[p] = d2f(f2d(x[p]) + f2d(v[p]) * cd);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -303,9 +303,9 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                 const float *sl = Ub + c * 3 * TP + t;
                 float x = sl[0];
                 if (a.mode == 0)
-                    x = (float)((double)x + a.dt * (double)sl[TP] + a.half_dt_sq * (double)sl[2 * TP]);
+                    x = d2f(f2d(x) + a.dt * f2d(sl[TP]) + a.half_dt_sq * f2d(sl[2 * TP]));
                 else if (a.mode == 1)
-                    x = (float)((double)x + (double)sl[TP] * a.dt);
+                    x = d2f(f2d(x) + f2d(sl[TP]) * a.dt);
                 if (ORDER == 0) { if (c == 0) u1 = x; else u3 = x; }
                 else { if (c == 0) u1 = x; else if (c == 1) u2 = x; else u3 = x; }
             }
@@ -471,11 +471,11 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                 trace = trace + g3;
                 const float dmu = cg[G_dmu * TE * 4], dka = cg[G_dka * TE * 4];
                 const double third = 1.0 / 3.0;
-                const double dm2 = (double)(dmu * 2);
+                const double dm2 = f2d(dmu * 2);
                 float *src = x_src + el * 28 + cgk;
-                src[0] = (float)(dm2 * ((double)g1 - (double)trace * third));
-                src[4] = (float)(dm2 * ((double)g2 - (double)trace * third));
-                src[8] = (float)(dm2 * ((double)g3 - (double)trace * third));
+                src[0] = d2f(dm2 * (f2d(g1) - f2d(trace) * third));
+                src[4] = d2f(dm2 * (f2d(g2) - f2d(trace) * third));
+                src[8] = d2f(dm2 * (f2d(g3) - f2d(trace) * third));
                 src[12] = (ORDER == 0) ? 0.0f : dmu * g4;
                 src[16] = dmu * g5;
                 src[20] = (ORDER == 0) ? 0.0f : dmu * g6;
@@ -604,7 +604,8 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
             }
             if (anel_stiff) {
                 const float *Sa = x_anS + el * 36;
-                const float *ga = ax ? g1_row : L.g2_row;        // GA(i,k)
+                const float ga1 = ax ? g1_row[1] : L.g2_row[1];  // GA(i,1), GA(i,3)
+                const float ga3 = ax ? g1_row[3] : L.g2_row[3];
                 // mxm_cg4_sparse_b(GA, S1): c(i,1) = GA(i,1) S1(1) + GA(i,3) S1(3);
                 //                           c(i,3) = GA(i,1) S1(2) + GA(i,3) S1(4)
                 // mxm_cg4_sparse_a(S2, G2T): c(1,j) = S2(1) G2T(1,j) + S2(2) G2T(3,j);
@@ -615,7 +616,7 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
 #pragma unroll
                 for (int m = 0; m < 3; m++) {
                     const float *S1 = Sa + 8 * m, *S2 = Sa + 8 * m + 4;
-                    Xb[m] = colb ? (ga[1] * S1[kb] + ga[3] * S1[kb + 2]) : 0.0f;
+                    Xb[m] = colb ? (ga1 * S1[kb] + ga3 * S1[kb + 2]) : 0.0f;
                     Xa[m] = rowa ? (S2[ka] * L.g2t_col[1] + S2[ka + 1] * L.g2t_col[3]) : 0.0f;
                 }
                 const bool cg2 = rowa && colb;
@@ -658,9 +659,9 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
             const float s_dev_tm1 = S[Ly.sdev + t];
             const size_t meg = (size_t)tile * TE + mel;
             if (mv_lane) {
-                const double src_tr_t = (double)x_src[mel * 28 + 24 + mv_k];
-                const double s_tr_tm1 = (double)S[Ly.str + mel * 4 + mv_k];
-                const double dsrc_t = (double)src_dev_t, dsrc_tm1 = (double)s_dev_tm1;
+                const double src_tr_t = f2d(x_src[mel * 28 + 24 + mv_k]);
+                const double s_tr_tm1 = f2d(S[Ly.str + mel * 4 + mv_k]);
+                const double dsrc_t = f2d(src_dev_t), dsrc_tm1 = f2d(s_dev_tm1);
                 const double2 *c_mu = a.c_mu_tab + (size_t)n_sls * meta[TE + mel];
                 const double2 *c_ka = a.c_ka_tab + (size_t)n_sls * meta[2 * TE + mel];
                 const float *mv = S + Ly.mv + mel * 24 * n_sls + ml;
@@ -668,14 +669,14 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
 #pragma unroll
                 for (int sl = 0; sl < n_sls; sl++) {
                     const double2 cm = c_mu[sl];
-                    const float dev_buf = (float)(cm.x * dsrc_t + cm.y * dsrc_tm1);
+                    const float dev_buf = d2f(cm.x * dsrc_t + cm.y * dsrc_tm1);
                     float nv;
                     if (mv_v < 3) {
                         const double2 ck = c_ka[sl];
-                        const float tr_buf = (float)(ck.x * src_tr_t + ck.y * s_tr_tm1);
-                        nv = (float)(a.exp_w[sl] * (double)mv[24 * sl] + (double)dev_buf + (double)tr_buf);
+                        const float tr_buf = d2f(ck.x * src_tr_t + ck.y * s_tr_tm1);
+                        nv = d2f(a.exp_w[sl] * f2d(mv[24 * sl]) + f2d(dev_buf) + f2d(tr_buf));
                     } else {
-                        nv = (float)(a.exp_w[sl] * (double)mv[24 * sl] + (double)dev_buf);
+                        nv = d2f(a.exp_w[sl] * f2d(mv[24 * sl]) + f2d(dev_buf));
                     }
                     out[24 * sl] = nv;
                 }

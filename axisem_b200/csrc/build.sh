@@ -8,5 +8,5 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 COMMON=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --ftz=true
         -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -Xlinker -Bsymbolic -Xlinker "--version-script=$HERE/axb.map" -shared -Xptxas -v)
 "$NVCC" "${COMMON[@]}" -o "$OUT/libaxisem_b200.so" "$HERE/axb_api.cu" 2> "$HERE/ptxas_fast.log" || { cat "$HERE/ptxas_fast.log"; exit 1; }
-"$NVCC" "${COMMON[@]}" -fmad=false -o "$OUT/libaxisem_b200_strict.so" "$HERE/axb_api.cu" 2> "$HERE/ptxas_strict.log" || { cat "$HERE/ptxas_strict.log"; exit 1; }
+"$NVCC" "${COMMON[@]}" -fmad=false -DAXB_STRICT=1 -o "$OUT/libaxisem_b200_strict.so" "$HERE/axb_api.cu" 2> "$HERE/ptxas_strict.log" || { cat "$HERE/ptxas_strict.log"; exit 1; }
 echo "built $OUT/libaxisem_b200.so and libaxisem_b200_strict.so"
