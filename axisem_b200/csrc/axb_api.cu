@@ -67,6 +67,9 @@ struct axb_handle_s {
     GMat G;
     int order = 0;
     // solid element kernel inputs in their device layout (axb_solid_tile.cuh)
+    bool rows = true;              // S_A variant: k_solid_rows (tiles of TB) or k_solid_tile (tiles of TE)
+    int te_s = TB;                 // elements per solid tile of the chosen variant
+    int npair = 0;                 // k_solid_rows: warp pairs (= stages) per CTA
     int nel_pad_s = 0;             // nel_s rounded up to whole tiles
     size_t css = 0;                // component stride of disp/velo/acc* = 25 * nel_pad_s
     float *d_coef = nullptr;       // [tile][plane][TP]
@@ -446,7 +449,9 @@ int axb_set_mesh(axb_handle h, int32_t npol, int32_t nel_solid, int32_t nel_flui
     if (npol != 4) return fail("axb_set_mesh: npol must be 4");
     if (use(h)) return 1;
     h->nel_s = nel_solid; h->nel_f = nel_fluid; h->nglob_s = nglob_solid; h->nglob_f = nglob_fluid;
-    h->nel_pad_s = (nel_solid + TE - 1) / TE * TE;
+    if (const char *ev = getenv("AXB_SOLID_KERNEL")) h->rows = std::string(ev) != "tile";
+    h->te_s = h->rows ? TB : TE;
+    h->nel_pad_s = (nel_solid + h->te_s - 1) / h->te_s * h->te_s;
     h->nel_pad_f = (nel_fluid + TE - 1) / TE * TE;
     h->css = (size_t)NPT * h->nel_pad_s;
     h->igloc_s.assign(igloc_solid, igloc_solid + (size_t)NPT * nel_solid);
@@ -485,7 +490,7 @@ static int plane_to_slab(axb_handle_s *h, const float *host_plane, float *d_tmp,
     const size_t n = (size_t)NPT * h->nel_s;
     if (n == 0) return 0;
     CK(cudaMemcpy(d_tmp, host_plane, n * sizeof(float), cudaMemcpyHostToDevice));
-    k_plane_to_slab<<<(unsigned)((n + 255) / 256), 256>>>(d_tmp, h->d_coef, pl, npl, h->nel_s);
+    k_plane_to_slab<<<(unsigned)((n + 255) / 256), 256>>>(d_tmp, h->d_coef, pl, npl, h->nel_s, h->te_s);
     CK(cudaGetLastError());
     return 0;
 }
@@ -514,8 +519,8 @@ int axb_set_solid_terms(axb_handle h, int32_t src_order, const axb_solid_terms *
     for (const float *q : pl)
         if (!q) return fail("axb_set_solid_terms: a plane required for this source order is NULL");
     if (!ok0) return fail("axb_set_solid_terms: an axial vector required for this source order is NULL");
-    const size_t ntiles = h->nel_pad_s / TE;
-    if (dzeros(h, h->d_coef, ntiles * npl * TP)) return 1;
+    const size_t ntiles = h->nel_pad_s / h->te_s;
+    if (dzeros(h, h->d_coef, ntiles * npl * h->te_s * NPT)) return 1;
     float *d_tmp = nullptr;
     CK(cudaMalloc((void **)&d_tmp, (size_t)NPT * h->nel_s * sizeof(float)));
     for (int k = 0; k < npl; k++)
@@ -551,7 +556,7 @@ int axb_set_fluid_terms(axb_handle h, const float *M1chi_fl, const float *M2chi_
     CK(cudaMalloc((void **)&d_tmp, n * sizeof(float)));
     for (int k = 0; k < h->npl_f; k++) {
         CK(cudaMemcpy(d_tmp, pl[k], n * sizeof(float), cudaMemcpyHostToDevice));
-        k_plane_to_slab<<<(unsigned)((n + 255) / 256), 256>>>(d_tmp, h->d_coef_f, k, h->npl_f, h->nel_f);
+        k_plane_to_slab<<<(unsigned)((n + 255) / 256), 256>>>(d_tmp, h->d_coef_f, k, h->npl_f, h->nel_f, TE);
         CK(cudaGetLastError());
     }
     CK(cudaDeviceSynchronize());
@@ -622,14 +627,14 @@ int axb_set_attenuation(axb_handle h, const axb_attenuation *a) {
     for (int k = 0; k < NCG; k++)
         if (!cgp[k]) return fail("axb_set_attenuation: NULL cg4 array");
     if (!a->inv_s_solid) return fail("axb_set_attenuation: NULL inv_s_solid");
-    const size_t ntiles = h->nel_pad_s / TE;
-    if (dzeros(h, h->d_cg, ntiles * NCG * TE * 4)) return 1;
+    const size_t ntiles = h->nel_pad_s / h->te_s;
+    if (dzeros(h, h->d_cg, ntiles * NCG * h->te_s * 4)) return 1;
     if (n4) {
         float *d_tmp = nullptr;
         CK(cudaMalloc((void **)&d_tmp, n4 * sizeof(float)));
         for (int k = 0; k < NCG; k++) {
             CK(cudaMemcpy(d_tmp, cgp[k], n4 * sizeof(float), cudaMemcpyHostToDevice));
-            k_cg_to_slab<<<(unsigned)((n4 + 255) / 256), 256>>>(d_tmp, h->d_cg, k, h->nel_s);
+            k_cg_to_slab<<<(unsigned)((n4 + 255) / 256), 256>>>(d_tmp, h->d_cg, k, h->nel_s, h->te_s);
             CK(cudaGetLastError());
         }
         CK(cudaDeviceSynchronize());
@@ -771,8 +776,9 @@ int axb_finalize_setup(axb_handle h) {
         UP(h->d_meta_f, mf.data(), mf.size());
     }
     // per-tile element metadata of the solid kernel: axis flag, a_j table rows
-    std::vector<int> meta((size_t)std::max(h->nel_pad_s, TE) * 3, 0);
-    auto meta_at = [&](int e, int row) -> int & { return meta[((size_t)(e / TE) * 3 + row) * TE + e % TE]; };
+    const int te = h->te_s;
+    std::vector<int> meta((size_t)std::max(h->nel_pad_s, te) * 3, 0);
+    auto meta_at = [&](int e, int row) -> int & { return meta[((size_t)(e / te) * 3 + row) * te + e % te]; };
     for (int e = 0; e < h->nel_s; e++) meta_at(e, 0) = h->axis_s_h[e] != 0;
     if (h->anel) {
         // a_j tables per distinct Q (time_step_memvars_cg4 recomputes them whenever Q changes)
@@ -847,26 +853,41 @@ int axb_finalize_setup(axb_handle h) {
         CK(cudaFuncSetAttribute(k_fluid_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fluid));
     }
     if (h->nel_s > 0) {
-        // S_A: one persistent CTA per SM; the ring takes all the shared memory it can get
-        const SolidTileLayout Ly = solid_tile_layout(h->order, h->anel, h->n_sls);
-        // shared memory per CTA: the opt-in maximum, or an equal share of the SM (minus the
-        // 1 KiB the driver reserves per CTA) when several CTAs are resident
-        const size_t cap = SOLID_CTAS_PER_SM == 1 ? prop.sharedMemPerBlockOptin
-                         : std::min<size_t>(prop.sharedMemPerBlockOptin,
-                                            prop.sharedMemPerMultiprocessor / SOLID_CTAS_PER_SM - 1024);
-        if (cap < Ly.hdr_bytes + 2 * Ly.stage_bytes) return fail("not enough shared memory for the solid tile ring");
-        int nst = (int)std::min<size_t>(MAX_STAGES, (cap - Ly.hdr_bytes) / Ly.stage_bytes);
-        if (const char *ev = getenv("AXB_SOLID_STAGES")) nst = std::max(2, std::min(nst, atoi(ev)));
-        h->nst = nst;
-        h->smem_solid = Ly.hdr_bytes + (size_t)nst * Ly.stage_bytes;
-        h->grid_s = std::max(1, std::min(h->nel_pad_s / TE, sms * SOLID_CTAS_PER_SM));
         // compiled variants: elastic, the reference default NR_LIN_SOLIDS 5, any other n_sls
         const int v = !h->anel ? 0 : (h->n_sls == 5 ? 1 : 2);
-        static solid_kernel_t const table[3][3] = {
-            {k_solid_tile<0, 0>, k_solid_tile<0, 5>, k_solid_tile<0, -1>},
-            {k_solid_tile<1, 0>, k_solid_tile<1, 5>, k_solid_tile<1, -1>},
-            {k_solid_tile<2, 0>, k_solid_tile<2, 5>, k_solid_tile<2, -1>}};
-        h->solid_kernel = table[h->order][v];
+        const size_t optin = prop.sharedMemPerBlockOptin;
+        if (h->rows) {
+            // S_A (rows): one persistent CTA per SM, one stage per warp pair
+            const SolidRowsLayout Ly = solid_rows_layout(h->order, h->anel, h->n_sls);
+            int npair = (int)std::min<size_t>(ROWS_MAX_PAIRS, (optin - ROWS_HDR_BYTES) / Ly.stage_bytes);
+            if (const char *ev = getenv("AXB_SOLID_PAIRS")) npair = std::max(1, std::min(npair, atoi(ev)));
+            if (npair < 1) return fail("not enough shared memory for one solid stage");
+            h->npair = npair;
+            h->smem_solid = ROWS_HDR_BYTES + (size_t)npair * Ly.stage_bytes;
+            const int ntiles = h->nel_pad_s / TB;
+            h->grid_s = std::max(1, std::min(cdiv(ntiles, npair), sms));
+            static solid_kernel_t const table[3][3] = {
+                {k_solid_rows<0, 0>, k_solid_rows<0, 5>, k_solid_rows<0, -1>},
+                {k_solid_rows<1, 0>, k_solid_rows<1, 5>, k_solid_rows<1, -1>},
+                {k_solid_rows<2, 0>, k_solid_rows<2, 5>, k_solid_rows<2, -1>}};
+            h->solid_kernel = table[h->order][v];
+        } else {
+            // S_A (tile): persistent CTAs; the ring takes all the shared memory it can get
+            const SolidTileLayout Ly = solid_tile_layout(h->order, h->anel, h->n_sls);
+            const size_t cap = SOLID_CTAS_PER_SM == 1 ? optin
+                             : std::min<size_t>(optin, prop.sharedMemPerMultiprocessor / SOLID_CTAS_PER_SM - 1024);
+            if (cap < Ly.hdr_bytes + 2 * Ly.stage_bytes) return fail("not enough shared memory for the solid tile ring");
+            int nst = (int)std::min<size_t>(MAX_STAGES, (cap - Ly.hdr_bytes) / Ly.stage_bytes);
+            if (const char *ev = getenv("AXB_SOLID_STAGES")) nst = std::max(2, std::min(nst, atoi(ev)));
+            h->nst = nst;
+            h->smem_solid = Ly.hdr_bytes + (size_t)nst * Ly.stage_bytes;
+            h->grid_s = std::max(1, std::min(h->nel_pad_s / TE, sms * SOLID_CTAS_PER_SM));
+            static solid_kernel_t const table[3][3] = {
+                {k_solid_tile<0, 0>, k_solid_tile<0, 5>, k_solid_tile<0, -1>},
+                {k_solid_tile<1, 0>, k_solid_tile<1, 5>, k_solid_tile<1, -1>},
+                {k_solid_tile<2, 0>, k_solid_tile<2, 5>, k_solid_tile<2, -1>}};
+            h->solid_kernel = table[h->order][v];
+        }
         CK(cudaFuncSetAttribute(h->solid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_solid));
     }
     h->iter = h->iseismo = h->istrain = 0;
@@ -997,8 +1018,9 @@ static void prof_mark(axb_handle_s *h, bool begin) {
 static SolidTileArgs solid_args(axb_handle_s *h, int mode, double c0, double c1, int anel, int do_stiff) {
     SolidTileArgs a;
     std::memset(&a, 0, sizeof a);
-    a.ntiles = h->nel_pad_s / TE; a.mode = mode; a.do_stiff = do_stiff; a.anel = anel;
+    a.ntiles = h->nel_pad_s / h->te_s; a.mode = mode; a.do_stiff = do_stiff; a.anel = anel;
     a.nst = h->nst; a.n_sls = h->n_sls; a.dt = c0; a.half_dt_sq = c1;
+    if (const char *ev = getenv("AXB_DEBUG_SOLID")) a.dbg = atoi(ev);
     a.disp = h->disp; a.velo = h->velo; a.acc0 = h->acc0; a.acc1 = h->acc1; a.cs = h->css;
     a.coef = h->d_coef; a.meta = h->d_meta;
     for (int k = 0; k < 10; k++) a.M0_w[k] = h->d_M0_w[k];
@@ -1017,7 +1039,7 @@ static SolidTileArgs solid_args(axb_handle_s *h, int mode, double c0, double c1,
 static void launch_solid_element(axb_handle_s *h, const SolidTileArgs &a) {
     if (h->nel_s == 0) return;
     CLS(h, 0);
-    LAUNCH_SMEM(h, h->solid_kernel, h->grid_s, SOLID_THREADS, h->smem_solid, h->G, a);
+    LAUNCH_SMEM(h, h->solid_kernel, h->grid_s, h->rows ? 64 * h->npair : SOLID_THREADS, h->smem_solid, h->G, a);
 }
 static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1, int full, int use_mask) {
     if (h->nel_f == 0) return;

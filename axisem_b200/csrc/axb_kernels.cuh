@@ -105,6 +105,7 @@ __device__ __forceinline__ void load_lane_g(const GMat &G, int i, int j, LaneG &
 
 }  // namespace axb
 #include "axb_solid_tile.cuh"
+#include "axb_solid_rows.cuh"
 #include "axb_fluid_tile.cuh"
 namespace axb {
 

@@ -88,6 +88,7 @@ struct SolidTileArgs {
     int anel;                 // 0 none, 1 cg4 stiffness only, 2 stiffness + memvar update, 3 update only
     int nst;                  // ring depth
     int n_sls;
+    int dbg;                  // developer diagnostics: 1 = consumers only drain the ring (pure load rate)
     double dt, half_dt_sq;    // Newmark: dt, dt^2/2 ; symplectic: coefd in dt
     float *disp, *velo, *acc0, *acc1;
     size_t cs;                // component stride = 25 * padded element count
@@ -287,6 +288,12 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
         mbar_wait(&full[s], ph);
+        if (a.dbg == 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == a.nst) { s = 0; ph ^= 1; }
+            continue;
+        }
         float *S = reinterpret_cast<float *>(ring + (size_t)s * Ly.stage_bytes);
         const int *meta = reinterpret_cast<const int *>(S + Ly.meta);
         const bool ax = meta[el] != 0;
@@ -694,18 +701,18 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
 
 // ---- layout conversion (set-up only): host planes -> tile slabs -------------------------
 // plane (25*nel) -> slab[tile][pl][TP]
-__global__ void k_plane_to_slab(const float *src, float *slab, int pl, int npl, int nel) {
+__global__ void k_plane_to_slab(const float *src, float *slab, int pl, int npl, int nel, int te) {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (size_t)NPT * nel) return;
     const int e = (int)(p / NPT), q = (int)(p - (size_t)e * NPT);
-    slab[((size_t)(e / TE) * npl + pl) * TP + (e % TE) * NPT + q] = src[p];
+    slab[((size_t)(e / te) * npl + pl) * (te * NPT) + (e % te) * NPT + q] = src[p];
 }
 // (4, nel) -> slab[tile][pl][TE*4]
-__global__ void k_cg_to_slab(const float *src, float *slab, int pl, int nel) {
+__global__ void k_cg_to_slab(const float *src, float *slab, int pl, int nel, int te) {
     const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (size_t)4 * nel) return;
     const int e = (int)(p / 4), k = (int)(p & 3);
-    slab[((size_t)(e / TE) * NCG + pl) * TE * 4 + (e % TE) * 4 + k] = src[p];
+    slab[((size_t)(e / te) * NCG + pl) * te * 4 + (e % te) * 4 + k] = src[p];
 }
 
 }  // namespace axb
