@@ -67,8 +67,8 @@ struct axb_handle_s {
     GMat G;
     int order = 0;
     // solid element kernel inputs in their device layout (axb_solid_tile.cuh)
-    bool rows = true;              // S_A variant: k_solid_rows (tiles of TB) or k_solid_tile (tiles of TE)
-    int te_s = TB;                 // elements per solid tile of the chosen variant
+    bool rows = false;             // S_A variant: k_solid_tile (tiles of TE, default) or k_solid_rows (tiles of TB)
+    int te_s = TE;                 // elements per solid tile of the chosen variant
     int npair = 0;                 // k_solid_rows: warp pairs (= stages) per CTA
     int nel_pad_s = 0;             // nel_s rounded up to whole tiles
     size_t css = 0;                // component stride of disp/velo/acc* = 25 * nel_pad_s
@@ -101,8 +101,7 @@ struct axb_handle_s {
     float *d_cg = nullptr;         // [tile][NCG][TE*4]
     float *d_inv_s = nullptr;      // (25 * nel_pad_s)
     double2 *d_c_mu_tab = nullptr, *d_c_ka_tab = nullptr;
-    double *d_exp_w = nullptr;
-    std::vector<double> ts_t_h, ts_tm1_h;
+    std::vector<double> ts_t_h, ts_tm1_h, exp_w_h;
     float *memvar = nullptr, *src_dev_tm1 = nullptr, *src_tr_tm1 = nullptr;
     std::vector<float> Qmu_h, Qka_h;
     std::vector<double> y_j;
@@ -449,7 +448,7 @@ int axb_set_mesh(axb_handle h, int32_t npol, int32_t nel_solid, int32_t nel_flui
     if (npol != 4) return fail("axb_set_mesh: npol must be 4");
     if (use(h)) return 1;
     h->nel_s = nel_solid; h->nel_f = nel_fluid; h->nglob_s = nglob_solid; h->nglob_f = nglob_fluid;
-    if (const char *ev = getenv("AXB_SOLID_KERNEL")) h->rows = std::string(ev) != "tile";
+    if (const char *ev = getenv("AXB_SOLID_KERNEL")) h->rows = std::string(ev) == "rows";
     h->te_s = h->rows ? TB : TE;
     h->nel_pad_s = (nel_solid + h->te_s - 1) / h->te_s * h->te_s;
     h->nel_pad_f = (nel_fluid + TE - 1) / TE * TE;
@@ -613,7 +612,7 @@ int axb_set_attenuation(axb_handle h, const axb_attenuation *a) {
     h->anel = true; h->cg = true; h->corr_lowq = a->do_corr_lowq;
     h->n_sls = a->n_sls;
     h->y_j.assign(a->y_j, a->y_j + a->n_sls);
-    UP(h->d_exp_w, a->exp_w_j_deltat, a->n_sls);
+    h->exp_w_h.assign(a->exp_w_j_deltat, a->exp_w_j_deltat + a->n_sls);
     h->ts_t_h.assign(a->ts_fac_t, a->ts_fac_t + a->n_sls);
     h->ts_tm1_h.assign(a->ts_fac_tm1, a->ts_fac_tm1 + a->n_sls);
     if (!a->Q_mu || !a->Q_kappa) return fail("axb_set_attenuation: NULL Q array");
@@ -1025,7 +1024,8 @@ static SolidTileArgs solid_args(axb_handle_s *h, int mode, double c0, double c1,
     a.coef = h->d_coef; a.meta = h->d_meta;
     for (int k = 0; k < 10; k++) a.M0_w[k] = h->d_M0_w[k];
     a.cg = h->d_cg; a.inv_s = h->d_inv_s;
-    a.c_mu_tab = h->d_c_mu_tab; a.c_ka_tab = h->d_c_ka_tab; a.exp_w = h->d_exp_w;
+    a.c_mu_tab = h->d_c_mu_tab; a.c_ka_tab = h->d_c_ka_tab;
+    for (int k = 0; k < 8; k++) a.exp_w[k] = k < h->n_sls ? h->exp_w_h[k] : 0.0;
     a.memvar = h->memvar; a.src_dev_tm1 = h->src_dev_tm1; a.src_tr_tm1 = h->src_tr_tm1;
     return a;
 }

@@ -632,14 +632,14 @@ k_solid_rows(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
 #pragma unroll
                     for (int sl = 0; sl < n_sls; sl++) {
                         const double2 cm = c_mu[sl];
-                        const float dev_buf = d2f(cm.x * dsrc_t + cm.y * dsrc_tm1);
+                        const double dev_buf = rnd32(cm.x * dsrc_t + cm.y * dsrc_tm1);
                         float nv;
                         if (v < 3) {
                             const double2 ck = c_ka[sl];
-                            const float tr_buf = d2f(ck.x * src_tr_t + ck.y * s_tr_tm1);
-                            nv = d2f(a.exp_w[sl] * f2d(mv[24 * sl]) + f2d(dev_buf) + f2d(tr_buf));
+                            const double tr_buf = rnd32(ck.x * src_tr_t + ck.y * s_tr_tm1);
+                            nv = d2f(a.exp_w[sl] * f2d(mv[24 * sl]) + dev_buf + tr_buf);
                         } else {
-                            nv = d2f(a.exp_w[sl] * f2d(mv[24 * sl]) + f2d(dev_buf));
+                            nv = d2f(a.exp_w[sl] * f2d(mv[24 * sl]) + dev_buf);
                         }
                         mv[24 * sl] = nv;
                     }

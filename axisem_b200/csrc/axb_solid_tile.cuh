@@ -100,7 +100,7 @@ struct SolidTileArgs {
     // per distinct Q and SLS: {ts_fac_t * a_j, ts_fac_tm1 * a_j} (attenuation.f90:162-175 evaluates
     // ts_fac_t(j) * a_j_mu(j) * src left to right, so the first product can be formed once)
     const double2 *c_mu_tab, *c_ka_tab;
-    const double *exp_w;
+    double exp_w[8];          // exp(-w_j deltat) per SLS (constant bank)
     float *memvar, *src_dev_tm1, *src_tr_tm1;
 };
 
@@ -676,14 +676,14 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
 #pragma unroll
                 for (int sl = 0; sl < n_sls; sl++) {
                     const double2 cm = c_mu[sl];
-                    const float dev_buf = d2f(cm.x * dsrc_t + cm.y * dsrc_tm1);
+                    const double dev_buf = rnd32(cm.x * dsrc_t + cm.y * dsrc_tm1);
                     float nv;
                     if (mv_v < 3) {
                         const double2 ck = c_ka[sl];
-                        const float tr_buf = d2f(ck.x * src_tr_t + ck.y * s_tr_tm1);
-                        nv = d2f(a.exp_w[sl] * f2d(mv[24 * sl]) + f2d(dev_buf) + f2d(tr_buf));
+                        const double tr_buf = rnd32(ck.x * src_tr_t + ck.y * s_tr_tm1);
+                        nv = d2f(a.exp_w[sl] * f2d(mv[24 * sl]) + dev_buf + tr_buf);
                     } else {
-                        nv = d2f(a.exp_w[sl] * f2d(mv[24 * sl]) + f2d(dev_buf));
+                        nv = d2f(a.exp_w[sl] * f2d(mv[24 * sl]) + dev_buf);
                     }
                     out[24 * sl] = nv;
                 }
