@@ -68,7 +68,7 @@ struct axb_handle_s {
     int order = 0;
     // solid element kernel inputs in their device layout (axb_solid_tile.cuh)
     bool rows = false;             // S_A variant: k_solid_tile (tiles of TE, default) or k_solid_rows (tiles of TB)
-    int te_s = TE;                 // elements per solid tile of the chosen variant
+    int te_s = TES;                // elements per solid tile of the chosen variant
     int npair = 0;                 // k_solid_rows: warp pairs (= stages) per CTA
     int nel_pad_s = 0;             // nel_s rounded up to whole tiles
     size_t css = 0;                // component stride of disp/velo/acc* = 25 * nel_pad_s
@@ -449,7 +449,7 @@ int axb_set_mesh(axb_handle h, int32_t npol, int32_t nel_solid, int32_t nel_flui
     if (use(h)) return 1;
     h->nel_s = nel_solid; h->nel_f = nel_fluid; h->nglob_s = nglob_solid; h->nglob_f = nglob_fluid;
     if (const char *ev = getenv("AXB_SOLID_KERNEL")) h->rows = std::string(ev) == "rows";
-    h->te_s = h->rows ? TB : TE;
+    h->te_s = h->rows ? TB : TES;
     h->nel_pad_s = (nel_solid + h->te_s - 1) / h->te_s * h->te_s;
     h->nel_pad_f = (nel_fluid + TE - 1) / TE * TE;
     h->css = (size_t)NPT * h->nel_pad_s;
@@ -880,7 +880,7 @@ int axb_finalize_setup(axb_handle h) {
             if (const char *ev = getenv("AXB_SOLID_STAGES")) nst = std::max(2, std::min(nst, atoi(ev)));
             h->nst = nst;
             h->smem_solid = Ly.hdr_bytes + (size_t)nst * Ly.stage_bytes;
-            h->grid_s = std::max(1, std::min(h->nel_pad_s / TE, sms * SOLID_CTAS_PER_SM));
+            h->grid_s = std::max(1, std::min(h->nel_pad_s / TES, sms * SOLID_CTAS_PER_SM));
             static solid_kernel_t const table[3][3] = {
                 {k_solid_tile<0, 0>, k_solid_tile<0, 5>, k_solid_tile<0, -1>},
                 {k_solid_tile<1, 0>, k_solid_tile<1, 5>, k_solid_tile<1, -1>},
@@ -1055,7 +1055,7 @@ static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1
     a.nelsrc = h->fluid_src ? h->nelsrc : 0;
     for (int k = 0; k < 8; k++) a.ielsrc[k] = h->ielsrc[k];
     a.src_term = h->d_src_term; a.stf = h->d_stf; a.iter = h->d_counters; a.use_mask = use_mask;
-    LAUNCH_SMEM(h, k_fluid_tile, h->grid_ft, SOLID_THREADS, h->smem_fluid, h->G, a);
+    LAUNCH_SMEM(h, k_fluid_tile, h->grid_ft, FLUID_THREADS, h->smem_fluid, h->G, a);
 }
 static void launch_fluid_corr(axb_handle_s *h, int mode, double c, int assemble_only) {
     if (h->nel_f == 0) return;
@@ -1180,12 +1180,27 @@ static int newmark_b(axb_handle_s *h) {
     if (halo_send(h, 0, h->acc1, h->css)) return 1;
     return 0;
 }
+// blow-up guard of runtime_info (time_evol_wave.F90:1042-1054), every 100 steps on the device
+static void launch_runtime_info(axb_handle_s *h) {
+    if (h->nel_s == 0 || h->magnitude == 0.0 || h->iter % 100 != 0) return;
+    CLS(h, 7);
+    LAUNCH(h, k_blowup_check, cdiv(h->nel_s, 256), 256, h->disp, h->css, h->nel_s,
+           (float)(10.0 * std::fabs(h->magnitude)), h->d_counters);
+}
+static int check_blowup(axb_handle_s *h) {
+    int it = 0;
+    CK(cudaMemcpyAsync(&it, h->d_counters + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (it != 0) return fail("DISPLACEMENTS BLEW UP: |disp(1,1,:,:)| > 10 |magnitude| at or before time step " + std::to_string(it));
+    return 0;
+}
 static int newmark_c(axb_handle_s *h) {
     halo_wait(h, 0);
     launch_solid_corr(h, 0, h->half_dt, 1, 0, 0);
     CLS(h, 7);
     LAUNCH(h, k_next_iter, 1, 32, h->d_counters);
     h->iter++;
+    launch_runtime_info(h);
     launch_dumps(h);
     return 0;
 }
@@ -1223,6 +1238,7 @@ static int symp_finish(axb_handle_s *h) {
     CLS(h, 7);
     LAUNCH(h, k_next_iter, 1, 32, h->d_counters);
     h->iter++;
+    launch_runtime_info(h);
     launch_dumps(h);
     return 0;
 }
@@ -1267,6 +1283,7 @@ int axb_synchronize(axb_handle h) {
     if (use(h)) return 1;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
+    if (h->finalized && check_blowup(h)) return 1;
     return 0;
 }
 

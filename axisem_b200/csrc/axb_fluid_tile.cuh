@@ -47,7 +47,7 @@ __host__ __device__ constexpr size_t fluid_stage_bytes(int npl) {
 }
 constexpr size_t FLUID_HDR_BYTES = 640;
 
-__global__ void __launch_bounds__(SOLID_THREADS, 2)
+__global__ void __launch_bounds__(FLUID_THREADS, 2)
 k_fluid_tile(const __grid_constant__ GMat G, const __grid_constant__ FluidTileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);

@@ -487,6 +487,18 @@ k_dump_fluid(const __grid_constant__ GMat G, const __grid_constant__ DumpArgs a)
     }
 }
 
+// runtime_info (time_evol_wave.F90:998-1056), the part that matters on the device: the run is
+// declared blown up when max |disp(1,1,:,:)| exceeds 10 |magnitude| (:1042) or is not finite.
+// counters[3] keeps the first offending iteration (0 = fine).
+__global__ void k_blowup_check(const float *disp, size_t cs, int nel, float thresh, int *counters) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nel) return;
+    const size_t p = (size_t)NPT * e + NP + 1;          // point (ipol, jpol) = (1, 1)
+    // written so that NaN counts as blown up (fmaxf would drop it)
+    const bool ok = fabsf(disp[p]) <= thresh && fabsf(disp[p + cs]) <= thresh && fabsf(disp[p + 2 * cs]) <= thresh;
+    if (!ok) atomicCAS(&counters[3], 0, counters[0] > 0 ? counters[0] : 1);
+}
+
 // end of step: iter += 1 ; sample counters advance where a dump happened
 __global__ void k_advance(int *counters, int seis_it, int strain_it, int num_rec, int have_kwf,
                           int nseismo_max, int nstrain_max, int pre) {

@@ -25,23 +25,29 @@
 
 namespace axb {
 
-#ifndef AXB_TE
-#define AXB_TE 16
+#ifndef AXB_TES
+#define AXB_TES 8
 #endif
-constexpr int TE = AXB_TE;               // elements per tile (multiple of 4: 16-byte TMA granules)
-constexpr int TP = TE * NPT;             // points per tile
-constexpr int NCW = (TP + 31) / 32;      // consumer warps
-constexpr int NCT = NCW * 32;            // consumer threads
-constexpr int SOLID_THREADS = NCT + 32;  // + one producer warp
-constexpr int MAX_STAGES = 8;
 #ifndef AXB_SOLID_CTAS
-#define AXB_SOLID_CTAS 1
+#define AXB_SOLID_CTAS 3
 #endif
+constexpr int TES = AXB_TES;             // elements per solid tile (multiple of 4: 16-byte TMA granules)
+constexpr int TPS = TES * NPT;           // points per solid tile
+constexpr int NCWS = (TPS + 31) / 32;    // consumer warps
+constexpr int NCTS = NCWS * 32;          // consumer threads
+constexpr int SOLID_THREADS = NCTS + 32; // + one producer warp
 constexpr int SOLID_CTAS_PER_SM = AXB_SOLID_CTAS;   // resident CTAs per SM the ring is sized for
+constexpr int MAX_STAGES = 8;
 constexpr int NCG = 11;                  // planes of the coarse-grained attenuation slab
-static_assert(TE % 4 == 0, "tile must be a multiple of 4 elements");
+// fluid tiles (axb_fluid_tile.cuh) and the layout-conversion kernels
+constexpr int TE = 16;
+constexpr int TP = TE * NPT;
+constexpr int NCW = (TP + 31) / 32;
+constexpr int NCT = NCW * 32;
+constexpr int FLUID_THREADS = NCT + 32;
+static_assert(TES % 4 == 0 && TE % 4 == 0, "tiles must be multiples of 4 elements");
 
-// plane order inside the coefficient slab [tile][plane][TP]
+// plane order inside the coefficient slab [tile][plane][TPS]
 enum {
     C_M11s = 0, C_M21s, C_M41s, C_M12s, C_M22s, C_M32s, C_M42s, C_M11z, C_M21z, C_M41z,
     C_M_1, C_M_2, C_M_3, C_M_4, C_M_w1,                       // 15: every source order
@@ -50,7 +56,7 @@ enum {
     C_M_5 = 18, C_M_6, C_M_7, C_M_8, C_M_w2, C_M_w3,          // dipole + quadrupole
     C_M_w4 = 24, C_M_w5 = 25                                  // quadrupole
 };
-// plane order inside the attenuation slab [tile][plane][TE*4]
+// plane order inside the attenuation slab [tile][plane][TES*4]
 enum { G_Y = 0, G_Vse, G_Vsx, G_Vze, G_Vzx, G_Dse, G_Dze, G_Dsx, G_Dzx, G_dmu, G_dka };
 
 __host__ __device__ constexpr int solid_ncomp(int order) { return order == 0 ? 2 : 3; }
@@ -64,20 +70,20 @@ struct SolidTileLayout {
 __host__ __device__ constexpr SolidTileLayout solid_tile_layout(int order, bool anel, int n_sls) {
     SolidTileLayout L{};
     int o = 0;
-    L.u = o; o += solid_ncomp(order) * 3 * TP;       // [comp][disp|velo|acc0][TP]
-    L.coef = o; o += solid_nplanes(order) * TP;
-    L.meta = o; o += (3 * TE + 3) / 4 * 4;           // ints: axis, qidx_mu, qidx_ka
+    L.u = o; o += solid_ncomp(order) * 3 * TPS;       // [comp][disp|velo|acc0][TPS]
+    L.coef = o; o += solid_nplanes(order) * TPS;
+    L.meta = o; o += (3 * TES + 3) / 4 * 4;           // ints: axis, qidx_mu, qidx_ka
     L.cg = L.invs = L.sdev = L.str = L.mv = o;
     if (anel) {
-        L.cg = o; o += NCG * TE * 4;
-        L.invs = o; o += TP;
-        L.sdev = o; o += TE * 24;
-        L.str = o; o += TE * 4;
-        L.mv = o; o += TE * 24 * n_sls;
+        L.cg = o; o += NCG * TES * 4;
+        L.invs = o; o += TPS;
+        L.sdev = o; o += TES * 24;
+        L.str = o; o += TES * 4;
+        L.mv = o; o += TES * 24 * n_sls;
     }
     L.floats = o;
     L.stage_bytes = ((size_t)o * 4 + 127) / 128 * 128;
-    L.hdr_bytes = ((size_t)640 + (size_t)TE * 88 * 4 + 127) / 128 * 128;
+    L.hdr_bytes = ((size_t)640 + (size_t)TES * 88 * 4 + 127) / 128 * 128;
     return L;
 }
 
@@ -92,10 +98,10 @@ struct SolidTileArgs {
     double dt, half_dt_sq;    // Newmark: dt, dt^2/2 ; symplectic: coefd in dt
     float *disp, *velo, *acc0, *acc1;
     size_t cs;                // component stride = 25 * padded element count
-    const float *coef;        // [tile][plane][TP]
-    const int *meta;          // [tile][3][TE]
+    const float *coef;        // [tile][plane][TPS]
+    const int *meta;          // [tile][3][TES]
     const float *M0_w[10];    // axial vectors (5, nel_pad); index = number - 1
-    const float *cg;          // [tile][NCG][TE*4]
+    const float *cg;          // [tile][NCG][TES*4]
     const float *inv_s;       // (25 * nel_pad)
     // per distinct Q and SLS: {ts_fac_t * a_j, ts_fac_tm1 * a_j} (attenuation.f90:162-175 evaluates
     // ts_fac_t(j) * a_j_mu(j) * src left to right, so the first product can be formed once)
@@ -194,16 +200,16 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + MAX_STAGES;
     GMat &sG = *reinterpret_cast<GMat *>(smem + 128);
-    float *x_rsum = reinterpret_cast<float *>(smem + 640);     // [TE][24]
-    float *x_anS = x_rsum + TE * 24;                            // [TE][36]
-    float *x_src = x_anS + TE * 36;                             // [TE][28]
+    float *x_rsum = reinterpret_cast<float *>(smem + 640);     // [TES][24]
+    float *x_anS = x_rsum + TES * 24;                            // [TES][36]
+    float *x_src = x_anS + TES * 36;                             // [TES][28]
     const SolidTileLayout Ly = solid_tile_layout(ORDER, NSLS != 0, n_sls);
     unsigned char *ring = smem + Ly.hdr_bytes;
 
     const int t = threadIdx.x;
     const int warp = t >> 5, lane = t & 31;
     if (t == 0) {
-        for (int s = 0; s < a.nst; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
+        for (int s = 0; s < a.nst; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCWS); }
         fence_mbar_init();
     }
     {   // stage the derivative matrices
@@ -217,40 +223,40 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
     const bool anel_update = anel >= 2;
 
     // ---------------------------------------------------------------- producer warp ----
-    if (warp == NCW) {
+    if (warp == NCWS) {
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            const uint32_t plane_b = TP * 4;
-            uint32_t bytes = NC * plane_b * (a.mode == 0 ? 3 : (a.mode == 1 ? 2 : 1)) + 3 * TE * 4;
+            const uint32_t plane_b = TPS * 4;
+            uint32_t bytes = NC * plane_b * (a.mode == 0 ? 3 : (a.mode == 1 ? 2 : 1)) + 3 * TES * 4;
             if (a.do_stiff) bytes += NPL * plane_b;
             if (anel) {
-                bytes += NCG * TE * 16 + TE * 96 * n_sls;
-                if (anel_update) bytes += plane_b + TE * 96 + TE * 16;
+                bytes += NCG * TES * 16 + TES * 96 * n_sls;
+                if (anel_update) bytes += plane_b + TES * 96 + TES * 16;
             }
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 mbar_wait(&empty[s], ph ^ 1);
                 float *S = reinterpret_cast<float *>(ring + (size_t)s * Ly.stage_bytes);
                 uint64_t *bar = &full[s];
                 mbar_expect_tx(bar, bytes);
-                const size_t pg = (size_t)tile * TP;
+                const size_t pg = (size_t)tile * TPS;
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
                     const size_t off = (size_t)((ORDER == 0) ? 2 * c : c) * a.cs + pg;
-                    float *d = S + Ly.u + c * 3 * TP;
+                    float *d = S + Ly.u + c * 3 * TPS;
                     bulk_g2s(d, a.disp + off, plane_b, bar);
-                    if (a.mode != 2) bulk_g2s(d + TP, a.velo + off, plane_b, bar);
-                    if (a.mode == 0) bulk_g2s(d + 2 * TP, a.acc0 + off, plane_b, bar);
+                    if (a.mode != 2) bulk_g2s(d + TPS, a.velo + off, plane_b, bar);
+                    if (a.mode == 0) bulk_g2s(d + 2 * TPS, a.acc0 + off, plane_b, bar);
                 }
-                if (a.do_stiff) bulk_g2s(S + Ly.coef, a.coef + (size_t)tile * NPL * TP, NPL * plane_b, bar);
-                bulk_g2s(S + Ly.meta, a.meta + (size_t)tile * 3 * TE, 3 * TE * 4, bar);
+                if (a.do_stiff) bulk_g2s(S + Ly.coef, a.coef + (size_t)tile * NPL * TPS, NPL * plane_b, bar);
+                bulk_g2s(S + Ly.meta, a.meta + (size_t)tile * 3 * TES, 3 * TES * 4, bar);
                 if (anel) {
-                    bulk_g2s(S + Ly.cg, a.cg + (size_t)tile * NCG * TE * 4, NCG * TE * 16, bar);
-                    bulk_g2s(S + Ly.mv, a.memvar + (size_t)tile * TE * 24 * n_sls, TE * 96 * n_sls, bar);
+                    bulk_g2s(S + Ly.cg, a.cg + (size_t)tile * NCG * TES * 4, NCG * TES * 16, bar);
+                    bulk_g2s(S + Ly.mv, a.memvar + (size_t)tile * TES * 24 * n_sls, TES * 96 * n_sls, bar);
                     if (anel_update) {
                         bulk_g2s(S + Ly.invs, a.inv_s + pg, plane_b, bar);
-                        bulk_g2s(S + Ly.sdev, a.src_dev_tm1 + (size_t)tile * TE * 24, TE * 96, bar);
-                        bulk_g2s(S + Ly.str, a.src_tr_tm1 + (size_t)tile * TE * 4, TE * 16, bar);
+                        bulk_g2s(S + Ly.sdev, a.src_dev_tm1 + (size_t)tile * TES * 24, TES * 96, bar);
+                        bulk_g2s(S + Ly.str, a.src_tr_tm1 + (size_t)tile * TES * 4, TES * 16, bar);
                     }
                 }
                 if (++s == a.nst) { s = 0; ph ^= 1; }
@@ -260,7 +266,7 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
     }
 
     // --------------------------------------------------------------- consumer warps ----
-    const bool pt = t < TP;                     // this thread owns point t of the tile
+    const bool pt = t < TPS;                     // this thread owns point t of the tile
     const int el = pt ? t / NPT : 0;            // element inside the tile
     const int q = pt ? t - el * NPT : 0;
     const int i = q % NP, j = q / NP;
@@ -277,8 +283,8 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
     const bool rowa = (i == 1) || (i == 3), colb = (j == 1) || (j == 3);
     const bool cgpt = pt && rowa && colb;
     const int cgk = (i == 1 ? 0 : 2) + (j == 1 ? 0 : 1);       // coarse index of (i,j)
-    // memory-variable role: t < 24*TE  <->  (element t/24, l = t%24 = 4*v + k)
-    const bool mvt = t < TE * 24;
+    // memory-variable role: t < 24*TES  <->  (element t/24, l = t%24 = 4*v + k)
+    const bool mvt = t < TES * 24;
     const int mel = mvt ? t / 24 : 0;
     const int ml = mvt ? t - mel * 24 : 0;
     const int mv_v = ml >> 2, mv_k = ml & 3;
@@ -297,22 +303,22 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
         float *S = reinterpret_cast<float *>(ring + (size_t)s * Ly.stage_bytes);
         const int *meta = reinterpret_cast<const int *>(S + Ly.meta);
         const bool ax = meta[el] != 0;
-        const size_t pg = (size_t)tile * TP + t;
-        const int eg = tile * TE + el;
-        float *Ub = S + Ly.u;                   // slot (c, k) at Ub + (3c + k) * TP
-        const float *Cf = S + Ly.coef + t;      // coefficient n of this point: Cf[n * TP]
+        const size_t pg = (size_t)tile * TPS + t;
+        const int eg = tile * TES + el;
+        float *Ub = S + Ly.u;                   // slot (c, k) at Ub + (3c + k) * TPS
+        const float *Cf = S + Ly.coef + t;      // coefficient n of this point: Cf[n * TPS]
 
         // ---- phase 1: predictor / drift, axis mask -> U in shared memory + disp in HBM ----
         float u1 = 0.f, u2 = 0.f, u3 = 0.f;
         if (pt) {
 #pragma unroll
             for (int c = 0; c < NC; c++) {
-                const float *sl = Ub + c * 3 * TP + t;
+                const float *sl = Ub + c * 3 * TPS + t;
                 float x = sl[0];
                 if (a.mode == 0)
-                    x = d2f(f2d(x) + a.dt * f2d(sl[TP]) + a.half_dt_sq * f2d(sl[2 * TP]));
+                    x = d2f(f2d(x) + a.dt * f2d(sl[TPS]) + a.half_dt_sq * f2d(sl[2 * TPS]));
                 else if (a.mode == 1)
-                    x = d2f(f2d(x) + f2d(sl[TP]) * a.dt);
+                    x = d2f(f2d(x) + f2d(sl[TPS]) * a.dt);
                 if (ORDER == 0) { if (c == 0) u1 = x; else u3 = x; }
                 else { if (c == 0) u1 = x; else if (c == 1) u2 = x; else u3 = x; }
             }
@@ -324,10 +330,10 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
             }
             if (a.mode != 2) {
                 if (ORDER == 0) {
-                    Ub[t] = u1; Ub[3 * TP + t] = u3;
+                    Ub[t] = u1; Ub[3 * TPS + t] = u3;
                     a.disp[pg] = u1; a.disp[pg + 2 * a.cs] = u3;
                 } else {
-                    Ub[t] = u1; Ub[3 * TP + t] = u2; Ub[6 * TP + t] = u3;
+                    Ub[t] = u1; Ub[3 * TPS + t] = u2; Ub[6 * TPS + t] = u3;
                     a.disp[pg] = u1; a.disp[pg + a.cs] = u2; a.disp[pg + 2 * a.cs] = u3;
                 }
             }
@@ -342,13 +348,13 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
             }
             x_rsum[t] = rsum;
         }
-        bar_consumers<NCT>();
+        bar_consumers<NCTS>();
 
         // ---- phase 2: first-stage contractions, point-wise combinations -> S planes ----
         const int cu3 = (ORDER == 0) ? 1 : 2;   // slot row of the z component
         const float *U1xi = Ub + e25 + 5 * j, *U1et = Ub + e25 + i;
-        const float *U2xi = U1xi + 3 * TP, *U2et = U1et + 3 * TP;              // ORDER != 0
-        const float *U3xi = U1xi + cu3 * 3 * TP, *U3et = U1et + cu3 * 3 * TP;
+        const float *U2xi = U1xi + 3 * TPS, *U2et = U1et + 3 * TPS;              // ORDER != 0
+        const float *U3xi = U1xi + cu3 * 3 * TPS, *U3et = U1et + cu3 * 3 * TPS;
         float l1 = 0.f, l2 = 0.f, l3 = 0.f;
         float X[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (pt) {
@@ -365,12 +371,12 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                 }
             }
             if (a.do_stiff) {
-                const float m11s = Cf[C_M11s * TP], m21s = Cf[C_M21s * TP], m41s = Cf[C_M41s * TP];
-                const float m12s = Cf[C_M12s * TP], m22s = Cf[C_M22s * TP], m32s = Cf[C_M32s * TP];
-                const float m42s = Cf[C_M42s * TP];
-                const float m11z = Cf[C_M11z * TP], m21z = Cf[C_M21z * TP], m41z = Cf[C_M41z * TP];
-                const float m_1 = Cf[C_M_1 * TP], m_2 = Cf[C_M_2 * TP], m_3 = Cf[C_M_3 * TP], m_4 = Cf[C_M_4 * TP];
-                const float m_w1 = Cf[C_M_w1 * TP];
+                const float m11s = Cf[C_M11s * TPS], m21s = Cf[C_M21s * TPS], m41s = Cf[C_M41s * TPS];
+                const float m12s = Cf[C_M12s * TPS], m22s = Cf[C_M22s * TPS], m32s = Cf[C_M32s * TPS];
+                const float m42s = Cf[C_M42s * TPS];
+                const float m11z = Cf[C_M11z * TPS], m21z = Cf[C_M21z * TPS], m41z = Cf[C_M41z * TPS];
+                const float m_1 = Cf[C_M_1 * TPS], m_2 = Cf[C_M_2 * TPS], m_3 = Cf[C_M_3 * TPS], m_4 = Cf[C_M_4 * TPS];
+                const float m_w1 = Cf[C_M_w1 * TPS];
                 float *Sb = Ub + t;              // S planes: slots (c,1) and (c,2)
                 if (ORDER == 0) {
                     // stiffness_mono.f90:60-157
@@ -380,12 +386,12 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                     const float S2s = m11s * X1 + m41s * X3 + m32s * X2 + m42s * X4 + m_2 * us;
                     const float S1z = m11z * X4 + m21z * X2 + m32s * X3 + m22s * X1 + m_3 * us;
                     const float S2z = m11z * X2 + m41z * X4 + m12s * X1 + m42s * X3 + m_4 * us;
-                    Sb[1 * TP] = S1s; Sb[2 * TP] = S2s; Sb[4 * TP] = S1z; Sb[5 * TP] = S2z;
+                    Sb[1 * TPS] = S1s; Sb[2 * TPS] = S2s; Sb[4 * TPS] = S1z; Sb[5 * TPS] = S2z;
                 } else if (ORDER == 1) {
                     // stiffness_di.f90:60-256
-                    const float m13s = Cf[C_M13s * TP], m23s = m32s, m33s = Cf[C_M33s * TP], m43s = Cf[C_M43s * TP];
-                    const float m_5 = Cf[C_M_5 * TP], m_6 = Cf[C_M_6 * TP], m_7 = Cf[C_M_7 * TP], m_8 = Cf[C_M_8 * TP];
-                    const float m_w2 = Cf[C_M_w2 * TP], m_w3 = Cf[C_M_w3 * TP];
+                    const float m13s = Cf[C_M13s * TPS], m23s = m32s, m33s = Cf[C_M33s * TPS], m43s = Cf[C_M43s * TPS];
+                    const float m_5 = Cf[C_M_5 * TPS], m_6 = Cf[C_M_6 * TPS], m_7 = Cf[C_M_7 * TPS], m_8 = Cf[C_M_8 * TPS];
+                    const float m_w2 = Cf[C_M_w2 * TPS], m_w3 = Cf[C_M_w3 * TPS];
                     const float X1 = X[0], X2 = X[1], X3 = X[2], X4 = X[3], X5 = X[4], X6 = X[5];
                     const float X7 = X1 + X2;
                     const float X8 = X4 + X5;
@@ -399,14 +405,14 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                     const float S2m = c1 + c2 - c3 + m11s * X2 + m41s * X5 + m12s * X1 + m42s * X4 + m_6 * u2;
                     const float S1z = m33s * X8 + m23s * X7 + m11z * X6 + m21z * X3 + m_7 * u2;
                     const float S2z = m13s * X7 + m43s * X8 + m11z * X3 + m41z * X6 + m_8 * u2;
-                    Sb[1 * TP] = S1p; Sb[2 * TP] = S2p; Sb[4 * TP] = S1m; Sb[5 * TP] = S2m;
-                    Sb[7 * TP] = S1z; Sb[8 * TP] = S2z;
+                    Sb[1 * TPS] = S1p; Sb[2 * TPS] = S2p; Sb[4 * TPS] = S1m; Sb[5 * TPS] = S2m;
+                    Sb[7 * TPS] = S1z; Sb[8 * TPS] = S2z;
                 } else {
                     // stiffness_quad.f90:238-412
-                    const float m1phi = Cf[C_M1phi * TP], m2phi = Cf[C_M2phi * TP], m4phi = Cf[C_M4phi * TP];
-                    const float m_5 = Cf[C_M_5 * TP], m_6 = Cf[C_M_6 * TP], m_7 = Cf[C_M_7 * TP], m_8 = Cf[C_M_8 * TP];
-                    const float m_w2 = Cf[C_M_w2 * TP], m_w3 = Cf[C_M_w3 * TP];
-                    const float m_w4 = Cf[C_M_w4 * TP], m_w5 = Cf[C_M_w5 * TP];
+                    const float m1phi = Cf[C_M1phi * TPS], m2phi = Cf[C_M2phi * TPS], m4phi = Cf[C_M4phi * TPS];
+                    const float m_5 = Cf[C_M_5 * TPS], m_6 = Cf[C_M_6 * TPS], m_7 = Cf[C_M_7 * TPS], m_8 = Cf[C_M_8 * TPS];
+                    const float m_w2 = Cf[C_M_w2 * TPS], m_w3 = Cf[C_M_w3 * TPS];
+                    const float m_w4 = Cf[C_M_w4 * TPS], m_w5 = Cf[C_M_w5 * TPS];
                     const float X1 = X[0], X2 = X[1], X3 = X[2], X4 = X[3], X5 = X[4], X6 = X[5];
                     const float us = u1, up = u2, uz = u3;
                     const float c1 = m_2 * X4, c2 = m_1 * X1, c3 = m_6 * X5, c4 = m_5 * X2, c5 = m_4 * X6, c6 = m_3 * X3;
@@ -419,8 +425,8 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                     const float S2z = m11z * X3 + m41z * X6 + m12s * X1 + m42s * X4 + m_4 * (us - 2 * up);
                     const float S1p = m1phi * X5 + m2phi * X2 + m_5 * (2 * us - up) + 2 * m_7 * uz;
                     const float S2p = m1phi * X2 + m4phi * X5 + m_6 * (2 * us - up) + 2 * m_8 * uz;
-                    Sb[1 * TP] = S1s; Sb[2 * TP] = S2s; Sb[4 * TP] = S1p; Sb[5 * TP] = S2p;
-                    Sb[7 * TP] = S1z; Sb[8 * TP] = S2z;
+                    Sb[1 * TPS] = S1s; Sb[2 * TPS] = S2s; Sb[4 * TPS] = S1p; Sb[5 * TPS] = S2p;
+                    Sb[7 * TPS] = S1z; Sb[8 * TPS] = S2z;
                 }
             } else {
                 // anelastic-only operator test: start from the stored acc1
@@ -431,8 +437,8 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
             // ---- strain at the coarse points (compute_strain_att_el_cg4, attenuation.f90:471-535)
             if (anel_update && cgpt) {
                 const float *cg = S + Ly.cg + el * 4 + cgk;
-                const float dzdeta = cg[G_Dze * TE * 4], dzdxi = cg[G_Dzx * TE * 4];
-                const float dsdeta = cg[G_Dse * TE * 4], dsdxi = cg[G_Dsx * TE * 4];
+                const float dzdeta = cg[G_Dze * TES * 4], dzdxi = cg[G_Dzx * TES * 4];
+                const float dsdeta = cg[G_Dse * TES * 4], dsdxi = cg[G_Dsx * TES * 4];
                 const float is = S[Ly.invs + t];
                 float g1, g2, g3, g4 = 0.f, g5, g6 = 0.f;
                 // gradient of f: ds = dzdeta*m1 + dzdxi*m2 ; dz = dsdeta*m1 + dsdxi*m2
@@ -476,7 +482,7 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                 }
                 float trace = g1 + g2;
                 trace = trace + g3;
-                const float dmu = cg[G_dmu * TE * 4], dka = cg[G_dka * TE * 4];
+                const float dmu = cg[G_dmu * TES * 4], dka = cg[G_dka * TES * 4];
                 const double third = 1.0 / 3.0;
                 const double dm2 = f2d(dmu * 2);
                 float *src = x_src + el * 28 + cgk;
@@ -490,12 +496,12 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
             }
         }
         // ---- anelastic S terms at the four coarse points (glob_anel_stiffness_*_cg4) ----
-        if (anel_stiff && t < TE * 4) {
+        if (anel_stiff && t < TES * 4) {
             const int ce = t >> 2, ck = t & 3;
-            const float *cg = S + Ly.cg + t;                // [plane][TE*4], index ce*4+ck = t
-            const float yl = cg[G_Y * TE * 4];
-            const float vse = cg[G_Vse * TE * 4], vsx = cg[G_Vsx * TE * 4];
-            const float vze = cg[G_Vze * TE * 4], vzx = cg[G_Vzx * TE * 4];
+            const float *cg = S + Ly.cg + t;                // [plane][TES*4], index ce*4+ck = t
+            const float yl = cg[G_Y * TES * 4];
+            const float vse = cg[G_Vse * TES * 4], vsx = cg[G_Vsx * TES * 4];
+            const float vze = cg[G_Vze * TES * 4], vzx = cg[G_Vzx * TES * 4];
             const float *r = x_rsum + ce * 24 + ck;
             const float r1 = r[0], r2 = r[4], r3 = r[8], r4 = r[12], r5 = r[16], r6 = r[20];
             float *Sa = x_anS + ce * 36 + ck;               // Sa[4a], a = 0..5 ; extras at 24,28,32
@@ -526,7 +532,7 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                 Sa[32] = 2 * yl * r4;
             }
         }
-        bar_consumers<NCT>();
+        bar_consumers<NCTS>();
 
         // ---- phase 3: second-stage contractions, axial terms, anelastic correction ----
         if (pt) {
@@ -534,10 +540,10 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
             if (ax) axial_rows(sG, i, g1t_row, g1_row, g0);
             if (a.do_stiff) {
                 const float *Sxi = Ub + e25 + 5 * j, *Set = Ub + e25 + i;
-                const float Y1 = ax ? cxi(Sxi + 1 * TP, g1_row) : cxi(Sxi + 1 * TP, L.g2_row);
-                const float Y2 = ceta(Set + 2 * TP, L.g2t_col);
-                const float Y3 = ax ? cxi(Sxi + 4 * TP, g1_row) : cxi(Sxi + 4 * TP, L.g2_row);
-                const float Y4 = ceta(Set + 5 * TP, L.g2t_col);
+                const float Y1 = ax ? cxi(Sxi + 1 * TPS, g1_row) : cxi(Sxi + 1 * TPS, L.g2_row);
+                const float Y2 = ceta(Set + 2 * TPS, L.g2t_col);
+                const float Y3 = ax ? cxi(Sxi + 4 * TPS, g1_row) : cxi(Sxi + 4 * TPS, L.g2_row);
+                const float Y4 = ceta(Set + 5 * TPS, L.g2t_col);
                 if (ORDER == 0) {
                     l1 = l1 + Y1 + Y2;
                     l3 = Y3 + Y4;
@@ -545,7 +551,7 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                         const size_t a0 = j + NP * (size_t)eg, b0 = NP * (size_t)eg;
                         const float w1 = a.M0_w[0][a0], w2 = a.M0_w[1][a0], w3 = a.M0_w[2][a0];
                         const float V1 = cxi(U1xi, g0);                    // vxm_4(G0, us)
-                        const float V2 = ceta(Ub + 3 * TP + e25, L.g2_col); // vxm_4(uz0, G2): uz(0,k)
+                        const float V2 = ceta(Ub + 3 * TPS + e25, L.g2_col); // vxm_4(uz0, G2): uz(0,k)
                         float V4 = w1 * V1 + w3 * V2;
                         const float V3 = cxi(U3xi, g0);                    // vxm_4(G0, uz)
                         V4 = V4 + w2 * V3;
@@ -561,8 +567,8 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                         l3 = X2a + l3;
                     }
                 } else {
-                    const float Y5 = ax ? cxi(Sxi + 7 * TP, g1_row) : cxi(Sxi + 7 * TP, L.g2_row);
-                    const float Y6 = ceta(Set + 8 * TP, L.g2t_col);
+                    const float Y5 = ax ? cxi(Sxi + 7 * TPS, g1_row) : cxi(Sxi + 7 * TPS, L.g2_row);
+                    const float Y6 = ceta(Set + 8 * TPS, L.g2t_col);
                     if (ORDER == 1) {
                         l1 = Y1 + Y2;
                         l2 = Y3 + Y4 + l2;
@@ -584,8 +590,8 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                                 for (int k = 0; k < NP; k++) {
                                     const float k2 = a.M0_w[1][b0 + k], k6 = a.M0_w[5][b0 + k];
                                     const float k4 = a.M0_w[3][b0 + k], k8 = a.M0_w[7][b0 + k];
-                                    vb[k] = (k2 + k6) * cxi(Ub + 3 * TP + e25 + 5 * k, g0)
-                                          + (k4 + k8) * cxi(Ub + 6 * TP + e25 + 5 * k, g0);
+                                    vb[k] = (k2 + k6) * cxi(Ub + 3 * TPS + e25 + 5 * k, g0)
+                                          + (k4 + k8) * cxi(Ub + 6 * TPS + e25 + 5 * k, g0);
                                 }
                                 s1p = s1p + cxi(vb, L.g2t_col);
                             }
@@ -664,13 +670,13 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
         if (anel_update && mvt) {
             const float src_dev_t = x_src[mel * 28 + ml];
             const float s_dev_tm1 = S[Ly.sdev + t];
-            const size_t meg = (size_t)tile * TE + mel;
+            const size_t meg = (size_t)tile * TES + mel;
             if (mv_lane) {
                 const double src_tr_t = f2d(x_src[mel * 28 + 24 + mv_k]);
                 const double s_tr_tm1 = f2d(S[Ly.str + mel * 4 + mv_k]);
                 const double dsrc_t = f2d(src_dev_t), dsrc_tm1 = f2d(s_dev_tm1);
-                const double2 *c_mu = a.c_mu_tab + (size_t)n_sls * meta[TE + mel];
-                const double2 *c_ka = a.c_ka_tab + (size_t)n_sls * meta[2 * TE + mel];
+                const double2 *c_mu = a.c_mu_tab + (size_t)n_sls * meta[TES + mel];
+                const double2 *c_ka = a.c_ka_tab + (size_t)n_sls * meta[2 * TES + mel];
                 const float *mv = S + Ly.mv + mel * 24 * n_sls + ml;
                 float *out = a.memvar + meg * 24 * n_sls + ml;
 #pragma unroll
@@ -689,7 +695,7 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                 }
             }
             a.src_dev_tm1[meg * 24 + ml] = src_dev_t;
-            if (t < TE * 4) a.src_tr_tm1[(size_t)tile * TE * 4 + t] = x_src[(t >> 2) * 28 + 24 + (t & 3)];
+            if (t < TES * 4) a.src_tr_tm1[(size_t)tile * TES * 4 + t] = x_src[(t >> 2) * 28 + 24 + (t & 3)];
         }
         // release the stage: generic-proxy accesses are ordered before the next TMA write
         fence_proxy_async();

@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--nr", type=int, default=1116)
     ap.add_argument("--source", default="mtr")
     ap.add_argument("--no-anel", action="store_true")
-    ap.add_argument("--cpu-sample-cols", type=int, default=64,
+    ap.add_argument("--cpu-sample-cols", type=int, default=384,
                     help="theta columns of the CPU-baseline sample mesh (same radial structure)")
     ap.add_argument("--cpu-steps", type=int, default=0, help="0 = size for ~15 s")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -328,7 +328,7 @@ def main():
         "clocks": clk,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": f"k_solid_element<{pole}>",
+        "roofline": {"bound": "hbm", "kernel": f"k_solid_tile<{pole}> (S_A)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else

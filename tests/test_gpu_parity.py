@@ -173,3 +173,18 @@ def test_two_slices_loopback_matches_oracle_and_one_slice(src):
     for p, g in zip(probs, gl):
         s2[:, p.rec_index, :] = g.seismograms()
     assert rel_l2(s2, s1) <= 1e-5
+
+
+def test_blowup_guard_reports_like_the_reference_stop():
+    """runtime_info (time_evol_wave.F90:1042-1054): |disp(1,1,:,:)| > 10 |magnitude| stops the
+    run; on the device the check runs every 100 steps and surfaces through axb_synchronize."""
+    from axisem_b200 import solver
+    from axisem_b200.capi import AxbError
+    prob = make_problem("explosion", niter=120)
+    G = solver.time_loop(prob)
+    d = np.zeros(G._field_shape("disp"), np.float32)
+    d[0, 3, 1, 1] = 1e30                      # far above 10 x 1e20
+    G.set("disp", d)
+    G.run(99)                                 # not checked yet
+    with pytest.raises(AxbError, match="BLEW UP"):
+        G.run(1)
