@@ -103,6 +103,12 @@ struct axb_handle_s {
     double2 *d_c_mu_tab = nullptr, *d_c_ka_tab = nullptr;
     std::vector<double> ts_t_h, ts_tm1_h, exp_w_h;
     float *memvar = nullptr, *src_dev_tm1 = nullptr, *src_tr_tm1 = nullptr;
+    // COARSE_GRAINED false: flat (25 nel) planes and (5 nel) axial vectors (axb_anel_full.cuh)
+    const float *f_Y = nullptr, *f_Vse = nullptr, *f_Vsx = nullptr, *f_Vze = nullptr, *f_Vzx = nullptr;
+    const float *f_Y0 = nullptr, *f_V0se = nullptr, *f_V0sx = nullptr, *f_V0ze = nullptr, *f_V0zx = nullptr;
+    const float *f_Dse = nullptr, *f_Dze = nullptr, *f_Dsx = nullptr, *f_Dzx = nullptr;
+    const float *f_dmu = nullptr, *f_dka = nullptr;
+    int *d_qidx_mu = nullptr, *d_qidx_ka = nullptr;
     std::vector<float> Qmu_h, Qka_h;
     std::vector<double> y_j;
     int corr_lowq = 0;
@@ -605,11 +611,8 @@ int axb_set_sf_boundary(axb_handle h, int32_t nel_bdry, const int32_t *bdry_soli
 int axb_set_attenuation(axb_handle h, const axb_attenuation *a) {
     if (use(h)) return 1;
     if (a->n_sls < 1 || a->n_sls > 8) return fail("n_sls must be in 1..8");
-    if (!a->coarse_grained)
-        return fail("axb_set_attenuation: only COARSE_GRAINED true (the reference default) is "
-                    "implemented on the device in this round");
     const size_t n4 = (size_t)4 * h->nel_s, n = (size_t)NPT * h->nel_s;
-    h->anel = true; h->cg = true; h->corr_lowq = a->do_corr_lowq;
+    h->anel = true; h->cg = a->coarse_grained != 0; h->corr_lowq = a->do_corr_lowq;
     h->n_sls = a->n_sls;
     h->y_j.assign(a->y_j, a->y_j + a->n_sls);
     h->exp_w_h.assign(a->exp_w_j_deltat, a->exp_w_j_deltat + a->n_sls);
@@ -618,6 +621,27 @@ int axb_set_attenuation(axb_handle h, const axb_attenuation *a) {
     if (!a->Q_mu || !a->Q_kappa) return fail("axb_set_attenuation: NULL Q array");
     h->Qmu_h.assign(a->Q_mu, a->Q_mu + h->nel_s);
     h->Qka_h.assign(a->Q_kappa, a->Q_kappa + h->nel_s);
+    if (!h->cg) {
+        // memory variables at all 25 points (attenuation.f90:210-334): flat planes
+        const float *pl[11] = {a->Y, a->V_s_eta, a->V_s_xi, a->V_z_eta, a->V_z_xi, a->DsDeta_over_J_sol,
+                               a->DzDeta_over_J_sol, a->DsDxi_over_J_sol, a->DzDxi_over_J_sol,
+                               a->delta_mu, a->delta_kappa};
+        const float **dst[11] = {&h->f_Y, &h->f_Vse, &h->f_Vsx, &h->f_Vze, &h->f_Vzx, &h->f_Dse,
+                                 &h->f_Dze, &h->f_Dsx, &h->f_Dzx, &h->f_dmu, &h->f_dka};
+        for (int k = 0; k < 11; k++) {
+            if (!pl[k]) return fail("axb_set_attenuation: NULL (0:4,0:4,nel_solid) array");
+            UPC(*dst[k], pl[k], n);
+        }
+        const float *p0[5] = {a->Y0, a->V0_s_eta, a->V0_s_xi, a->V0_z_eta, a->V0_z_xi};
+        const float **d0[5] = {&h->f_Y0, &h->f_V0se, &h->f_V0sx, &h->f_V0ze, &h->f_V0zx};
+        for (int k = 0; k < 5; k++) {
+            if (!p0[k]) return fail("axb_set_attenuation: NULL axial (0:4,nel_solid) array");
+            UPC(*d0[k], p0[k], (size_t)NP * h->nel_s);
+        }
+        if (!a->inv_s_solid) return fail("axb_set_attenuation: NULL inv_s_solid");
+        if (upload_padded(h, h->d_inv_s, a->inv_s_solid, n, h->css)) return 1;
+        return 0;
+    }
     // slab plane order: enum G_* in axb_solid_tile.cuh
     const float *cgp[NCG] = {a->Y_cg4, a->V_s_eta_cg4, a->V_s_xi_cg4, a->V_z_eta_cg4, a->V_z_xi_cg4,
                              a->DsDeta_over_J_sol_cg4, a->DzDeta_over_J_sol_cg4,
@@ -807,9 +831,16 @@ int axb_finalize_setup(axb_handle h) {
         if (tab_mu.empty()) { tab_mu.assign(h->n_sls, make_double2(0, 0)); tab_ka.assign(h->n_sls, make_double2(0, 0)); }
         UP(h->d_c_mu_tab, tab_mu.data(), tab_mu.size());
         UP(h->d_c_ka_tab, tab_ka.data(), tab_ka.size());
-        if (dzeros(h, h->memvar, (size_t)24 * h->n_sls * h->nel_pad_s)) return 1;
-        if (dzeros(h, h->src_dev_tm1, (size_t)24 * h->nel_pad_s)) return 1;
-        if (dzeros(h, h->src_tr_tm1, (size_t)4 * h->nel_pad_s)) return 1;
+        const size_t np = h->cg ? 4 : NPT;
+        if (dzeros(h, h->memvar, np * 6 * h->n_sls * h->nel_pad_s)) return 1;
+        if (dzeros(h, h->src_dev_tm1, np * 6 * h->nel_pad_s)) return 1;
+        if (dzeros(h, h->src_tr_tm1, np * h->nel_pad_s)) return 1;
+        if (!h->cg) {
+            std::vector<int> qm(std::max(h->nel_s, 1), 0), qk(std::max(h->nel_s, 1), 0);
+            for (int e = 0; e < h->nel_s; e++) { qm[e] = meta_at(e, 1); qk[e] = meta_at(e, 2); }
+            UP(h->d_qidx_mu, qm.data(), qm.size());
+            UP(h->d_qidx_ka, qk.data(), qk.size());
+        }
     }
     UP(h->d_meta, meta.data(), meta.size());
     if (h->scheme != AXB_NEWMARK2) {
@@ -853,11 +884,11 @@ int axb_finalize_setup(axb_handle h) {
     }
     if (h->nel_s > 0) {
         // compiled variants: elastic, the reference default NR_LIN_SOLIDS 5, any other n_sls
-        const int v = !h->anel ? 0 : (h->n_sls == 5 ? 1 : 2);
+        const int v = (!h->anel || !h->cg) ? 0 : (h->n_sls == 5 ? 1 : 2);
         const size_t optin = prop.sharedMemPerBlockOptin;
         if (h->rows) {
             // S_A (rows): one persistent CTA per SM, one stage per warp pair
-            const SolidRowsLayout Ly = solid_rows_layout(h->order, h->anel, h->n_sls);
+            const SolidRowsLayout Ly = solid_rows_layout(h->order, h->anel && h->cg, h->n_sls);
             int npair = (int)std::min<size_t>(ROWS_MAX_PAIRS, (optin - ROWS_HDR_BYTES) / Ly.stage_bytes);
             if (const char *ev = getenv("AXB_SOLID_PAIRS")) npair = std::max(1, std::min(npair, atoi(ev)));
             if (npair < 1) return fail("not enough shared memory for one solid stage");
@@ -872,7 +903,7 @@ int axb_finalize_setup(axb_handle h) {
             h->solid_kernel = table[h->order][v];
         } else {
             // S_A (tile): persistent CTAs; the ring takes all the shared memory it can get
-            const SolidTileLayout Ly = solid_tile_layout(h->order, h->anel, h->n_sls);
+            const SolidTileLayout Ly = solid_tile_layout(h->order, h->anel && h->cg, h->n_sls);
             const size_t cap = SOLID_CTAS_PER_SM == 1 ? optin
                              : std::min<size_t>(optin, prop.sharedMemPerMultiprocessor / SOLID_CTAS_PER_SM - 1024);
             if (cap < Ly.hdr_bytes + 2 * Ly.stage_bytes) return fail("not enough shared memory for the solid tile ring");
@@ -1041,6 +1072,38 @@ static void launch_solid_element(axb_handle_s *h, const SolidTileArgs &a) {
     CLS(h, 0);
     LAUNCH_SMEM(h, h->solid_kernel, h->grid_s, h->rows ? 64 * h->npair : SOLID_THREADS, h->smem_solid, h->G, a);
 }
+// COARSE_GRAINED false: the anelastic K term and/or the memory-variable update at all 25
+// points, behind S_A (axb_anel_full.cuh)
+static void launch_anel_full(axb_handle_s *h, int do_stiff, int do_update, int mask) {
+    if (h->nel_s == 0) return;
+    CLS(h, 0);
+    AnelFullArgs a;
+    std::memset(&a, 0, sizeof a);
+    a.nel = h->nel_s; a.n_sls = h->n_sls; a.do_stiff = do_stiff; a.do_update = do_update; a.mask = mask;
+    a.disp = h->disp; a.acc1 = h->acc1; a.cs = h->css; a.axis = h->d_axis_s;
+    a.Y = h->f_Y; a.Vse = h->f_Vse; a.Vsx = h->f_Vsx; a.Vze = h->f_Vze; a.Vzx = h->f_Vzx;
+    a.Y0 = h->f_Y0; a.V0se = h->f_V0se; a.V0sx = h->f_V0sx; a.V0ze = h->f_V0ze; a.V0zx = h->f_V0zx;
+    a.Dse = h->f_Dse; a.Dze = h->f_Dze; a.Dsx = h->f_Dsx; a.Dzx = h->f_Dzx; a.inv_s = h->d_inv_s;
+    a.dmu = h->f_dmu; a.dka = h->f_dka; a.qidx_mu = h->d_qidx_mu; a.qidx_ka = h->d_qidx_ka;
+    a.c_mu_tab = h->d_c_mu_tab; a.c_ka_tab = h->d_c_ka_tab;
+    for (int k = 0; k < 8; k++) a.exp_w[k] = k < h->n_sls ? h->exp_w_h[k] : 0.0;
+    a.memvar = h->memvar; a.src_dev_tm1 = h->src_dev_tm1; a.src_tr_tm1 = h->src_tr_tm1;
+    const int grid = cdiv(h->nel_s, TEA);
+    if (h->order == 0) LAUNCH(h, k_anel_full<0>, grid, ANEL_THREADS, h->G, a);
+    else if (h->order == 1) LAUNCH(h, k_anel_full<1>, grid, ANEL_THREADS, h->G, a);
+    else LAUNCH(h, k_anel_full<2>, grid, ANEL_THREADS, h->G, a);
+}
+// S_A of one (sub)step: predictor/drift + K u, with the anelastic work fused (coarse-grained)
+// or in the kernel behind it (all 25 points).  anel: 0 none, 1 K term only, 2 K term + update
+static void launch_solid_step(axb_handle_s *h, int mode, double c0, double c1, int anel) {
+    if (!h->anel) anel = 0;
+    if (h->anel && !h->cg) {
+        launch_solid_element(h, solid_args(h, mode, c0, c1, 0, 1));
+        launch_anel_full(h, 1, anel == 2, 1);
+    } else {
+        launch_solid_element(h, solid_args(h, mode, c0, c1, anel, 1));
+    }
+}
 static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1, int full, int use_mask) {
     if (h->nel_f == 0) return;
     CLS(h, 1);
@@ -1168,7 +1231,7 @@ static void launch_dumps(axb_handle_s *h) {
 // enqueued rank by rank (every send is enqueued before the matching wait of any rank).
 static int newmark_a(axb_handle_s *h) {
     // S_A first: the fluid needs the *predicted* solid displacement on the S/F boundary
-    launch_solid_element(h, solid_args(h, 0, h->deltat, h->half_dt_sq, h->anel ? 2 : 0, 1));
+    launch_solid_step(h, 0, h->deltat, h->half_dt_sq, 2);
     launch_fluid_element(h, 0, h->deltat, h->half_dt_sq, 1, 1);
     if (halo_send(h, 1, h->ddchi1, (size_t)NPT * h->nel_f)) return 1;
     return 0;
@@ -1205,7 +1268,7 @@ static int newmark_c(axb_handle_s *h) {
     return 0;
 }
 static int symp_a(axb_handle_s *h, int k) {
-    launch_solid_element(h, solid_args(h, 1, h->coefd[k], 0.0, h->anel ? 1 : 0, 1));
+    launch_solid_step(h, 1, h->coefd[k], 0.0, 1);
     launch_fluid_element(h, 1, h->coefd[k], 0.0, 1, 0);
     return halo_send(h, 1, h->ddchi1, (size_t)NPT * h->nel_f);
 }
@@ -1234,7 +1297,8 @@ static int symp_finish(axb_handle_s *h) {
             LAUNCH(h, k_drift, cdiv(3 * cs, 256), 256, (int)(3 * cs), h->disp, h->velo, cd);
         }
     }
-    if (h->anel) launch_solid_element(h, solid_args(h, 2, 0.0, 0.0, 3, 0));
+    if (h->anel && h->cg) launch_solid_element(h, solid_args(h, 2, 0.0, 0.0, 3, 0));
+    else if (h->anel) launch_anel_full(h, 0, 1, 0);
     CLS(h, 7);
     LAUNCH(h, k_next_iter, 1, 32, h->d_counters);
     h->iter++;
@@ -1355,9 +1419,9 @@ static float *field_ptr(axb_handle_s *o, int f, size_t *n, bool *planes, bool re
     case AXB_F_DCHI: *n = nf; return o->dchi;
     case AXB_F_DDCHI0: *n = nf; return o->ddchi0;
     case AXB_F_DDCHI1: *n = nf; return (reading && o->acc1_is_acc0) ? o->ddchi0 : o->ddchi1;
-    case AXB_F_MEMVAR: if (!o->anel) return nullptr; *n = (size_t)24 * o->n_sls * o->nel_s; return o->memvar;
-    case AXB_F_SRC_DEV_TM1: if (!o->anel) return nullptr; *n = (size_t)24 * o->nel_s; return o->src_dev_tm1;
-    case AXB_F_SRC_TR_TM1: if (!o->anel) return nullptr; *n = (size_t)4 * o->nel_s; return o->src_tr_tm1;
+    case AXB_F_MEMVAR: if (!o->anel) return nullptr; *n = (size_t)(o->cg ? 4 : NPT) * 6 * o->n_sls * o->nel_s; return o->memvar;
+    case AXB_F_SRC_DEV_TM1: if (!o->anel) return nullptr; *n = (size_t)(o->cg ? 4 : NPT) * 6 * o->nel_s; return o->src_dev_tm1;
+    case AXB_F_SRC_TR_TM1: if (!o->anel) return nullptr; *n = (size_t)(o->cg ? 4 : NPT) * o->nel_s; return o->src_tr_tm1;
     }
     return nullptr;
 }
@@ -1402,7 +1466,9 @@ int axb_apply_op(axb_handle h, int32_t op) {
     case AXB_OP_SOLID_STIFFNESS: launch_solid_element(h, solid_args(h, 2, 0, 0, 0, 1)); break;
     case AXB_OP_ANEL_STIFFNESS:
         if (!h->anel) return fail("no attenuation");
-        launch_solid_element(h, solid_args(h, 2, 0, 0, 1, 0)); break;
+        if (h->cg) launch_solid_element(h, solid_args(h, 2, 0, 0, 1, 0));
+        else launch_anel_full(h, 1, 0, 0);
+        break;
     case AXB_OP_FLUID_STIFFNESS: launch_fluid_element(h, 2, 0, 0, 0, 0); break;
     case AXB_OP_PDISTSUM_SOLID:
         if (h->halo[0].nmsg) return fail("apply_op(pdistsum) is single-rank only");
@@ -1416,7 +1482,9 @@ int axb_apply_op(axb_handle h, int32_t op) {
         break;
     case AXB_OP_MEMVARS:
         if (!h->anel) return fail("no attenuation");
-        launch_solid_element(h, solid_args(h, 2, 0, 0, 3, 0)); break;
+        if (h->cg) launch_solid_element(h, solid_args(h, 2, 0, 0, 3, 0));
+        else launch_anel_full(h, 0, 1, 0);
+        break;
     case AXB_OP_BDRY2FLUID:
         if (h->nel_bdry)
             LAUNCH(h, k_bdry2fluid, cdiv(h->nel_bdry * NP, 128), 128, h->nel_bdry, h->order, h->d_bsel,

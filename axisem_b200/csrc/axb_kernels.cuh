@@ -112,6 +112,7 @@ __device__ __forceinline__ void load_lane_g(const GMat &G, int i, int j, LaneG &
 #include "axb_solid_tile.cuh"
 #include "axb_solid_rows.cuh"
 #include "axb_fluid_tile.cuh"
+#include "axb_anel_full.cuh"
 namespace axb {
 
 // ---------------------------------------------------------------------------------------

@@ -29,12 +29,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from axisem_b200.host import SourceParams, build_problem, prem_mesh_spec  # noqa: E402
+from axisem_b200.host import AttenuationModel, SourceParams, build_problem, prem_mesh_spec  # noqa: E402
 
 # algorithmic bytes per element-local GLL point and time step
 B_SOLID = {"monopole": 112.0, "dipole": 172.0, "quadpole": 180.0}
 B_FLUID = {"monopole": 44.0, "dipole": 48.0, "quadpole": 48.0}
 B_ANEL = {"monopole": 40.0, "dipole": 55.0, "quadpole": 55.0}
+B_ANEL_FULL = {"monopole": 248.0, "dipole": 344.0, "quadpole": 344.0}   # COARSE_GRAINED false
 # the share of those bytes that belongs to the solid element kernel S_A:
 # disp r+w (2 nc) + all M planes (ncoef - inv_mass) [+ the whole anelastic part]
 NC = {"monopole": 2, "dipole": 3, "quadpole": 3}
@@ -51,6 +52,8 @@ def parse():
     ap.add_argument("--nr", type=int, default=1116)
     ap.add_argument("--source", default="mtr")
     ap.add_argument("--no-anel", action="store_true")
+    ap.add_argument("--full-memvars", action="store_true",
+                    help="COARSE_GRAINED false: memory variables at all 25 points (not the headline config)")
     ap.add_argument("--cpu-sample-cols", type=int, default=384,
                     help="theta columns of the CPU-baseline sample mesh (same radial structure)")
     ap.add_argument("--cpu-steps", type=int, default=0, help="0 = size for ~15 s")
@@ -117,7 +120,8 @@ def cpu_reference_rate(args, src, anel, cores=None):
     spec = prem_mesh_spec(ntheta=ncols, nr_target=args.nr)
     lib = oracle.load()
     nsteps = args.cpu_steps or 4
-    probs = [build_problem(spec, SourceParams(src_type2=src), anel=anel, niter=400, rank=r,
+    att = AttenuationModel(coarse_grained=False) if (anel and args.full_memvars) else None
+    probs = [build_problem(spec, SourceParams(src_type2=src), anel=anel, att=att, niter=400, rank=r,
                            nranks=cores, rec_colat_deg=[]) for r in range(cores)]
     loops = [oracle.make_loop(p) for p in probs]
     rng = np.random.default_rng(1234)
@@ -157,7 +161,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     N = args.gpus
     workload = (f"PREM-type synthetic mesh {args.ntheta}x{args.nr} (theta x r), {pole} ({src}) "
-                f"source, {'cg4 attenuation 5 SLS' if anel else 'elastic'}, newmark2")
+                f"source, {('full (25-point) attenuation 5 SLS' if args.full_memvars else 'cg4 attenuation 5 SLS') if anel else 'elastic'}, newmark2")
 
     if args.impl == "reference":
         if rank != 0:
@@ -197,7 +201,8 @@ def main():
     niter = W + 2 * K + 8
     spec = prem_mesh_spec(ntheta=args.ntheta, nr_target=args.nr)
     t0 = time.perf_counter()
-    prob = build_problem(spec, sp, anel=anel, niter=niter, rank=rank, nranks=world)
+    att = AttenuationModel(coarse_grained=False) if (anel and args.full_memvars) else None
+    prob = build_problem(spec, sp, anel=anel, att=att, niter=niter, rank=rank, nranks=world)
     t_build = time.perf_counter() - t0
     t0 = time.perf_counter()
     loop = solver.time_loop(prob, device=local)
@@ -298,9 +303,13 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    bytes_pt_sa = 4.0 * (2 * NC[pole] + NCOEF[pole]) + (B_ANEL[pole] if anel else 0.0)
+    full = anel and args.full_memvars
+    b_anel = (B_ANEL_FULL[pole] if full else B_ANEL[pole]) if anel else 0.0
+    bytes_pt_sa = 4.0 * (2 * NC[pole] + NCOEF[pole]) + b_anel
     bytes_sa = bytes_pt_sa * 25 * m.nel_solid
-    ms_sa = prof_ms[0] / max(prof_n[0], 1)
+    # full memory variables: S_A is followed by k_anel_full (same profile class); one "launch"
+    # below is then the pair
+    ms_sa = prof_ms[0] / max(prof_n[0], 1) * (2 if full else 1)
     achieved = bytes_sa / (ms_sa * 1e-3) / 1e9 if ms_sa > 0 else None
     traffic = None
     try:
@@ -310,7 +319,7 @@ def main():
             traffic = tr[key]["bytes_per_solid_element"] * m.nel_solid
     except Exception:
         pass
-    step_bytes = 25.0 * ((B_SOLID[pole] + (B_ANEL[pole] if anel else 0.0)) * m.nel_solid * world
+    step_bytes = 25.0 * ((B_SOLID[pole] + b_anel) * m.nel_solid * world
                          + B_FLUID[pole] * m.nel_fluid * world)
     names = ["solid_element(S_A)", "fluid_element(F_A)", "fluid_corrector(F_B)", "sf_coupling",
              "solid_corrector(S_B)", "halo", "sampling", "other"]
@@ -328,7 +337,7 @@ def main():
         "clocks": clk,
         "e2e": e2e,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": f"k_solid_tile<{pole}> (S_A)",
+        "roofline": {"bound": "hbm", "kernel": f"k_solid_tile<{pole}> (S_A)" + (" + k_anel_full" if full else ""),
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else

@@ -11,7 +11,7 @@ The reference itself cannot be run here (Fortran; no compiler in the image) and 
 array-level vectors for this path, so these vectors pin the *oracle*, not the Fortran —
 see DESIGN.md section 2 ("parity unpinned").
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case names]
 """
 import os
 import sys
@@ -21,7 +21,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from axisem_b200.host import (SourceParams, SpectralBasis, build_problem, prem_mesh_spec,  # noqa: E402
+from axisem_b200.host import (AttenuationModel, SourceParams, SpectralBasis, build_problem, prem_mesh_spec,  # noqa: E402
                               stable_timestep)
 from axisem_b200.host.problem_io import save_problem  # noqa: E402
 from oracle import oracle  # noqa: E402
@@ -32,16 +32,23 @@ CASES = {
     "dipole_anel_iso": ("mtr", True, False, "newmark2", 40),
     "quad_anel_ani": ("mtp", True, True, "newmark2", 40),
     "dipole_elastic_symplec4": ("thetaforce", False, True, "symplec4", 12),
+    # COARSE_GRAINED false: memory variables at all 25 points (attenuation.f90:210-334)
+    "dipole_anel_full_ani": ("mtr", "full", True, "newmark2", 40),
 }
 
 
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
+    only = set(sys.argv[1:])
     for name, (src, anel, ani, scheme, n) in CASES.items():
+        if only and name not in only:
+            continue
+        att = AttenuationModel(coarse_grained=False) if anel == "full" else None
+        anel = bool(anel)
         spec = prem_mesh_spec(ntheta=4, nr_target=9, anisotropic=ani)
         dt = stable_timestep(spec, SpectralBasis(4)) * (1.5 if scheme != "newmark2" else 1.0)
         # a short source so that the STF peaks inside the run
-        prob = build_problem(spec, SourceParams(src_type2=src, t_0=8.0 * dt), anel=anel, niter=n,
+        prob = build_problem(spec, SourceParams(src_type2=src, t_0=8.0 * dt), anel=anel, att=att, niter=n,
                              time_scheme=scheme, dump=True, strain_it=8, seis_it=2,
                              rec_colat_deg=[10.0, 60.0, 120.0, 170.0], threads=1)
         loop = oracle.make_loop(prob)

@@ -34,7 +34,7 @@ def _replay(lib, path, device=0):
 
 
 def test_golden_files_present():
-    assert len(CASES) == 4
+    assert len(CASES) == 5
 
 
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[5:-4] for p in CASES])

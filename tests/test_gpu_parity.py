@@ -72,6 +72,42 @@ def test_anelastic_stiffness_and_memvars(src, strict):
         _cmp(f, G.get(f), O.get(f), strict, 2e-6)
 
 
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("src", SRCS)
+def test_full_memvar_attenuation_ops(src, strict):
+    """COARSE_GRAINED false: glob_anel_stiffness_*_4 and time_step_memvars_4 at all 25 points,
+    axial L'Hopital branch included (attenuation.f90:210-334, :542-606)."""
+    prob = make_problem(src, anel=True, coarse_grained=False, anisotropic=True)
+    G, O = _pair(prob, strict)
+    st = seeded_state(G, fields=("disp", "acc1", "memvar", "src_dev_tm1", "src_tr_tm1"))
+    assert st["memvar"].shape[-2:] == (5, 5)
+    for L in (G, O):
+        apply_state(L, st)
+        L.apply_op("anel_stiffness")
+    comps = [0, 2] if src == "explosion" else [0, 1, 2]
+    _cmp("acc1", G.get("acc1")[comps], O.get("acc1")[comps], strict, 2e-6)
+    for L in (G, O):
+        L.apply_op("memvars")
+    for f in ("memvar", "src_dev_tm1", "src_tr_tm1"):
+        _cmp(f, G.get(f), O.get(f), strict, 2e-6)
+
+
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("src,scheme", [("explosion", "newmark2"), ("mtr", "newmark2"),
+                                        ("mtp", "newmark2"), ("mtr", "symplec4")])
+def test_full_memvar_time_loop(src, scheme, strict):
+    n = 30 if scheme == "newmark2" else 12
+    prob = make_problem(src, anel=True, coarse_grained=False, niter=n, scheme=scheme, t_0=20.0)
+    G, O = _pair(prob, strict)
+    for L in (G, O):
+        L.run(n)
+    a, b = G.seismograms(), O.seismograms()
+    assert np.abs(b).max() > 0
+    _cmp("seismograms", a, b, strict, 1e-5)
+    for f in ("disp", "velo", "memvar", "src_dev_tm1", "src_tr_tm1"):
+        _cmp(f, G.get(f), O.get(f), strict, 1e-5)
+
+
 @pytest.mark.parametrize("src", SRCS)
 def test_assembly_is_bit_exact(src):
     """pdistsum_* is pure summation in a fixed order: bit-exact in both builds."""

@@ -210,3 +210,93 @@ def test_theta_slices_reproduce_single_rank(src, anel, nranks):
     assert np.abs(ref).max() > 0
     # only the order of the halo sums differs (commpi.F90:469-477): a few ulp per step
     assert rel_l2(got, ref) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------
+# Anelastic K term: virtual work.  glob_anel_stiffness_* subtracts B^T R, so for any test
+# field v and memory variables R (Voigt, engineering shear)  v . l(R) = int R : E(v) s ds dz
+# with E(v) the strain of compute_strain_att_el_* formed independently in float64.
+def _voigt_strain(prob, u, src):
+    m, b = prob.mesh, prob.mesh.basis
+    pw = {k: v.astype(np.float64) for k, v in prob.pw_solid.items()}
+    ax = m.axis_solid.astype(bool)
+    u1, u2, u3 = u.astype(np.float64)
+    gr = lambda f: _grad(f, pw, ax, b)
+    fs = lambda f: _over_s(f, pw, ax, b)
+    b1 = gr(u1 + u2) if src == "mtr" else gr(u1)
+    b2 = gr(u3)
+    E = [b1[0], None, b2[1], 0 * u1, b1[1] + b2[0], 0 * u1]
+    if src == "explosion":
+        E[1] = fs(u1)
+    elif src == "mtr":
+        E[1] = 2 * fs(u2)
+        c = gr(u1 - u2)
+        E[3] = -fs(u3) - c[1]
+        E[5] = -E[1] - c[0]
+    else:
+        E[1] = fs(u1 - 2 * u2)
+        c = gr(u2)
+        E[3] = -2 * fs(u3) - c[1]
+        E[5] = fs(u2 - 2 * u1) - c[0]
+    return np.stack(E, axis=1)                       # (nel, 6, jpol, ipol)
+
+
+def _anel_work(prob, src, cg, v, rng, u):
+    O = oracle.make_loop(prob)
+    R = np.zeros(O._field_shape("memvar"), np.float32)
+    R[:, 1, v] = rng.standard_normal(R[:, 1, v].shape)      # one SLS, one Voigt component
+    R[:, 3, v] = rng.standard_normal(R[:, 3, v].shape)      # and a second one: they add up
+    O.set("memvar", R)
+    O.set("acc1", np.zeros_like(u))
+    O.apply_op("anel_stiffness")
+    lhs = -(u * O.get("acc1").astype(np.float64)).sum(axis=(0, 2, 3))
+    g = geometry(prob.mesh.solid, prob.mesh.basis)
+    E = _voigt_strain(prob, u, src)[:, v]
+    Rs = R.astype(np.float64).sum(axis=1)[:, v]
+    if cg:
+        w = np.stack([g.massmat_k[:, 1, 1], g.massmat_k[:, 3, 1], g.massmat_k[:, 1, 3], g.massmat_k[:, 3, 3]], axis=1)
+        Ek = np.stack([E[:, 1, 1], E[:, 3, 1], E[:, 1, 3], E[:, 3, 3]], axis=1)
+        rhs = (w * Rs * Ek).sum(axis=1)
+    else:
+        rhs = (g.massmat_k * Rs * E).sum(axis=(1, 2))
+    return lhs, rhs
+
+
+@pytest.mark.parametrize("cg", [True, False])
+@pytest.mark.parametrize("src", SRCS)
+def test_anelastic_stiffness_is_the_adjoint_of_the_strain(src, cg):
+    prob = make_problem(src, anel=True, coarse_grained=cg, ntheta=8, nr=10)
+    ax = prob.mesh.axis_solid.astype(bool)
+    rng = np.random.default_rng(5)
+    u = _axis_bc(rng.standard_normal((3,) + prob.pw_solid["inv_s"].shape).astype(np.float32), src, ax)
+    for v in ([0, 1, 2, 4] if src == "explosion" else range(6)):
+        lhs, rhs = _anel_work(prob, src, cg, v, rng, u)
+        scale = np.abs(rhs[~ax]).max()
+        assert np.abs(lhs - rhs)[~ax].max() <= 5e-6 * scale, (src, cg, v)
+
+
+@pytest.mark.parametrize("src", SRCS)
+def test_full_memvar_axial_terms_are_adjoint_once_the_reference_s_quirk_is_removed(src):
+    """In axial elements the reference evaluates s of V_* at eta(ipol) instead of xi_k(ipol)
+    (def_precomp_terms.f90:1485-1496; reproduced by host/precomp.py).  With s put back at the
+    GLJ point the Y0/V0_* axial branch of glob_anel_stiffness_*_4 is the exact adjoint of the
+    L'Hopital strain for every component the reference's axial branch treats completely
+    (dipole r4/r5 and quadrupole r4/r5 are not: stiffness_di.f90:708-711,
+    stiffness_quad.f90:645-656)."""
+    prob = make_problem(src, anel=True, coarse_grained=False, ntheta=8, nr=10)
+    m, b = prob.mesh, prob.mesh.basis
+    ax = m.axis_solid.astype(bool)
+    g = geometry(m.solid, b)
+    th_q = 0.5 * ((1.0 - b.eta[None, :]) * m.solid.th_a[:, None] + (1.0 + b.eta[None, :]) * m.solid.th_b[:, None])
+    s_q = g.r[:, :, None] * np.sin(th_q)[:, None, :]
+    ratio = np.ones_like(g.s)
+    ok = ax[:, None, None] & (s_q > 0)
+    ratio[ok] = g.s[ok] / s_q[ok]
+    for n in ("V_s_eta", "V_s_xi", "V_z_eta", "V_z_xi"):
+        prob.solid[n] = (prob.solid[n].astype(np.float64) * ratio).astype(np.float32)
+    rng = np.random.default_rng(6)
+    u = _axis_bc(rng.standard_normal((3,) + prob.pw_solid["inv_s"].shape).astype(np.float32), src, ax)
+    for v in ([0, 1, 2, 4] if src == "explosion" else [0, 1, 2, 5]):
+        lhs, rhs = _anel_work(prob, src, False, v, rng, u)
+        scale = np.abs(rhs[ax]).max()
+        assert np.abs(lhs - rhs)[ax].max() <= 1e-4 * scale, (src, v)
