@@ -233,7 +233,8 @@ class TimeLoop:
     def synchronize(self):
         self.lib.check(self.lib.fn["synchronize"](self.h))
 
-    def profile(self, enable: bool = True):
+    def profile(self, enable=True):
+        """0/False off, 1/True events around every launch, 2 around the solid element kernel only."""
         self.lib.check(self.lib.fn["profile"](self.h, C.c_int32(int(enable))))
 
     def get_profile(self):

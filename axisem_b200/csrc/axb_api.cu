@@ -48,6 +48,7 @@ struct Halo {
     // receive slab (owned): [parity 2][nc][nslots] floats, then flags
     float *recv = nullptr;
     int *flags = nullptr;                     // [MAXMSG] one per message (written by the peer)
+    int *d_done = nullptr;                    // block counter of k_halo_pack
     // where my messages go (peer memory)
     float *peer_recv[MAXMSG] = {nullptr};
     int peer_nslots[MAXMSG] = {0}, peer_offset[MAXMSG] = {0};
@@ -145,7 +146,7 @@ struct axb_handle_s {
     int64_t launches = 0;
     int grid_s = 0, grid_f = 0, grid_ft = 0, sms = 0;
     // per-kernel event timing (axb_profile)
-    bool prof = false;
+    int prof = 0;                         // 0 off, 1 every launch, 2 the solid element kernel only
     int prof_cls = 7;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_cls;              // class of each (start, stop) pair
@@ -573,7 +574,8 @@ int axb_set_fluid_terms(axb_handle h, const float *M1chi_fl, const float *M2chi_
 
 int axb_set_mass(axb_handle h, const float *inv_mass_rho) {
     if (use(h)) return 1;
-    UP(h->inv_mass_rho, inv_mass_rho, (size_t)NPT * h->nel_s);
+    if (!inv_mass_rho && h->nel_s > 0) return fail("axb_set_mass: NULL inv_mass_rho");
+    if (upload_padded(h, h->inv_mass_rho, inv_mass_rho, (size_t)NPT * h->nel_s, h->css)) return 1;
     return 0;
 }
 
@@ -643,11 +645,12 @@ int axb_set_attenuation(axb_handle h, const axb_attenuation *a) {
         return 0;
     }
     // slab plane order: enum G_* in axb_solid_tile.cuh
-    const float *cgp[NCG] = {a->Y_cg4, a->V_s_eta_cg4, a->V_s_xi_cg4, a->V_z_eta_cg4, a->V_z_xi_cg4,
+    constexpr int NCGH = 11;      // planes that come from the host as (4, nel) arrays
+    const float *cgp[NCGH] = {a->Y_cg4, a->V_s_eta_cg4, a->V_s_xi_cg4, a->V_z_eta_cg4, a->V_z_xi_cg4,
                              a->DsDeta_over_J_sol_cg4, a->DzDeta_over_J_sol_cg4,
                              a->DsDxi_over_J_sol_cg4, a->DzDxi_over_J_sol_cg4,
                              a->delta_mu_cg4, a->delta_kappa_cg4};
-    for (int k = 0; k < NCG; k++)
+    for (int k = 0; k < NCGH; k++)
         if (!cgp[k]) return fail("axb_set_attenuation: NULL cg4 array");
     if (!a->inv_s_solid) return fail("axb_set_attenuation: NULL inv_s_solid");
     const size_t ntiles = h->nel_pad_s / h->te_s;
@@ -655,7 +658,7 @@ int axb_set_attenuation(axb_handle h, const axb_attenuation *a) {
     if (n4) {
         float *d_tmp = nullptr;
         CK(cudaMalloc((void **)&d_tmp, n4 * sizeof(float)));
-        for (int k = 0; k < NCG; k++) {
+        for (int k = 0; k < NCGH; k++) {
             CK(cudaMemcpy(d_tmp, cgp[k], n4 * sizeof(float), cudaMemcpyHostToDevice));
             k_cg_to_slab<<<(unsigned)((n4 + 255) / 256), 256>>>(d_tmp, h->d_cg, k, h->nel_s, h->te_s);
             CK(cudaGetLastError());
@@ -664,6 +667,12 @@ int axb_set_attenuation(axb_handle h, const axb_attenuation *a) {
         cudaFree(d_tmp);
     }
     if (upload_padded(h, h->d_inv_s, a->inv_s_solid, n, h->css)) return 1;
+    if (n4) {
+        // the coarse-grained kernels only need 1/s at the four coarse points
+        k_invs_to_slab<<<(unsigned)((n4 + 255) / 256), 256>>>(h->d_inv_s, h->d_cg, h->nel_s, h->te_s);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+    }
     return 0;
 }
 
@@ -780,6 +789,7 @@ int axb_finalize_setup(axb_handle h) {
         if (H.nmsg == 0) continue;
         if (dzeros(h, H.recv, (size_t)2 * H.nc * H.nslots)) return 1;
         if (dzeros(h, H.flags, MAXMSG)) return 1;
+        if (dzeros(h, H.d_done, 1)) return 1;
     }
     if (build_asm(h, h->nel_s, h->nglob_s, h->igloc_s, h->halo[0], h->d_asm_cp_s, h->d_asm_grp_s)) return 1;
     if (build_asm(h, h->nel_f, h->nglob_f, h->igloc_f, h->halo[1], h->d_asm_cp_f, h->d_asm_grp_f)) return 1;
@@ -1027,7 +1037,7 @@ int axb_ipc_import(axb_handle h, int32_t peer_rank, const void *blob, int32_t bl
 // --------------------------------------------------------------------------------------
 // kernel launches
 static void prof_mark(axb_handle_s *h, bool begin) {
-    if (!h->prof) return;
+    if (!h->prof || (h->prof == 2 && h->prof_cls != 0)) return;
     if (h->ev_used == h->ev_pool.size()) {
         cudaEvent_t e;
         cudaEventCreate(&e);
@@ -1045,6 +1055,16 @@ static void prof_mark(axb_handle_s *h, bool begin) {
     } while (0)
 #define CLS(h, c) (h)->prof_cls = (c)
 
+static bool halo_wait_kernel() {
+    static const bool v = [] { const char *e = getenv("AXB_HALO_WAIT_KERNEL"); return e && atoi(e) != 0; }();
+    return v;
+}
+static HaloArrival halo_arrival(const Halo &H) {
+    HaloArrival r;
+    r.flags = (H.nmsg == 0 || halo_wait_kernel()) ? nullptr : H.flags;
+    r.nmsg = H.nmsg; r.value = H.seq;
+    return r;
+}
 static SolidTileArgs solid_args(axb_handle_s *h, int mode, double c0, double c1, int anel, int do_stiff) {
     SolidTileArgs a;
     std::memset(&a, 0, sizeof a);
@@ -1117,7 +1137,7 @@ static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1
     a.disp = h->disp; a.cs_solid = h->css;
     a.nelsrc = h->fluid_src ? h->nelsrc : 0;
     for (int k = 0; k < 8; k++) a.ielsrc[k] = h->ielsrc[k];
-    a.src_term = h->d_src_term; a.stf = h->d_stf; a.iter = h->d_counters; a.use_mask = use_mask;
+    a.src_term = h->d_src_term; a.stf = h->d_stf; a.iter = h->iter; a.use_mask = use_mask;
     LAUNCH_SMEM(h, k_fluid_tile, h->grid_ft, FLUID_THREADS, h->smem_fluid, h->G, a);
 }
 static void launch_fluid_corr(axb_handle_s *h, int mode, double c, int assemble_only) {
@@ -1131,6 +1151,7 @@ static void launch_fluid_corr(axb_handle_s *h, int mode, double c, int assemble_
     Halo &H = h->halo[1];
     a.recv = H.recv ? H.recv + (size_t)((H.seq + 1) & 1) * H.nc * H.nslots : nullptr;
     a.recv_cs = H.nslots; a.assemble_only = assemble_only;
+    a.arrival = halo_arrival(H);
     LAUNCH(h, k_fluid_corrector, cdiv(a.npts, 256), 256, a);
 }
 static void launch_solid_corr(axb_handle_s *h, int mode, double c, int stf_stride, int stf_off, int assemble_only) {
@@ -1144,11 +1165,12 @@ static void launch_solid_corr(axb_handle_s *h, int mode, double c, int stf_strid
     Halo &H = h->halo[0];
     a.recv = H.recv ? H.recv + (size_t)((H.seq + 1) & 1) * H.nc * H.nslots : nullptr;
     a.recv_cs = H.nslots;
+    a.arrival = halo_arrival(H);
     a.nelsrc = h->fluid_src ? 0 : h->nelsrc;
     for (int k = 0; k < 8; k++) a.ielsrc[k] = h->ielsrc[k];
     a.src_term = h->d_src_term;
     a.stf = (mode == 0) ? h->d_stf : h->d_stf_symp;
-    a.iter = h->d_counters; a.stf_stride = stf_stride; a.stf_off = stf_off;
+    a.iter = h->iter; a.stf_stride = stf_stride; a.stf_off = stf_off;
     a.assemble_only = assemble_only;
     const int grid = cdiv(a.npts, 256);
     if (h->order == 0) LAUNCH(h, k_solid_corrector<0>, grid, 256, a);
@@ -1174,24 +1196,24 @@ static int halo_send(axb_handle_s *h, int d, const float *vec, size_t cs) {
     std::memset(&a, 0, sizeof a);
     a.nentries = H.nentries; a.nc = H.nc; a.start = H.d_start; a.addr = H.d_addr; a.vec = vec; a.cs = cs;
     a.dst_msg = H.d_dst_msg; a.dst_slot = H.d_dst_slot;
-    FlagArgs f;
-    std::memset(&f, 0, sizeof f);
-    f.n = H.nmsg; f.value = H.seq + 1;
+    a.done = H.d_done; a.nflag = H.nmsg; a.value = H.seq + 1;
     for (int m = 0; m < H.nmsg; m++) {
         if (!H.peer_recv[m]) return fail("halo peers not connected (axb_connect_local / axb_ipc_import)");
         a.dst_base[m] = H.peer_recv[m] + (size_t)parity * H.nc * H.peer_nslots[m] + H.peer_offset[m];
         a.dst_cs[m] = H.peer_nslots[m];
-        f.flag[m] = H.peer_flag[m];
+        a.flag[m] = H.peer_flag[m];
     }
-    LAUNCH(h, k_halo_pack, cdiv((long long)a.nentries * a.nc, 128), 128, a);
-    LAUNCH(h, k_halo_signal, 1, 32, f);
+    // pack + signal in one launch: the last block raises the neighbours' arrival counters
+    LAUNCH(h, k_halo_pack, std::max(1, cdiv((long long)a.nentries * a.nc, 128)), 128, a);
     H.seq++;
     return 0;
 }
-// phase 2: wait until every neighbour's message of this exchange has landed
+// phase 2: wait until every neighbour's message of this exchange has landed.  By default the
+// wait lives inside the corrector (only the threads of cut points spin, the rest of the
+// kernel overlaps the exchange); AXB_HALO_WAIT_KERNEL=1 puts a one-warp wait kernel in front.
 static void halo_wait(axb_handle_s *h, int d) {
     Halo &H = h->halo[d];
-    if (H.nmsg == 0) return;
+    if (H.nmsg == 0 || !halo_wait_kernel()) return;
     CLS(h, 5);
     FlagArgs f;
     std::memset(&f, 0, sizeof f);
@@ -1201,15 +1223,14 @@ static void halo_wait(axb_handle_s *h, int d) {
 }
 static void launch_dumps(axb_handle_s *h) {
     // dump_stuff (time_evol_wave.F90:1104-1251): receivers every seis_it, wavefield every strain_it
-    bool any = false;
     CLS(h, 6);
     if (h->num_rec > 0 && h->iter % h->seis_it == 0 && h->iseismo < h->nseismo_max) {
         RecArgs a;
         a.num_rec = h->num_rec; a.order = h->order; a.seis_it = h->seis_it; a.nseismo_max = h->nseismo_max;
         a.recfile_el = h->d_recfile; a.disp = h->disp; a.cs = h->css;
-        a.recdump = h->d_recdump; a.counters = h->d_counters;
+        a.recdump = h->d_recdump; a.iter = h->iter; a.iseismo = h->iseismo;
         LAUNCH(h, k_sample_receivers, cdiv(h->num_rec, 128), 128, a);
-        h->iseismo++; any = true;
+        h->iseismo++;
     }
     if (h->have_kwf && h->strain_it > 0 && h->iter % h->strain_it == 0 && h->istrain < h->nstrain_max) {
         DumpArgs a;
@@ -1217,14 +1238,11 @@ static void launch_dumps(axb_handle_s *h) {
         a.nstrain_max = h->nstrain_max; a.kwf_mask = h->d_kwf_mask; a.kwf_map = h->d_kwf_map;
         a.disp = h->disp; a.chi = h->chi; a.cs = h->css; a.axis_f = h->d_axis_f;
         a.inv_rho = h->d_inv_rho; a.Dse = h->d_Dse_f; a.Dze = h->d_Dze_f; a.Dsx = h->d_Dsx_f; a.Dzx = h->d_Dzx_f;
-        a.snap = h->d_snap; a.npts = (size_t)h->npt_s_kwf + h->npt_f_kwf; a.counters = h->d_counters;
+        a.snap = h->d_snap; a.npts = (size_t)h->npt_s_kwf + h->npt_f_kwf; a.iter = h->iter; a.istrain = h->istrain;
         if (h->nel_s) LAUNCH(h, k_dump_solid, cdiv((long long)NPT * h->nel_s, 256), 256, a);
         if (h->nel_f) LAUNCH(h, k_dump_fluid, h->grid_f, 256, h->G, a);
-        h->istrain++; any = true;
+        h->istrain++;
     }
-    if (any)
-        LAUNCH(h, k_advance, 1, 32, h->d_counters, h->seis_it, h->strain_it, h->num_rec,
-               (int)h->have_kwf, h->nseismo_max, h->nstrain_max, 1);
 }
 
 // One Newmark step, split at the two exchange points so that in-process groups can be
@@ -1248,7 +1266,7 @@ static void launch_runtime_info(axb_handle_s *h) {
     if (h->nel_s == 0 || h->magnitude == 0.0 || h->iter % 100 != 0) return;
     CLS(h, 7);
     LAUNCH(h, k_blowup_check, cdiv(h->nel_s, 256), 256, h->disp, h->css, h->nel_s,
-           (float)(10.0 * std::fabs(h->magnitude)), h->d_counters);
+           (float)(10.0 * std::fabs(h->magnitude)), h->iter, h->d_counters);
 }
 static int check_blowup(axb_handle_s *h) {
     int it = 0;
@@ -1260,8 +1278,6 @@ static int check_blowup(axb_handle_s *h) {
 static int newmark_c(axb_handle_s *h) {
     halo_wait(h, 0);
     launch_solid_corr(h, 0, h->half_dt, 1, 0, 0);
-    CLS(h, 7);
-    LAUNCH(h, k_next_iter, 1, 32, h->d_counters);
     h->iter++;
     launch_runtime_info(h);
     launch_dumps(h);
@@ -1299,8 +1315,6 @@ static int symp_finish(axb_handle_s *h) {
     }
     if (h->anel && h->cg) launch_solid_element(h, solid_args(h, 2, 0.0, 0.0, 3, 0));
     else if (h->anel) launch_anel_full(h, 0, 1, 0);
-    CLS(h, 7);
-    LAUNCH(h, k_next_iter, 1, 32, h->d_counters);
     h->iter++;
     launch_runtime_info(h);
     launch_dumps(h);
@@ -1354,7 +1368,7 @@ int axb_synchronize(axb_handle h) {
 int axb_profile(axb_handle h, int32_t enable) {
     if (use(h)) return 1;
     CK(cudaStreamSynchronize(h->stream));
-    h->prof = enable != 0;
+    h->prof = enable < 0 ? 0 : (enable > 2 ? 1 : enable);
     h->ev_used = 0; h->ev_cls.clear();
     for (int i = 0; i < 8; i++) { h->prof_ms[i] = 0.0; h->prof_n[i] = 0; }
     return 0;

@@ -38,7 +38,7 @@ struct FluidTileArgs {
     int ielsrc[8];
     const float *src_term;    // (5,5,8)
     const float *stf;
-    const int *iter;
+    int iter;
     int use_mask;             // Newmark multiplies by the free-surface mask, symplectic does not
 };
 
@@ -161,7 +161,7 @@ k_fluid_tile(const __grid_constant__ GMat G, const __grid_constant__ FluidTileAr
             if (a.full) {
                 // add_source_fl (time_evol_wave.F90:1062-1076)
                 if (a.nelsrc > 0) {
-                    const float stf1 = a.stf[*a.iter];
+                    const float stf1 = a.stf[a.iter];
                     if (stf1 != 0.f)
                         for (int k = 0; k < a.nelsrc; k++)
                             if (a.ielsrc[k] - 1 == eg) l = l - a.src_term[q + NPT * k] * stf1;

@@ -108,13 +108,6 @@ __device__ __forceinline__ void load_lane_g(const GMat &G, int i, int j, LaneG &
     L.g0_i = G.G0[i];
 }
 
-}  // namespace axb
-#include "axb_solid_tile.cuh"
-#include "axb_solid_rows.cuh"
-#include "axb_fluid_tile.cuh"
-#include "axb_anel_full.cuh"
-namespace axb {
-
 // ---------------------------------------------------------------------------------------
 // Assembly tables (pull-style direct stiffness summation).  Only the 16
 // edge points of an element can be shared (commun.F90:110-120); each has one int4 entry
@@ -141,6 +134,28 @@ __device__ __forceinline__ int edge_slot(int q) {
     return -1;
 }
 
+// Arrival counters of the current halo exchange (one per message, raised by the peer GPU
+// after its partial sums have landed in this rank's receive slab).  Only the threads of cut
+// points look at them, so the rest of a corrector overlaps the exchange (the reference
+// overlaps it with the next stiffness call, time_evol_wave.F90:386-427).
+struct HaloArrival {
+    const volatile int *flags;   // null: a k_halo_wait launch has already waited
+    int nmsg, value;
+};
+__device__ __forceinline__ void halo_arrived(const HaloArrival &h) {
+    if (!h.flags) return;
+    for (int m = 0; m < h.nmsg; m++)
+        while (h.flags[m] < h.value) { __nanosleep(100); }
+    __threadfence_system();
+}
+
+}  // namespace axb
+#include "axb_solid_tile.cuh"
+#include "axb_solid_rows.cuh"
+#include "axb_fluid_tile.cuh"
+#include "axb_anel_full.cuh"
+namespace axb {
+
 struct FluidCorrArgs {
     int npts;
     int mode;                 // 0 Newmark, 1 symplectic
@@ -150,6 +165,7 @@ struct FluidCorrArgs {
     const float *inv_mass_fluid, *gamma;   // gamma may be null
     AsmTable T;
     const float *recv; size_t recv_cs;
+    HaloArrival arrival;
     int assemble_only;
 };
 
@@ -177,7 +193,9 @@ __global__ void __launch_bounds__(256) k_fluid_corrector(const __grid_constant__
             const int nloc = a.T.grp[g], nrem = a.T.grp[g + 1];
             float s = 0.0f;
             for (int m = 0; m < nloc; m++) s = s + a.ddchi1[a.T.grp[g + 2 + m]];
-            for (int m = 0; m < nrem; m++) s = s + a.recv[a.T.grp[g + 2 + nloc + m]];
+            if (nrem > 0) halo_arrived(a.arrival);
+            // peer-written data: read at L2 (the slab is reused every second exchange)
+            for (int m = 0; m < nrem; m++) s = s + __ldcg(a.recv + a.T.grp[g + 2 + nloc + m]);
             v = s;
         }
     }
@@ -251,11 +269,12 @@ struct SolidCorrArgs {
     const float *inv_mass_rho, *gamma;
     AsmTable T;
     const float *recv; size_t recv_cs;
+    HaloArrival arrival;
     int nelsrc;
     int ielsrc[8];
     const float *src_term;    // (5,5,8,3)
     const float *stf;         // Newmark: stf(niter), symplectic: stf_symp(nstages, niter)
-    const int *iter;
+    int iter;                 // time steps completed before this one (index into stf)
     int stf_stride, stf_off;  // index = iter*stride + off
     int assemble_only;
 };
@@ -308,11 +327,12 @@ __global__ void __launch_bounds__(256) k_solid_corrector(const __grid_constant__
                 for (int c = 0; c < 3; c++)
                     if (!(ORDER == 0 && c == 1)) s[c] = s[c] + a.acc1[ad + cs * c];
             }
+            if (nrem > 0) halo_arrived(a.arrival);
             for (int m = 0; m < nrem; m++) {
                 const int sl = a.T.grp[g + 2 + nloc + m];
 #pragma unroll
                 for (int c = 0; c < 3; c++)
-                    if (!(ORDER == 0 && c == 1)) s[c] = s[c] + a.recv[sl + a.recv_cs * c];
+                    if (!(ORDER == 0 && c == 1)) s[c] = s[c] + __ldcg(a.recv + sl + a.recv_cs * c);
             }
 #pragma unroll
             for (int c = 0; c < 3; c++) v[c] = s[c];
@@ -327,7 +347,7 @@ __global__ void __launch_bounds__(256) k_solid_corrector(const __grid_constant__
     }
     // add_source_el (time_evol_wave.F90:1082-1097)
     if (a.nelsrc > 0) {
-        const float stf1 = a.stf[(size_t)(*a.iter) * a.stf_stride + a.stf_off];
+        const float stf1 = a.stf[(size_t)a.iter * a.stf_stride + a.stf_off];
         if (stf1 != 0.f) {
             for (int k = 0; k < a.nelsrc; k++)
                 if (a.ielsrc[k] - 1 == e) {
@@ -375,24 +395,33 @@ struct PackArgs {
     const int *dst_slot;      // slot inside the peer's slab
     float *dst_base[8];       // per message: peer slab base for the current parity
     size_t dst_cs[8];         // per message: component stride of the peer slab
+    // signal: the last block to finish raises the peers' arrival counters
+    int *done;                // local block counter (zero between launches)
+    int nflag, value;
+    volatile int *flag[8];
 };
 __global__ void k_halo_pack(const __grid_constant__ PackArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.nentries * a.nc) return;
-    const int en = t % a.nentries, c = t / a.nentries;
-    float s = 0.0f;
-    for (int m = a.start[en]; m < a.start[en + 1]; m++) s = s + a.vec[a.addr[m] + a.cs * c];
-    const int msg = a.dst_msg[en];
-    a.dst_base[msg][a.dst_slot[en] + a.dst_cs[msg] * c] = s;
-}
-// release: all packed data of this kernel-ordered stream is visible before the flag
-struct FlagArgs { int n; volatile int *flag[8]; int value; };
-__global__ void k_halo_signal(const __grid_constant__ FlagArgs a) {
-    if (threadIdx.x < a.n) {
-        __threadfence_system();
-        *a.flag[threadIdx.x] = a.value;
+    if (t < a.nentries * a.nc) {
+        const int en = t % a.nentries, c = t / a.nentries;
+        float s = 0.0f;
+        for (int m = a.start[en]; m < a.start[en + 1]; m++) s = s + a.vec[a.addr[m] + a.cs * c];
+        const int msg = a.dst_msg[en];
+        a.dst_base[msg][a.dst_slot[en] + a.dst_cs[msg] * c] = s;
+        __threadfence_system();        // release: my peer store is visible before any flag
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int prev = atomicAdd(a.done, 1);
+        if (prev == (int)gridDim.x - 1) {
+            *a.done = 0;
+            __threadfence_system();
+            for (int m = 0; m < a.nflag; m++) *a.flag[m] = a.value;
+        }
     }
 }
+struct FlagArgs { int n; volatile int *flag[8]; int value; };
+// stand-alone wait (AXB_HALO_WAIT_KERNEL=1): one warp spins on the arrival counters
 __global__ void k_halo_wait(const __grid_constant__ FlagArgs a) {
     if (threadIdx.x < a.n) {
         while (*a.flag[threadIdx.x] < a.value) { __nanosleep(200); }
@@ -406,13 +435,13 @@ struct RecArgs {
     const int *recfile_el;    // (num_rec,3)
     const float *disp; size_t cs;
     float *recdump;           // (3, num_rec, nseismo_max)
-    int *counters;            // [0] iter, [1] iseismo, [2] istrain
+    int iter, iseismo;        // host-tracked: time step just completed, next sample slot
 };
 // nc_compute_recfile_seis_bare (seismograms.f90:783-820) every seis_it steps
 __global__ void k_sample_receivers(const __grid_constant__ RecArgs a) {
-    const int iter = a.counters[0];
+    const int iter = a.iter;
     if (iter % a.seis_it != 0) return;
-    const int is = a.counters[1];
+    const int is = a.iseismo;
     if (is >= a.nseismo_max) return;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.num_rec) return;
@@ -432,13 +461,13 @@ struct DumpArgs {
     const int *axis_f;
     const float *inv_rho, *Dse, *Dze, *Dsx, *Dzx;
     float *snap; size_t npts;
-    int *counters;
+    int iter, istrain;        // host-tracked: time step just completed, next snapshot slot
 };
 // dump_disp_global, solid part (wavefields_io.f90:1041-1052, 743-762)
 __global__ void k_dump_solid(const __grid_constant__ DumpArgs a) {
-    const int iter = a.counters[0];
+    const int iter = a.iter;
     if (iter % a.strain_it != 0) return;
-    const int is = a.counters[2];
+    const int is = a.istrain;
     if (is >= a.nstrain_max) return;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= NPT * a.nel_s) return;
@@ -457,9 +486,9 @@ __global__ void k_dump_solid(const __grid_constant__ DumpArgs a) {
 // pointwise_derivatives.f90:509-546); one warp per fluid element
 __global__ void __launch_bounds__(256)
 k_dump_fluid(const __grid_constant__ GMat G, const __grid_constant__ DumpArgs a) {
-    const int iter = a.counters[0];
+    const int iter = a.iter;
     if (iter % a.strain_it != 0) return;
-    const int is = a.counters[2];
+    const int is = a.istrain;
     if (is >= a.nstrain_max) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const bool active = lane < NPT;
@@ -491,28 +520,13 @@ k_dump_fluid(const __grid_constant__ GMat G, const __grid_constant__ DumpArgs a)
 // runtime_info (time_evol_wave.F90:998-1056), the part that matters on the device: the run is
 // declared blown up when max |disp(1,1,:,:)| exceeds 10 |magnitude| (:1042) or is not finite.
 // counters[3] keeps the first offending iteration (0 = fine).
-__global__ void k_blowup_check(const float *disp, size_t cs, int nel, float thresh, int *counters) {
+__global__ void k_blowup_check(const float *disp, size_t cs, int nel, float thresh, int iter, int *counters) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nel) return;
     const size_t p = (size_t)NPT * e + NP + 1;          // point (ipol, jpol) = (1, 1)
     // written so that NaN counts as blown up (fmaxf would drop it)
     const bool ok = fabsf(disp[p]) <= thresh && fabsf(disp[p + cs]) <= thresh && fabsf(disp[p + 2 * cs]) <= thresh;
-    if (!ok) atomicCAS(&counters[3], 0, counters[0] > 0 ? counters[0] : 1);
-}
-
-// end of step: iter += 1 ; sample counters advance where a dump happened
-__global__ void k_advance(int *counters, int seis_it, int strain_it, int num_rec, int have_kwf,
-                          int nseismo_max, int nstrain_max, int pre) {
-    // pre = 1: account for the dumps of the current iter (called after the dump kernels)
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const int iter = counters[0];
-        if (num_rec > 0 && iter % seis_it == 0 && counters[1] < nseismo_max) counters[1] += 1;
-        if (have_kwf && strain_it > 0 && iter % strain_it == 0 && counters[2] < nstrain_max) counters[2] += 1;
-        (void)pre;
-    }
-}
-__global__ void k_next_iter(int *counters) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) counters[0] += 1;
+    if (!ok) atomicCAS(&counters[3], 0, iter > 0 ? iter : 1);
 }
 
 }  // namespace axb

@@ -38,7 +38,7 @@ constexpr int NCTS = NCWS * 32;          // consumer threads
 constexpr int SOLID_THREADS = NCTS + 32; // + one producer warp
 constexpr int SOLID_CTAS_PER_SM = AXB_SOLID_CTAS;   // resident CTAs per SM the ring is sized for
 constexpr int MAX_STAGES = 8;
-constexpr int NCG = 11;                  // planes of the coarse-grained attenuation slab
+constexpr int NCG = 12;                  // planes of the coarse-grained attenuation slab
 // fluid tiles (axb_fluid_tile.cuh) and the layout-conversion kernels
 constexpr int TE = 16;
 constexpr int TP = TE * NPT;
@@ -57,14 +57,15 @@ enum {
     C_M_w4 = 24, C_M_w5 = 25                                  // quadrupole
 };
 // plane order inside the attenuation slab [tile][plane][TES*4]
-enum { G_Y = 0, G_Vse, G_Vsx, G_Vze, G_Vzx, G_Dse, G_Dze, G_Dsx, G_Dzx, G_dmu, G_dka };
+enum { G_Y = 0, G_Vse, G_Vsx, G_Vze, G_Vzx, G_Dse, G_Dze, G_Dsx, G_Dzx, G_dmu, G_dka,
+       G_invs };   // G_invs: inv_s_solid sampled at the four coarse points
 
 __host__ __device__ constexpr int solid_ncomp(int order) { return order == 0 ? 2 : 3; }
 __host__ __device__ constexpr int solid_nplanes(int order) { return order == 0 ? 15 : (order == 1 ? 24 : 26); }
 
 // float offsets of one ring stage
 struct SolidTileLayout {
-    int u, coef, meta, cg, invs, sdev, str, mv, floats;
+    int u, coef, meta, cg, sdev, str, mv, floats;
     size_t stage_bytes, hdr_bytes;
 };
 __host__ __device__ constexpr SolidTileLayout solid_tile_layout(int order, bool anel, int n_sls) {
@@ -73,10 +74,9 @@ __host__ __device__ constexpr SolidTileLayout solid_tile_layout(int order, bool 
     L.u = o; o += solid_ncomp(order) * 3 * TPS;       // [comp][disp|velo|acc0][TPS]
     L.coef = o; o += solid_nplanes(order) * TPS;
     L.meta = o; o += (3 * TES + 3) / 4 * 4;           // ints: axis, qidx_mu, qidx_ka
-    L.cg = L.invs = L.sdev = L.str = L.mv = o;
+    L.cg = L.sdev = L.str = L.mv = o;
     if (anel) {
         L.cg = o; o += NCG * TES * 4;
-        L.invs = o; o += TPS;
         L.sdev = o; o += TES * 24;
         L.str = o; o += TES * 4;
         L.mv = o; o += TES * 24 * n_sls;
@@ -102,7 +102,7 @@ struct SolidTileArgs {
     const int *meta;          // [tile][3][TES]
     const float *M0_w[10];    // axial vectors (5, nel_pad); index = number - 1
     const float *cg;          // [tile][NCG][TES*4]
-    const float *inv_s;       // (25 * nel_pad)
+    const float *inv_s;       // (25 * nel_pad); k_solid_rows only (the tile kernel reads plane G_invs)
     // per distinct Q and SLS: {ts_fac_t * a_j, ts_fac_tm1 * a_j} (attenuation.f90:162-175 evaluates
     // ts_fac_t(j) * a_j_mu(j) * src left to right, so the first product can be formed once)
     const double2 *c_mu_tab, *c_ka_tab;
@@ -232,7 +232,7 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
             if (a.do_stiff) bytes += NPL * plane_b;
             if (anel) {
                 bytes += NCG * TES * 16 + TES * 96 * n_sls;
-                if (anel_update) bytes += plane_b + TES * 96 + TES * 16;
+                if (anel_update) bytes += TES * 96 + TES * 16;
             }
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 mbar_wait(&empty[s], ph ^ 1);
@@ -254,7 +254,6 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                     bulk_g2s(S + Ly.cg, a.cg + (size_t)tile * NCG * TES * 4, NCG * TES * 16, bar);
                     bulk_g2s(S + Ly.mv, a.memvar + (size_t)tile * TES * 24 * n_sls, TES * 96 * n_sls, bar);
                     if (anel_update) {
-                        bulk_g2s(S + Ly.invs, a.inv_s + pg, plane_b, bar);
                         bulk_g2s(S + Ly.sdev, a.src_dev_tm1 + (size_t)tile * TES * 24, TES * 96, bar);
                         bulk_g2s(S + Ly.str, a.src_tr_tm1 + (size_t)tile * TES * 4, TES * 16, bar);
                     }
@@ -439,7 +438,7 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                 const float *cg = S + Ly.cg + el * 4 + cgk;
                 const float dzdeta = cg[G_Dze * TES * 4], dzdxi = cg[G_Dzx * TES * 4];
                 const float dsdeta = cg[G_Dse * TES * 4], dsdxi = cg[G_Dsx * TES * 4];
-                const float is = S[Ly.invs + t];
+                const float is = cg[G_invs * TES * 4];
                 float g1, g2, g3, g4 = 0.f, g5, g6 = 0.f;
                 // gradient of f: ds = dzdeta*m1 + dzdxi*m2 ; dz = dsdeta*m1 + dsdxi*m2
                 const float b2s = dzdeta * X[2] + dzdxi * X[5];     // d_s u3
@@ -719,6 +718,15 @@ __global__ void k_cg_to_slab(const float *src, float *slab, int pl, int nel, int
     if (p >= (size_t)4 * nel) return;
     const int e = (int)(p / 4), k = (int)(p & 3);
     slab[((size_t)(e / te) * NCG + pl) * te * 4 + (e % te) * 4 + k] = src[p];
+}
+
+// inv_s_solid (25*nel) at the four coarse points -> plane G_invs of the attenuation slab
+__global__ void k_invs_to_slab(const float *inv_s, float *slab, int nel, int te) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (size_t)4 * nel) return;
+    const int e = (int)(p / 4), k = (int)(p & 3);
+    const int i = (k & 2) ? 3 : 1, j = (k & 1) ? 3 : 1;      // coarse index = 2*(i==3) + (j==3)
+    slab[((size_t)(e / te) * NCG + G_invs) * te * 4 + (e % te) * 4 + k] = inv_s[(size_t)e * NPT + i + NP * j];
 }
 
 }  // namespace axb

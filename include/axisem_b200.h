@@ -218,7 +218,9 @@ int AXB(run_group)(axb_handle *handles, int32_t n, int32_t nsteps);
  * Classes: 0 solid element kernel (S_A), 1 fluid element kernel (F_A), 2 fluid corrector
  * (F_B), 3 S/F coupling, 4 solid corrector (S_B), 5 halo pack/signal/wait, 6 sampling and
  * dumps, 7 other.  get_profile synchronises, returns accumulated milliseconds and launch
- * counts per class (arrays of 8) and resets the accumulators. */
+ * counts per class (arrays of 8) and resets the accumulators.  enable: 0 off, 1 events around
+ * every launch, 2 events around the solid element kernel only (two records per step, so the
+ * step time is not disturbed). */
 int AXB(profile)(axb_handle h, int32_t enable);
 int AXB(get_profile)(axb_handle h, double *ms, int64_t *launches);
 
