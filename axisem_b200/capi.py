@@ -194,7 +194,7 @@ class TimeLoop:
             for n in ATT_F:
                 setattr(a, n, _fp(src.get(n), k))
             ck(fn["set_attenuation"](h, C.byref(a)))
-        ck(fn["set_source"](h, 0, C.c_int32(p.nelsrc), _ip(p.ielsrc, k),
+        ck(fn["set_source"](h, C.c_int32(int(getattr(p, "fluid_src", False))), C.c_int32(p.nelsrc), _ip(p.ielsrc, k),
                             _fp(p.source_term_el, k), _fp(p.stf, k), C.c_int32(p.stf.size)))
         s = p.source
         shift = float(np.ceil(s.shift_fact * s.t_0 / p.deltat) * p.deltat)

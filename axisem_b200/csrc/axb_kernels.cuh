@@ -156,6 +156,9 @@ __device__ __forceinline__ void halo_arrived(const HaloArrival &h) {
 #include "axb_anel_full.cuh"
 namespace axb {
 
+#ifndef AXB_CORR_MINB
+#define AXB_CORR_MINB 6      // resident 256-thread blocks per SM the correctors are compiled for
+#endif
 struct FluidCorrArgs {
     int npts;
     int mode;                 // 0 Newmark, 1 symplectic
@@ -171,7 +174,7 @@ struct FluidCorrArgs {
 
 // F_B: pdistsum_fluid + mass inversion + sponge + velocity-potential update.
 // Replaces commun.F90:180-283 (+commpi.F90:587-637) and time_evol_wave.F90:430-434, 459-460.
-__global__ void __launch_bounds__(256) k_fluid_corrector(const __grid_constant__ FluidCorrArgs a) {
+__global__ void __launch_bounds__(256, AXB_CORR_MINB) k_fluid_corrector(const __grid_constant__ FluidCorrArgs a) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.npts) return;
     float v = a.ddchi1[p];
@@ -282,7 +285,7 @@ struct SolidCorrArgs {
 // S_B: pdistsum_solid + source + mass inversion + sponge + velocity update.
 // Replaces commun.F90:69-171 (+commpi.F90:453-500) and time_evol_wave.F90:466-494 / :689-715.
 template <int ORDER>
-__global__ void __launch_bounds__(256) k_solid_corrector(const __grid_constant__ SolidCorrArgs a) {
+__global__ void __launch_bounds__(256, AXB_CORR_MINB) k_solid_corrector(const __grid_constant__ SolidCorrArgs a) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.npts) return;
     const size_t cs = a.cs;

@@ -75,6 +75,7 @@ class Problem:
     rec_index: np.ndarray
     solid_absorbing_gamma: Optional[np.ndarray] = None
     fluid_absorbing_gamma: Optional[np.ndarray] = None
+    fluid_src: bool = False            # source inside the fluid (have_src in the fluid: add_source_fl)
     kwf: Optional[Dict[str, np.ndarray]] = None
 
     @property

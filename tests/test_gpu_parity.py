@@ -211,6 +211,88 @@ def test_two_slices_loopback_matches_oracle_and_one_slice(src):
     assert rel_l2(s2, s1) <= 1e-5
 
 
+@pytest.mark.parametrize("src", ["vertforce", "thetaforce", "mrr", "mpr", "mtt_m_mpp"])
+def test_other_source_types(src):
+    """The remaining src_type(2) values (source.f90:985-1168); vertforce/thetaforce are what the
+    reference's own CI runs on TEST01 (TESTING/test_external.sh, PZ and PX)."""
+    n = 40
+    prob = make_problem(src, anel=True, niter=n, seis_it=3)
+    G, O = _pair(prob, True)
+    for L in (G, O):
+        L.run(n)
+    assert G.nseismo == O.nseismo == n // 3 + 1
+    for f in ("disp", "velo", "chi", "memvar"):
+        assert np.array_equal(G.get(f), O.get(f)), f
+    assert np.array_equal(G.seismograms(), O.seismograms())
+    assert np.abs(O.seismograms()).max() > 0
+
+
+@pytest.mark.parametrize("scheme", ["newmark2", "symplec4"])
+def test_sponge_layer(scheme):
+    """solid/fluid_absorbing_gamma (time_evol_wave.F90:468-494, 430-434): the sponge terms of
+    both correctors."""
+    n = 30
+    prob = make_problem("mtr", anel=True, niter=n, scheme=scheme)
+    rng = np.random.default_rng(7)
+    m = prob.mesh
+    prob.solid_absorbing_gamma = (rng.uniform(0, 2e-2, (m.nel_solid, 5, 5)) / prob.deltat).astype(np.float32)
+    prob.fluid_absorbing_gamma = (rng.uniform(0, 2e-2, (m.nel_fluid, 5, 5)) / prob.deltat).astype(np.float32)
+    G, O = _pair(prob, True)
+    st = seeded_state(G, scale=1e-9, fields=("disp", "velo", "chi", "dchi"))
+    for L in (G, O):
+        apply_state(L, st)
+        L.run(n)
+    for f in ("disp", "velo", "chi", "dchi"):
+        assert np.array_equal(G.get(f), O.get(f)), f
+    assert np.array_equal(G.seismograms(), O.seismograms())
+    # and the sponge does something
+    prob0 = make_problem("mtr", anel=True, niter=n, scheme=scheme)
+    O0 = _pair(prob0, True)[1]
+    apply_state(O0, st)
+    O0.run(n)
+    assert not np.array_equal(O0.get("disp"), O.get("disp"))
+
+
+@pytest.mark.parametrize("src", ["explosion", "mtr"])
+def test_source_in_the_fluid(src):
+    """add_source_fl (time_evol_wave.F90:1062-1080): a source term on fluid elements goes into
+    ddchi before the fluid assembly."""
+    n = 30
+    prob = make_problem(src, niter=n)
+    m = prob.mesh
+    rng = np.random.default_rng(11)
+    prob.fluid_src = True
+    prob.nelsrc = 2
+    prob.ielsrc = np.zeros(8, dtype=np.int32)
+    prob.ielsrc[:2] = [m.nel_fluid // 2 + 1, m.nel_fluid // 2 + 2]
+    st = np.zeros((3, 8, 5, 5), dtype=np.float32)
+    st[0, :2] = rng.standard_normal((2, 5, 5)).astype(np.float32) * 1e-20
+    prob.source_term_el = st
+    G, O = _pair(prob, True)
+    for L in (G, O):
+        L.run(n)
+    for f in ("disp", "chi", "dchi"):
+        assert np.array_equal(G.get(f), O.get(f)), f
+    assert np.abs(O.get("chi")).max() > 0
+    assert np.array_equal(G.seismograms(), O.seismograms())
+
+
+def test_anisotropic_anelastic_newmark_long():
+    """TEST04-type case (anelastic + TI): 200 steps, product build within the north_star
+    tolerance of the oracle, strict build bit-identical."""
+    n = 200
+    prob = make_problem("mtr", anel=True, anisotropic=True, niter=n)
+    from axisem_b200 import solver
+    from oracle import oracle
+    O = oracle.make_loop(prob)
+    O.run(n)
+    for strict in (True, False):
+        G = solver.time_loop(prob, strict=strict)
+        G.run(n)
+        _cmp("seismograms", G.seismograms(), O.seismograms(), strict, 1e-5)
+        _cmp("disp", G.get("disp"), O.get("disp"), strict, 1e-5)
+
+
 def test_blowup_guard_reports_like_the_reference_stop():
     """runtime_info (time_evol_wave.F90:1042-1054): |disp(1,1,:,:)| > 10 |magnitude| stops the
     run; on the device the check runs every 100 steps and surfaces through axb_synchronize."""
