@@ -1,0 +1,12 @@
+#!/bin/bash
+# Builds the native host of the time-loop seam against the CUDA product library:
+#   axisem_b200/axisem_b200_solver  (rpath $ORIGIN -> libaxisem_b200.so next to it)
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+ROOT="$HERE/../.."
+CXX="${CXX:-g++}"
+OUT="${OUT:-$HERE/../axisem_b200_solver}"
+"$CXX" -O2 -std=c++17 -Wall -Wextra -I"$ROOT/include" -o "$OUT" \
+    "$HERE/main.cpp" "$HERE/time_loop.cpp" "$HERE/modules.cpp" \
+    -L"$HERE/.." -laxisem_b200 -Wl,-rpath,'$ORIGIN'
+echo "built $OUT"

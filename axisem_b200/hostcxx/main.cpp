@@ -1,0 +1,123 @@
+// axisem_b200_solver — stand-in for `program axisem` from `call time_loop` on
+// (SOLVER/main.f90:92-110): reads one AXBPROB1 container per theta-slice (what read_db +
+// prepare_waves leave in the Fortran modules), runs the device-resident time loop for all of
+// them in this process (one GPU per slice), and writes the receiver / wavefield buffers the
+// reference hands to its NetCDF writers as raw real(4) files:
+//   PREFIX.rankNNNN.seis.f32   recdumpvar(3, num_rec, nseismo)      (nc_routines.F90:530-540)
+//   PREFIX.rankNNNN.snap.f32   oneddumpvar(npoints, nstrain, 3)     (nc_routines.F90:248,275)
+//   PREFIX.info                key = value summary
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "time_loop.hpp"
+
+namespace {
+
+struct FileSink : axisem::OutputSink {
+    struct Rank {
+        int num_rec = 0, nseis = 0, nsnap = 0;
+        size_t npoints = 0;
+        std::vector<float> seis;                 // (3, num_rec, nseis)
+        std::vector<std::vector<float>> snap;    // chunks of (npoints, n, 3)
+        std::vector<int> snap_n;
+    };
+    std::map<int, Rank> ranks;
+    void seismograms(int rank, int num_rec, int first, int n, const float *v) override {
+        Rank &r = ranks[rank];
+        r.num_rec = num_rec;
+        if (first != r.nseis) throw axisem::SolverError("seismogram chunks out of order");
+        r.seis.insert(r.seis.end(), v, v + (size_t)3 * num_rec * n);
+        r.nseis += n;
+    }
+    void snapshots(int rank, size_t npoints, int first, int n, const float *v) override {
+        Rank &r = ranks[rank];
+        r.npoints = npoints;
+        if (first != r.nsnap) throw axisem::SolverError("snapshot chunks out of order");
+        r.snap.emplace_back(v, v + npoints * n * 3);
+        r.snap_n.push_back(n);
+        r.nsnap += n;
+    }
+    void write(const std::string &prefix) const {
+        for (const auto &kv : ranks) {
+            char app[32];
+            std::snprintf(app, sizeof app, ".rank%04d", kv.first);
+            const Rank &r = kv.second;
+            if (r.nseis) {
+                FILE *f = std::fopen((prefix + app + ".seis.f32").c_str(), "wb");
+                if (!f) throw axisem::SolverError("cannot write " + prefix + app + ".seis.f32");
+                std::fwrite(r.seis.data(), sizeof(float), r.seis.size(), f);
+                std::fclose(f);
+            }
+            if (r.nsnap) {
+                // reassemble oneddumpvar(npoints, nsnap, 3) from the buffered chunks
+                std::vector<float> all(r.npoints * r.nsnap * 3);
+                int off = 0;
+                for (size_t c = 0; c < r.snap.size(); c++) {
+                    const int n = r.snap_n[c];
+                    for (int v = 0; v < 3; v++)
+                        std::memcpy(&all[(size_t)v * r.npoints * r.nsnap + (size_t)off * r.npoints],
+                                    &r.snap[c][(size_t)v * r.npoints * n], sizeof(float) * r.npoints * n);
+                    off += n;
+                }
+                FILE *f = std::fopen((prefix + app + ".snap.f32").c_str(), "wb");
+                if (!f) throw axisem::SolverError("cannot write " + prefix + app + ".snap.f32");
+                std::fwrite(all.data(), sizeof(float), all.size(), f);
+                std::fclose(f);
+            }
+        }
+    }
+};
+
+void usage() {
+    std::fprintf(stderr,
+                 "usage: axisem_b200_solver [--steps N] [--devices D] [--dumpbuffer B] [--quiet] --out PREFIX "
+                 "rank0.axbp [rank1.axbp ...]\n");
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    axisem::TimeLoopOptions opt;
+    std::string prefix;
+    std::vector<std::string> files;
+    for (int k = 1; k < argc; k++) {
+        const std::string a = argv[k];
+        auto need = [&](const char *what) -> const char * {
+            if (k + 1 >= argc) { std::fprintf(stderr, "%s needs a value\n", what); std::exit(2); }
+            return argv[++k];
+        };
+        if (a == "--steps") opt.nsteps = std::atoi(need("--steps"));
+        else if (a == "--devices") opt.ndevices = std::atoi(need("--devices"));
+        else if (a == "--dumpbuffer") opt.nc_dumpbuffersize = std::atoi(need("--dumpbuffer"));
+        else if (a == "--quiet") opt.verbose = false;
+        else if (a == "--out") prefix = need("--out");
+        else if (a == "-h" || a == "--help") { usage(); return 0; }
+        else files.push_back(a);
+    }
+    if (files.empty() || prefix.empty()) { usage(); return 2; }
+    try {
+        std::vector<axisem::Modules> ranks;
+        for (const std::string &f : files) ranks.push_back(axisem::Modules::read(f));
+        FileSink sink;
+        const axisem::TimeLoopResult res = axisem::time_loop(ranks, opt, &sink);
+        sink.write(prefix);
+        FILE *f = std::fopen((prefix + ".info").c_str(), "w");
+        if (!f) throw axisem::SolverError("cannot write " + prefix + ".info");
+        std::fprintf(f, "ranks = %zu\niter = %d\nnseismo = %d\nnstrain = %d\ngpu_launches = %lld\nseconds = %.6f\n",
+                     ranks.size(), res.iter, res.nseismo, res.nstrain, (long long)res.gpu_launches, res.seconds);
+        for (const auto &kv : sink.ranks)
+            std::fprintf(f, "rank%04d = num_rec %d nseis %d npoints %zu nsnap %d\n", kv.first, kv.second.num_rec,
+                         kv.second.nseis, kv.second.npoints, kv.second.nsnap);
+        std::fclose(f);
+        if (opt.verbose) std::printf("time loop done: %d steps, %.3f s\n", res.iter, res.seconds);
+    } catch (const std::exception &e) {
+        // the reference writes the message and stops (pcheck / stop)
+        std::fprintf(stderr, "ERROR: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

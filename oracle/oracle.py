@@ -35,3 +35,23 @@ def load() -> Library:
 
 def make_loop(prob) -> TimeLoop:
     return TimeLoop(load(), prob)
+
+
+HOST_EXE = os.path.join(HERE, "axisem_host_oracle")
+
+
+def build_host(force: bool = False) -> str:
+    """The native (C++) host of the time-loop seam, axisem_b200/hostcxx/, compiled against this
+    oracle's implementation of the header (prefix axo_): lets the CPU tests drive the host
+    logic without a GPU."""
+    build()
+    src_dir = os.path.join(HERE, "..", "axisem_b200", "hostcxx")
+    srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cpp", ".hpp"))]
+    stale = (not os.path.exists(HOST_EXE)
+             or os.path.getmtime(HOST_EXE) < max([os.path.getmtime(f) for f in srcs] + [os.path.getmtime(LIB)]))
+    if force or stale:
+        cpp = [f for f in srcs if f.endswith(".cpp")]
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(HERE, "..", "include"),
+                               "-DAXB_PREFIX=axo_", "-o", HOST_EXE] + cpp
+                              + ["-L" + HERE, "-laxisem_oracle", "-Wl,-rpath," + HERE])
+    return HOST_EXE
