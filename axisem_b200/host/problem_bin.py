@@ -132,8 +132,21 @@ def problem_records(p):
     return r
 
 
-def save_problem_bin(prob, path: str):
+# what read_meshdb (hostcxx/meshdb.cpp) provides from the MESHER's database
+MESH_LEVEL = ("data_proc%nproc", "data_mesh%nel_solid", "data_mesh%nel_fluid", "data_mesh%nglob_solid",
+              "data_mesh%nglob_fluid", "data_mesh%nel_bdry", "data_mesh%igloc_solid", "data_mesh%igloc_fluid",
+              "data_mesh%axis_solid", "data_mesh%axis_fluid", "data_mesh%ax_el_solid", "data_mesh%ax_el_fluid",
+              "data_spec%G0", "data_spec%G1", "data_spec%G1T", "data_spec%G2", "data_spec%G2T",
+              "data_mesh%bdry_solid_el", "data_mesh%bdry_fluid_el", "data_mesh%bdry_jpol_solid",
+              "data_mesh%bdry_jpol_fluid")
+
+
+def save_problem_bin(prob, path: str, without_mesh: bool = False):
+    """without_mesh: leave out everything the mesher's database holds (and the halo lists), for
+    `axisem_b200_solver terms.axbp+meshdb.datNNNN`."""
     recs = problem_records(prob)
+    if without_mesh:
+        recs = [r for r in recs if r[0] not in MESH_LEVEL and not r[0].startswith("data_comm%")]
     out = [b"AXBPROB1", struct.pack("<I", len(recs))]
     for name, a, t in recs:
         _rec(out, name, a, t)

@@ -7,6 +7,10 @@ ROOT="$HERE/../.."
 CXX="${CXX:-g++}"
 OUT="${OUT:-$HERE/../axisem_b200_solver}"
 "$CXX" -O2 -std=c++17 -Wall -Wextra -I"$ROOT/include" -o "$OUT" \
-    "$HERE/main.cpp" "$HERE/time_loop.cpp" "$HERE/modules.cpp" \
+    "$HERE/main.cpp" "$HERE/time_loop.cpp" "$HERE/modules.cpp" "$HERE/meshdb.cpp" \
     -L"$HERE/.." -laxisem_b200 -Wl,-rpath,'$ORIGIN'
 echo "built $OUT"
+# mesher database -> module variables (no device code)
+"$CXX" -O2 -std=c++17 -Wall -Wextra -I"$ROOT/include" -o "$HERE/../axisem_b200_meshdb2axbp" \
+    "$HERE/meshdb2axbp.cpp" "$HERE/meshdb.cpp" "$HERE/modules.cpp"
+echo "built $HERE/../axisem_b200_meshdb2axbp"

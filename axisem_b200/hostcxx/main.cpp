@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "meshdb.hpp"
 #include "time_loop.hpp"
 
 namespace {
@@ -75,7 +76,7 @@ struct FileSink : axisem::OutputSink {
 void usage() {
     std::fprintf(stderr,
                  "usage: axisem_b200_solver [--steps N] [--devices D] [--dumpbuffer B] [--quiet] --out PREFIX "
-                 "rank0.axbp [rank1.axbp ...]\n");
+                 "rank0.axbp[+meshdb.dat0000] [rank1.axbp[+meshdb.dat0001] ...]\n");
 }
 
 }  // namespace
@@ -101,7 +102,14 @@ int main(int argc, char **argv) {
     if (files.empty() || prefix.empty()) { usage(); return 2; }
     try {
         std::vector<axisem::Modules> ranks;
-        for (const std::string &f : files) ranks.push_back(axisem::Modules::read(f));
+        for (const std::string &f : files) {
+            // "terms.axbp+meshdb.datNNNN": mesh-level variables straight from the MESHER's database
+            const size_t plus = f.find('+');
+            axisem::Modules m = axisem::Modules::read(f.substr(0, plus));
+            if (plus != std::string::npos)
+                m.merge_missing(axisem::read_meshdb(f.substr(plus + 1), m.int_of("data_proc%mynum")));
+            ranks.push_back(std::move(m));
+        }
         FileSink sink;
         const axisem::TimeLoopResult res = axisem::time_loop(ranks, opt, &sink);
         sink.write(prefix);

@@ -8,6 +8,7 @@
 // pointers can be handed to the C ABI of include/axisem_b200.h unchanged.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -44,7 +45,14 @@ public:
     int32_t int_of(const std::string &name, int32_t dflt) const;
     double real_of(const std::string &name) const;
     void put(const std::string &name, Array a) { vars_[name] = std::move(a); }
+    // take every variable of `other` that is not set here
+    void merge_missing(const Modules &other) {
+        for (const auto &kv : other.vars_) vars_.insert(kv);
+    }
     size_t size() const { return vars_.size(); }
+    void for_each(const std::function<void(const std::string &, const Array &)> &fn) const {
+        for (const auto &kv : vars_) fn(kv.first, kv.second);
+    }
 
 private:
     std::map<std::string, Array> vars_;

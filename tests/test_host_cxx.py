@@ -102,6 +102,34 @@ def test_host_two_slices_in_one_process(tmp_path):
         assert np.array_equal(got, s)
 
 
+def test_host_takes_the_mesh_from_the_meshers_database(tmp_path):
+    """terms.axbp+meshdb.datNNNN: topology, spectral matrices and message lists come from the
+    MESHER-format database through the native reader; the result is the same run."""
+    from axisem_b200.capi import connect_local, run_group
+    from axisem_b200.host.meshdb_io import write_meshdb
+    from oracle import oracle
+    n = 40
+    probs = [make_problem("mtr", anel=True, niter=n, rank=r, nranks=2) for r in range(2)]
+    args = []
+    for r, p in enumerate(probs):
+        save_problem_bin(p, str(tmp_path / f"t{r}.axbp"), without_mesh=True)
+        write_meshdb(p.mesh, str(tmp_path / f"meshdb.dat{r:04d}"), dt=p.deltat)
+        args.append(f"{tmp_path}/t{r}.axbp+{tmp_path}/meshdb.dat{r:04d}")
+    r = _run(_oracle_exe(), ["--quiet", "--out", str(tmp_path / "m")] + args)
+    assert r.returncode == 0, r.stderr
+    ol = [oracle.make_loop(p) for p in probs]
+    olib = oracle.load()
+    connect_local(olib, ol)
+    run_group(olib, ol, n)
+    for k, o in enumerate(ol):
+        s = o.seismograms()
+        got = np.fromfile(tmp_path / f"m.rank{k:04d}.seis.f32", dtype=np.float32).reshape(s.shape)
+        assert np.array_equal(got, s)
+    # without the database the stripped container is not enough, and the host says what is missing
+    r = _run(_oracle_exe(), ["--quiet", "--out", str(tmp_path / "x"), str(tmp_path / "t0.axbp")])
+    assert r.returncode == 1 and "data_" in r.stderr
+
+
 def test_host_error_behaviour(tmp_path):
     exe = _oracle_exe()
     # a file that is not a container: message + non-zero exit, like the reference's stop
