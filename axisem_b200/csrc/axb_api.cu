@@ -68,9 +68,7 @@ struct axb_handle_s {
     GMat G;
     int order = 0;
     // solid element kernel inputs in their device layout (axb_solid_tile.cuh)
-    bool rows = false;             // S_A variant: k_solid_tile (tiles of TE, default) or k_solid_rows (tiles of TB)
     int te_s = TES;                // elements per solid tile of the chosen variant
-    int npair = 0;                 // k_solid_rows: warp pairs (= stages) per CTA
     int nel_pad_s = 0;             // nel_s rounded up to whole tiles
     size_t css = 0;                // component stride of disp/velo/acc* = 25 * nel_pad_s
     float *d_coef = nullptr;       // [tile][plane][TP]
@@ -102,6 +100,8 @@ struct axb_handle_s {
     float *d_cg = nullptr;         // [tile][NCG][TE*4]
     float *d_inv_s = nullptr;      // (25 * nel_pad_s)
     double2 *d_c_mu_tab = nullptr, *d_c_ka_tab = nullptr;
+    int ntab_mu = 0, ntab_ka = 0;  // rows (distinct Q values) of the two tables
+    int tab_smem = 0, ring_off = 0; // S_A: tables staged in shared memory, ring offset
     std::vector<double> ts_t_h, ts_tm1_h, exp_w_h;
     float *memvar = nullptr, *src_dev_tm1 = nullptr, *src_tr_tm1 = nullptr;
     // COARSE_GRAINED false: flat (25 nel) planes and (5 nel) axial vectors (axb_anel_full.cuh)
@@ -455,8 +455,7 @@ int axb_set_mesh(axb_handle h, int32_t npol, int32_t nel_solid, int32_t nel_flui
     if (npol != 4) return fail("axb_set_mesh: npol must be 4");
     if (use(h)) return 1;
     h->nel_s = nel_solid; h->nel_f = nel_fluid; h->nglob_s = nglob_solid; h->nglob_f = nglob_fluid;
-    if (const char *ev = getenv("AXB_SOLID_KERNEL")) h->rows = std::string(ev) == "rows";
-    h->te_s = h->rows ? TB : TES;
+    h->te_s = TES;
     h->nel_pad_s = (nel_solid + h->te_s - 1) / h->te_s * h->te_s;
     h->nel_pad_f = (nel_fluid + TE - 1) / TE * TE;
     h->css = (size_t)NPT * h->nel_pad_s;
@@ -666,12 +665,15 @@ int axb_set_attenuation(axb_handle h, const axb_attenuation *a) {
         CK(cudaDeviceSynchronize());
         cudaFree(d_tmp);
     }
-    if (upload_padded(h, h->d_inv_s, a->inv_s_solid, n, h->css)) return 1;
     if (n4) {
         // the coarse-grained kernels only need 1/s at the four coarse points
-        k_invs_to_slab<<<(unsigned)((n4 + 255) / 256), 256>>>(h->d_inv_s, h->d_cg, h->nel_s, h->te_s);
+        float *d_tmp = nullptr;
+        CK(cudaMalloc((void **)&d_tmp, n * sizeof(float)));
+        CK(cudaMemcpy(d_tmp, a->inv_s_solid, n * sizeof(float), cudaMemcpyHostToDevice));
+        k_invs_to_slab<<<(unsigned)((n4 + 255) / 256), 256>>>(d_tmp, h->d_cg, h->nel_s, h->te_s);
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
+        cudaFree(d_tmp);
     }
     return 0;
 }
@@ -841,6 +843,8 @@ int axb_finalize_setup(axb_handle h) {
         if (tab_mu.empty()) { tab_mu.assign(h->n_sls, make_double2(0, 0)); tab_ka.assign(h->n_sls, make_double2(0, 0)); }
         UP(h->d_c_mu_tab, tab_mu.data(), tab_mu.size());
         UP(h->d_c_ka_tab, tab_ka.data(), tab_ka.size());
+        h->ntab_mu = (int)(tab_mu.size() / h->n_sls);
+        h->ntab_ka = (int)(tab_ka.size() / h->n_sls);
         const size_t np = h->cg ? 4 : NPT;
         if (dzeros(h, h->memvar, np * 6 * h->n_sls * h->nel_pad_s)) return 1;
         if (dzeros(h, h->src_dev_tm1, np * 6 * h->nel_pad_s)) return 1;
@@ -896,22 +900,7 @@ int axb_finalize_setup(axb_handle h) {
         // compiled variants: elastic, the reference default NR_LIN_SOLIDS 5, any other n_sls
         const int v = (!h->anel || !h->cg) ? 0 : (h->n_sls == 5 ? 1 : 2);
         const size_t optin = prop.sharedMemPerBlockOptin;
-        if (h->rows) {
-            // S_A (rows): one persistent CTA per SM, one stage per warp pair
-            const SolidRowsLayout Ly = solid_rows_layout(h->order, h->anel && h->cg, h->n_sls);
-            int npair = (int)std::min<size_t>(ROWS_MAX_PAIRS, (optin - ROWS_HDR_BYTES) / Ly.stage_bytes);
-            if (const char *ev = getenv("AXB_SOLID_PAIRS")) npair = std::max(1, std::min(npair, atoi(ev)));
-            if (npair < 1) return fail("not enough shared memory for one solid stage");
-            h->npair = npair;
-            h->smem_solid = ROWS_HDR_BYTES + (size_t)npair * Ly.stage_bytes;
-            const int ntiles = h->nel_pad_s / TB;
-            h->grid_s = std::max(1, std::min(cdiv(ntiles, npair), sms));
-            static solid_kernel_t const table[3][3] = {
-                {k_solid_rows<0, 0>, k_solid_rows<0, 5>, k_solid_rows<0, -1>},
-                {k_solid_rows<1, 0>, k_solid_rows<1, 5>, k_solid_rows<1, -1>},
-                {k_solid_rows<2, 0>, k_solid_rows<2, 5>, k_solid_rows<2, -1>}};
-            h->solid_kernel = table[h->order][v];
-        } else {
+        {
             // S_A (tile): persistent CTAs; the ring takes all the shared memory it can get
             const SolidTileLayout Ly = solid_tile_layout(h->order, h->anel && h->cg, h->n_sls);
             const size_t cap = SOLID_CTAS_PER_SM == 1 ? optin
@@ -920,7 +909,19 @@ int axb_finalize_setup(axb_handle h) {
             int nst = (int)std::min<size_t>(MAX_STAGES, (cap - Ly.hdr_bytes) / Ly.stage_bytes);
             if (const char *ev = getenv("AXB_SOLID_STAGES")) nst = std::max(2, std::min(nst, atoi(ev)));
             h->nst = nst;
-            h->smem_solid = Ly.hdr_bytes + (size_t)nst * Ly.stage_bytes;
+            // the a_j tables go to shared memory when that does not cost a ring stage
+            size_t tab_bytes = 0;
+            h->tab_smem = 0;
+            if (h->anel && h->cg) {
+                const size_t need = ((size_t)(h->ntab_mu + h->ntab_ka) * h->n_sls * sizeof(double2) + 127) / 128 * 128;
+                const char *ev = getenv("AXB_TAB_SMEM");
+                if (Ly.hdr_bytes + need + (size_t)nst * Ly.stage_bytes <= cap && !(ev && atoi(ev) == 0)) {
+                    tab_bytes = need;
+                    h->tab_smem = 1;
+                }
+            }
+            h->ring_off = (int)(Ly.hdr_bytes + tab_bytes);
+            h->smem_solid = Ly.hdr_bytes + tab_bytes + (size_t)nst * Ly.stage_bytes;
             h->grid_s = std::max(1, std::min(h->nel_pad_s / TES, sms * SOLID_CTAS_PER_SM));
             static solid_kernel_t const table[3][3] = {
                 {k_solid_tile<0, 0>, k_solid_tile<0, 5>, k_solid_tile<0, -1>},
@@ -1074,8 +1075,9 @@ static SolidTileArgs solid_args(axb_handle_s *h, int mode, double c0, double c1,
     a.disp = h->disp; a.velo = h->velo; a.acc0 = h->acc0; a.acc1 = h->acc1; a.cs = h->css;
     a.coef = h->d_coef; a.meta = h->d_meta;
     for (int k = 0; k < 10; k++) a.M0_w[k] = h->d_M0_w[k];
-    a.cg = h->d_cg; a.inv_s = h->d_inv_s;
+    a.cg = h->d_cg;
     a.c_mu_tab = h->d_c_mu_tab; a.c_ka_tab = h->d_c_ka_tab;
+    a.tab_smem = h->tab_smem; a.ntab_mu = h->ntab_mu; a.ntab_ka = h->ntab_ka; a.ring_off = h->ring_off;
     for (int k = 0; k < 8; k++) a.exp_w[k] = k < h->n_sls ? h->exp_w_h[k] : 0.0;
     a.memvar = h->memvar; a.src_dev_tm1 = h->src_dev_tm1; a.src_tr_tm1 = h->src_tr_tm1;
     return a;
@@ -1090,7 +1092,7 @@ static SolidTileArgs solid_args(axb_handle_s *h, int mode, double c0, double c1,
 static void launch_solid_element(axb_handle_s *h, const SolidTileArgs &a) {
     if (h->nel_s == 0) return;
     CLS(h, 0);
-    LAUNCH_SMEM(h, h->solid_kernel, h->grid_s, h->rows ? 64 * h->npair : SOLID_THREADS, h->smem_solid, h->G, a);
+    LAUNCH_SMEM(h, h->solid_kernel, h->grid_s, SOLID_THREADS, h->smem_solid, h->G, a);
 }
 // COARSE_GRAINED false: the anelastic K term and/or the memory-variable update at all 25
 // points, behind S_A (axb_anel_full.cuh)

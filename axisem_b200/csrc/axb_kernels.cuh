@@ -151,7 +151,6 @@ __device__ __forceinline__ void halo_arrived(const HaloArrival &h) {
 
 }  // namespace axb
 #include "axb_solid_tile.cuh"
-#include "axb_solid_rows.cuh"
 #include "axb_fluid_tile.cuh"
 #include "axb_anel_full.cuh"
 namespace axb {

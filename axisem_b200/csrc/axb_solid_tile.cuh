@@ -102,10 +102,13 @@ struct SolidTileArgs {
     const int *meta;          // [tile][3][TES]
     const float *M0_w[10];    // axial vectors (5, nel_pad); index = number - 1
     const float *cg;          // [tile][NCG][TES*4]
-    const float *inv_s;       // (25 * nel_pad); k_solid_rows only (the tile kernel reads plane G_invs)
     // per distinct Q and SLS: {ts_fac_t * a_j, ts_fac_tm1 * a_j} (attenuation.f90:162-175 evaluates
     // ts_fac_t(j) * a_j_mu(j) * src left to right, so the first product can be formed once)
     const double2 *c_mu_tab, *c_ka_tab;
+    // the tables are small (one row per distinct Q): when they fit they are staged in shared
+    // memory behind the header, and the ring starts at ring_off
+    int tab_smem, ntab_mu, ntab_ka;
+    int ring_off;             // byte offset of the ring in dynamic shared memory
     double exp_w[8];          // exp(-w_j deltat) per SLS (constant bank)
     float *memvar, *src_dev_tm1, *src_tr_tm1;
 };
@@ -204,7 +207,8 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
     float *x_anS = x_rsum + TES * 24;                            // [TES][36]
     float *x_src = x_anS + TES * 36;                             // [TES][28]
     const SolidTileLayout Ly = solid_tile_layout(ORDER, NSLS != 0, n_sls);
-    unsigned char *ring = smem + Ly.hdr_bytes;
+    unsigned char *ring = smem + a.ring_off;
+    double2 *s_tab = reinterpret_cast<double2 *>(smem + Ly.hdr_bytes);   // [mu rows | kappa rows][n_sls]
 
     const int t = threadIdx.x;
     const int warp = t >> 5, lane = t & 31;
@@ -216,6 +220,11 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
         const float *src = reinterpret_cast<const float *>(&G);
         float *dst = reinterpret_cast<float *>(&sG);
         for (int k = t; k < (int)(sizeof(GMat) / sizeof(float)); k += blockDim.x) dst[k] = src[k];
+        if (NSLS != 0 && a.tab_smem) {
+            const int nmu = a.ntab_mu * n_sls, nka = a.ntab_ka * n_sls;
+            for (int k = t; k < nmu; k += blockDim.x) s_tab[k] = a.c_mu_tab[k];
+            for (int k = t; k < nka; k += blockDim.x) s_tab[nmu + k] = a.c_ka_tab[k];
+        }
     }
     __syncthreads();
 
@@ -674,8 +683,10 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                 const double src_tr_t = f2d(x_src[mel * 28 + 24 + mv_k]);
                 const double s_tr_tm1 = f2d(S[Ly.str + mel * 4 + mv_k]);
                 const double dsrc_t = f2d(src_dev_t), dsrc_tm1 = f2d(s_dev_tm1);
-                const double2 *c_mu = a.c_mu_tab + (size_t)n_sls * meta[TES + mel];
-                const double2 *c_ka = a.c_ka_tab + (size_t)n_sls * meta[2 * TES + mel];
+                const double2 *c_mu = a.tab_smem ? s_tab + n_sls * meta[TES + mel]
+                                                 : a.c_mu_tab + (size_t)n_sls * meta[TES + mel];
+                const double2 *c_ka = a.tab_smem ? s_tab + n_sls * (a.ntab_mu + meta[2 * TES + mel])
+                                                 : a.c_ka_tab + (size_t)n_sls * meta[2 * TES + mel];
                 const float *mv = S + Ly.mv + mel * 24 * n_sls + ml;
                 float *out = a.memvar + meg * 24 * n_sls + ml;
 #pragma unroll
