@@ -110,20 +110,23 @@ class ClockSampler:
 
 
 def cpu_reference_rate(args, src, anel, cores=None):
-    """The oracle (line-by-line CPU restatement of the reference loop), one thread per
-    theta-slice = one 'MPI rank' per host core, on a bounded sample of the workload: the
-    same radial structure and physics, fewer theta columns."""
+    """The oracle (line-by-line CPU restatement of the reference loop) compiled -O3 with FMA
+    contraction (oracle/libaxisem_oracle_fast.so: the way a production CPU build would be; the
+    parity checks use the strict build), one thread per theta-slice = one 'MPI rank' per host
+    core, on a bounded sample of the workload: the same radial structure and physics, fewer
+    theta columns."""
     from oracle import oracle
     from axisem_b200.capi import connect_local, run_group
     cores = cores or (os.cpu_count() or 1)
     ncols = max(args.cpu_sample_cols // cores, 2) * cores
     spec = prem_mesh_spec(ntheta=ncols, nr_target=args.nr)
-    lib = oracle.load()
+    lib = oracle.load_fast()
     nsteps = args.cpu_steps or 4
     att = AttenuationModel(coarse_grained=False) if (anel and args.full_memvars) else None
     probs = [build_problem(spec, SourceParams(src_type2=src), anel=anel, att=att, niter=400, rank=r,
                            nranks=cores, rec_colat_deg=[]) for r in range(cores)]
-    loops = [oracle.make_loop(p) for p in probs]
+    from axisem_b200.capi import TimeLoop
+    loops = [TimeLoop(lib, p) for p in probs]
     rng = np.random.default_rng(1234)
     for L in loops:
         for f in ("disp", "velo"):

@@ -23,7 +23,26 @@ def build(force: bool = False) -> str:
     return LIB
 
 
+LIB_FAST = os.path.join(HERE, "libaxisem_oracle_fast.so")
+
+
+def build_fast(force: bool = False) -> str:
+    """-O3 / FMA build of the same source: the CPU baseline of bench.py (timing only)."""
+    src = os.path.join(HERE, "axisem_oracle.c")
+    if force or not os.path.exists(LIB_FAST) or os.path.getmtime(LIB_FAST) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "-B", "libaxisem_oracle_fast.so"], stdout=subprocess.DEVNULL)
+    return LIB_FAST
+
+
 _lib = None
+_lib_fast = None
+
+
+def load_fast() -> Library:
+    global _lib_fast
+    if _lib_fast is None:
+        _lib_fast = Library(build_fast(), "axo_")
+    return _lib_fast
 
 
 def load() -> Library:
