@@ -60,11 +60,11 @@ OPS = {"solid_stiffness": 0, "anel_stiffness": 1, "fluid_stiffness": 2, "pdistsu
 
 # every symbol include/axisem_b200.h declares
 SYMBOLS = ["last_error", "create", "destroy", "set_mesh", "set_solid_terms", "set_fluid_terms",
-           "set_mass", "set_sponge", "set_sf_boundary", "set_attenuation", "set_source",
+           "set_mass", "set_energy", "set_sponge", "set_sf_boundary", "set_attenuation", "set_source",
            "set_stf_values", "set_stf_params", "set_receivers", "set_kwf", "set_halo", "set_time",
            "finalize_setup", "set_stream", "synchronize", "connect_local", "ipc_export", "ipc_import", "run", "run_group",
            "profile", "get_profile", "iter", "nseismo", "nstrain", "gpu_launches", "fetch_seismograms",
-           "fetch_snapshots", "get_state", "set_state", "apply_op"]
+           "fetch_snapshots", "fetch_energy", "get_state", "set_state", "apply_op"]
 
 
 class AxbError(RuntimeError):
@@ -159,6 +159,8 @@ class TimeLoop:
                                      _fp(f.get("M0_w_fl"), k), _fp(p.inv_mass_fluid, k),
                                      _fp(p.fluid_free_surface_mask, k)))
         ck(fn["set_mass"](h, _fp(p.inv_mass_rho, k)))
+        if getattr(p, "unassem_mass_rho_solid", None) is not None:
+            ck(fn["set_energy"](h, _fp(p.unassem_mass_rho_solid, k), _fp(p.unassem_mass_lam_fluid, k)))
         if p.solid_absorbing_gamma is not None or p.fluid_absorbing_gamma is not None:
             ck(fn["set_sponge"](h, _fp(p.solid_absorbing_gamma, k), _fp(p.fluid_absorbing_gamma, k)))
         if m.nel_bdry:
@@ -285,6 +287,15 @@ class TimeLoop:
         if n > 0:
             self.lib.check(self.lib.fn["fetch_snapshots"](
                 self.h, C.c_int32(first), C.c_int32(n), out.ctypes.data_as(_F)))
+        return out
+
+    def energy(self, first: int = 0, n: Optional[int] = None) -> np.ndarray:
+        """(n, 4): epot_sol, ekin_sol, epot_flu, ekin_flu sums of this rank for iter first..first+n-1."""
+        n = self.iter + 1 - first if n is None else n
+        out = np.zeros((n, 4), dtype=np.float32)
+        if n > 0:
+            self.lib.check(self.lib.fn["fetch_energy"](self.h, C.c_int32(first), C.c_int32(n),
+                                                       out.ctypes.data_as(_F)))
         return out
 
     def _field_shape(self, name: str):

@@ -89,6 +89,11 @@ struct axb_handle_s {
     int nst_f = 0;
     size_t smem_fluid = 0;
     float *inv_mass_rho = nullptr, *gamma_s = nullptr, *gamma_f = nullptr;
+    // dump_energy
+    bool dump_energy = false;
+    float *um_rho_s = nullptr, *um_lam_f = nullptr;
+    double *d_energy = nullptr;    // (4, niter + 1): epot_sol, ekin_sol, epot_flu, ekin_flu
+    int ienergy = 0;               // next energy sample (== iter it belongs to)
     // boundary
     int nel_bdry = 0;
     std::vector<int> bdry_fel_h, bdry_jf_h;
@@ -578,6 +583,16 @@ int axb_set_mass(axb_handle h, const float *inv_mass_rho) {
     return 0;
 }
 
+int axb_set_energy(axb_handle h, const float *unassem_mass_rho_solid, const float *unassem_mass_lam_fluid) {
+    if (use(h)) return 1;
+    if (!unassem_mass_rho_solid && h->nel_s > 0) return fail("axb_set_energy: NULL unassem_mass_rho_solid");
+    if (!unassem_mass_lam_fluid && h->nel_f > 0) return fail("axb_set_energy: NULL unassem_mass_lam_fluid");
+    if (h->nel_s > 0) UP(h->um_rho_s, unassem_mass_rho_solid, (size_t)NPT * h->nel_s);
+    if (h->nel_f > 0) UP(h->um_lam_f, unassem_mass_lam_fluid, (size_t)NPT * h->nel_f);
+    h->dump_energy = true;
+    return 0;
+}
+
 int axb_set_sponge(axb_handle h, const float *solid_gamma, const float *fluid_gamma) {
     if (use(h)) return 1;
     if (!solid_gamma && !fluid_gamma) return 0;
@@ -879,6 +894,7 @@ int axb_finalize_setup(axb_handle h) {
         if (dzeros(h, h->d_snap, (size_t)(h->npt_s_kwf + h->npt_f_kwf) * h->nstrain_max * 3)) return 1;
     }
     if (dzeros(h, h->d_counters, 4)) return 1;
+    if (h->dump_energy && dzeros(h, h->d_energy, (size_t)4 * (h->niter + 1))) return 1;
     // persistent grids: whole multiples of the SM count
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
@@ -931,7 +947,7 @@ int axb_finalize_setup(axb_handle h) {
         }
         CK(cudaFuncSetAttribute(h->solid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_solid));
     }
-    h->iter = h->iseismo = h->istrain = 0;
+    h->iter = h->iseismo = h->istrain = h->ienergy = 0;
     h->finalized = true;
     CK(cudaDeviceSynchronize());
     // host copies no longer needed
@@ -1126,14 +1142,15 @@ static void launch_solid_step(axb_handle_s *h, int mode, double c0, double c1, i
         launch_solid_element(h, solid_args(h, mode, c0, c1, anel, 1));
     }
 }
-static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1, int full, int use_mask) {
+static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1, int full, int use_mask, int energy = 0) {
     if (h->nel_f == 0) return;
     CLS(h, 1);
     FluidTileArgs a;
     std::memset(&a, 0, sizeof a);
     a.ntiles = h->nel_pad_f / TE; a.mode = mode; a.order = h->order; a.full = full;
     a.npl = h->npl_f; a.mask_plane = h->mask_plane_f; a.nst = h->nst_f; a.dt = c0; a.half_dt_sq = c1;
-    a.chi = h->chi; a.ddchi1 = h->ddchi1; a.dchi = h->dchi; a.ddchi0 = h->ddchi0;
+    a.chi = energy ? h->dchi : h->chi; a.ddchi1 = h->ddchi1; a.dchi = h->dchi; a.ddchi0 = h->ddchi0;
+    a.emask = energy;
     a.coef = h->d_coef_f; a.meta = h->d_meta_f; a.M0_w_fl = h->M0_w_fl;
     a.bdry_sel = h->d_bsel; a.bdry_js = h->d_bjs; a.bdry_matr = h->d_bmatr; a.nel_bdry = h->nel_bdry;
     a.disp = h->disp; a.cs_solid = h->css;
@@ -1223,8 +1240,36 @@ static void halo_wait(axb_handle_s *h, int d) {
     for (int m = 0; m < H.nmsg; m++) f.flag[m] = H.flags + m;
     LAUNCH(h, k_halo_wait, 1, 32, f);
 }
+// energy (time_evol_wave.F90:1424-1526) of the state after step `iter`.  K u and K dchi go
+// to acc1 / ddchi1, which are dead between steps.
+static void launch_energy(axb_handle_s *h) {
+    if (!h->dump_energy || h->iter > h->niter || h->iter != h->ienergy) return;
+    h->ienergy++;
+    CLS(h, 6);
+    double *out = h->d_energy + (size_t)4 * h->iter;
+    if (h->nel_s > 0) {
+        SolidTileArgs a = solid_args(h, 2, 0.0, 0.0, 0, 1);
+        a.emask = 1;
+        launch_solid_element(h, a);
+        CLS(h, 6);
+        EnergyArgs e;
+        e.npts = NPT * h->nel_s; e.cs = h->css; e.order = h->order;
+        e.stiff = h->acc1; e.u = h->disp; e.v = h->velo; e.mass = h->um_rho_s; e.axis = h->d_axis_s; e.out = out;
+        LAUNCH(h, k_energy_solid, cdiv(e.npts, 256), 256, e);
+    }
+    if (h->nel_f > 0) {
+        launch_fluid_element(h, 2, 0.0, 0.0, 0, 0, 1);
+        CLS(h, 6);
+        EnergyArgs e;
+        e.npts = NPT * h->nel_f; e.cs = 0; e.order = h->order;
+        e.stiff = h->ddchi1; e.u = h->dchi; e.v = h->ddchi0; e.mass = h->um_lam_f; e.axis = h->d_axis_f; e.out = out + 2;
+        LAUNCH(h, k_energy_fluid, cdiv(e.npts, 256), 256, e);
+    }
+    h->acc1_is_acc0 = true;
+}
 static void launch_dumps(axb_handle_s *h) {
     // dump_stuff (time_evol_wave.F90:1104-1251): receivers every seis_it, wavefield every strain_it
+    launch_energy(h);
     CLS(h, 6);
     if (h->num_rec > 0 && h->iter % h->seis_it == 0 && h->iseismo < h->nseismo_max) {
         RecArgs a;
@@ -1410,6 +1455,16 @@ int axb_fetch_seismograms(axb_handle h, int32_t first, int32_t nsamples, float *
     return 0;
 }
 
+int axb_fetch_energy(axb_handle h, int32_t first, int32_t n, float *out) {
+    if (use(h)) return 1;
+    if (!h->dump_energy || !h->d_energy) return fail("energy diagnostic not enabled (axb_set_energy)");
+    if (first < 0 || n < 0 || first + n > h->iter + 1) return fail("fetch_energy: range beyond the computed samples");
+    std::vector<double> tmp((size_t)4 * std::max(n, 1));
+    CK(cudaMemcpyAsync(tmp.data(), h->d_energy + (size_t)4 * first, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t k = 0; k < (size_t)4 * n; k++) out[k] = (float)tmp[k];
+    return 0;
+}
 int axb_fetch_snapshots(axb_handle h, int32_t first, int32_t nsnap, float *out) {
     if (use(h)) return 1;
     const size_t npts = (size_t)h->npt_s_kwf + h->npt_f_kwf;

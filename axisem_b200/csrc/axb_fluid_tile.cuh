@@ -40,6 +40,7 @@ struct FluidTileArgs {
     const float *stf;
     int iter;
     int use_mask;             // Newmark multiplies by the free-surface mask, symplectic does not
+    int emask;                // mode 2 only: axis mask on the input copy and on the result (energy)
 };
 
 __host__ __device__ constexpr size_t fluid_stage_bytes(int npl) {
@@ -127,8 +128,9 @@ k_fluid_tile(const __grid_constant__ GMat G, const __grid_constant__ FluidTileAr
                 c = d2f(f2d(c) + a.dt * f2d(S[TP + t]) + a.half_dt_sq * f2d(S[2 * TP + t]));
             else if (a.mode == 1)
                 c = d2f(f2d(c) + f2d(S[TP + t]) * a.dt);
-            if (a.full && a.order != 0 && ax && i == 0) c = 0.f;     // apply_axis_mask_scal(chi)
+            if ((a.full || a.emask) && a.order != 0 && ax && i == 0) c = 0.f;     // apply_axis_mask_scal(chi)
             if (a.mode != 2) { S[t] = c; a.chi[pg] = c; }
+            else if (a.emask) S[t] = c;
         }
         bar_consumers<NCT>();
 
@@ -181,6 +183,7 @@ k_fluid_tile(const __grid_constant__ GMat G, const __grid_constant__ FluidTileAr
                 if (a.order != 0 && ax && i == 0) l = 0.f;            // apply_axis_mask_scal(ddchi1)
                 if (a.use_mask && a.mask_plane >= 0) l = l * Cf[a.mask_plane * TP];
             }
+            if (a.emask && a.order != 0 && ax && i == 0) l = 0.f;
             a.ddchi1[pg] = l;
         }
         fence_proxy_async();

@@ -531,4 +531,62 @@ __global__ void k_blowup_check(const float *disp, size_t cs, int nel, float thre
     if (!ok) atomicCAS(&counters[3], 0, iter > 0 ? iter : 1);
 }
 
+// ---------------------------------------------------------------------------------------
+// energy (time_evol_wave.F90:1424-1526): the four sums of one sample, accumulated in real(8)
+// (the reference's sum() runs over real(4) arrays in an order the compiler chooses).
+struct EnergyArgs {
+    int npts; size_t cs; int order;
+    const float *stiff, *u, *v, *mass;     // solid: K u (masked), disp, velo, unassem_mass_rho_solid
+    const int *axis;                       // fluid: K dchi (masked), dchi, ddchi, unassem_mass_lam_fluid
+    double *out;                           // [0] potential-type sum, [1] kinetic-type sum of this domain
+};
+__device__ __forceinline__ void energy_block_sum(double a, double b, double *out) {
+    __shared__ double sa[8], sb[8];
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(FULL, a, o); b += __shfl_down_sync(FULL, b, o); }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sa[w] = a; sb[w] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); k++) { a += sa[k]; b += sb[k]; }
+        atomicAdd(out, a);
+        atomicAdd(out + 1, b);
+    }
+}
+__global__ void __launch_bounds__(256) k_energy_solid(const __grid_constant__ EnergyArgs a) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    double epot = 0.0, ekin = 0.0;
+    if (p < a.npts) {
+        const int e = p / NPT, i = (p - e * NPT) % NP;
+        const bool ax0 = a.axis[e] != 0 && i == 0;
+        const float m = a.mass[p];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            // monopole: stiff(:,:,:,2) stays zero, vel(:,:,:,2) is summed like the other two
+            if (!(a.order == 0 && c == 1)) {
+                const bool masked = ax0 && (a.order == 0 ? c == 0 : (a.order == 1 ? c != 0 : true));
+                const float d = masked ? 0.f : a.u[p + a.cs * c];
+                epot += (double)(a.stiff[p + a.cs * c] * d);         // stiff = stiff * disp
+            }
+            const float v = a.v[p + a.cs * c];
+            float x = v * v * m;                                      // vel**2 * unassem_mass_rho_solid
+            if (a.order == 1 && c == 2) x = 2.0f * x;
+            ekin += (double)x;
+        }
+    }
+    energy_block_sum(epot, ekin, a.out);
+}
+__global__ void __launch_bounds__(256) k_energy_fluid(const __grid_constant__ EnergyArgs a) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    double epot = 0.0, ekin = 0.0;
+    if (p < a.npts) {
+        const int e = p / NPT, i = (p - e * NPT) % NP;
+        const bool masked = a.order != 0 && a.axis[e] != 0 && i == 0;
+        const float dd = a.v[p];
+        epot = (double)(dd * dd * a.mass[p]);                        // ddchi**2 * unassem_mass_lam_fluid
+        const float d = masked ? 0.f : a.u[p];
+        ekin = (double)(a.stiff[p] * d);                             // stiff_flu * dchi
+    }
+    energy_block_sum(epot, ekin, a.out);
+}
+
 }  // namespace axb

@@ -109,6 +109,7 @@ struct SolidTileArgs {
     // memory behind the header, and the ring starts at ring_off
     int tab_smem, ntab_mu, ntab_ka;
     int ring_off;             // byte offset of the ring in dynamic shared memory
+    int emask;                // mode 2 only: axis masks on the input copy and on K u (energy, time_evol_wave.F90:1459-1471)
     double exp_w[8];          // exp(-w_j deltat) per SLS (constant bank)
     float *memvar, *src_dev_tm1, *src_tr_tm1;
 };
@@ -331,19 +332,18 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                 else { if (c == 0) u1 = x; else if (c == 1) u2 = x; else u3 = x; }
             }
             // apply_axis_mask_{one,two,three}comp (apply_masks.f90:55-100)
-            if (ax && i == 0 && a.mode != 2) {
+            if (ax && i == 0 && (a.mode != 2 || a.emask)) {
                 if (ORDER == 0) u1 = 0.f;
                 else if (ORDER == 1) { u2 = 0.f; u3 = 0.f; }
                 else { u1 = 0.f; u2 = 0.f; u3 = 0.f; }
             }
+            if (a.mode != 2 || a.emask) {
+                if (ORDER == 0) { Ub[t] = u1; Ub[3 * TPS + t] = u3; }
+                else { Ub[t] = u1; Ub[3 * TPS + t] = u2; Ub[6 * TPS + t] = u3; }
+            }
             if (a.mode != 2) {
-                if (ORDER == 0) {
-                    Ub[t] = u1; Ub[3 * TPS + t] = u3;
-                    a.disp[pg] = u1; a.disp[pg + 2 * a.cs] = u3;
-                } else {
-                    Ub[t] = u1; Ub[3 * TPS + t] = u2; Ub[6 * TPS + t] = u3;
-                    a.disp[pg] = u1; a.disp[pg + a.cs] = u2; a.disp[pg + 2 * a.cs] = u3;
-                }
+                if (ORDER == 0) { a.disp[pg] = u1; a.disp[pg + 2 * a.cs] = u3; }
+                else { a.disp[pg] = u1; a.disp[pg + a.cs] = u2; a.disp[pg + 2 * a.cs] = u3; }
             }
         }
         if (anel && mvt) {
@@ -664,7 +664,7 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
             if (a.do_stiff || anel_stiff) {
                 // apply_axis_mask_*(acc1) (time_evol_wave.F90:438-447); k_bdry2solid re-applies
                 // it to the few points the S/F term touches afterwards
-                if (ax && i == 0 && a.mode != 2) {
+                if (ax && i == 0 && (a.mode != 2 || a.emask)) {
                     if (ORDER == 0) l1 = 0.f;
                     else if (ORDER == 1) { l2 = 0.f; l3 = 0.f; }
                     else { l1 = 0.f; l2 = 0.f; l3 = 0.f; }

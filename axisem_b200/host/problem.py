@@ -75,6 +75,8 @@ class Problem:
     rec_index: np.ndarray
     solid_absorbing_gamma: Optional[np.ndarray] = None
     fluid_absorbing_gamma: Optional[np.ndarray] = None
+    unassem_mass_rho_solid: Optional[np.ndarray] = None   # dump_energy (def_precomp_terms.f90:745-751)
+    unassem_mass_lam_fluid: Optional[np.ndarray] = None   # (:812-815)
     fluid_src: bool = False            # source inside the fluid (have_src in the fluid: add_source_fl)
     kwf: Optional[Dict[str, np.ndarray]] = None
 
@@ -192,7 +194,7 @@ def build_problem(spec: MeshSpec, source: Optional[SourceParams] = None, *, rank
                   nranks: int = 1, anel: bool = False, att: Optional[AttenuationModel] = None,
                   time_scheme: str = "newmark2", niter: int = 100, seis_it: int = 1,
                   strain_it: int = 0, courant: float = 0.6, deltat: Optional[float] = None,
-                  rec_colat_deg=None, dump: bool = False, chunk_cols: int = 32,
+                  rec_colat_deg=None, dump: bool = False, energy: bool = False, chunk_cols: int = 32,
                   threads: Optional[int] = None) -> Problem:
     assert time_scheme in TIME_SCHEMES
     source = source or SourceParams()
@@ -245,6 +247,10 @@ def build_problem(spec: MeshSpec, source: Optional[SourceParams] = None, *, rank
             return (g.massmat_k / m[1]) if fluidflag else (m[0] * g.massmat_k)
         return f
 
+    um_s = um_f = None
+    if energy:
+        um_s = _f32(_concat(parts, "mass_s") * (2.0 if src_type == "dipole" else 1.0))
+        um_f = _f32(_concat(parts, "mass_f")) if has_fluid else np.zeros((0, 5, 5), np.float32)
     m_s = _assemble_columns(spec, mesh.it0, mesh.it1, False, _concat(parts, "mass_s"), ghost(False))
     inv_mass_rho = (1.0 / m_s.astype(np.float64))
     if src_type == "dipole":
@@ -284,6 +290,7 @@ def build_problem(spec: MeshSpec, source: Optional[SourceParams] = None, *, rank
         rec_index=rec["index"])
     if dump:
         prob.kwf = kwf_maps(mesh)
+    prob.unassem_mass_rho_solid, prob.unassem_mass_lam_fluid = um_s, um_f
     return prob
 
 

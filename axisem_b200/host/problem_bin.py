@@ -57,6 +57,10 @@ def problem_records(p):
         if p.fluid_free_surface_mask is not None:
             add("data_mesh%fluid_free_surface_mask", p.fluid_free_surface_mask, f32)
     add("data_matr%inv_mass_rho", p.inv_mass_rho, f32)
+    if getattr(p, "unassem_mass_rho_solid", None) is not None:
+        add("data_matr%unassem_mass_rho_solid", p.unassem_mass_rho_solid, f32)
+        if m.nel_fluid:
+            add("data_matr%unassem_mass_lam_fluid", p.unassem_mass_lam_fluid, f32)
     if p.solid_absorbing_gamma is not None:
         add("data_mesh%solid_absorbing_gamma", p.solid_absorbing_gamma, f32)
     if p.fluid_absorbing_gamma is not None:

@@ -42,7 +42,23 @@ struct FileSink : axisem::OutputSink {
         r.snap_n.push_back(n);
         r.nsnap += n;
     }
+    std::map<int, std::vector<float>> en;
+    void energy(int rank, int n, const float *v) override { en[rank].assign(v, v + (size_t)4 * n); }
     void write(const std::string &prefix) const {
+        if (!en.empty()) {
+            // energy.dat of the reference: t-less table  epot+..., summed over ranks, times two*pi
+            const size_t n = en.begin()->second.size() / 4;
+            FILE *f = std::fopen((prefix + ".energy.txt").c_str(), "w");
+            if (!f) throw axisem::SolverError("cannot write " + prefix + ".energy.txt");
+            for (size_t k = 0; k < n; k++) {
+                double s[4] = {0, 0, 0, 0};
+                for (const auto &kv : en) for (int c = 0; c < 4; c++) s[c] += kv.second[4 * k + c];
+                const double tp = 2.0 * 3.14159265358979323846;
+                std::fprintf(f, "%zu %.6e %.6e %.6e %.6e %.6e\n", k, tp * s[0], tp * s[1], tp * s[2], tp * s[3],
+                             0.5 * tp * (s[0] + s[1] + s[2] + s[3]));
+            }
+            std::fclose(f);
+        }
         for (const auto &kv : ranks) {
             char app[32];
             std::snprintf(app, sizeof app, ".rank%04d", kv.first);

@@ -45,6 +45,8 @@ axb_handle hand_over(const Modules &m, int device) {
                                 F("data_matr%M4chi_fl"), m.f("data_matr%M_w_fl"), m.f("data_matr%M0_w_fl"),
                                 F("data_matr%inv_mass_fluid"), m.f("data_mesh%fluid_free_surface_mask")));
     CK(AXB(set_mass)(h, F("data_matr%inv_mass_rho")));
+    if (m.has("data_matr%unassem_mass_rho_solid"))          // dump_energy
+        CK(AXB(set_energy)(h, m.f("data_matr%unassem_mass_rho_solid"), m.f("data_matr%unassem_mass_lam_fluid")));
     if (m.has("data_mesh%solid_absorbing_gamma") || m.has("data_mesh%fluid_absorbing_gamma"))
         CK(AXB(set_sponge)(h, m.f("data_mesh%solid_absorbing_gamma"), m.f("data_mesh%fluid_absorbing_gamma")));
     const int nel_bdry = m.int_of("data_mesh%nel_bdry");
@@ -193,6 +195,13 @@ TimeLoopResult time_loop(const std::vector<Modules> &ranks, const TimeLoopOption
         }
     }
     const auto t1 = std::chrono::steady_clock::now();
+    if (sink)
+        for (int r = 0; r < n; r++)
+            if (ranks[r].has("data_matr%unassem_mass_rho_solid")) {
+                buf.resize((size_t)4 * (iter + 1));
+                CK(AXB(fetch_energy)(H.h[r], 0, iter + 1, buf.data()));
+                sink->energy(ranks[r].int_of("data_proc%mynum"), iter + 1, buf.data());
+            }
 
     TimeLoopResult res;
     res.iter = AXB(iter)(H.h[0]);

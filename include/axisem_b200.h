@@ -192,6 +192,13 @@ int AXB(set_halo)(axb_handle h, int32_t domain, int32_t nmsg, const int32_t *lis
 int AXB(set_time)(axb_handle h, int32_t scheme, double deltat, int32_t niter,
                   int32_t seis_it, int32_t strain_it);
 
+/* dump_energy (time_evol_wave.F90:1424-1526, called from dump_stuff :1150 at iter 0 and after
+ * every step): unassem_mass_rho_solid(0:4,0:4,nel_solid) (dipole: factor two folded in,
+ * def_precomp_terms.f90:745-751) and unassem_mass_lam_fluid(0:4,0:4,nel_fluid) (:812-815;
+ * NULL without a fluid).  Enables the diagnostic. */
+int AXB(set_energy)(axb_handle h, const float *unassem_mass_rho_solid,
+                    const float *unassem_mass_lam_fluid);
+
 /* builds the derived (device) structures; must follow all axb_set_* calls */
 int AXB(finalize_setup)(axb_handle h);
 
@@ -234,6 +241,11 @@ int64_t AXB(gpu_launches)(axb_handle h); /* kernels launched by this handle (0: 
 int AXB(fetch_seismograms)(axb_handle h, int32_t first, int32_t nsamples, float *out);
 /* oneddumpvar slice: out(npoints, nsnap, 3) with var order (s, p, z); nc_routines.F90:248,275 */
 int AXB(fetch_snapshots)(axb_handle h, int32_t first, int32_t nsnap, float *out);
+
+/* energy samples first..first+n-1 (0-based; sample k belongs to iter k): out(4, n) =
+ * sum(stiff*disp), sum(vel**2*mass) of the solid, sum(ddchi**2*mass) and sum(stiff*dchi) of the
+ * fluid — this rank's sums; the host applies psum and two*pi as time_evol_wave.F90:1474-1510 */
+int AXB(fetch_energy)(axb_handle h, int32_t first, int32_t n, float *out);
 
 int AXB(get_state)(axb_handle h, int32_t field, float *out);
 int AXB(set_state)(axb_handle h, int32_t field, const float *in);

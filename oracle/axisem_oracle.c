@@ -117,6 +117,9 @@ struct axb_handle_s {
     float *gvec_s, *gvec_f;
     int iter, iseismo, istrain;
     float *recdump;      /* (3, num_rec, nseismo_max) */
+    int dump_energy;     /* time_evol_wave.F90:1150 */
+    float *um_rho_s, *um_lam_f;   /* unassem_mass_rho_solid, unassem_mass_lam_fluid */
+    float *energy;       /* (4, niter + 1) */
     int nseismo_max;
     float *snapdump;     /* (npoints, nstrain_max, 3) */
     int nstrain_max;
@@ -233,6 +236,14 @@ int axo_set_mass(axb_handle h, const float *inv_mass_rho) {
     return 0;
 }
 
+int axo_set_energy(axb_handle h, const float *um_rho, const float *um_lam) {
+    if (!um_rho && h->nel_s > 0) return fail("axo_set_energy: NULL unassem_mass_rho_solid");
+    if (!um_lam && h->nel_f > 0) return fail("axo_set_energy: NULL unassem_mass_lam_fluid");
+    h->um_rho_s = dupf(um_rho, (size_t)NPT * h->nel_s);
+    h->um_lam_f = dupf(um_lam, (size_t)NPT * h->nel_f);
+    h->dump_energy = 1;
+    return 0;
+}
 int axo_set_sponge(axb_handle h, const float *solid_gamma, const float *fluid_gamma) {
     h->have_abc = (solid_gamma != NULL) || (fluid_gamma != NULL);
     h->gamma_s = dupf(solid_gamma, (size_t)NPT * h->nel_s);
@@ -446,6 +457,7 @@ int axo_finalize_setup(axb_handle h) {
     /* nseismo = floor(niter/seis_it) + 1 (parameters.F90:929) */
     h->nseismo_max = h->niter / h->seis_it + 1;
     h->recdump = zerosf((size_t)3 * h->num_rec * h->nseismo_max);
+    if (h->dump_energy) h->energy = zerosf((size_t)4 * (h->niter + 1));
     if (h->strain_it > 0 && h->have_kwf) {
         h->nstrain_max = h->niter / h->strain_it + 1;
         h->snapdump = zerosf((size_t)(h->npt_s_kwf + h->npt_f_kwf) * h->nstrain_max * 3);
@@ -1325,7 +1337,47 @@ static void dump_disp_global(axo_t *o) {
 }
 
 /* time_evol_wave.F90:1104-1251, the parts on the hot path */
+static void solid_stiffness(axo_t *o, float *acc, const float *u);
+/* time_evol_wave.F90:1424-1526.  sum() is taken in array order with a real(4) accumulator;
+ * psum and the factor two*pi are left to the caller (see the header). */
+static void energy(axo_t *o, int iter) {
+    const size_t ns = (size_t)NPT * o->nel_s, nf = (size_t)NPT * o->nel_f;
+    float *out = o->energy + (size_t)4 * iter;
+    float ekin_sol = 0.0f, epot_sol = 0.0f, ekin_flu = 0.0f, epot_flu = 0.0f;
+    float *disp = (float *)malloc(sizeof(float) * (3 * ns + 1));
+    float *stiff = zerosf(3 * ns);
+    memcpy(disp, o->disp, sizeof(float) * 3 * ns);
+    mask_solid(o, disp);
+    solid_stiffness(o, stiff, disp);
+    mask_solid(o, stiff);
+    for (size_t k = 0; k < 3 * ns; k++) { stiff[k] = stiff[k] * disp[k]; epot_sol = epot_sol + stiff[k]; }
+    for (int c = 0; c < 3; c++)
+        for (size_t p = 0; p < ns; p++) {
+            float v = o->velo[p + ns * c];
+            float x = v * v * o->um_rho_s[p];
+            if (c == 2 && o->src_order == AXB_DIPOLE) x = 2.0f * x;
+            stiff[p + ns * c] = x;
+        }
+    for (size_t k = 0; k < 3 * ns; k++) ekin_sol = ekin_sol + stiff[k];
+    free(disp); free(stiff);
+    if (o->nel_f > 0) {
+        /* the reference passes ddchi0 (Newmark) / ddchi (symplectic: our ddchi1) */
+        const float *ddchi = o->scheme == AXB_NEWMARK2 ? o->ddchi0 : o->ddchi1;
+        float *dchi = (float *)malloc(sizeof(float) * (nf + 1));
+        float *sf = zerosf(nf);
+        for (size_t p = 0; p < nf; p++) { float x = ddchi[p] * ddchi[p] * o->um_lam_f[p]; epot_flu = epot_flu + x; }
+        memcpy(dchi, o->dchi, sizeof(float) * nf);
+        if (o->src_order != AXB_MONOPOLE) axis_mask(dchi, 0, o->ax_el_f, o->naxel_f, 0, 0);
+        glob_fluid_stiffness_4(o, sf, dchi);
+        if (o->src_order != AXB_MONOPOLE) axis_mask(sf, 0, o->ax_el_f, o->naxel_f, 0, 0);
+        for (size_t p = 0; p < nf; p++) { sf[p] = sf[p] * dchi[p]; ekin_flu = ekin_flu + sf[p]; }
+        free(dchi); free(sf);
+    }
+    out[0] = epot_sol; out[1] = ekin_sol; out[2] = epot_flu; out[3] = ekin_flu;
+}
+
 static void dump_stuff(axo_t *o, int iter) {
+    if (o->dump_energy) energy(o, iter);
     if (o->num_rec > 0 && iter % o->seis_it == 0 && o->iseismo < o->nseismo_max) sample_receivers(o);
     if (o->strain_it > 0 && o->have_kwf && iter % o->strain_it == 0 && o->istrain < o->nstrain_max)
         dump_disp_global(o);
@@ -1756,6 +1808,12 @@ int64_t axo_gpu_launches(axb_handle h) { (void)h; return 0; }
 int axo_fetch_seismograms(axb_handle h, int32_t first, int32_t nsamples, float *out) {
     if (first < 0 || first + nsamples > h->iseismo) return fail("seismogram range");
     memcpy(out, h->recdump + (size_t)3 * h->num_rec * first, sizeof(float) * 3 * h->num_rec * nsamples);
+    return 0;
+}
+int axo_fetch_energy(axb_handle h, int32_t first, int32_t n, float *out) {
+    if (!h->dump_energy) return fail("energy diagnostic not enabled (axo_set_energy)");
+    if (first < 0 || n < 0 || first + n > h->iter + 1) return fail("fetch_energy: range beyond the computed samples");
+    memcpy(out, h->energy + (size_t)4 * first, sizeof(float) * 4 * n);
     return 0;
 }
 int axo_fetch_snapshots(axb_handle h, int32_t first, int32_t nsnap, float *out) {

@@ -70,6 +70,24 @@ def test_host_against_oracle_single_rank(tmp_path):
     assert np.array_equal(got, sn)          # chunked wavefield buffers reassembled in order
 
 
+def test_host_writes_the_energy_table(tmp_path):
+    from axisem_b200.host import SourceParams, build_problem
+    from oracle import oracle
+    from tests.util import small_spec
+    n = 30
+    prob = build_problem(small_spec(), SourceParams(src_type2="explosion", t_0=40.0), niter=n, energy=True)
+    save_problem_bin(prob, str(tmp_path / "r0.axbp"))
+    r = _run(_oracle_exe(), ["--quiet", "--out", str(tmp_path / "e"), str(tmp_path / "r0.axbp")])
+    assert r.returncode == 0, r.stderr
+    tab = np.loadtxt(tmp_path / "e.energy.txt")
+    O = oracle.make_loop(prob)
+    O.run(n)
+    e = O.energy().astype(np.float64)
+    assert tab.shape == (n + 1, 6)
+    np.testing.assert_allclose(tab[:, 1:5], 2 * np.pi * e, rtol=2e-6)
+    np.testing.assert_allclose(tab[:, 5], np.pi * e.sum(axis=1), rtol=2e-6)
+
+
 def test_host_progress_lines_like_runtime_info(tmp_path):
     prob = make_problem("explosion", niter=230)
     save_problem_bin(prob, str(tmp_path / "r0.axbp"))
