@@ -319,6 +319,33 @@ def test_energy_diagnostic(src, scheme):
         assert np.array_equal(G.get(f), O.get(f)), f
 
 
+@pytest.mark.parametrize("cg", [True, False])
+@pytest.mark.parametrize("src", ["explosion", "mtr"])
+def test_other_numbers_of_linear_solids(src, cg):
+    """NR_LIN_SOLIDS other than the default 5 (the run-time n_sls variant of S_A / k_anel_full),
+    without the low-Q correction (do_corr_lowq false, attenuation.f90:116-134)."""
+    from axisem_b200.host import AttenuationModel, SourceParams, build_problem
+    from tests.util import small_spec
+    n = 40
+    att = AttenuationModel(n_sls=3, w_j=2 * np.pi * np.array([0.004, 0.06, 0.9]), y_j=np.array([1.4, 1.1, 1.6]),
+                           do_corr_lowq=False, coarse_grained=cg)
+    prob = build_problem(small_spec(), SourceParams(src_type2=src, t_0=40.0), anel=True, att=att, niter=n)
+    G, O = _pair(prob, True)
+    st = seeded_state(G, scale=1e-9, fields=("disp", "velo", "chi", "dchi"))
+    for L in (G, O):
+        apply_state(L, st)
+        L.run(n)
+    assert G.get("memvar").shape[1] == 3
+    for f in ("disp", "velo", "chi", "memvar", "src_dev_tm1", "src_tr_tm1"):
+        assert np.array_equal(G.get(f), O.get(f)), f
+    assert np.array_equal(G.seismograms(), O.seismograms())
+    # and the product build within tolerance
+    P = _pair(prob, False)[0]
+    apply_state(P, st)
+    P.run(n)
+    _cmp("seismograms", P.seismograms(), O.seismograms(), False, 1e-5)
+
+
 def test_blowup_guard_reports_like_the_reference_stop():
     """runtime_info (time_evol_wave.F90:1042-1054): |disp(1,1,:,:)| > 10 |magnitude| stops the
     run; on the device the check runs every 100 steps and surfaces through axb_synchronize."""
