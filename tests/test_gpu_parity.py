@@ -346,6 +346,39 @@ def test_other_numbers_of_linear_solids(src, cg):
     _cmp("seismograms", P.seismograms(), O.seismograms(), False, 1e-5)
 
 
+@pytest.mark.parametrize("src,anel", [("explosion", False), ("mtr", True)])
+def test_mesh_without_a_fluid(src, anel):
+    """have_fluid false (a solid sphere): no fluid kernels, no S/F coupling; also no receivers
+    on this rank (num_rec = 0) and a 2-slice run of the same mesh."""
+    from axisem_b200 import solver
+    from axisem_b200.capi import connect_local, run_group
+    from axisem_b200.host import SourceParams, build_problem, homogeneous_layers
+    from axisem_b200.host.mesh import MeshSpec
+    from oracle import oracle
+    spec = MeshSpec(ntheta=8, layers=homogeneous_layers(), nrad=[8])
+    n = 40
+    prob = build_problem(spec, SourceParams(src_type2=src, t_0=40.0), anel=anel, niter=n, rec_colat_deg=[])
+    assert prob.mesh.nel_fluid == 0 and prob.num_rec == 0
+    G, O = _pair(prob, True)
+    for L in (G, O):
+        L.run(n)
+    for f in ("disp", "velo", "acc0"):
+        assert np.array_equal(G.get(f), O.get(f)), f
+    assert np.abs(O.get("disp")).max() > 0
+    probs = [build_problem(spec, SourceParams(src_type2=src, t_0=40.0), anel=anel, niter=n, rank=r, nranks=2)
+             for r in range(2)]
+    lib, gl = solver.time_loop_group(probs, strict=True)
+    ol = [oracle.make_loop(p) for p in probs]
+    olib = oracle.load()
+    connect_local(olib, ol)
+    run_group(lib, gl, n)
+    run_group(olib, ol, n)
+    for g, o in zip(gl, ol):
+        g.synchronize()
+        assert np.array_equal(g.get("disp"), o.get("disp"))
+        assert np.array_equal(g.seismograms(), o.seismograms())
+
+
 def test_blowup_guard_reports_like_the_reference_stop():
     """runtime_info (time_evol_wave.F90:1042-1054): |disp(1,1,:,:)| > 10 |magnitude| stops the
     run; on the device the check runs every 100 steps and surfaces through axb_synchronize."""
