@@ -90,7 +90,8 @@ def prem_layers(anisotropic: bool = False, r_min_km: float = 400.0) -> List[Laye
         else:
             iso(r0, r1, False, qmu, 57827.0, rho_um,
                 _poly(4.1875, 3.9382), _poly(2.1519, 2.3481), name)
-    iso(6346.6, 6371.0, False, 600.0, 57827.0, _poly(2.9), _poly(6.8), _poly(3.9), "crust")
+    iso(6346.6, 6356.0, False, 600.0, 57827.0, _poly(2.9), _poly(6.8), _poly(3.9), "lower crust")
+    iso(6356.0, 6371.0, False, 600.0, 57827.0, _poly(2.6), _poly(5.8), _poly(3.2), "upper crust")
     return lay
 
 

@@ -309,14 +309,15 @@ def test_reference_energy_diagnostic_is_conserved(src):
     which pins the restated stiffness, mass and S/F coupling against each other."""
     from axisem_b200.host import prem_mesh_spec
     spec = prem_mesh_spec(ntheta=16, nr_target=18)
-    n = 400
-    prob = build_problem(spec, SourceParams(src_type2=src, t_0=40.0), niter=n, energy=True)
+    prob = build_problem(spec, SourceParams(src_type2=src, t_0=40.0), niter=1200, energy=True)
+    over = int((1.5 * 40.0 + 40.0) / prob.deltat)          # gauss_0: shift 1.5 t_0, width t_0 / 3.5
+    n = over + 130
+    assert n <= 1200
     O = oracle.make_loop(prob)
     O.run(n)
     e = O.energy().astype(np.float64)
     assert e.shape == (n + 1, 4) and np.all(e[0] == 0.0)
     tot = 0.5 * e.sum(axis=1) * 2 * np.pi
-    over = int((1.5 * 40.0 + 40.0) / prob.deltat)          # gauss_0: shift 1.5 t_0, width t_0 / 3.5
     assert tot[over] > 0
     assert np.abs(tot[over:] / tot[over] - 1.0).max() < 2e-4
 
@@ -329,11 +330,12 @@ def test_reference_energy_diagnostic_dipole_quirk():
     device restate the reference's formula as it is."""
     from axisem_b200.host import prem_mesh_spec
     spec = prem_mesh_spec(ntheta=16, nr_target=18)
-    n = 400
-    prob = build_problem(spec, SourceParams(src_type2="mtr", t_0=40.0), niter=n, energy=True)
+    prob = build_problem(spec, SourceParams(src_type2="mtr", t_0=40.0), niter=1200, energy=True)
     O = oracle.make_loop(prob)
     um = prob.unassem_mass_rho_solid.astype(np.float64)
     over = int((1.5 * 40.0 + 40.0) / prob.deltat)
+    n = over + 132
+    assert n <= 1200
     O.run(over)
     ref, fixed = [], []
     for _ in range(4):
