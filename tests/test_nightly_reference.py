@@ -20,17 +20,17 @@ from tests.nightly_compare import compare, stations, to_enz
 T_0 = 70.0          # Gaussian source period [s]: keeps the comparison inside the band both meshes resolve
 
 
-def _setup(src, ntheta, nr, nranks):
+def _setup(src, ntheta, nr, nranks, scheme="newmark2"):
     names, lat, lon = stations()
     colat = 90.0 - lat
     spec = prem_mesh_spec(ntheta=ntheta, nr_target=nr, anisotropic=True, r_min_km=800.0)
     sp = SourceParams(src_type2=src, depth=100e3, magnitude=1e20, t_0=T_0)
-    dt = build_problem(spec, sp, niter=4, rec_colat_deg=colat).deltat
+    dt = build_problem(spec, sp, niter=4, rec_colat_deg=colat, time_scheme=scheme).deltat
     shift = np.ceil(1.5 * T_0 / dt) * dt
     niter = int((1800.0 + shift) / dt) + 1
     seis_it = max(1, int(0.8 / dt))
-    probs = [build_problem(spec, sp, niter=niter, rec_colat_deg=colat, seis_it=seis_it, rank=r, nranks=nranks)
-             for r in range(nranks)]
+    probs = [build_problem(spec, sp, niter=niter, rec_colat_deg=colat, seis_it=seis_it, rank=r, nranks=nranks,
+                           time_scheme=scheme) for r in range(nranks)]
     return probs, niter, seis_it, dt, shift, np.deg2rad(colat), np.deg2rad(lon)
 
 
@@ -78,3 +78,19 @@ def test_cuda_reproduces_the_references_seismograms(src):
     assert cc.size >= 35
     assert cc.min() > 0.85 and np.median(cc) > 0.98, (cc.min(), np.median(cc))
     assert amp.min() > 0.70 and amp.max() < 1.30, (amp.min(), amp.max())
+
+
+@pytest.mark.gpu
+def test_cuda_symplectic_scheme_reproduces_the_references_dipole_seismograms():
+    """The 4th-order symplectic loop (time step 1.5 x Newmark's, point-wise source time function
+    of compute_stf_t) against the same golden traces; the oracle gives the same numbers."""
+    from axisem_b200 import solver
+    probs, niter, *rest = _setup("mtr", 128, 40, 1, scheme="symplec4")
+    loop = solver.time_loop(probs[0])
+    loop.run(niter)
+    cc, amp, _ = _score("mtr", [loop], probs, niter, *rest)
+    print(f"symplec4 mtr: {cc.size} traces, correlation min {cc.min():.4f} median {np.median(cc):.4f}, "
+          f"amplitude ratio {amp.min():.3f} .. {amp.max():.3f}")
+    assert cc.size >= 40
+    assert cc.min() > 0.80 and np.median(cc) > 0.97, (cc.min(), np.median(cc))
+    assert amp.min() > 0.80 and amp.max() < 1.20, (amp.min(), amp.max())
