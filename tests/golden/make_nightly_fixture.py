@@ -71,6 +71,26 @@ for test, src in (("test_01", "explosion"), ("test_02", "mtr"), ("test_03", "mtp
     out["lon"] = np.array([float(s[3]) for s in st])
     out["names"] = np.array(names)
     print(test, src, arr.shape, 1.0 / sr, t0, np.abs(arr).max())
+# The independent solution the reference ships next to its own traces: YSPEC (direct radial
+# integration, full sphere, no attenuation, no gravity: test_01/yspec.in) for the same explosion,
+# *velocity* of the moment-step response = displacement of the moment-rate delta response that
+# AxiSEM's dirac_0 gives.  10 Hz, 18001 samples: smoothed with a 1.5 s Gaussian and decimated to
+# 0.8 s (the comparison band ends at 0.05 Hz), Z and N only (E is zero for an explosion).
+ys = read_mseed(os.path.join(ROOT, "test_01", "ref_data", "yspec.mseed"))
+names = [l.split()[0] for l in open(os.path.join(ROOT, "test_01", "STATIONS")) if l.strip()]
+sr, t0, d0 = ys[(names[0], "Z")]
+assert abs(sr - 10.0) < 1e-9 and t0 == 0.0
+tg = np.arange(-8.0, 8.0001, 0.1)
+g = np.exp(-0.5 * (tg / 1.5) ** 2)
+g /= g.sum()
+dec = np.zeros((len(names), 2, len(d0[::8])), dtype=np.float32)
+for i, n in enumerate(names):
+    for c, comp in enumerate("NZ"):
+        dec[i, c] = np.convolve(ys[(n, comp)][2], g, mode="same")[::8]
+out["yspec_explosion_NZ"] = dec                                # (station, N/Z, sample)
+out["yspec_dt"] = np.float64(0.8)
+out["yspec_smoothing_sigma"] = np.float64(1.5)
+print("yspec", dec.shape)
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "nightly_ref_seismograms.npz")
 np.savez_compressed(path, **out)
 print(path, os.path.getsize(path))

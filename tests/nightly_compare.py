@@ -45,11 +45,19 @@ def to_enz(src, seis, colat_rad, lon_rad):
     return np.stack([up.T, n.T, z.T], axis=1)
 
 
-def compare(src, mine_enz, t_mine, t_0, decay=3.5, max_lag=6.0, window=(50.0, 1650.0)):
+def compare(src, mine_enz, t_mine, t_0, decay=3.5, max_lag=6.0, window=(50.0, 1650.0), against="axisem"):
     """Per station and component: (correlation, lag [s], amplitude ratio mine/reference,
-    peak amplitude of the band-limited reference trace)."""
+    peak amplitude of the band-limited reference trace).  against="yspec": the independent
+    YSPEC solution of the explosion case instead of the reference's own traces (N and Z)."""
     z = np.load(FIXTURE)
-    ref, dt, t0 = z[src + "_traces"].astype(np.float64), float(z[src + "_dt"]), float(z[src + "_t0"])
+    if against == "yspec":
+        assert src == "explosion"
+        nz = z["yspec_explosion_NZ"].astype(np.float64)
+        ref = np.zeros((nz.shape[0], 3, nz.shape[2]))
+        ref[:, 1:, :] = nz
+        dt, t0 = float(z["yspec_dt"]), 0.0
+    else:
+        ref, dt, t0 = z[src + "_traces"].astype(np.float64), float(z[src + "_dt"]), float(z[src + "_t0"])
     tr = t0 + np.arange(ref.shape[2]) * dt
     a = decay / t_0
     tg = np.arange(-4 * t_0, 4 * t_0 + dt / 2, dt)

@@ -34,14 +34,14 @@ def _setup(src, ntheta, nr, nranks, scheme="newmark2"):
     return probs, niter, seis_it, dt, shift, np.deg2rad(colat), np.deg2rad(lon)
 
 
-def _score(src, loops, probs, niter, seis_it, dt, shift, colat, lon):
+def _score(src, loops, probs, niter, seis_it, dt, shift, colat, lon, against="axisem"):
     ns = max(L.nseismo for L in loops)
     s = np.zeros((ns, colat.size, 3))
     for p, L in zip(probs, loops):
         if p.num_rec:
             s[:, p.rec_index, :] = L.seismograms()
     t = np.arange(ns) * seis_it * dt - shift                 # origin time = centre of the Gaussian
-    r = compare(src, to_enz(src, s, colat, lon), t, T_0)
+    r = compare(src, to_enz(src, s, colat, lon), t, T_0, against=against)
     big = r[:, :, 3] > 0.002 * r[:, :, 3].max()              # traces that carry signal (explosion: E is zero)
     return r[:, :, 0][big], r[:, :, 2][big], r
 
@@ -78,6 +78,14 @@ def test_cuda_reproduces_the_references_seismograms(src):
     assert cc.size >= 35
     assert cc.min() > 0.85 and np.median(cc) > 0.98, (cc.min(), np.median(cc))
     assert amp.min() > 0.70 and amp.max() < 1.30, (amp.min(), amp.max())
+    if src == "explosion":
+        # the independent YSPEC solution (full sphere, no attenuation, no gravity) that the
+        # reference ships next to its own traces: test_01/ref_data/yspec.mseed
+        cy, ay, _ = _score(src, [loop], probs, niter, *rest, against="yspec")
+        print(f"  against yspec: {cy.size} traces, correlation min {cy.min():.4f} median {np.median(cy):.4f}, "
+              f"amplitude ratio {ay.min():.3f} .. {ay.max():.3f}")
+        assert cy.size >= 35 and cy.min() > 0.85 and np.median(cy) > 0.98, (cy.min(), np.median(cy))
+        assert ay.min() > 0.70 and ay.max() < 1.30, (ay.min(), ay.max())
 
 
 @pytest.mark.gpu
