@@ -12,8 +12,9 @@
  * axisem.mseed: explosion, mtr, mtp in elastic prem_ani) and the tabulated background model of
  * TEST04.  Both are committed as fixtures (tests/golden/nightly_ref_seismograms.npz,
  * prem_ani_model_bm.npz) and this restatement reproduces them: the model to print precision,
- * the seismograms of all three source orders with waveform correlation 0.92-0.998 (median
- * 0.99) and amplitude ratios 0.8-1.14 on a synthetic mesh that differs from the reference's
+ * the seismograms of all three source orders with median waveform correlation 0.9985 /
+ * 0.9997 / 0.9998 (explosion / mtr / mtp; minimum 0.92 / 0.99 / 0.996) and median amplitude
+ * ratio 1.003-1.006 on a synthetic mesh that differs from the reference's
  * (tests/test_nightly_reference.py, tests/nightly_compare.py).  Sample-level identity with an
  * execution of the Fortran is not established; beyond the two fixtures the restatement is
  * pinned by the analytic / self-consistency checks the reference itself uses

@@ -20,11 +20,24 @@ from tests.nightly_compare import compare, stations, to_enz
 T_0 = 70.0          # Gaussian source period [s]: keeps the comparison inside the band both meshes resolve
 
 
-def _setup(src, ntheta, nr, nranks, scheme="newmark2"):
+# The reference puts the source on the GLL point nearest to the requested 100 km
+# (find_srcloc, source.f90:454-476).  Its 50 s mesh (1.5 elements per wavelength) has one element
+# between the 80 km and 220 km discontinuities, whose GLL radii are 6151 + 140 (0, 0.1727, 0.5,
+# 0.8273, 1) km: the point nearest to 100 km depth lies at 104.2 km.  (Inferred from the mesher's
+# rules, not read from a mesh; with the source at 100 km instead, Rayleigh-wave amplitudes at
+# near stations come out 10 % high.)  The meshes here get a GLL point within 1 km of that depth.
+SOURCE_DEPTH = 104.2e3
+
+
+def _setup(src, ntheta, nr, nranks, scheme="newmark2", lvz_elements=1):
+    from axisem_b200.host.mesh import MeshSpec
     names, lat, lon = stations()
     colat = 90.0 - lat
-    spec = prem_mesh_spec(ntheta=ntheta, nr_target=nr, anisotropic=True, r_min_km=800.0)
-    sp = SourceParams(src_type2=src, depth=100e3, magnitude=1e20, t_0=T_0)
+    base = prem_mesh_spec(ntheta=ntheta, nr_target=nr, anisotropic=True, r_min_km=800.0)
+    nrad = list(base.nrad)
+    nrad[[L.name for L in base.layers].index("LVZ")] = lvz_elements      # 1 or 3: GLL point at 104.2 / 103.3 km
+    spec = MeshSpec(ntheta=ntheta, layers=base.layers, nrad=nrad)
+    sp = SourceParams(src_type2=src, depth=SOURCE_DEPTH, magnitude=1e20, t_0=T_0)
     dt = build_problem(spec, sp, niter=4, rec_colat_deg=colat, time_scheme=scheme).deltat
     shift = np.ceil(1.5 * T_0 / dt) * dt
     niter = int((1800.0 + shift) / dt) + 1
@@ -60,32 +73,42 @@ def test_oracle_reproduces_the_references_dipole_seismograms():
         loops[0].run(niter)
     cc, amp, _ = _score("mtr", loops, probs, niter, *rest)
     assert cc.size >= 40                                      # of 20 stations x (E, N, Z)
-    assert cc.min() > 0.80 and np.median(cc) > 0.97, (cc.min(), np.median(cc))
-    assert amp.min() > 0.80 and amp.max() < 1.20, (amp.min(), amp.max())
+    assert cc.min() > 0.85 and np.median(cc) > 0.99, (cc.min(), np.median(cc))       # measured 0.878 / 0.9958
+    assert amp.min() > 0.93 and amp.max() < 1.08, (amp.min(), amp.max())              # measured 0.959 .. 1.049
+    assert abs(np.median(amp) - 1.0) < 0.02
+
+
+# measured on the 224 x 60 mesh (oracle and CUDA library alike): correlation min / median, amplitude range
+#   explosion 0.921 / 0.9985, 0.84 .. 1.07 (median 1.006)   [the low ones are small core phases at > 130 degrees]
+#   mtr       0.991 / 0.9997, 0.97 .. 1.04 (median 1.005)
+#   mtp       0.996 / 0.9998, 0.99 .. 1.02 (median 1.003)
+BAR = {"explosion": (0.90, 0.997, 0.80, 1.10), "mtr": (0.98, 0.999, 0.95, 1.06), "mtp": (0.98, 0.999, 0.95, 1.06)}
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("src", ["explosion", "mtr", "mtp"])
 def test_cuda_reproduces_the_references_seismograms(src):
     from axisem_b200 import solver
-    probs, niter, *rest = _setup(src, 224, 60, 1)
+    probs, niter, *rest = _setup(src, 224, 60, 1, lvz_elements=3)
     loop = solver.time_loop(probs[0])
     loop.run(niter)
     cc, amp, r = _score(src, [loop], probs, niter, *rest)
     print(f"{src}: {cc.size} traces, correlation min {cc.min():.4f} median {np.median(cc):.4f}, "
           f"amplitude ratio {amp.min():.3f} .. {amp.max():.3f}, launches {loop.gpu_launches}")
     assert loop.gpu_launches > 0
+    cmin, cmed, alo, ahi = BAR[src]
     assert cc.size >= 35
-    assert cc.min() > 0.85 and np.median(cc) > 0.98, (cc.min(), np.median(cc))
-    assert amp.min() > 0.70 and amp.max() < 1.30, (amp.min(), amp.max())
+    assert cc.min() > cmin and np.median(cc) > cmed, (cc.min(), np.median(cc))
+    assert amp.min() > alo and amp.max() < ahi, (amp.min(), amp.max())
+    assert abs(np.median(amp) - 1.0) < 0.02, np.median(amp)
     if src == "explosion":
         # the independent YSPEC solution (full sphere, no attenuation, no gravity) that the
         # reference ships next to its own traces: test_01/ref_data/yspec.mseed
         cy, ay, _ = _score(src, [loop], probs, niter, *rest, against="yspec")
         print(f"  against yspec: {cy.size} traces, correlation min {cy.min():.4f} median {np.median(cy):.4f}, "
               f"amplitude ratio {ay.min():.3f} .. {ay.max():.3f}")
-        assert cy.size >= 35 and cy.min() > 0.85 and np.median(cy) > 0.98, (cy.min(), np.median(cy))
-        assert ay.min() > 0.70 and ay.max() < 1.30, (ay.min(), ay.max())
+        assert cy.size >= 35 and cy.min() > 0.90 and np.median(cy) > 0.997, (cy.min(), np.median(cy))   # 0.920 / 0.9984
+        assert ay.min() > 0.80 and ay.max() < 1.12 and abs(np.median(ay) - 1.0) < 0.02, (ay.min(), ay.max())
 
 
 @pytest.mark.gpu
@@ -100,5 +123,5 @@ def test_cuda_symplectic_scheme_reproduces_the_references_dipole_seismograms():
     print(f"symplec4 mtr: {cc.size} traces, correlation min {cc.min():.4f} median {np.median(cc):.4f}, "
           f"amplitude ratio {amp.min():.3f} .. {amp.max():.3f}")
     assert cc.size >= 40
-    assert cc.min() > 0.80 and np.median(cc) > 0.97, (cc.min(), np.median(cc))
-    assert amp.min() > 0.80 and amp.max() < 1.20, (amp.min(), amp.max())
+    assert cc.min() > 0.85 and np.median(cc) > 0.99, (cc.min(), np.median(cc))       # measured 0.878 / 0.9957
+    assert amp.min() > 0.93 and amp.max() < 1.08, (amp.min(), amp.max())
