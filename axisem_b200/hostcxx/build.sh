@@ -12,5 +12,9 @@ OUT="${OUT:-$HERE/../axisem_b200_solver}"
 echo "built $OUT"
 # mesher database -> module variables (no device code)
 "$CXX" -O2 -std=c++17 -Wall -Wextra -I"$ROOT/include" -o "$HERE/../axisem_b200_meshdb2axbp" \
-    "$HERE/meshdb2axbp.cpp" "$HERE/meshdb.cpp" "$HERE/modules.cpp"
+    "$HERE/meshdb2axbp.cpp" "$HERE/meshdb.cpp" "$HERE/modules.cpp" "$HERE/spectral.cpp"
 echo "built $HERE/../axisem_b200_meshdb2axbp"
+# spectral basis and background models (the first pieces of the native pre-processing)
+"$CXX" -O2 -std=c++17 -Wall -Wextra -o "$HERE/../axisem_b200_hosttool" \
+    "$HERE/hosttool.cpp" "$HERE/spectral.cpp" "$HERE/background_models.cpp"
+echo "built $HERE/../axisem_b200_hosttool"

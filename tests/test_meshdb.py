@@ -32,6 +32,9 @@ def _convert(mesh, tmp_path, rank):
     write_meshdb(mesh, db, period=50.0, courant=0.6, dt=0.25)
     r = subprocess.run([_exe(), db, str(rank), out], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    # the converter checks the database's GLL/GLJ arrays against the native spectral basis
+    dev = float(r.stdout.split("max deviation")[1].split()[0])
+    assert dev < 1e-6, r.stdout
     return read_axbprob(out), db
 
 
