@@ -18,3 +18,6 @@ echo "built $HERE/../axisem_b200_meshdb2axbp"
 "$CXX" -O2 -std=c++17 -Wall -Wextra -o "$HERE/../axisem_b200_hosttool" \
     "$HERE/hosttool.cpp" "$HERE/spectral.cpp" "$HERE/background_models.cpp"
 echo "built $HERE/../axisem_b200_hosttool"
+# post-processing of the solver output (radiation factors, rotation, STF convolution)
+"$CXX" -O2 -std=c++17 -Wall -Wextra -o "$HERE/../axisem_b200_postproc" "$HERE/postproc_main.cpp" "$HERE/postprocess.cpp"
+echo "built $HERE/../axisem_b200_postproc"

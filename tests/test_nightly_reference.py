@@ -59,23 +59,97 @@ def _score(src, loops, probs, niter, seis_it, dt, shift, colat, lon, against="ax
     return r[:, :, 0][big], r[:, :, 2][big], r
 
 
-def test_oracle_reproduces_the_references_dipole_seismograms():
-    from axisem_b200.capi import TimeLoop, connect_local, run_group
+@pytest.fixture(scope="module")
+def native_oracle_run(tmp_path_factory):
+    """The dipole case through the native pipeline on the CPU: AXBPROB1 containers of 8
+    theta-slices -> the C++ host (axisem_b200/hostcxx, compiled against the oracle's
+    implementation of the header) -> RUN.rankNNNN.seis.f32."""
+    import subprocess
+    from axisem_b200.host.problem_bin import save_problem_bin
     from oracle import oracle
+    tmp = tmp_path_factory.mktemp("nightly")
     nranks = min(8, os.cpu_count() or 1)
     probs, niter, *rest = _setup("mtr", 128, 40, nranks)
-    lib = oracle.load_fast()
-    loops = [TimeLoop(lib, p) for p in probs]
-    if nranks > 1:
-        connect_local(lib, loops)
-        run_group(lib, loops, niter)
-    else:
-        loops[0].run(niter)
-    cc, amp, _ = _score("mtr", loops, probs, niter, *rest)
+    files = []
+    for r, p in enumerate(probs):
+        files.append(str(tmp / f"r{r}.axbp"))
+        save_problem_bin(p, files[-1])
+    run = subprocess.run([oracle.build_host(), "--quiet", "--out", str(tmp / "run")] + files,
+                         capture_output=True, text=True, timeout=900)
+    assert run.returncode == 0, run.stderr
+    return tmp, probs, niter, rest
+
+
+def _native_seismograms(tmp, probs, nsta):
+    s = None
+    for r, p in enumerate(probs):
+        if not p.num_rec:
+            continue
+        raw = np.fromfile(tmp / f"run.rank{r:04d}.seis.f32", dtype=np.float32)
+        raw = raw.reshape(-1, p.num_rec, 3)                     # recdumpvar(3, num_rec, nseismo)
+        if s is None:
+            s = np.zeros((raw.shape[0], nsta, 3))
+        s[:, p.rec_index, :] = raw
+    return s
+
+
+def test_oracle_reproduces_the_references_dipole_seismograms(native_oracle_run):
+    tmp, probs, niter, (seis_it, dt, shift, colat, lon) = native_oracle_run
+    s = _native_seismograms(tmp, probs, colat.size)
+    t = np.arange(s.shape[0]) * seis_it * dt - shift
+    r = compare("mtr", to_enz("mtr", s, colat, lon), t, T_0)
+    big = r[:, :, 3] > 0.002 * r[:, :, 3].max()
+    cc, amp = r[:, :, 0][big], r[:, :, 2][big]
     assert cc.size >= 40                                      # of 20 stations x (E, N, Z)
     assert cc.min() > 0.85 and np.median(cc) > 0.99, (cc.min(), np.median(cc))       # measured 0.878 / 0.9958
     assert amp.min() > 0.93 and amp.max() < 1.08, (amp.min(), amp.max())              # measured 0.959 .. 1.049
     assert abs(np.median(amp) - 1.0) < 0.02
+
+
+def test_native_postprocessing_of_the_same_run(native_oracle_run):
+    """axisem_b200_postproc (radiation factors, rotation into E, N, Z: hostcxx/postprocess.cpp)
+    on the files the C++ host wrote: equal to the Python restatement, and therefore as close to
+    the reference's traces."""
+    import subprocess
+    tmp, probs, niter, (seis_it, dt, shift, colat, lon) = native_oracle_run
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "axisem_b200", "axisem_b200_postproc")
+    if not os.path.exists(exe):
+        subprocess.check_call(["bash", os.path.join(root, "axisem_b200", "hostcxx", "build.sh")])
+    s = _native_seismograms(tmp, probs, colat.size)
+    want = to_enz("mtr", s, colat, lon)                       # (station, E/N/Z, sample)
+    got = np.zeros_like(want)
+    for r, p in enumerate(probs):
+        if not p.num_rec:
+            continue
+        st = tmp / f"st{r}.txt"
+        st.write_text("".join(f"{np.rad2deg(colat[k]):.10f} {np.rad2deg(lon[k]):.10f}\n" for k in p.rec_index))
+        out = tmp / f"enz{r}.f32"
+        run = subprocess.run([exe, "--src", "mtr", "--sys", "enz", "--stations", str(st), "--seis",
+                              str(tmp / f"run.rank{r:04d}.seis.f32"), "--out", str(out)], capture_output=True, text=True)
+        assert run.returncode == 0, run.stderr
+        got[p.rec_index] = np.fromfile(out, dtype=np.float32).reshape(p.num_rec, 3, -1)
+    scale = np.abs(want).max(axis=2, keepdims=True)
+    assert np.all(np.abs(got - want) <= 3e-7 * scale + 1e-30)
+    # Gaussian convolution of the tool against numpy's
+    k = int(probs[0].rec_index[0]) if probs[0].num_rec else 0
+    src_rank = next(r for r, p in enumerate(probs) if p.num_rec)
+    p = probs[src_rank]
+    out = tmp / "conv.f32"
+    sdt = seis_it * dt
+    run = subprocess.run([exe, "--src", "mtr", "--sys", "cyl", "--conv", "60.0", "3.5", f"{sdt:.12f}", "--stations",
+                          str(tmp / f"st{src_rank}.txt"), "--seis", str(tmp / f"run.rank{src_rank:04d}.seis.f32"),
+                          "--out", str(out)], capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr
+    conv = np.fromfile(out, dtype=np.float32).reshape(p.num_rec, 3, -1)
+    a = 3.5 / 60.0
+    half = int(np.ceil(4 * 60.0 / sdt))
+    g = a / np.sqrt(np.pi) * np.exp(-(a * np.arange(-half, half + 1) * sdt) ** 2) * sdt
+    st0 = int(p.rec_index[0])
+    raw = np.fromfile(tmp / f"run.rank{src_rank:04d}.seis.f32", dtype=np.float32).reshape(-1, p.num_rec, 3)
+    z = raw[:, 0, 2].astype(np.float64) * np.cos(lon[st0])    # mtr: the z factor is cos(phi)
+    ref = np.convolve(z, g)[half:half + z.size]
+    assert np.allclose(conv[0, 2], ref, rtol=0, atol=3e-6 * np.abs(ref).max())
 
 
 # measured on the 224 x 60 mesh (oracle and CUDA library alike): correlation min / median, amplitude range
