@@ -199,3 +199,39 @@ def test_cuda_symplectic_scheme_reproduces_the_references_dipole_seismograms():
     assert cc.size >= 40
     assert cc.min() > 0.85 and np.median(cc) > 0.99, (cc.min(), np.median(cc))       # measured 0.878 / 0.9957
     assert amp.min() > 0.93 and amp.max() < 1.08, (amp.min(), amp.max())
+
+
+@pytest.mark.gpu
+def test_the_two_attenuation_formulations_agree_with_each_other():
+    """No reference trace exists for the anelastic loop, so its two independent formulations
+    check each other on the nightly dipole set-up: coarse-grained memory variables at 4 points
+    (attenuation.f90:81-202, stiffness_*:glob_anel_stiffness_*_cg4) against memory variables at
+    all 25 points (:210-334, glob_anel_stiffness_*_4) — different arrays, different kernels
+    (fused in S_A / k_anel_full).  Measured with the oracle on this mesh: relative L2 difference
+    of the seismograms 0.040 between the two, 0.7 between either and the elastic run."""
+    from axisem_b200 import solver
+    from axisem_b200.host import AttenuationModel
+    from tests.util import rel_l2
+    t_0 = 100.0
+    colat = np.array([20.0, 50.0, 80.0, 110.0, 140.0, 170.0])
+    spec = prem_mesh_spec(ntheta=96, nr_target=32, anisotropic=True, r_min_km=1000.0)
+    sp = SourceParams(src_type2="mtr", depth=100e3, magnitude=1e20, t_0=t_0)
+    out = {}
+    for key, anel, cg in (("elastic", False, True), ("cg4", True, True), ("full", True, False)):
+        att = AttenuationModel(coarse_grained=cg) if anel else None
+        dt = build_problem(spec, sp, niter=4, rec_colat_deg=colat, anel=anel, att=att).deltat
+        shift = np.ceil(1.5 * t_0 / dt) * dt
+        niter = int((1800.0 + shift) / dt) + 1
+        prob = build_problem(spec, sp, niter=niter, rec_colat_deg=colat, seis_it=max(1, int(2.0 / dt)),
+                             anel=anel, att=att)
+        loop = solver.time_loop(prob)
+        loop.run(niter)
+        out[key] = loop.seismograms().astype(np.float64)
+        assert np.isfinite(out[key]).all() and np.abs(out[key]).max() > 0
+    d_formulations = rel_l2(out["cg4"], out["full"])
+    d_physics = rel_l2(out["cg4"], out["elastic"])
+    print(f"cg4 vs full memory variables: {d_formulations:.4f}; anelastic vs elastic: {d_physics:.3f}")
+    assert d_formulations < 0.08, d_formulations
+    assert d_physics > 0.4, d_physics
+    peak = np.abs(out["cg4"]).max(axis=(0, 2)) / np.abs(out["elastic"]).max(axis=(0, 2))
+    assert np.all(peak < 1.0) and np.all(peak > 0.4), peak          # attenuation lowers every station's peak
