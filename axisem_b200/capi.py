@@ -62,7 +62,7 @@ OPS = {"solid_stiffness": 0, "anel_stiffness": 1, "fluid_stiffness": 2, "pdistsu
 SYMBOLS = ["last_error", "create", "destroy", "set_mesh", "set_solid_terms", "set_fluid_terms",
            "set_mass", "set_energy", "set_sponge", "set_sf_boundary", "set_attenuation", "set_source",
            "set_stf_values", "set_stf_params", "set_receivers", "set_kwf", "set_halo", "set_time",
-           "finalize_setup", "set_stream", "synchronize", "connect_local", "ipc_export", "ipc_import", "run", "run_group",
+           "finalize_setup", "set_stream", "synchronize", "connect_local", "ipc_blob_bytes", "ipc_export", "ipc_import", "run", "run_group",
            "profile", "get_profile", "iter", "nseismo", "nstrain", "gpu_launches", "fetch_seismograms",
            "fetch_snapshots", "fetch_energy", "get_state", "set_state", "apply_op"]
 

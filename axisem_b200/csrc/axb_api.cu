@@ -144,8 +144,22 @@ struct axb_handle_s {
     float *chi = nullptr, *dchi = nullptr, *ddchi0 = nullptr, *ddchi1 = nullptr;
     int4 *d_asm_cp_s = nullptr, *d_asm_cp_f = nullptr;
     int *d_asm_grp_s = nullptr, *d_asm_grp_f = nullptr;
-    int *d_counters = nullptr;
+    int *d_counters = nullptr;     // [2] halo abort flag, [3] first blown-up iteration
     int iter = 0, iseismo = 0, istrain = 0;
+    // lean Newmark: between steps the velo / dchi buffers hold v + dt/2 a and
+    // dchi + dt/2 ddchi, acc0 is not maintained; the reference's state is re-formed on demand
+    bool lean = false;             // formulation selected at finalize_setup
+    bool lean_state = false;       // the buffers currently hold the lean quantities
+    int lean_entry_iter = 0;       // iter at which they were formed
+    // CUDA-graph replay of a Newmark step: device-resident step counters + the instantiated graph
+    bool use_graph = false;
+    int *d_dyn = nullptr;
+    bool dyn_synced = false;
+    cudaGraphExec_t step_graph = nullptr;
+    int step_graph_nodes = 0;
+    unsigned long long halo_timeout_ns = 10000000000ull;
+    bool have_M_w_fl = false;
+    std::vector<void *> ipc_opened;
     bool acc1_is_acc0 = false;     // after a full step acc1/ddchi1 == acc0/ddchi0 in the reference
     bool finalized = false;
     int64_t launches = 0;
@@ -436,6 +450,8 @@ int axb_destroy(axb_handle h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+    for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void *p : h->allocs) cudaFree(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -448,6 +464,7 @@ int axb_set_stream(axb_handle h, void *cuda_stream) {
     if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
     h->stream = (cudaStream_t)cuda_stream;
     h->own_stream = false;
+    if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }
     return 0;
 }
 
@@ -556,6 +573,7 @@ int axb_set_fluid_terms(axb_handle h, const float *M1chi_fl, const float *M2chi_
         for (size_t p = 0; p < n; p++) if (fluid_free_surface_mask[p] != 1.0f) { mask_needed = true; break; }
     std::vector<const float *> pl = {M1chi_fl, M2chi_fl, M4chi_fl};
     // slot 3 is always M_w_fl for non-monopole sources (axb_fluid_tile.cuh reads it there)
+    h->have_M_w_fl = M_w_fl != nullptr;
     if (M_w_fl) pl.push_back(M_w_fl);
     h->mask_plane_f = -1;
     if (mask_needed) { h->mask_plane_f = (int)pl.size(); pl.push_back(fluid_free_surface_mask); }
@@ -709,6 +727,9 @@ int axb_set_source(axb_handle h, int32_t fluid_src, int32_t nelsrc, const int32_
 
 int axb_set_stf_params(axb_handle h, int32_t stf_type, double decay, double t_0,
                        double shift_fact, double magnitude) {
+    if (stf_type != AXB_STF_GAUSS_0 && stf_type != AXB_STF_GAUSS_1 && stf_type != AXB_STF_GAUSS_2)
+        return fail("axb_set_stf_params: stf_type must be gauss_0, gauss_1 or gauss_2 (compute_stf_t, source.f90:206-233)");
+    if (!(t_0 > 0)) return fail("axb_set_stf_params: t_0 must be positive");
     h->stf_type = stf_type; h->decay = decay; h->t_0 = t_0; h->shift = shift_fact;
     h->magnitude = magnitude;
     return 0;
@@ -794,7 +815,7 @@ int axb_finalize_setup(axb_handle h) {
     if (h->nel_s > 0 && !h->inv_mass_rho) return fail("axb_set_mass not called");
     if (h->nel_s > 0 && !h->have_solid_terms) return fail("axb_set_solid_terms not called");
     if (h->nel_f > 0 && !h->d_coef_f) return fail("axb_set_fluid_terms not called");
-    if (h->nel_f > 0 && h->order != 0 && h->npl_f < 4) return fail("axb_set_fluid_terms: M_w_fl is required for dipole/quadrupole sources");
+    if (h->nel_f > 0 && h->order != 0 && !h->have_M_w_fl) return fail("axb_set_fluid_terms: M_w_fl is required for dipole/quadrupole sources");
     if (h->nel_f > 0 && h->order != 0 && !h->M0_w_fl) return fail("axb_set_fluid_terms: M0_w_fl is required for dipole/quadrupole sources");
     const size_t ns = h->css * 3, nf = (size_t)NPT * h->nel_pad_f;
     if (ns > 0x7fffffffULL) return fail("too many solid points for 32-bit point addresses");
@@ -872,6 +893,9 @@ int axb_finalize_setup(axb_handle h) {
         }
     }
     UP(h->d_meta, meta.data(), meta.size());
+    if (h->scheme != AXB_NEWMARK2 && h->fluid_src && h->nelsrc > 0)
+        return fail("a source in the fluid is only defined for the Newmark scheme: the reference's "
+                    "symplectic loop never calls add_source_fl (time_evol_wave.F90:584-739)");
     if (h->scheme != AXB_NEWMARK2) {
         if (symplectic_coefficients(h)) return 1;
         // stf at the sub-stage times of every step: subdt = t - deltat + coeff
@@ -894,6 +918,24 @@ int axb_finalize_setup(axb_handle h) {
         if (dzeros(h, h->d_snap, (size_t)(h->npt_s_kwf + h->npt_f_kwf) * h->nstrain_max * 3)) return 1;
     }
     if (dzeros(h, h->d_counters, 4)) return 1;
+    if (dzeros(h, h->d_dyn, 4)) return 1;
+    {
+        // Lean Newmark formulation: the product build's default; the bit-exact build keeps the
+        // reference's statement order.  Not with a sponge (its terms need v and u at the old time
+        // level) and not with the energy diagnostic (needs v after every step).  AXB_LEAN=0/1.
+#ifdef AXB_STRICT
+        bool lean = false;
+#else
+        bool lean = true;
+#endif
+        if (const char *ev = getenv("AXB_LEAN")) lean = atoi(ev) != 0;
+        h->lean = lean && h->scheme == AXB_NEWMARK2 && !h->gamma_s && !h->gamma_f && !h->dump_energy;
+        h->lean_state = false;
+        bool graph = true;
+        if (const char *ev = getenv("AXB_GRAPH")) graph = atoi(ev) != 0;
+        h->use_graph = graph && h->scheme == AXB_NEWMARK2 && !h->dump_energy;
+        if (const char *ev = getenv("AXB_HALO_TIMEOUT_MS")) h->halo_timeout_ns = (unsigned long long)std::max(1, atoi(ev)) * 1000000ull;
+    }
     if (h->dump_energy && dzeros(h, h->d_energy, (size_t)4 * (h->niter + 1))) return 1;
     // persistent grids: whole multiples of the SM count
     cudaDeviceProp prop;
@@ -907,9 +949,13 @@ int axb_finalize_setup(axb_handle h) {
         const size_t sb = fluid_stage_bytes(h->npl_f);
         int nst = (int)std::min<size_t>(FLUID_MAX_STAGES, (cap - FLUID_HDR_BYTES) / sb);
         if (nst < 2) return fail("not enough shared memory for the fluid tile ring");
+        // test hooks: a shallow ring / a small grid make every CTA wrap its ring many times on a
+        // small mesh (tests/test_gpu_scale.py)
+        if (const char *ev = getenv("AXB_FLUID_STAGES")) nst = std::max(2, std::min(nst, atoi(ev)));
         h->nst_f = nst;
         h->smem_fluid = FLUID_HDR_BYTES + (size_t)nst * sb;
         h->grid_ft = std::max(1, std::min(h->nel_pad_f / TE, 2 * sms));
+        if (const char *ev = getenv("AXB_FLUID_GRID")) h->grid_ft = std::max(1, std::min(h->grid_ft, atoi(ev)));
         CK(cudaFuncSetAttribute(k_fluid_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_fluid));
     }
     if (h->nel_s > 0) {
@@ -939,6 +985,7 @@ int axb_finalize_setup(axb_handle h) {
             h->ring_off = (int)(Ly.hdr_bytes + tab_bytes);
             h->smem_solid = Ly.hdr_bytes + tab_bytes + (size_t)nst * Ly.stage_bytes;
             h->grid_s = std::max(1, std::min(h->nel_pad_s / TES, sms * SOLID_CTAS_PER_SM));
+            if (const char *ev = getenv("AXB_SOLID_GRID")) h->grid_s = std::max(1, std::min(h->grid_s, atoi(ev)));
             static solid_kernel_t const table[3][3] = {
                 {k_solid_tile<0, 0>, k_solid_tile<0, 5>, k_solid_tile<0, -1>},
                 {k_solid_tile<1, 0>, k_solid_tile<1, 5>, k_solid_tile<1, -1>},
@@ -1009,9 +1056,12 @@ struct IpcBlob {
     int peer[2][MAXMSG], size[2][MAXMSG], offset[2][MAXMSG];
 };
 
+static_assert(sizeof(IpcBlob) <= AXB_IPC_BLOB_BYTES, "AXB_IPC_BLOB_BYTES too small");
+int32_t axb_ipc_blob_bytes(void) { return AXB_IPC_BLOB_BYTES; }
+
 int axb_ipc_export(axb_handle h, void *blob, int32_t blob_bytes) {
     if (use(h)) return 1;
-    if ((size_t)blob_bytes < sizeof(IpcBlob)) return fail("ipc blob too small");
+    if (blob_bytes < AXB_IPC_BLOB_BYTES) return fail("ipc blob too small: AXB_IPC_BLOB_BYTES (1024) are required");
     if (!h->finalized) return fail("ipc_export before finalize_setup");
     IpcBlob b;
     std::memset(&b, 0, sizeof b);
@@ -1031,7 +1081,7 @@ int axb_ipc_export(axb_handle h, void *blob, int32_t blob_bytes) {
 
 int axb_ipc_import(axb_handle h, int32_t peer_rank, const void *blob, int32_t blob_bytes) {
     if (use(h)) return 1;
-    if ((size_t)blob_bytes < sizeof(IpcBlob)) return fail("ipc blob too small");
+    if (blob_bytes < AXB_IPC_BLOB_BYTES) return fail("ipc blob too small: AXB_IPC_BLOB_BYTES (1024) are required");
     IpcBlob b;
     std::memcpy(&b, blob, sizeof b);
     if (b.rank != peer_rank) return fail("ipc blob does not belong to that rank");
@@ -1045,6 +1095,8 @@ int axb_ipc_import(axb_handle h, int32_t peer_rank, const void *blob, int32_t bl
             void *pr = nullptr, *pf = nullptr;
             CK(cudaIpcOpenMemHandle(&pr, b.recv[d], cudaIpcMemLazyEnablePeerAccess));
             CK(cudaIpcOpenMemHandle(&pf, b.flags[d], cudaIpcMemLazyEnablePeerAccess));
+            h->ipc_opened.push_back(pr);
+            h->ipc_opened.push_back(pf);
             wire(h, d, m, (float *)pr, (int *)pf, b.nslots[d], b.offset[d][mm], mm);
         }
     }
@@ -1076,10 +1128,14 @@ static bool halo_wait_kernel() {
     static const bool v = [] { const char *e = getenv("AXB_HALO_WAIT_KERNEL"); return e && atoi(e) != 0; }();
     return v;
 }
-static HaloArrival halo_arrival(const Halo &H) {
+// dyn: the kernel is being captured into the step graph and takes the exchange number from
+// the device-resident counters (value = dyn[DYN_SEQ] + 1)
+static HaloArrival halo_arrival(const axb_handle_s *h, const Halo &H, bool dyn) {
     HaloArrival r;
     r.flags = (H.nmsg == 0 || halo_wait_kernel()) ? nullptr : H.flags;
-    r.nmsg = H.nmsg; r.value = H.seq;
+    r.nmsg = H.nmsg; r.value = dyn ? 1 : H.seq;
+    r.abort = h->d_counters + 2; r.timeout_ns = h->halo_timeout_ns;
+    r.dyn = dyn ? h->d_dyn : nullptr;
     return r;
 }
 static SolidTileArgs solid_args(axb_handle_s *h, int mode, double c0, double c1, int anel, int do_stiff) {
@@ -1142,7 +1198,8 @@ static void launch_solid_step(axb_handle_s *h, int mode, double c0, double c1, i
         launch_solid_element(h, solid_args(h, mode, c0, c1, anel, 1));
     }
 }
-static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1, int full, int use_mask, int energy = 0) {
+static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1, int full, int use_mask, int energy = 0,
+                                 bool dyn = false) {
     if (h->nel_f == 0) return;
     CLS(h, 1);
     FluidTileArgs a;
@@ -1157,9 +1214,10 @@ static void launch_fluid_element(axb_handle_s *h, int mode, double c0, double c1
     a.nelsrc = h->fluid_src ? h->nelsrc : 0;
     for (int k = 0; k < 8; k++) a.ielsrc[k] = h->ielsrc[k];
     a.src_term = h->d_src_term; a.stf = h->d_stf; a.iter = h->iter; a.use_mask = use_mask;
+    a.dyn = dyn ? h->d_dyn : nullptr;
     LAUNCH_SMEM(h, k_fluid_tile, h->grid_ft, FLUID_THREADS, h->smem_fluid, h->G, a);
 }
-static void launch_fluid_corr(axb_handle_s *h, int mode, double c, int assemble_only) {
+static void launch_fluid_corr(axb_handle_s *h, int mode, double c, int assemble_only, bool dyn = false) {
     if (h->nel_f == 0) return;
     CLS(h, 2);
     FluidCorrArgs a;
@@ -1168,12 +1226,13 @@ static void launch_fluid_corr(axb_handle_s *h, int mode, double c, int assemble_
     a.inv_mass_fluid = h->inv_mass_fluid; a.gamma = h->gamma_f;
     a.T.cp = h->d_asm_cp_f; a.T.grp = h->d_asm_grp_f;
     Halo &H = h->halo[1];
-    a.recv = H.recv ? H.recv + (size_t)((H.seq + 1) & 1) * H.nc * H.nslots : nullptr;
+    a.recv = H.recv; a.recv_parity = (H.seq + 1) & 1;
     a.recv_cs = H.nslots; a.assemble_only = assemble_only;
-    a.arrival = halo_arrival(H);
+    a.arrival = halo_arrival(h, H, dyn);
     LAUNCH(h, k_fluid_corrector, cdiv(a.npts, 256), 256, a);
 }
-static void launch_solid_corr(axb_handle_s *h, int mode, double c, int stf_stride, int stf_off, int assemble_only) {
+static void launch_solid_corr(axb_handle_s *h, int mode, double c, int stf_stride, int stf_off, int assemble_only,
+                              bool dyn = false) {
     if (h->nel_s == 0) return;
     CLS(h, 4);
     SolidCorrArgs a;
@@ -1182,13 +1241,14 @@ static void launch_solid_corr(axb_handle_s *h, int mode, double c, int stf_strid
     a.inv_mass_rho = h->inv_mass_rho; a.gamma = h->gamma_s;
     a.T.cp = h->d_asm_cp_s; a.T.grp = h->d_asm_grp_s;
     Halo &H = h->halo[0];
-    a.recv = H.recv ? H.recv + (size_t)((H.seq + 1) & 1) * H.nc * H.nslots : nullptr;
+    a.recv = H.recv; a.recv_parity = (H.seq + 1) & 1;
     a.recv_cs = H.nslots;
-    a.arrival = halo_arrival(H);
+    a.arrival = halo_arrival(h, H, dyn);
+    a.dyn = dyn ? h->d_dyn : nullptr;
     a.nelsrc = h->fluid_src ? 0 : h->nelsrc;
     for (int k = 0; k < 8; k++) a.ielsrc[k] = h->ielsrc[k];
     a.src_term = h->d_src_term;
-    a.stf = (mode == 0) ? h->d_stf : h->d_stf_symp;
+    a.stf = (mode != 1) ? h->d_stf : h->d_stf_symp;
     a.iter = h->iter; a.stf_stride = stf_stride; a.stf_off = stf_off;
     a.assemble_only = assemble_only;
     const int grid = cdiv(a.npts, 256);
@@ -1206,7 +1266,7 @@ static void launch_bdry2solid(axb_handle_s *h) {
     LAUNCH(h, k_bdry2solid, cdiv(h->nel_bdry * NP, 128), 128, a);
 }
 // phase 1 of pdistsum_*: pack partial sums into the neighbours' slabs and raise their flags
-static int halo_send(axb_handle_s *h, int d, const float *vec, size_t cs) {
+static int halo_send(axb_handle_s *h, int d, const float *vec, size_t cs, bool dyn = false) {
     Halo &H = h->halo[d];
     if (H.nmsg == 0) return 0;
     CLS(h, 5);
@@ -1218,13 +1278,15 @@ static int halo_send(axb_handle_s *h, int d, const float *vec, size_t cs) {
     a.done = H.d_done; a.nflag = H.nmsg; a.value = H.seq + 1;
     for (int m = 0; m < H.nmsg; m++) {
         if (!H.peer_recv[m]) return fail("halo peers not connected (axb_connect_local / axb_ipc_import)");
-        a.dst_base[m] = H.peer_recv[m] + (size_t)parity * H.nc * H.peer_nslots[m] + H.peer_offset[m];
+        a.dst_base[m] = H.peer_recv[m] + H.peer_offset[m];
         a.dst_cs[m] = H.peer_nslots[m];
         a.flag[m] = H.peer_flag[m];
     }
+    a.parity = parity;
+    a.dyn = dyn ? h->d_dyn : nullptr;
     // pack + signal in one launch: the last block raises the neighbours' arrival counters
     LAUNCH(h, k_halo_pack, std::max(1, cdiv((long long)a.nentries * a.nc, 128)), 128, a);
-    H.seq++;
+    if (!dyn) H.seq++;
     return 0;
 }
 // phase 2: wait until every neighbour's message of this exchange has landed.  By default the
@@ -1237,6 +1299,7 @@ static void halo_wait(axb_handle_s *h, int d) {
     FlagArgs f;
     std::memset(&f, 0, sizeof f);
     f.n = H.nmsg; f.value = H.seq;
+    f.abort = h->d_counters + 2; f.timeout_ns = h->halo_timeout_ns;
     for (int m = 0; m < H.nmsg; m++) f.flag[m] = H.flags + m;
     LAUNCH(h, k_halo_wait, 1, 32, f);
 }
@@ -1267,18 +1330,30 @@ static void launch_energy(axb_handle_s *h) {
     }
     h->acc1_is_acc0 = true;
 }
+static RecArgs rec_args(axb_handle_s *h) {
+    RecArgs a;
+    a.num_rec = h->num_rec; a.order = h->order; a.seis_it = h->seis_it; a.nseismo_max = h->nseismo_max;
+    a.recfile_el = h->d_recfile; a.disp = h->disp; a.cs = h->css;
+    a.recdump = h->d_recdump; a.iter = h->iter; a.iseismo = h->iseismo; a.dyn = nullptr;
+    return a;
+}
+static bool receivers_due(const axb_handle_s *h) {
+    return h->num_rec > 0 && h->iter % h->seis_it == 0 && h->iseismo < h->nseismo_max;
+}
+static void launch_wavefield_dump(axb_handle_s *h);
 static void launch_dumps(axb_handle_s *h) {
     // dump_stuff (time_evol_wave.F90:1104-1251): receivers every seis_it, wavefield every strain_it
     launch_energy(h);
     CLS(h, 6);
-    if (h->num_rec > 0 && h->iter % h->seis_it == 0 && h->iseismo < h->nseismo_max) {
-        RecArgs a;
-        a.num_rec = h->num_rec; a.order = h->order; a.seis_it = h->seis_it; a.nseismo_max = h->nseismo_max;
-        a.recfile_el = h->d_recfile; a.disp = h->disp; a.cs = h->css;
-        a.recdump = h->d_recdump; a.iter = h->iter; a.iseismo = h->iseismo;
+    if (receivers_due(h)) {
+        RecArgs a = rec_args(h);
         LAUNCH(h, k_sample_receivers, cdiv(h->num_rec, 128), 128, a);
         h->iseismo++;
     }
+    launch_wavefield_dump(h);
+}
+static void launch_wavefield_dump(axb_handle_s *h) {
+    CLS(h, 6);
     if (h->have_kwf && h->strain_it > 0 && h->iter % h->strain_it == 0 && h->istrain < h->nstrain_max) {
         DumpArgs a;
         a.nel_s = h->nel_s; a.nel_f = h->nel_f; a.order = h->order; a.strain_it = h->strain_it;
@@ -1292,20 +1367,53 @@ static void launch_dumps(axb_handle_s *h) {
     }
 }
 
+// classic <-> lean Newmark state (see axb_handle_s::lean)
+static int lean_steps_since(axb_handle_s *h) { return h->iter - h->lean_entry_iter; }
+static void to_lean(axb_handle_s *h) {
+    if (!h->lean || h->lean_state) return;
+    CLS(h, 7);
+    const int ns = (int)(3 * h->css), nf = NPT * h->nel_f;
+    if (h->nel_s) LAUNCH(h, k_axpy, cdiv(ns, 256), 256, ns, h->velo, h->acc0, h->half_dt);
+    if (nf) LAUNCH(h, k_axpy, cdiv(nf, 256), 256, nf, h->dchi, h->ddchi0, h->half_dt);
+    h->lean_state = true;
+    h->lean_entry_iter = h->iter;
+}
+static void to_classic(axb_handle_s *h) {
+    if (!h->lean_state) return;
+    CLS(h, 7);
+    const int ns = (int)(3 * h->css), nf = NPT * h->nel_f;
+    if (h->nel_s) {
+        if (lean_steps_since(h) == 0) {
+            LAUNCH(h, k_axpy, cdiv(ns, 256), 256, ns, h->velo, h->acc0, -h->half_dt);
+        } else {
+            // a of the last step from the still intact acc1 (same assembly, source and mass
+            // terms as the corrector that ran), then v = (v + dt/2 a) - dt/2 a
+            h->iter--;
+            launch_solid_corr(h, 3, h->half_dt, 1, 0, 0, false);
+            h->iter++;
+        }
+    }
+    if (nf) LAUNCH(h, k_axpy, cdiv(nf, 256), 256, nf, h->dchi, h->ddchi0, -h->half_dt);
+    h->lean_state = false;
+}
+
 // One Newmark step, split at the two exchange points so that in-process groups can be
 // enqueued rank by rank (every send is enqueued before the matching wait of any rank).
-static int newmark_a(axb_handle_s *h) {
+// dyn: the launches are being captured into the step graph (device-resident counters).
+static int newmark_a(axb_handle_s *h, bool dyn = false) {
     // S_A first: the fluid needs the *predicted* solid displacement on the S/F boundary
-    launch_solid_step(h, 0, h->deltat, h->half_dt_sq, 2);
-    launch_fluid_element(h, 0, h->deltat, h->half_dt_sq, 1, 1);
-    if (halo_send(h, 1, h->ddchi1, (size_t)NPT * h->nel_f)) return 1;
+    const int mode = h->lean ? 3 : 0;
+    launch_solid_step(h, mode, h->deltat, h->half_dt_sq, 2);
+    launch_fluid_element(h, mode, h->deltat, h->half_dt_sq, 1, 1, 0, dyn);
+    if (halo_send(h, 1, h->ddchi1, (size_t)NPT * h->nel_f, dyn)) return 1;
     return 0;
 }
-static int newmark_b(axb_handle_s *h) {
+static int newmark_b(axb_handle_s *h, bool dyn = false) {
     halo_wait(h, 1);
-    launch_fluid_corr(h, 0, h->half_dt, 0);
+    if (h->lean) launch_fluid_corr(h, 2, h->deltat, 0, dyn);
+    else launch_fluid_corr(h, 0, h->half_dt, 0, dyn);
     launch_bdry2solid(h);
-    if (halo_send(h, 0, h->acc1, h->css)) return 1;
+    if (halo_send(h, 0, h->acc1, h->css, dyn)) return 1;
     return 0;
 }
 // blow-up guard of runtime_info (time_evol_wave.F90:1042-1054), every 100 steps on the device
@@ -1316,18 +1424,71 @@ static void launch_runtime_info(axb_handle_s *h) {
            (float)(10.0 * std::fabs(h->magnitude)), h->iter, h->d_counters);
 }
 static int check_blowup(axb_handle_s *h) {
-    int it = 0;
-    CK(cudaMemcpyAsync(&it, h->d_counters + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    int c[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(c, h->d_counters, sizeof c, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (it != 0) return fail("DISPLACEMENTS BLEW UP: |disp(1,1,:,:)| > 10 |magnitude| at or before time step " + std::to_string(it));
+    if (c[2] != 0) {
+        // the reference's pcheck stops every rank when one fails (commpi.F90:64-111)
+        return fail("HALO EXCHANGE TIMED OUT on rank " + std::to_string(h->rank) + ": message " +
+                    std::to_string(c[2] - 1) + " of a neighbour never arrived (peer not stepped, or dead); "
+                    "the state of this rank is no longer valid");
+    }
+    if (c[3] != 0) return fail("DISPLACEMENTS BLEW UP: |disp(1,1,:,:)| > 10 |magnitude| at or before time step " + std::to_string(c[3]));
     return 0;
 }
-static int newmark_c(axb_handle_s *h) {
+static int newmark_c(axb_handle_s *h, bool dyn = false) {
     halo_wait(h, 0);
-    launch_solid_corr(h, 0, h->half_dt, 1, 0, 0);
+    if (h->lean) launch_solid_corr(h, 2, h->deltat, 1, 0, 0, dyn);
+    else launch_solid_corr(h, 0, h->half_dt, 1, 0, 0, dyn);
+    if (dyn) {
+        // last node of the graph: receiver sampling + the device counters move on
+        CLS(h, 6);
+        RecArgs a = rec_args(h);
+        a.dyn = h->d_dyn;
+        LAUNCH(h, k_step_end, 1, 256, a);
+        return 0;
+    }
     h->iter++;
     launch_runtime_info(h);
     launch_dumps(h);
+    return 0;
+}
+// The Newmark step as one CUDA graph (S_A, F_A, pack, F_B, coupling, pack, S_B, step end): one
+// launch per step from the host, kernel-to-kernel hand-over on the device.
+static int ensure_step_graph(axb_handle_s *h) {
+    if (h->step_graph || !h->use_graph) return 0;
+    const int64_t l0 = h->launches;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        h->use_graph = false;           // e.g. the legacy default stream: keep launching directly
+        return 0;
+    }
+    int rc = newmark_a(h, true) || newmark_b(h, true) || newmark_c(h, true);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    h->step_graph_nodes = (int)(h->launches - l0);
+    h->launches = l0;
+    if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+    if (e != cudaSuccess || !g) { cudaGetLastError(); h->use_graph = false; return 0; }
+    e = cudaGraphInstantiate(&h->step_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { cudaGetLastError(); h->step_graph = nullptr; h->use_graph = false; }
+    return 0;
+}
+static int newmark_graph_step(axb_handle_s *h) {
+    if (!h->dyn_synced) {
+        CLS(h, 7);
+        LAUNCH(h, k_set_dyn, 1, 1, h->d_dyn, h->iter, std::max(h->halo[0].seq, h->halo[1].seq), h->iseismo);
+        h->dyn_synced = true;
+    }
+    CK(cudaGraphLaunch(h->step_graph, h->stream));
+    h->launches += h->step_graph_nodes;
+    // host mirrors of what the graph did on the device
+    for (int d = 0; d < 2; d++) if (h->halo[d].nmsg) h->halo[d].seq++;
+    h->iter++;
+    if (receivers_due(h)) h->iseismo++;
+    launch_runtime_info(h);
+    launch_wavefield_dump(h);
     return 0;
 }
 static int symp_a(axb_handle_s *h, int k) {
@@ -1377,8 +1538,18 @@ int axb_run_group(axb_handle *hs, int32_t n, int32_t nsteps) {
         if (use(hs[i])) return 1;
         if (hs[i]->iter == 0 && hs[i]->iseismo == 0 && hs[i]->istrain == 0) launch_dumps(hs[i]);
         hs[i]->acc1_is_acc0 = true;
+        to_lean(hs[i]);
     }
+    // one handle, Newmark, no per-kernel events: the step is replayed from its CUDA graph
+    const bool graph = n == 1 && hs[0]->use_graph && hs[0]->scheme == AXB_NEWMARK2 && !hs[0]->prof &&
+                       !halo_wait_kernel();
+    if (graph && ensure_step_graph(hs[0])) return 1;
     for (int s = 0; s < nsteps; s++) {
+        if (graph && hs[0]->step_graph) {
+            if (newmark_graph_step(hs[0])) return 1;
+            continue;
+        }
+        for (int i = 0; i < n; i++) hs[i]->dyn_synced = false;
         if (hs[0]->scheme == AXB_NEWMARK2) {
             for (int i = 0; i < n; i++) { if (use(hs[i]) || newmark_a(hs[i])) return 1; }
             for (int i = 0; i < n; i++) { if (use(hs[i]) || newmark_b(hs[i])) return 1; }
@@ -1437,7 +1608,19 @@ int axb_get_profile(axb_handle h, double *ms, int64_t *launches) {
 int axb_set_stf_values(axb_handle h, int32_t first_iter, int32_t n, const float *values) {
     if (use(h)) return 1;
     if (!h->d_stf || first_iter < 0 || n < 0 || first_iter + n > h->niter_stf) return fail("stf range");
+    // the caller's buffer is borrowed for the duration of the call only: a handful of samples
+    // travel as kernel arguments, anything longer is copied synchronously
+    if (n <= 32) {
+        if (n == 0) return 0;
+        StfPatch a;
+        a.first = first_iter; a.n = n;
+        for (int k = 0; k < 32; k++) a.v[k] = k < n ? values[k] : 0.f;
+        CLS(h, 7);
+        LAUNCH(h, k_patch_stf, 1, 32, h->d_stf, a);
+        return 0;
+    }
     CK(cudaMemcpyAsync(h->d_stf + first_iter, values, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -1499,6 +1682,7 @@ static float *field_ptr(axb_handle_s *o, int f, size_t *n, bool *planes, bool re
 int axb_get_state(axb_handle h, int32_t field, float *out) {
     if (use(h)) return 1;
     if (!h->finalized) return fail("get_state before finalize_setup");
+    to_classic(h);
     size_t n = 0; bool planes = false;
     float *p = field_ptr(h, field, &n, &planes, true);
     if (!p) return fail("no such field");
@@ -1514,6 +1698,7 @@ int axb_get_state(axb_handle h, int32_t field, float *out) {
 int axb_set_state(axb_handle h, int32_t field, const float *in) {
     if (use(h)) return 1;
     if (!h->finalized) return fail("set_state before finalize_setup");
+    to_classic(h);
     if (field == AXB_F_ACC1 || field == AXB_F_DDCHI1) h->acc1_is_acc0 = false;
     size_t n = 0; bool planes = false;
     float *p = field_ptr(h, field, &n, &planes, false);
@@ -1531,6 +1716,7 @@ int axb_set_state(axb_handle h, int32_t field, const float *in) {
 int axb_apply_op(axb_handle h, int32_t op) {
     if (use(h)) return 1;
     if (!h->finalized) return fail("apply_op before finalize_setup");
+    to_classic(h);
     h->acc1_is_acc0 = false;
     const size_t css = h->css;
     switch (op) {

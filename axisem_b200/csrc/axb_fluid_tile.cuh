@@ -17,7 +17,8 @@ constexpr int FLUID_MAX_STAGES = 8;
 // stage layout (floats): [chi | dchi | ddchi0][TP], coef[npl][TP], meta ints [3][TE]
 struct FluidTileArgs {
     int ntiles;
-    int mode;                 // 0 Newmark, 1 symplectic drift, 2 none (op test)
+    int mode;                 // 0 Newmark, 1 symplectic drift, 2 none (op test),
+                              // 3 lean Newmark (dchi holds dchi + dt/2 ddchi: chi += dt * dchi)
     int order;                // source order (monopole: no M_w term / no axis masks)
     int full;                 // 1: source, S/F coupling and masks (time loop); 0: bare stiffness
     int npl;                  // coefficient planes in the slab: M1chi, M2chi, M4chi [, M_w_fl] [, fs_mask]
@@ -39,6 +40,7 @@ struct FluidTileArgs {
     const float *src_term;    // (5,5,8)
     const float *stf;
     int iter;
+    const int *dyn;           // graph replay: iter = dyn[DYN_ITER]
     int use_mask;             // Newmark multiplies by the free-surface mask, symplectic does not
     int emask;                // mode 2 only: axis mask on the input copy and on the result (energy)
 };
@@ -76,7 +78,7 @@ k_fluid_tile(const __grid_constant__ GMat G, const __grid_constant__ FluidTileAr
             int s = 0;
             uint32_t ph = 0;
             const uint32_t plane_b = TP * 4;
-            const uint32_t bytes = plane_b * (a.mode == 0 ? 3 : (a.mode == 1 ? 2 : 1)) + a.npl * plane_b + 3 * TE * 4;
+            const uint32_t bytes = plane_b * (a.mode == 0 ? 3 : (a.mode == 2 ? 1 : 2)) + a.npl * plane_b + 3 * TE * 4;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 mbar_wait(&empty[s], ph ^ 1);
                 float *S = reinterpret_cast<float *>(ring + (size_t)s * stage_bytes);
@@ -128,6 +130,8 @@ k_fluid_tile(const __grid_constant__ GMat G, const __grid_constant__ FluidTileAr
                 c = d2f(f2d(c) + a.dt * f2d(S[TP + t]) + a.half_dt_sq * f2d(S[2 * TP + t]));
             else if (a.mode == 1)
                 c = d2f(f2d(c) + f2d(S[TP + t]) * a.dt);
+            else if (a.mode == 3)
+                c = d2f(f2d(c) + a.dt * f2d(S[TP + t]));
             if ((a.full || a.emask) && a.order != 0 && ax && i == 0) c = 0.f;     // apply_axis_mask_scal(chi)
             if (a.mode != 2) { S[t] = c; a.chi[pg] = c; }
             else if (a.emask) S[t] = c;
@@ -163,7 +167,7 @@ k_fluid_tile(const __grid_constant__ GMat G, const __grid_constant__ FluidTileAr
             if (a.full) {
                 // add_source_fl (time_evol_wave.F90:1062-1076)
                 if (a.nelsrc > 0) {
-                    const float stf1 = a.stf[a.iter];
+                    const float stf1 = a.stf[a.dyn ? a.dyn[DYN_ITER] : a.iter];
                     if (stf1 != 0.f)
                         for (int k = 0; k < a.nelsrc; k++)
                             if (a.ielsrc[k] - 1 == eg) l = l - a.src_term[q + NPT * k] * stf1;

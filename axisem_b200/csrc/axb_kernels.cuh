@@ -138,14 +138,41 @@ __device__ __forceinline__ int edge_slot(int q) {
 // after its partial sums have landed in this rank's receive slab).  Only the threads of cut
 // points look at them, so the rest of a corrector overlaps the exchange (the reference
 // overlaps it with the next stiffness call, time_evol_wave.F90:386-427).
+// A neighbour that never delivers (a dead peer process, a rank that was not stepped) must not
+// hang the GPU: the spin is bounded by `timeout_ns`, and the first thread to give up raises
+// the handle's abort flag, which every later wait honours at once.  axb_synchronize reports it
+// the way the reference's pcheck stops a run (commpi.F90:64-111).
 struct HaloArrival {
     const volatile int *flags;   // null: a k_halo_wait launch has already waited
     int nmsg, value;
+    volatile int *abort;         // counters[2]: 0 fine, m + 1 = message m timed out
+    unsigned long long timeout_ns;
+    const int *dyn;              // graph replay: value = dyn[DYN_SEQ] + value
 };
+// device-resident step counters, used instead of by-value arguments when a step is replayed
+// from a CUDA graph (axb_api.cu)
+enum { DYN_ITER = 0, DYN_SEQ = 1, DYN_ISEISMO = 2 };
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool wait_flag(const volatile int *flag, int value, volatile int *abort,
+                                          unsigned long long timeout_ns, int msg) {
+    if (*flag >= value) return true;
+    const unsigned long long t0 = global_ns();
+    while (*flag < value) {
+        if (*abort) return false;
+        if (global_ns() - t0 > timeout_ns) { *abort = msg + 1; __threadfence(); return false; }
+        __nanosleep(100);
+    }
+    return true;
+}
 __device__ __forceinline__ void halo_arrived(const HaloArrival &h) {
     if (!h.flags) return;
+    const int value = h.dyn ? h.dyn[DYN_SEQ] + h.value : h.value;
     for (int m = 0; m < h.nmsg; m++)
-        while (h.flags[m] < h.value) { __nanosleep(100); }
+        if (!wait_flag(h.flags + m, value, h.abort, h.timeout_ns, m)) break;
     __threadfence_system();
 }
 
@@ -160,16 +187,22 @@ namespace axb {
 #endif
 struct FluidCorrArgs {
     int npts;
-    int mode;                 // 0 Newmark, 1 symplectic
-    double half_dt;           // Newmark: dt/2 ; symplectic: coefv
+    int mode;                 // 0 Newmark, 1 symplectic, 2 lean Newmark (dchi holds dchi + dt/2 ddchi)
+    double half_dt;           // Newmark: dt/2 ; symplectic: coefv ; lean Newmark: dt
     float *ddchi1, *ddchi0, *dchi;
     const float *chi;
     const float *inv_mass_fluid, *gamma;   // gamma may be null
     AsmTable T;
-    const float *recv; size_t recv_cs;
+    const float *recv; size_t recv_cs;   // both parities: [2][nc][recv_cs]; recv_parity picks one
+    int recv_parity;
     HaloArrival arrival;
     int assemble_only;
 };
+// the receive slab of the current exchange (graph replay: parity from the device counter)
+__device__ __forceinline__ const float *recv_slab(const float *recv, size_t cs, int nc, int parity, const int *dyn) {
+    if (dyn) parity = dyn[DYN_SEQ] & 1;
+    return recv + (size_t)parity * nc * cs;
+}
 
 // F_B: pdistsum_fluid + mass inversion + sponge + velocity-potential update.
 // Replaces commun.F90:180-283 (+commpi.F90:587-637) and time_evol_wave.F90:430-434, 459-460.
@@ -197,12 +230,13 @@ __global__ void __launch_bounds__(256, AXB_CORR_MINB) k_fluid_corrector(const __
             for (int m = 0; m < nloc; m++) s = s + a.ddchi1[a.T.grp[g + 2 + m]];
             if (nrem > 0) halo_arrived(a.arrival);
             // peer-written data: read at L2 (the slab is reused every second exchange)
-            for (int m = 0; m < nrem; m++) s = s + __ldcg(a.recv + a.T.grp[g + 2 + nloc + m]);
+            const float *recv = recv_slab(a.recv, a.recv_cs, 1, a.recv_parity, a.arrival.dyn);
+            for (int m = 0; m < nrem; m++) s = s + __ldcg(recv + a.T.grp[g + 2 + nloc + m]);
             v = s;
         }
     }
     if (a.assemble_only) { a.ddchi0[p] = v; return; }   // op test: result staged in ddchi0
-    if (a.mode == 0) v = -imf * v;
+    if (a.mode != 1) v = -imf * v;
     else v = -v * imf;
     if (a.gamma) {
         const float gm = a.gamma[p];
@@ -211,6 +245,7 @@ __global__ void __launch_bounds__(256, AXB_CORR_MINB) k_fluid_corrector(const __
     if (a.mode == 0) {
         a.dchi[p] = d2f(f2d(dc) + a.half_dt * f2d(dd0 + v));
     } else {
+        // symplectic kick, or lean Newmark: (dchi + dt/2 ddchi)_new = (dchi + dt/2 ddchi)_old + dt ddchi_new
         a.dchi[p] = d2f(f2d(dc) + a.half_dt * f2d(v));
     }
     a.ddchi0[p] = v;          // ddchi0 = ddchi1 (Newmark); also where S_bdry reads it
@@ -264,14 +299,17 @@ __global__ void k_bdry2fluid(int nel_bdry, int order, const int *bsel, const int
 struct SolidCorrArgs {
     int npts;                 // 25 * nel
     size_t cs;                // component stride (25 * padded element count)
-    int order, mode;          // mode 0 Newmark, 1 symplectic
-    double half_dt;           // dt/2 or coefv
+    int order, mode;          // mode 0 Newmark, 1 symplectic, 2 lean Newmark (velo holds v + dt/2 a),
+                              // 3 back from lean: acc0 = a, velo = velo - dt/2 a
+    double half_dt;           // dt/2 or coefv ; lean: dt ; back from lean: dt/2
     float *acc1, *acc0, *velo;
     const float *disp;
     const float *inv_mass_rho, *gamma;
     AsmTable T;
-    const float *recv; size_t recv_cs;
+    const float *recv; size_t recv_cs;   // both parities: [2][3][recv_cs]
+    int recv_parity;
     HaloArrival arrival;
+    const int *dyn;           // graph replay: iter = dyn[DYN_ITER]
     int nelsrc;
     int ielsrc[8];
     const float *src_term;    // (5,5,8,3)
@@ -330,11 +368,12 @@ __global__ void __launch_bounds__(256, AXB_CORR_MINB) k_solid_corrector(const __
                     if (!(ORDER == 0 && c == 1)) s[c] = s[c] + a.acc1[ad + cs * c];
             }
             if (nrem > 0) halo_arrived(a.arrival);
+            const float *recv = recv_slab(a.recv, a.recv_cs, 3, a.recv_parity, a.arrival.dyn);
             for (int m = 0; m < nrem; m++) {
                 const int sl = a.T.grp[g + 2 + nloc + m];
 #pragma unroll
                 for (int c = 0; c < 3; c++)
-                    if (!(ORDER == 0 && c == 1)) s[c] = s[c] + __ldcg(a.recv + sl + a.recv_cs * c);
+                    if (!(ORDER == 0 && c == 1)) s[c] = s[c] + __ldcg(recv + sl + a.recv_cs * c);
             }
 #pragma unroll
             for (int c = 0; c < 3; c++) v[c] = s[c];
@@ -349,7 +388,8 @@ __global__ void __launch_bounds__(256, AXB_CORR_MINB) k_solid_corrector(const __
     }
     // add_source_el (time_evol_wave.F90:1082-1097)
     if (a.nelsrc > 0) {
-        const float stf1 = a.stf[(size_t)a.iter * a.stf_stride + a.stf_off];
+        const int iter = a.dyn ? a.dyn[DYN_ITER] : a.iter;
+        const float stf1 = a.stf[(size_t)iter * a.stf_stride + a.stf_off];
         if (stf1 != 0.f) {
             for (int k = 0; k < a.nelsrc; k++)
                 if (a.ielsrc[k] - 1 == e) {
@@ -363,12 +403,21 @@ __global__ void __launch_bounds__(256, AXB_CORR_MINB) k_solid_corrector(const __
     for (int c = 0; c < 3; c++) {
         if (ORDER == 0 && c == 1) continue;
         float x = v[c];
-        if (a.mode == 0) {
+        if (a.mode != 1) {
             if (ORDER == 1 && c == 2) x = d2f(-2.0 * f2d(im) * f2d(x));
             else x = -im * x;
             if (a.gamma) x = x - 2 * gm * vel[c] - (gm * gm) * dsp[c];
-            a.velo[p + cs * c] = d2f(f2d(vel[c]) + a.half_dt * f2d(a0[c] + x));
-            a.acc0[p + cs * c] = x;
+            if (a.mode == 0) {
+                a.velo[p + cs * c] = d2f(f2d(vel[c]) + a.half_dt * f2d(a0[c] + x));
+                a.acc0[p + cs * c] = x;
+            } else if (a.mode == 2) {
+                // lean Newmark: w = v + dt/2 a is the stored quantity; w_new = w_old + dt a_new
+                a.velo[p + cs * c] = d2f(f2d(vel[c]) + a.half_dt * f2d(x));
+            } else {
+                // back to the reference's state: a_new from the still intact acc1, v = w - dt/2 a
+                a.velo[p + cs * c] = d2f(f2d(vel[c]) - a.half_dt * f2d(x));
+                a.acc0[p + cs * c] = x;
+            }
         } else {
             x = -im * x;
             if (a.gamma) x = x - 2 * gm * vel[c] - (gm * gm) * dsp[c];
@@ -395,38 +444,45 @@ struct PackArgs {
     const float *vec; size_t cs;
     const int *dst_msg;       // message index of each entry
     const int *dst_slot;      // slot inside the peer's slab
-    float *dst_base[8];       // per message: peer slab base for the current parity
-    size_t dst_cs[8];         // per message: component stride of the peer slab
+    float *dst_base[8];       // per message: peer slab base (parity 0)
+    size_t dst_cs[8];         // per message: component stride of the peer slab (= its slot count)
+    int parity;               // which half of the peers' slabs this exchange writes
     // signal: the last block to finish raises the peers' arrival counters
     int *done;                // local block counter (zero between launches)
     int nflag, value;
     volatile int *flag[8];
+    const int *dyn;           // graph replay: parity = dyn[DYN_SEQ] & 1, value = dyn[DYN_SEQ] + 1
 };
 __global__ void k_halo_pack(const __grid_constant__ PackArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int seq = a.dyn ? a.dyn[DYN_SEQ] : 0;
+    const int parity = a.dyn ? (seq & 1) : a.parity;
     if (t < a.nentries * a.nc) {
         const int en = t % a.nentries, c = t / a.nentries;
         float s = 0.0f;
         for (int m = a.start[en]; m < a.start[en + 1]; m++) s = s + a.vec[a.addr[m] + a.cs * c];
         const int msg = a.dst_msg[en];
-        a.dst_base[msg][a.dst_slot[en] + a.dst_cs[msg] * c] = s;
-        __threadfence_system();        // release: my peer store is visible before any flag
+        a.dst_base[msg][(size_t)parity * a.nc * a.dst_cs[msg] + a.dst_slot[en] + a.dst_cs[msg] * c] = s;
     }
+    // release: the block's peer stores are ordered before the flag by one system-scope fence
+    // behind the barrier (fence cumulativity), not by one fence per thread
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const int prev = atomicAdd(a.done, 1);
         if (prev == (int)gridDim.x - 1) {
             *a.done = 0;
             __threadfence_system();
-            for (int m = 0; m < a.nflag; m++) *a.flag[m] = a.value;
+            const int value = a.dyn ? seq + 1 : a.value;
+            for (int m = 0; m < a.nflag; m++) *a.flag[m] = value;
         }
     }
 }
-struct FlagArgs { int n; volatile int *flag[8]; int value; };
+struct FlagArgs { int n; volatile int *flag[8]; int value; volatile int *abort; unsigned long long timeout_ns; };
 // stand-alone wait (AXB_HALO_WAIT_KERNEL=1): one warp spins on the arrival counters
 __global__ void k_halo_wait(const __grid_constant__ FlagArgs a) {
     if (threadIdx.x < a.n) {
-        while (*a.flag[threadIdx.x] < a.value) { __nanosleep(200); }
+        wait_flag(a.flag[threadIdx.x], a.value, a.abort, a.timeout_ns, threadIdx.x);
         __threadfence_system();
     }
 }
@@ -438,7 +494,17 @@ struct RecArgs {
     const float *disp; size_t cs;
     float *recdump;           // (3, num_rec, nseismo_max)
     int iter, iseismo;        // host-tracked: time step just completed, next sample slot
+    int *dyn;                 // graph replay (k_step_end): the step being completed is dyn[DYN_ITER] + 1
 };
+__device__ __forceinline__ void sample_receiver(const RecArgs &a, int r, int is) {
+    const int iel = a.recfile_el[r], ip = a.recfile_el[r + a.num_rec], jp = a.recfile_el[r + 2 * a.num_rec];
+    const size_t p = ip + NP * jp + (size_t)NPT * (iel - 1);
+    const float d1 = a.disp[p], d2 = a.disp[p + a.cs], d3 = a.disp[p + 2 * a.cs];
+    float *out = a.recdump + (size_t)3 * a.num_rec * is + 3 * r;
+    if (a.order == 0) { out[0] = d1; out[1] = 0.f; out[2] = d3; }
+    else if (a.order == 1) { out[0] = d1 + d2; out[1] = d1 - d2; out[2] = d3; }
+    else { out[0] = d1; out[1] = d2; out[2] = d3; }
+}
 // nc_compute_recfile_seis_bare (seismograms.f90:783-820) every seis_it steps
 __global__ void k_sample_receivers(const __grid_constant__ RecArgs a) {
     const int iter = a.iter;
@@ -447,13 +513,35 @@ __global__ void k_sample_receivers(const __grid_constant__ RecArgs a) {
     if (is >= a.nseismo_max) return;
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= a.num_rec) return;
-    const int iel = a.recfile_el[r], ip = a.recfile_el[r + a.num_rec], jp = a.recfile_el[r + 2 * a.num_rec];
-    const size_t p = ip + NP * jp + (size_t)NPT * (iel - 1);
-    const float d1 = a.disp[p], d2 = a.disp[p + a.cs], d3 = a.disp[p + 2 * a.cs];
-    float *out = a.recdump + (size_t)3 * a.num_rec * is + 3 * r;
-    if (a.order == 0) { out[0] = d1; out[1] = 0.f; out[2] = d3; }
-    else if (a.order == 1) { out[0] = d1 + d2; out[1] = d1 - d2; out[2] = d3; }
-    else { out[0] = d1; out[1] = d2; out[2] = d3; }
+    sample_receiver(a, r, is);
+}
+// Last node of a graph-replayed Newmark step (one block): receiver sampling of the step just
+// completed, then the device-resident step counters move on.
+__global__ void k_step_end(const __grid_constant__ RecArgs a) {
+    const int iter = a.dyn[DYN_ITER] + 1, is = a.dyn[DYN_ISEISMO];
+    const bool sample = a.num_rec > 0 && iter % a.seis_it == 0 && is < a.nseismo_max;
+    if (sample)
+        for (int r = threadIdx.x; r < a.num_rec; r += blockDim.x) sample_receiver(a, r, is);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a.dyn[DYN_ITER] = iter;
+        a.dyn[DYN_SEQ] = a.dyn[DYN_SEQ] + 1;
+        if (sample) a.dyn[DYN_ISEISMO] = is + 1;
+    }
+}
+__global__ void k_set_dyn(int *dyn, int iter, int seq, int iseismo) {
+    dyn[DYN_ITER] = iter; dyn[DYN_SEQ] = seq; dyn[DYN_ISEISMO] = iseismo;
+}
+// axb_set_stf_values for a handful of samples: the values travel as kernel arguments, so the
+// caller's buffer is free again when the call returns
+struct StfPatch { int first, n; float v[32]; };
+__global__ void k_patch_stf(float *stf, const __grid_constant__ StfPatch a) {
+    if (threadIdx.x < a.n) stf[a.first + threadIdx.x] = a.v[threadIdx.x];
+}
+// classic <-> lean Newmark state of the fluid: dchi +/- dt/2 ddchi0
+__global__ void k_axpy(int n, float *x, const float *y, double c) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) x[p] = d2f(f2d(x[p]) + c * f2d(y[p]));
 }
 
 struct DumpArgs {

@@ -89,7 +89,8 @@ __host__ __device__ constexpr SolidTileLayout solid_tile_layout(int order, bool 
 
 struct SolidTileArgs {
     int ntiles;
-    int mode;                 // 0: Newmark predictor, 1: symplectic drift, 2: none (op test)
+    int mode;                 // 0: Newmark predictor, 1: symplectic drift, 2: none (op test),
+                              // 3: lean Newmark (velo holds v + dt/2 a: disp += dt * velo, acc0 not read)
     int do_stiff;             // 0: skip elastic stiffness (anel-only op test keeps acc1)
     int anel;                 // 0 none, 1 cg4 stiffness only, 2 stiffness + memvar update, 3 update only
     int nst;                  // ring depth
@@ -238,7 +239,7 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
             int s = 0;
             uint32_t ph = 0;
             const uint32_t plane_b = TPS * 4;
-            uint32_t bytes = NC * plane_b * (a.mode == 0 ? 3 : (a.mode == 1 ? 2 : 1)) + 3 * TES * 4;
+            uint32_t bytes = NC * plane_b * (a.mode == 0 ? 3 : (a.mode == 2 ? 1 : 2)) + 3 * TES * 4;
             if (a.do_stiff) bytes += NPL * plane_b;
             if (anel) {
                 bytes += NCG * TES * 16 + TES * 96 * n_sls;
@@ -328,6 +329,8 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                     x = d2f(f2d(x) + a.dt * f2d(sl[TPS]) + a.half_dt_sq * f2d(sl[2 * TPS]));
                 else if (a.mode == 1)
                     x = d2f(f2d(x) + f2d(sl[TPS]) * a.dt);
+                else if (a.mode == 3)
+                    x = d2f(f2d(x) + a.dt * f2d(sl[TPS]));
                 if (ORDER == 0) { if (c == 0) u1 = x; else u3 = x; }
                 else { if (c == 0) u1 = x; else if (c == 1) u2 = x; else u3 = x; }
             }

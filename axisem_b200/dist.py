@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-BLOB_BYTES = 1024
+BLOB_BYTES = 1024          # AXB_IPC_BLOB_BYTES of include/axisem_b200.h (checked against axb_ipc_blob_bytes())
 
 
 def neighbours(prob):
@@ -28,6 +28,9 @@ def neighbours(prob):
 def connect_ranks(loop, rank: int, world: int, group=None):
     """Collective over `group`: export my blob, all-gather, import my neighbours' blobs."""
     import torch.distributed as dist
+    need = int(getattr(loop.lib.lib, loop.lib.prefix + "ipc_blob_bytes")())
+    if need != BLOB_BYTES:
+        raise RuntimeError(f"library wants {need}-byte IPC blobs, this module sends {BLOB_BYTES}")
     blob = bytearray(BLOB_BYTES)
     buf = (C.c_char * BLOB_BYTES).from_buffer(blob)
     loop.lib.check(loop.lib.fn["ipc_export"](loop.h, buf, C.c_int32(BLOB_BYTES)))

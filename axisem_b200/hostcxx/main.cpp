@@ -6,6 +6,7 @@
 //   PREFIX.rankNNNN.seis.f32   recdumpvar(3, num_rec, nseismo)      (nc_routines.F90:530-540)
 //   PREFIX.rankNNNN.snap.f32   oneddumpvar(npoints, nstrain, 3)     (nc_routines.F90:248,275)
 //   PREFIX.info                key = value summary
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -109,7 +110,7 @@ int main(int argc, char **argv) {
         };
         if (a == "--steps") opt.nsteps = std::atoi(need("--steps"));
         else if (a == "--devices") opt.ndevices = std::atoi(need("--devices"));
-        else if (a == "--dumpbuffer") opt.nc_dumpbuffersize = std::atoi(need("--dumpbuffer"));
+        else if (a == "--dumpbuffer") opt.nc_dumpbuffersize = std::max(1, std::atoi(need("--dumpbuffer")));
         else if (a == "--quiet") opt.verbose = false;
         else if (a == "--out") prefix = need("--out");
         else if (a == "-h" || a == "--help") { usage(); return 0; }

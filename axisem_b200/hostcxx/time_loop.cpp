@@ -121,7 +121,11 @@ struct Handles {
 
 }  // namespace
 
-TimeLoopResult time_loop(const std::vector<Modules> &ranks, const TimeLoopOptions &opt, OutputSink *sink) {
+TimeLoopResult time_loop(const std::vector<Modules> &ranks, const TimeLoopOptions &opt_in, OutputSink *sink) {
+    // a zero or negative cadence from the caller would divide by zero in the chunking below
+    TimeLoopOptions opt = opt_in;
+    opt.check_iter = std::max(1, opt_in.check_iter);
+    opt.nc_dumpbuffersize = std::max(1, opt_in.nc_dumpbuffersize);
     if (ranks.empty()) throw SolverError("time_loop: no ranks");
     const int n = (int)ranks.size();
     const Modules &m0 = ranks[0];
@@ -169,7 +173,8 @@ TimeLoopResult time_loop(const std::vector<Modules> &ranks, const TimeLoopOption
     };
 
     // chunks end where the host has something to do: progress line, check-point, a full
-    // wavefield buffer
+    // wavefield buffer (a zero or negative cadence from the caller would divide by zero below)
+
     const auto t0 = std::chrono::steady_clock::now();
     int iter = 0;
     while (iter < nsteps) {

@@ -45,8 +45,10 @@ NCOEF = {"monopole": 15, "dipole": 24, "quadpole": 26}
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--repeats", type=int, default=5,
+                    help="timed regions of --steps steps each; the line reports their median and spread")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ntheta", type=int, default=3584)
     ap.add_argument("--nr", type=int, default=1116)
@@ -54,11 +56,14 @@ def parse():
     ap.add_argument("--no-anel", action="store_true")
     ap.add_argument("--full-memvars", action="store_true",
                     help="COARSE_GRAINED false: memory variables at all 25 points (not the headline config)")
-    ap.add_argument("--cpu-sample-cols", type=int, default=384,
-                    help="theta columns of the CPU-baseline sample mesh (same radial structure)")
+    ap.add_argument("--cpu-sample-cols", type=int, default=0,
+                    help="theta columns of the CPU-baseline mesh (same radial structure); 0 = the named "
+                         "mesh itself when the host has the memory for it, else half of it")
     ap.add_argument("--cpu-steps", type=int, default=0, help="0 = size for ~15 s")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-check", action="store_true",
+                    help="skip the correctness check of the N-rank run against the committed 1-rank golden")
     return ap.parse_args()
 
 
@@ -118,10 +123,22 @@ def cpu_reference_rate(args, src, anel, cores=None):
     from oracle import oracle
     from axisem_b200.capi import connect_local, run_group
     cores = cores or (os.cpu_count() or 1)
-    ncols = max(args.cpu_sample_cols // cores, 2) * cores
+    want = args.cpu_sample_cols
+    if want <= 0:
+        # the oracle holds about 7 KB per element next to the host arrays it was given (same again)
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+        except Exception:
+            avail = 0
+        need_full = 16e3 * args.ntheta * args.nr
+        want = args.ntheta if avail > 1.5 * need_full else max(args.ntheta // 2, 2 * cores)
+    ncols = max(want // cores, 2) * cores
+    if ncols % 2:                                      # the mesh generator wants an even count
+        ncols += cores
     spec = prem_mesh_spec(ntheta=ncols, nr_target=args.nr)
     lib = oracle.load_fast()
-    nsteps = args.cpu_steps or 4
+    nsteps = args.cpu_steps or 3
     att = AttenuationModel(coarse_grained=False) if (anel and args.full_memvars) else None
     probs = [build_problem(spec, SourceParams(src_type2=src), anel=anel, att=att, niter=400, rank=r,
                            nranks=cores, rec_colat_deg=[]) for r in range(cores)]
@@ -139,7 +156,7 @@ def cpu_reference_rate(args, src, anel, cores=None):
     run(nsteps)
     dt = time.perf_counter() - t
     if not args.cpu_steps:                           # size the sample for ~15 s of CPU work
-        more = int(min(max(15.0 / (dt / nsteps) - nsteps, 0), 390 - nsteps))
+        more = int(min(max(12.0 / (dt / nsteps) - nsteps, 0), 390 - nsteps))
         if more > 0:
             t2 = time.perf_counter()
             run(more)
@@ -147,7 +164,7 @@ def cpu_reference_rate(args, src, anel, cores=None):
             nsteps += more
     pts = 25 * spec.nelem
     return {"value": pts * nsteps / dt, "unit": "GLL-point updates/s", "cores": cores,
-            "kind": "port",
+            "kind": "port", "same_mesh": bool(ncols == args.ntheta),
             "sample": f"{spec.nelem} elements ({ncols} theta columns x {spec.nr} radial, same "
                       f"layering/physics), {nsteps} steps, {dt:.1f} s",
             "ms_per_step": dt / nsteps * 1e3, "points": pts, "steps": nsteps}
@@ -207,8 +224,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         gloo = dist.new_group(backend="gloo")
 
-    K, W = args.steps, max(args.warmup, 3)
-    niter = W + 3 * K + 8
+    K, W, R = args.steps, max(args.warmup, 3), max(args.repeats, 1)
+    niter = W + (R + 2) * K + 8
     spec = prem_mesh_spec(ntheta=args.ntheta, nr_target=args.nr)
     t0 = time.perf_counter()
     att = AttenuationModel(coarse_grained=False) if (anel and args.full_memvars) else None
@@ -217,8 +234,14 @@ def main():
     t0 = time.perf_counter()
     loop = solver.time_loop(prob, device=local)
     t_upload = time.perf_counter() - t0
-    stream = torch.cuda.current_stream()
+    # a stream of our own (not the legacy default stream): the library replays the Newmark step
+    # from a CUDA graph captured on the stream it launches on
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
     loop.set_stream(stream.cuda_stream)
+    nel_s, nel_f, num_rec = prob.mesh.nel_solid, prob.mesh.nel_fluid, prob.num_rec
+    stf_all = prob.stf.copy()
+    prob.solid = prob.fluid = prob.att = prob.pw_solid = prob.pw_fluid = None   # host copies are no longer needed
 
     # seeded N(0,1)*1e-6 initial fields, so nothing is identically zero
     rng = np.random.default_rng(1234 + rank)
@@ -236,31 +259,39 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- warm-up -------------------------------------------------------------------
     loop.run(W, sync=False)
     sync_all()
     launches0 = loop.gpu_launches
 
-    # ---- timed region: K steps, device resident; CUDA events around every launch of the
-    # dominant kernel (S_A) only -- two event records per step
+    # ---- timed regions: R times exactly K steps, device resident, each bracketed by a
+    # barrier + synchronize; the line reports the median region (and min / max)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
         time.sleep(0.3)
-    loop.profile(2)
-    sync_all()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    loop.run(K, sync=False)
-    ev1.record(stream)
-    sync_all()
-    ms = ev0.elapsed_time(ev1)
-    sa_ms, sa_n = loop.get_profile()
-    loop.profile(False)
-    launches = loop.gpu_launches - launches0
+    region_ms = []
+    for r in range(R):
+        sync_all()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        loop.run(K, sync=False)
+        ev1.record(stream)
+        sync_all()
+        region_ms.append(max_over_ranks(ev0.elapsed_time(ev1)))
+    launches = (loop.gpu_launches - launches0) // R
     clk = clocks.stop() if rank == 0 else None
-    # per-kernel breakdown of a step: a separate, untimed pass with events around every launch
-    # (the event records themselves cost a few microseconds per launch)
+    ms = float(np.median(region_ms))
+    # per-kernel breakdown of a step and the average launch time of the dominant kernel: a
+    # separate pass of K steps with CUDA events around every launch (direct launches instead of
+    # the graph replay; the event records cost a few microseconds per launch)
     loop.profile(1)
     sync_all()
     loop.run(K, sync=False)
@@ -268,9 +299,6 @@ def main():
     prof_ms, prof_n = loop.get_profile()
     loop.profile(False)
     if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
         lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
@@ -281,33 +309,37 @@ def main():
     # ---- e2e: same metric through the C ABI with host buffers, per step ---------------
     e2e = None
     if not args.no_e2e:
-        stf_host = torch.from_numpy(prob.stf.copy()).pin_memory().numpy()
-        out = np.zeros((1, prob.num_rec, 3), dtype=np.float32)
+        stf_host = torch.from_numpy(stf_all).pin_memory().numpy()
+        out = np.zeros((1, num_rec, 3), dtype=np.float32)
         import ctypes as C
         sync_all()
         t0 = time.perf_counter()
         for k in range(K):
             it = loop.iter
-            loop.set_stf_values(it, stf_host[it:it + 1])               # H2D, pinned
+            loop.set_stf_values(it, stf_host[it:it + 1])               # host -> device
             loop.run(1, sync=False)
-            if prob.num_rec:                                           # D2H (synchronises)
+            if num_rec:                                                # D2H (synchronises)
                 loop.lib.check(loop.lib.fn["fetch_seismograms"](
                     loop.h, C.c_int32(loop.nseismo - 1), C.c_int32(1),
                     out.ctypes.data_as(C.POINTER(C.c_float))))
             else:
                 loop.synchronize()
         sync_all()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": total_pts * K / dt, "unit": "GLL-point updates/s",
-               "h2d_bytes_per_step": 4, "d2h_bytes_per_step": int(12 * prob.num_rec),
+               "h2d_bytes_per_step": 4, "d2h_bytes_per_step": int(12 * num_rec),
                "note": "per step: axb_set_stf_values (pinned host -> device), axb_run(1), "
                        "axb_fetch_seismograms (device -> host, synchronising); model arrays are "
                        "uploaded once at set-up (host->device "
                        f"{t_upload:.1f} s, not in the timed region)"}
+    loop.close()
+    del loop
+
+    # ---- correctness of what these N ranks compute: a mid-size mesh through the same library
+    # and halo wiring, seismograms against the committed 1-rank oracle golden
+    check = None
+    if not args.no_check:
+        check = correctness_check(rank, world, local, gloo)
 
     if rank != 0:
         if world > 1:
@@ -315,7 +347,6 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (S_A, class 0) -----------------------------
-    m = prob.mesh
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -325,21 +356,21 @@ def main():
     full = anel and args.full_memvars
     b_anel = (B_ANEL_FULL[pole] if full else B_ANEL[pole]) if anel else 0.0
     bytes_pt_sa = 4.0 * (2 * NC[pole] + NCOEF[pole]) + b_anel
-    bytes_sa = bytes_pt_sa * 25 * m.nel_solid
+    bytes_sa = bytes_pt_sa * 25 * nel_s
     # full memory variables: S_A is followed by k_anel_full (same profile class); one "launch"
     # below is then the pair
-    ms_sa = sa_ms[0] / max(sa_n[0], 1) * (2 if full else 1)
+    ms_sa = prof_ms[0] / max(prof_n[0], 1) * (2 if full else 1)
     achieved = bytes_sa / (ms_sa * 1e-3) / 1e9 if ms_sa > 0 else None
-    traffic = None
+    traffic = traffic_src = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
-        key = f"{pole}_{'anel' if anel else 'elastic'}"
+        key = f"{pole}_{('anel_full' if full else 'anel') if anel else 'elastic'}"
         if key in tr:
-            traffic = tr[key]["bytes_per_solid_element"] * m.nel_solid
+            traffic = tr[key]["bytes_per_solid_element"] * nel_s
+            traffic_src = tr[key]["source"]
     except Exception:
         pass
-    step_bytes = 25.0 * ((B_SOLID[pole] + b_anel) * m.nel_solid * world
-                         + B_FLUID[pole] * m.nel_fluid * world)
+    step_bytes = 25.0 * ((B_SOLID[pole] + b_anel) * nel_s * world + B_FLUID[pole] * nel_f * world)
     names = ["solid_element(S_A)", "fluid_element(F_A)", "fluid_corrector(F_B)", "sf_coupling",
              "solid_corrector(S_B)", "halo", "sampling", "other"]
     line = {
@@ -347,34 +378,86 @@ def main():
         "n_gpus": N, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "elements": int(spec.nelem),
+        "config": {"workload": workload + f"; {100.0 * nel_f / (nel_s + nel_f):.1f} % of the elements are fluid "
+                               "(outer core; 48 B/point against 227 for the anelastic solid)",
+                   "elements": int(spec.nelem),
                    "gll_points": int(total_pts), "elements_per_gpu": int(spec.nelem // world),
                    "parallelism": f"theta-slices x{world}",
                    "l2": "inputs larger than L2: %.1f GB of algorithmic traffic per GPU per step"
                          % (step_bytes / world / 1e9),
                    "host_build_s": round(t_build, 1), "host_to_device_setup_s": round(t_upload, 1)},
+        "repeats": {"n": R, "steps_each": K, "ms_per_step_median": ms / K,
+                    "ms_per_step_min": min(region_ms) / K, "ms_per_step_max": max(region_ms) / K,
+                    "spread_pct": 100.0 * (max(region_ms) - min(region_ms)) / ms},
         "clocks": clk,
         "e2e": e2e,
+        "check": check,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": f"k_solid_tile<{pole}> (S_A)" + (" + k_anel_full" if full else ""),
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                     "traffic_source": traffic_src,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else
                                     "fallback 6650 GB/s (of fallback)",
                      "algorithmic_bytes_per_launch": bytes_sa, "avg_ms_per_launch": ms_sa,
+                     "timing": "CUDA events around every S_A launch of a K-step pass next to the timed regions",
                      "step_algorithmic_GBs": step_bytes / world / (ms / K * 1e-3) / 1e9,
                      "step_frac_of_peak": step_bytes / world / (ms / K * 1e-3) / 1e9 / peak,
                      "kernel_ms_per_step": {n: prof_ms[i] / K for i, n in enumerate(names)
                                             if prof_n[i]}},
     }
     if N == 1 and not args.no_cpu_baseline:
-        del loop
+        del prob
         cb = cpu_reference_rate(args, src, anel)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "same_mesh")}
     json_out.write(json.dumps(line) + "\n")
     json_out.flush()
     if world > 1:
         dist.destroy_process_group()
+
+
+CHECK_GOLDEN = os.path.join(ROOT, "tests", "golden", "bench_check_mtr_cg4.npz")
+
+
+def check_problem(rank, world):
+    """The mid-size case of the correctness check (tests/golden/make_bench_check.py made the
+    golden from the same function with the oracle on one rank)."""
+    z = np.load(CHECK_GOLDEN)
+    spec = prem_mesh_spec(ntheta=int(z["ntheta"]), nr_target=int(z["nr"]), r_min_km=float(z["r_min_km"]))
+    sp = SourceParams(src_type2="mtr", t_0=float(z["t_0"]))
+    return build_problem(spec, sp, anel=True, niter=int(z["niter"]), rank=rank, nranks=world,
+                         rec_colat_deg=z["colat_deg"], seis_it=int(z["seis_it"])), z
+
+
+def correctness_check(rank, world, local, gloo):
+    """Seismograms of the N-rank run (product library, same halo wiring as the timed run) against
+    the 1-rank oracle golden: relative L2 over all stations and components."""
+    import torch.distributed as dist
+    from axisem_b200 import solver
+    prob, z = check_problem(rank, world)
+    loop = solver.time_loop(prob, device=local)
+    if world > 1:
+        from axisem_b200.dist import connect_ranks
+        connect_ranks(loop, rank, world, group=gloo)
+    loop.run(prob.niter)
+    mine = (prob.rec_index, loop.seismograms())
+    loop.close()
+    parts = [mine]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine, group=gloo)
+    if rank != 0:
+        return None
+    ref = z["seismograms"].astype(np.float64)
+    got = np.zeros_like(ref)
+    for idx, s in parts:
+        if len(idx):
+            got[:, idx, :] = s
+    err = float(np.sqrt(((got - ref) ** 2).sum()) / np.sqrt((ref ** 2).sum()))
+    return {"rel_l2": err, "tolerance": 1e-5, "ok": bool(err <= 1e-5), "ranks": world,
+            "case": f"{int(z['ntheta'])}x{int(z['nr'])} PREM mesh, dipole, cg4 attenuation, "
+                    f"{int(z['niter'])} Newmark steps, {ref.shape[1]} stations",
+            "golden": "tests/golden/bench_check_mtr_cg4.npz (oracle, 1 rank)"}
 
 
 if __name__ == "__main__":

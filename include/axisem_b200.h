@@ -204,9 +204,21 @@ int AXB(finalize_setup)(axb_handle h);
 
 /* Multi-rank runs: every rank's handle must be connected to its peers before axb_run.
  * In-process (oracle, single-process multi-GPU): axb_connect_local with all handles.
- * One process per GPU: exchange the 64-byte IPC blobs (e.g. over torch.distributed). */
+ * One process per GPU: every rank exports one opaque blob of AXB_IPC_BLOB_BYTES bytes
+ * (CUDA IPC handles of its receive slabs and arrival counters plus its message lists;
+ * axb_ipc_blob_bytes() returns the same number at run time), the blobs travel once over any
+ * channel (MPI_Allgather in the Fortran host, torch.distributed here), and each rank imports
+ * the blobs of the ranks its halo lists name.  A smaller buffer is rejected with an error.
+ * The mappings an import opens are closed by axb_destroy.
+ *
+ * A neighbour that never delivers does not hang the GPU: every wait on an arrival counter is
+ * bounded (10 s; AXB_HALO_TIMEOUT_MS overrides), the rank then raises its abort flag and
+ * axb_synchronize fails with "HALO EXCHANGE TIMED OUT ..." — the counterpart of the
+ * reference's pcheck, which stops all ranks when one fails (commpi.F90:64-111). */
+#define AXB_IPC_BLOB_BYTES 1024
+int32_t AXB(ipc_blob_bytes)(void);
 int AXB(connect_local)(axb_handle *handles, int32_t n);
-int AXB(ipc_export)(axb_handle h, void *blob, int32_t blob_bytes);   /* >= 256 bytes */
+int AXB(ipc_export)(axb_handle h, void *blob, int32_t blob_bytes);
 int AXB(ipc_import)(axb_handle h, int32_t peer_rank, const void *blob, int32_t blob_bytes);
 
 /* Launch on an existing CUDA stream (a cudaStream_t, e.g. torch's current stream) instead

@@ -1586,6 +1586,8 @@ static void ipc_layout(const axo_t *o, ipc_blob_t *b) {
     b->bytes = off * (long)sizeof(float);
 }
 
+int32_t axo_ipc_blob_bytes(void) { return AXB_IPC_BLOB_BYTES; }
+
 int axo_ipc_export(axb_handle h, void *blob, int32_t n) {
     static int counter = 0;
     ipc_blob_t b;

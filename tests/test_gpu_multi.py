@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, src, n, ndev, out_dir):
+def _worker(rank, world, port, src, n, ndev, out_dir, strict):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -32,7 +32,7 @@ def _worker(rank, world, port, src, n, ndev, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         prob = make_problem(src, anel=True, ntheta=16, nr=18, niter=n, rank=rank, nranks=world)
-        loop = solver.time_loop(prob, device=rank % ndev, strict=True)
+        loop = solver.time_loop(prob, device=rank % ndev, strict=strict)
         connect_ranks(loop, rank, world)
         loop.run(n)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), seis=loop.seismograms(),
@@ -43,16 +43,19 @@ def _worker(rank, world, port, src, n, ndev, out_dir):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("world,src", [(2, "mtr"), (4, "explosion")])
-def test_process_per_rank_ipc_halo_matches_oracle(world, src, tmp_path):
+@pytest.mark.parametrize("world,src,strict", [(2, "mtr", True), (4, "explosion", True), (8, "mtr", True),
+                                              (2, "mtr", False), (8, "mtr", False)])
+def test_process_per_rank_ipc_halo_matches_oracle(world, src, strict, tmp_path):
     import torch
     import torch.multiprocessing as mp
     from axisem_b200.capi import connect_local, run_group
     from oracle import oracle
     from tests.util import make_problem
     ndev = torch.cuda.device_count()
+    if world == 8 and ndev < 8:
+        pytest.skip("the 8-rank case wants 8 distinct devices (peer stores over NVLink)")
     n = 30 if ndev >= world else 8          # sharing one GPU time-slices the spinning waits
-    mp.spawn(_worker, args=(world, _free_port(), src, n, ndev, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), src, n, ndev, str(tmp_path), strict), nprocs=world, join=True)
     probs = [make_problem(src, anel=True, ntheta=16, nr=18, niter=n, rank=r, nranks=world) for r in range(world)]
     ol = [oracle.make_loop(p) for p in probs]
     olib = oracle.load()
@@ -61,7 +64,14 @@ def test_process_per_rank_ipc_halo_matches_oracle(world, src, tmp_path):
     for r, o in enumerate(ol):
         z = np.load(tmp_path / f"rank{r}.npz")
         assert int(z["launches"]) > 0
-        # -fmad=false build, same halo summation order as the oracle: bit-identical
-        assert np.array_equal(z["seis"], o.seismograms())
-        assert np.array_equal(z["disp"], o.get("disp"))
-        assert np.array_equal(z["chi"], o.get("chi"))
+        if strict:
+            # -fmad=false build, same halo summation order as the oracle: bit-identical
+            assert np.array_equal(z["seis"], o.seismograms())
+            assert np.array_equal(z["disp"], o.get("disp"))
+            assert np.array_equal(z["chi"], o.get("chi"))
+        else:
+            # product build (FMA contraction, lean Newmark, step graph) over the same wiring
+            from tests.util import rel_l2
+            assert rel_l2(z["seis"], o.seismograms()) <= 1e-5
+            assert rel_l2(z["disp"], o.get("disp")) <= 1e-5
+            assert rel_l2(z["chi"], o.get("chi")) <= 1e-5

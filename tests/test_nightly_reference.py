@@ -210,6 +210,55 @@ def test_cuda_reproduces_the_references_seismograms(src):
 
 
 @pytest.mark.gpu
+@pytest.mark.timeout(1800)
+@pytest.mark.parametrize("src", ["explosion", "mtr", "mtp"])
+def test_cuda_equals_the_oracle_over_the_whole_nightly_run(src):
+    """The sentence of DESIGN.md section 2 ("identical for the oracle and the CUDA library") as an
+    assertion: the same 224 x 60 mesh, all 18 293 steps of the 1800 s run.  The oracle runs as 8
+    theta-slices in threads; the strict build runs the same 8 slices (loop-back halo on one GPU)
+    and must be bit-identical in every seismogram sample; the product build (one slice, FMA
+    contraction, lean Newmark, graph replay) must stay within 1e-5 relative L2."""
+    from axisem_b200 import solver
+    from axisem_b200.capi import TimeLoop, connect_local, run_group
+    from oracle import oracle
+    from tests.util import rel_l2
+    nranks = 8
+    probs, niter, *rest = _setup(src, 224, 60, nranks, lvz_elements=3)
+    colat = rest[3]
+    olib = oracle.load()
+    ol = [TimeLoop(olib, p) for p in probs]
+    connect_local(olib, ol)
+    run_group(olib, ol, niter)
+
+    def gather(loops, ps):
+        ns = max(L.nseismo for L in loops)
+        s = np.zeros((ns, colat.size, 3), dtype=np.float32)
+        for p, L in zip(ps, loops):
+            if p.num_rec:
+                s[:, p.rec_index, :] = L.seismograms()
+        return s
+
+    ref = gather(ol, probs)
+    del ol
+    assert np.abs(ref).max() > 0
+    lib, gl = solver.time_loop_group(probs, strict=True)
+    run_group(lib, gl, niter)
+    for g in gl:
+        g.synchronize()
+    strict = gather(gl, probs)
+    del gl
+    assert np.array_equal(strict, ref), f"strict build, 8 slices: rel l2 {rel_l2(strict, ref):.3e}"
+    one, niter1, *_ = _setup(src, 224, 60, 1, lvz_elements=3)
+    assert niter1 == niter
+    P = solver.time_loop(one[0])
+    P.run(niter)
+    prod = gather([P], one)
+    err = rel_l2(prod, ref)
+    print(f"{src}: {niter} steps, product (1 slice) vs oracle (8 slices): rel l2 {err:.3e}; launches {P.gpu_launches}")
+    assert err <= 1e-5, err
+
+
+@pytest.mark.gpu
 def test_cuda_symplectic_scheme_reproduces_the_references_dipole_seismograms():
     """The 4th-order symplectic loop (time step 1.5 x Newmark's, point-wise source time function
     of compute_stf_t) against the same golden traces; the oracle gives the same numbers."""
