@@ -120,6 +120,7 @@ struct axb_handle_s {
     int corr_lowq = 0;
     // source
     int fluid_src = 0, nelsrc = 0, ielsrc[8] = {0}, niter_stf = 0;
+    int src_emin = 0, src_emax = -1;     // 0-based range spanned by ielsrc
     float *d_src_term = nullptr, *d_stf = nullptr;
     int stf_type = 0;
     double decay = 0, t_0 = 1, shift = 0, magnitude = 0;
@@ -717,6 +718,11 @@ int axb_set_source(axb_handle h, int32_t fluid_src, int32_t nelsrc, const int32_
     if (nelsrc < 0 || nelsrc > 8) return fail("nelsrc must be in 0..8");
     h->fluid_src = fluid_src; h->nelsrc = nelsrc;
     for (int k = 0; k < 8; k++) h->ielsrc[k] = (k < nelsrc) ? ielsrc[k] : 0;
+    h->src_emin = 0x7fffffff; h->src_emax = -1;
+    for (int k = 0; k < nelsrc; k++) {
+        h->src_emin = std::min(h->src_emin, ielsrc[k] - 1);
+        h->src_emax = std::max(h->src_emax, ielsrc[k] - 1);
+    }
     for (int k = 0; k < nelsrc; k++)
         if (ielsrc[k] < 1 || ielsrc[k] > (fluid_src ? h->nel_f : h->nel_s)) return fail("ielsrc out of range");
     UP(h->d_src_term, source_term, (size_t)NPT * 8 * (fluid_src ? 1 : 3));
@@ -1246,15 +1252,19 @@ static void launch_solid_corr(axb_handle_s *h, int mode, double c, int stf_strid
     a.arrival = halo_arrival(h, H, dyn);
     a.dyn = dyn ? h->d_dyn : nullptr;
     a.nelsrc = h->fluid_src ? 0 : h->nelsrc;
+    a.src_emin = h->src_emin; a.src_emax = h->src_emax;
     for (int k = 0; k < 8; k++) a.ielsrc[k] = h->ielsrc[k];
     a.src_term = h->d_src_term;
     a.stf = (mode != 1) ? h->d_stf : h->d_stf_symp;
     a.iter = h->iter; a.stf_stride = stf_stride; a.stf_off = stf_off;
     a.assemble_only = assemble_only;
     const int grid = cdiv(a.npts, 256);
-    if (h->order == 0) LAUNCH(h, k_solid_corrector<0>, grid, 256, a);
-    else if (h->order == 1) LAUNCH(h, k_solid_corrector<1>, grid, 256, a);
-    else LAUNCH(h, k_solid_corrector<2>, grid, 256, a);
+    typedef void (*corr_kernel_t)(SolidCorrArgs);
+    static corr_kernel_t const table[3][5] = {
+        {k_solid_corrector<0, 0>, k_solid_corrector<0, 1>, k_solid_corrector<0, 2>, k_solid_corrector<0, 3>, k_solid_corrector<0, 4>},
+        {k_solid_corrector<1, 0>, k_solid_corrector<1, 1>, k_solid_corrector<1, 2>, k_solid_corrector<1, 3>, k_solid_corrector<1, 4>},
+        {k_solid_corrector<2, 0>, k_solid_corrector<2, 1>, k_solid_corrector<2, 2>, k_solid_corrector<2, 3>, k_solid_corrector<2, 4>}};
+    LAUNCH(h, table[h->order][assemble_only ? 4 : mode], grid, 256, a);
 }
 static void launch_bdry2solid(axb_handle_s *h) {
     if (h->nel_bdry == 0) return;

@@ -124,14 +124,16 @@ struct AsmTable {
     const int4 *cp;
     const int *grp;
 };
-// slot of element-local point q among the 16 edge points (-1: interior)
+// slot of element-local point q among the 16 edge points (-1: interior): row j = 0 -> 0..4,
+// (i = 0 | 4, j = 1..3) -> 5..10, row j = 4 -> 11..15.  Looked up in two packed constants (four
+// bits per point) instead of the division and four branches it takes to compute.
 __device__ __forceinline__ int edge_slot(int q) {
-    const int j = q / NP, i = q - NP * j;
-    if (j == 0) return i;
-    if (j == NP - 1) return 11 + i;
-    if (i == 0) return 3 + 2 * j;
-    if (i == NP - 1) return 4 + 2 * j;
-    return -1;
+    constexpr unsigned INTERIOR = (7u << 6) | (7u << 11) | (7u << 16);
+    constexpr unsigned long long LO = 0x9800076000543210ull;   // q = 0..15
+    constexpr unsigned long long HI = 0x0000000fedcba000ull;   // q = 16..24
+    const unsigned long long w = (q & 16) ? HI : LO;
+    const int slot = (int)((w >> ((q & 15) * 4)) & 15ull);
+    return ((INTERIOR >> q) & 1u) ? -1 : slot;
 }
 
 // Arrival counters of the current halo exchange (one per message, raised by the peer GPU
@@ -311,6 +313,9 @@ struct SolidCorrArgs {
     HaloArrival arrival;
     const int *dyn;           // graph replay: iter = dyn[DYN_ITER]
     int nelsrc;
+    int src_emin, src_emax;   // 0-based range of the source elements: one compare pair per point in
+                              // front of the eight-way search (which was a quarter of this
+                              // kernel's instructions, profiles/r01i)
     int ielsrc[8];
     const float *src_term;    // (5,5,8,3)
     const float *stf;         // Newmark: stf(niter), symplectic: stf_symp(nstages, niter)
@@ -321,65 +326,70 @@ struct SolidCorrArgs {
 
 // S_B: pdistsum_solid + source + mass inversion + sponge + velocity update.
 // Replaces commun.F90:69-171 (+commpi.F90:453-500) and time_evol_wave.F90:466-494 / :689-715.
-template <int ORDER>
-__global__ void __launch_bounds__(256, AXB_CORR_MINB) k_solid_corrector(const __grid_constant__ SolidCorrArgs a) {
+// MODE (compile time, so that each variant carries only its own loads, stores and registers):
+// 0 Newmark, 1 symplectic, 2 lean Newmark, 3 back from lean, 4 assemble only (operator test).
+template <int ORDER, int MODE>
+__global__ void __launch_bounds__(256, MODE == 0 ? AXB_CORR_MINB - 1 : AXB_CORR_MINB)
+k_solid_corrector(const __grid_constant__ SolidCorrArgs a) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.npts) return;
     const size_t cs = a.cs;
     const int e = p / NPT, q = p - e * NPT, slot = edge_slot(q);
-    // every input of this point is requested up front (the stores below would otherwise
+    // the assembly entry first: it heads the only dependent chain (entry -> gather)
+    int4 cp = make_int4(-1, -1, -1, -1);
+    if (slot >= 0) cp = a.T.cp[16 * (size_t)e + slot];
+    // every other input of this point is requested up front (the stores below would otherwise
     // order the per-component loads behind them)
+    constexpr bool upd = MODE != 4;
+    const bool sponge = upd && a.gamma != nullptr;
     float v[3], vel[3], a0[3], dsp[3];
-    const float im = a.assemble_only ? 0.f : a.inv_mass_rho[p];
-    const float gm = (a.gamma && !a.assemble_only) ? a.gamma[p] : 0.f;
+    const float im = upd ? a.inv_mass_rho[p] : 0.f;
+    const float gm = sponge ? a.gamma[p] : 0.f;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         v[c] = vel[c] = a0[c] = dsp[c] = 0.f;
         if (ORDER == 0 && c == 1) continue;
         v[c] = a.acc1[p + cs * c];
-        if (!a.assemble_only) {
+        if (upd) {
             vel[c] = a.velo[p + cs * c];
-            if (a.mode == 0) a0[c] = a.acc0[p + cs * c];
-            if (a.gamma) dsp[c] = a.disp[p + cs * c];
+            if (MODE == 0) a0[c] = a.acc0[p + cs * c];
+            if (sponge) dsp[c] = a.disp[p + cs * c];
         }
     }
-    if (slot >= 0) {
-        const int4 cp = a.T.cp[16 * (size_t)e + slot];
-        if (cp.x >= 0) {
+    if (cp.x >= 0) {
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                if (ORDER == 0 && c == 1) continue;
-                const float *vec = a.acc1 + cs * c;
-                float s = 0.0f;
-                s = s + vec[cp.x];
-                s = s + vec[cp.y];
-                if (cp.z >= 0) s = s + vec[cp.z];
-                if (cp.w >= 0) s = s + vec[cp.w];
-                v[c] = s;
-            }
-        } else if (cp.x == -2) {
-            const int g = cp.y;
-            const int nloc = a.T.grp[g], nrem = a.T.grp[g + 1];
-            float s[3] = {0.f, 0.f, 0.f};
-            for (int m = 0; m < nloc; m++) {
-                const int ad = a.T.grp[g + 2 + m];
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-                    if (!(ORDER == 0 && c == 1)) s[c] = s[c] + a.acc1[ad + cs * c];
-            }
-            if (nrem > 0) halo_arrived(a.arrival);
-            const float *recv = recv_slab(a.recv, a.recv_cs, 3, a.recv_parity, a.arrival.dyn);
-            for (int m = 0; m < nrem; m++) {
-                const int sl = a.T.grp[g + 2 + nloc + m];
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-                    if (!(ORDER == 0 && c == 1)) s[c] = s[c] + __ldcg(recv + sl + a.recv_cs * c);
-            }
-#pragma unroll
-            for (int c = 0; c < 3; c++) v[c] = s[c];
+        for (int c = 0; c < 3; c++) {
+            if (ORDER == 0 && c == 1) continue;
+            const float *vec = a.acc1 + cs * c;
+            float s = 0.0f;
+            s = s + vec[cp.x];
+            s = s + vec[cp.y];
+            if (cp.z >= 0) s = s + vec[cp.z];
+            if (cp.w >= 0) s = s + vec[cp.w];
+            v[c] = s;
         }
+    } else if (cp.x == -2) {
+        const int g = cp.y;
+        const int nloc = a.T.grp[g], nrem = a.T.grp[g + 1];
+        float s[3] = {0.f, 0.f, 0.f};
+        for (int m = 0; m < nloc; m++) {
+            const int ad = a.T.grp[g + 2 + m];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                if (!(ORDER == 0 && c == 1)) s[c] = s[c] + a.acc1[ad + cs * c];
+        }
+        if (nrem > 0) halo_arrived(a.arrival);
+        const float *recv = recv_slab(a.recv, a.recv_cs, 3, a.recv_parity, a.arrival.dyn);
+        for (int m = 0; m < nrem; m++) {
+            const int sl = a.T.grp[g + 2 + nloc + m];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                if (!(ORDER == 0 && c == 1)) s[c] = s[c] + __ldcg(recv + sl + a.recv_cs * c);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) v[c] = s[c];
     }
-    if (a.assemble_only) {
+    if (MODE == 4) {
         // op test: stage the assembled field in acc0 (acc1 must stay intact while other
         // threads still pull from it)
 #pragma unroll
@@ -387,7 +397,7 @@ __global__ void __launch_bounds__(256, AXB_CORR_MINB) k_solid_corrector(const __
         return;
     }
     // add_source_el (time_evol_wave.F90:1082-1097)
-    if (a.nelsrc > 0) {
+    if (a.nelsrc > 0 && e >= a.src_emin && e <= a.src_emax) {
         const int iter = a.dyn ? a.dyn[DYN_ITER] : a.iter;
         const float stf1 = a.stf[(size_t)iter * a.stf_stride + a.stf_off];
         if (stf1 != 0.f) {
@@ -403,14 +413,14 @@ __global__ void __launch_bounds__(256, AXB_CORR_MINB) k_solid_corrector(const __
     for (int c = 0; c < 3; c++) {
         if (ORDER == 0 && c == 1) continue;
         float x = v[c];
-        if (a.mode != 1) {
+        if (MODE != 1) {
             if (ORDER == 1 && c == 2) x = d2f(-2.0 * f2d(im) * f2d(x));
             else x = -im * x;
-            if (a.gamma) x = x - 2 * gm * vel[c] - (gm * gm) * dsp[c];
-            if (a.mode == 0) {
+            if (sponge) x = x - 2 * gm * vel[c] - (gm * gm) * dsp[c];
+            if (MODE == 0) {
                 a.velo[p + cs * c] = d2f(f2d(vel[c]) + a.half_dt * f2d(a0[c] + x));
                 a.acc0[p + cs * c] = x;
-            } else if (a.mode == 2) {
+            } else if (MODE == 2) {
                 // lean Newmark: w = v + dt/2 a is the stored quantity; w_new = w_old + dt a_new
                 a.velo[p + cs * c] = d2f(f2d(vel[c]) + a.half_dt * f2d(x));
             } else {
@@ -420,7 +430,7 @@ __global__ void __launch_bounds__(256, AXB_CORR_MINB) k_solid_corrector(const __
             }
         } else {
             x = -im * x;
-            if (a.gamma) x = x - 2 * gm * vel[c] - (gm * gm) * dsp[c];
+            if (sponge) x = x - 2 * gm * vel[c] - (gm * gm) * dsp[c];
             if (ORDER == 1 && c == 2) a.velo[p + cs * c] = d2f(f2d(vel[c]) + 2.0 * f2d(x) * a.half_dt);
             else a.velo[p + cs * c] = d2f(f2d(vel[c]) + f2d(x) * a.half_dt);
             a.acc0[p + cs * c] = x;     // keeps the reference's `acc` available to get_state

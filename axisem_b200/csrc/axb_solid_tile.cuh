@@ -134,16 +134,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or
+// the hint runs out) instead of re-issuing the probe every few hundred cycles — the probes of
+// waiting warps otherwise take issue slots from the warps that work (they were 8 % of all
+// instructions of S_A: profiles/r01k vs r02c)
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 // 1-D TMA: global -> shared, completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -461,9 +465,15 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                     g1 = b1s; g3 = b2z; g5 = b1z + b2s;
                     g2 = is * u1;
                 } else if (ORDER == 1) {
-                    // the gradients of (u1+u2) and (u1-u2) are contracted separately, as
-                    // in the reference (attenuation.f90:489, :515)
-                    float up[NP], um[NP], Xp1, Xm1, Xp2, Xm2;
+                    // the gradients of (u1+u2) and (u1-u2) are contracted separately in the
+                    // reference (attenuation.f90:489, :515); the bit-exact build does the same.
+                    // The product build uses the linearity of the contraction, d(u1 +/- u2) =
+                    // d u1 +/- d u2, with the derivatives every point already has: four extra
+                    // 5-term contractions per warp less (they were 6 % of this kernel's
+                    // instructions, executed at 4/25 lane efficiency); differs by rounding only
+                    float Xp1, Xm1, Xp2, Xm2;
+#ifdef AXB_STRICT
+                    float up[NP], um[NP];
 #pragma unroll
                     for (int k = 0; k < NP; k++) { up[k] = U1xi[k] + U2xi[k]; um[k] = U1xi[k] - U2xi[k]; }
                     if (!ax) { Xp1 = cxi(up, L.g2t_row); Xm1 = cxi(um, L.g2t_row); }
@@ -473,6 +483,10 @@ k_solid_tile(const __grid_constant__ GMat G, const __grid_constant__ SolidTileAr
                     for (int k = 0; k < NP; k++) { vp[5 * k] = U1et[5 * k] + U2et[5 * k]; vm[5 * k] = U1et[5 * k] - U2et[5 * k]; }
                     Xp2 = ceta(vp, L.g2_col);
                     Xm2 = ceta(vm, L.g2_col);
+#else
+                    Xp1 = X[0] + X[1]; Xm1 = X[0] - X[1];
+                    Xp2 = X[3] + X[4]; Xm2 = X[3] - X[4];
+#endif
                     const float b1s = dzdeta * Xp1 + dzdxi * Xp2;
                     const float b1z = dsdeta * Xp1 + dsdxi * Xp2;
                     g1 = b1s; g3 = b2z; g5 = b1z + b2s;
