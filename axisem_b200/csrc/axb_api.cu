@@ -1251,6 +1251,11 @@ static void launch_solid_corr(axb_handle_s *h, int mode, double c, int stf_strid
     a.recv_cs = H.nslots;
     a.arrival = halo_arrival(h, H, dyn);
     a.dyn = dyn ? h->d_dyn : nullptr;
+    {
+        // one wave of resident blocks ahead
+        static const int ahead_env = [] { const char *e = getenv("AXB_CORR_AHEAD"); return e ? atoi(e) : -1; }();
+        a.ahead = ahead_env >= 0 ? ahead_env : h->sms * AXB_CORR_MINB * 256;
+    }
     a.nelsrc = h->fluid_src ? 0 : h->nelsrc;
     a.src_emin = h->src_emin; a.src_emax = h->src_emax;
     for (int k = 0; k < 8; k++) a.ielsrc[k] = h->ielsrc[k];

@@ -120,6 +120,12 @@ __device__ __forceinline__ void load_lane_g(const GMat &G, int i, int j, LaneG &
 //                  order (commpi.F90:469-477).
 // One coalesced 16-byte load then tells a thread everything, and the value loads that
 // follow are independent of each other.
+// Warm the L2 for the block that will run `ahead` points further on: the correctors are bound by
+// the latency of two dependent DRAM round trips per thread (assembly entry -> gather), not by
+// bandwidth; a prefetch one wave ahead turns the first of them into an L2 hit.
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 struct AsmTable {
     const int4 *cp;
     const int *grp;
@@ -208,7 +214,10 @@ __device__ __forceinline__ const float *recv_slab(const float *recv, size_t cs, 
 
 // F_B: pdistsum_fluid + mass inversion + sponge + velocity-potential update.
 // Replaces commun.F90:180-283 (+commpi.F90:587-637) and time_evol_wave.F90:430-434, 459-460.
-__global__ void __launch_bounds__(256, AXB_CORR_MINB) k_fluid_corrector(const __grid_constant__ FluidCorrArgs a) {
+#ifndef AXB_FCORR_MINB
+#define AXB_FCORR_MINB 8     // the fluid corrector fits 32 registers
+#endif
+__global__ void __launch_bounds__(256, AXB_FCORR_MINB) k_fluid_corrector(const __grid_constant__ FluidCorrArgs a) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.npts) return;
     float v = a.ddchi1[p];
@@ -312,6 +321,7 @@ struct SolidCorrArgs {
     int recv_parity;
     HaloArrival arrival;
     const int *dyn;           // graph replay: iter = dyn[DYN_ITER]
+    int ahead;                // points to prefetch ahead (0: off)
     int nelsrc;
     int src_emin, src_emax;   // 0-based range of the source elements: one compare pair per point in
                               // front of the eight-way search (which was a quarter of this
@@ -338,6 +348,21 @@ k_solid_corrector(const __grid_constant__ SolidCorrArgs a) {
     // the assembly entry first: it heads the only dependent chain (entry -> gather)
     int4 cp = make_int4(-1, -1, -1, -1);
     if (slot >= 0) cp = a.T.cp[16 * (size_t)e + slot];
+    if (a.ahead > 0 && p + a.ahead < a.npts) {
+        const int pn = p + a.ahead;
+        const int en = pn / NPT, sn = edge_slot(pn - en * NPT);
+        if (sn >= 0) prefetch_l2(a.T.cp + 16 * (size_t)en + sn);
+        if ((threadIdx.x & 7) == 0) {           // one request per 32-byte sector
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                if (ORDER == 0 && c == 1) continue;
+                prefetch_l2(a.acc1 + pn + cs * c);
+                if (MODE != 4) prefetch_l2(a.velo + pn + cs * c);
+                if (MODE == 0) prefetch_l2(a.acc0 + pn + cs * c);
+            }
+            if (MODE != 4) prefetch_l2(a.inv_mass_rho + pn);
+        }
+    }
     // every other input of this point is requested up front (the stores below would otherwise
     // order the per-component loads behind them)
     constexpr bool upd = MODE != 4;

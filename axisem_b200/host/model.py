@@ -96,9 +96,9 @@ def prem_layers(anisotropic: bool = False, r_min_km: float = 400.0) -> List[Laye
 
 
 def homogeneous_layers(r_min_km: float = 400.0, r_max_km: float = 6371.0,
-                       rho=3000.0, vp=8000.0, vs=4500.0) -> List[Layer]:
+                       rho=3000.0, vp=8000.0, vs=4500.0, qmu=300.0, qkappa=57827.0) -> List[Layer]:
     """Single solid layer; for analytic checks."""
-    return [Layer(r_min_km * 1e3, r_max_km * 1e3, False, 300.0, 57827.0,
+    return [Layer(r_min_km * 1e3, r_max_km * 1e3, False, qmu, qkappa,
                   _poly(rho / 1e3), _poly(vp / 1e3), _poly(vs / 1e3), _poly(vp / 1e3),
                   _poly(vs / 1e3), _one, "homogeneous")]
 

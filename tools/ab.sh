@@ -19,6 +19,7 @@ for v in "$@"; do
     case $v in
     default) run default AXB_NOP=1 ;;
     nolean) run nolean AXB_LEAN=0 ;;
+    noahead) run noahead AXB_CORR_AHEAD=0 ;;
     classic) run classic AXB_LEAN=0 AXB_GRAPH=0 ;;
     *) run "$v" AXB_LIBRARY="$PWD/axisem_b200/libaxisem_b200_$v.so" ;;
     esac
