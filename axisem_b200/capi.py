@@ -55,13 +55,14 @@ SCHEMES = {"newmark2": 0, "symplec4": 1, "ML_SO4m5": 2, "ML_SO6m7": 3, "KL_O8m17
 STF_TYPES = {"gauss_0": 0, "gauss_1": 1, "gauss_2": 2}
 FIELDS = {"disp": 0, "velo": 1, "acc0": 2, "acc1": 3, "chi": 4, "dchi": 5, "ddchi0": 6,
           "ddchi1": 7, "memvar": 8, "src_dev_tm1": 9, "src_tr_tm1": 10}
+DUMP_TYPES = {"displ_only": 0, "strain_only": 1, "fullfields": 2}
 OPS = {"solid_stiffness": 0, "anel_stiffness": 1, "fluid_stiffness": 2, "pdistsum_solid": 3,
        "pdistsum_fluid": 4, "memvars": 5, "bdry2fluid": 6, "bdry2solid": 7}
 
 # every symbol include/axisem_b200.h declares
 SYMBOLS = ["last_error", "create", "destroy", "set_mesh", "set_solid_terms", "set_fluid_terms",
            "set_mass", "set_energy", "set_sponge", "set_sf_boundary", "set_attenuation", "set_source",
-           "set_stf_values", "set_stf_params", "set_receivers", "set_kwf", "set_halo", "set_time",
+           "set_stf_values", "set_stf_params", "set_receivers", "set_kwf", "set_dump", "snapshot_layout", "set_halo", "set_time",
            "finalize_setup", "set_stream", "synchronize", "connect_local", "ipc_blob_bytes", "ipc_export", "ipc_import", "run", "run_group",
            "profile", "get_profile", "iter", "nseismo", "nstrain", "gpu_launches", "fetch_seismograms",
            "fetch_snapshots", "fetch_energy", "get_state", "set_state", "apply_op"]
@@ -213,6 +214,14 @@ class TimeLoop:
                              _fp(p.inv_rho_fluid, k), _fp(pf["DsDeta_over_J"], k),
                              _fp(pf["DzDeta_over_J"], k), _fp(pf["DsDxi_over_J"], k),
                              _fp(pf["DzDxi_over_J"], k)))
+        dump_type = getattr(p, "dump_type", "displ_only")
+        if dump_type != "displ_only":
+            ib, ie, jb, je = getattr(p, "dump_block", (0, 4, 0, 4))
+            ps = p.pw_solid
+            ck(fn["set_dump"](h, C.c_int32(DUMP_TYPES[dump_type]), C.c_int32(ib), C.c_int32(ie), C.c_int32(jb),
+                              C.c_int32(je), _fp(ps["DsDeta_over_J"], k), _fp(ps["DzDeta_over_J"], k),
+                              _fp(ps["DsDxi_over_J"], k), _fp(ps["DzDxi_over_J"], k), _fp(ps["inv_s"], k),
+                              _fp(p.pw_fluid.get("inv_s"), k)))
         for dom, hs in ((0, m.halo_solid), (1, m.halo_fluid)):
             if hs.nmsg:
                 maxmsg = hs.glocal_index_msg.shape[1]
@@ -280,10 +289,11 @@ class TimeLoop:
         return out
 
     def snapshots(self, first: int = 0, n: Optional[int] = None) -> np.ndarray:
-        """(3[s,p,z], nsnap, npoints)."""
+        """(nvars, nsnap, npoints); displ_only: nvars = 3 (s, p, z), see axb_snapshot_layout."""
         n = self.nstrain - first if n is None else n
-        npts = self.prob.kwf["npoint_solid_kwf"] + self.prob.kwf["npoint_fluid_kwf"]
-        out = np.zeros((3, n, npts), dtype=np.float32)
+        npts, nvars = C.c_int32(), C.c_int32()
+        self.lib.check(self.lib.fn["snapshot_layout"](self.h, C.byref(npts), C.byref(nvars)))
+        out = np.zeros((nvars.value, n, npts.value), dtype=np.float32)
         if n > 0:
             self.lib.check(self.lib.fn["fetch_snapshots"](
                 self.h, C.c_int32(first), C.c_int32(n), out.ctypes.data_as(_F)))

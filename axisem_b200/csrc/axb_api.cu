@@ -134,6 +134,9 @@ struct axb_handle_s {
     int *d_kwf_mask = nullptr, *d_kwf_map = nullptr;
     float *d_inv_rho = nullptr, *d_Dse_f = nullptr, *d_Dze_f = nullptr, *d_Dsx_f = nullptr, *d_Dzx_f = nullptr;
     float *d_snap = nullptr;
+    // dump_type strain_only / fullfields (axb_set_dump)
+    int dump_type = AXB_DUMP_DISPL_ONLY, ibeg = 0, iend = 4, jbeg = 0, jend = 4;
+    float *dDse = nullptr, *dDze = nullptr, *dDsx = nullptr, *dDzx = nullptr, *d_inv_s_dump = nullptr, *d_inv_s_f = nullptr;
     Halo halo[2];
     // time
     int scheme = 0, niter = 0, seis_it = 1, strain_it = 0, nstages = 0;
@@ -429,6 +432,8 @@ inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 extern "C" {
 
 const char *axb_last_error(void) { return g_err.c_str(); }
+static int snapshot_nvars(const axb_handle_s *h);
+static size_t snapshot_npoints(const axb_handle_s *h);
 
 int axb_create(axb_handle *out, int32_t device, int32_t rank, int32_t nranks) {
     int ndev = 0;
@@ -773,6 +778,40 @@ int axb_set_kwf(axb_handle h, const int32_t *kwf_mask, const int32_t *mapping_ij
     return 0;
 }
 
+int axb_set_dump(axb_handle h, int32_t dump_type, int32_t ibeg, int32_t iend, int32_t jbeg, int32_t jend,
+                 const float *DsDeta_over_J_sol, const float *DzDeta_over_J_sol,
+                 const float *DsDxi_over_J_sol, const float *DzDxi_over_J_sol,
+                 const float *inv_s_solid, const float *inv_s_fluid) {
+    if (use(h)) return 1;
+    if (dump_type < AXB_DUMP_DISPL_ONLY || dump_type > AXB_DUMP_FULLFIELDS) return fail("unknown dump_type");
+    if (ibeg < 0 || iend > 4 || ibeg > iend || jbeg < 0 || jend > 4 || jbeg > jend) return fail("bad ibeg..jend");
+    h->dump_type = dump_type; h->ibeg = ibeg; h->iend = iend; h->jbeg = jbeg; h->jend = jend;
+    if (dump_type == AXB_DUMP_DISPL_ONLY) return 0;
+    if (!DsDeta_over_J_sol || !DzDeta_over_J_sol || !DsDxi_over_J_sol || !DzDxi_over_J_sol || !inv_s_solid ||
+        (h->nel_f > 0 && !inv_s_fluid))
+        return fail("axb_set_dump: NULL plane");
+    const size_t n = (size_t)NPT * h->nel_s, nf = (size_t)NPT * h->nel_f;
+    UP(h->dDse, DsDeta_over_J_sol, n); UP(h->dDze, DzDeta_over_J_sol, n);
+    UP(h->dDsx, DsDxi_over_J_sol, n); UP(h->dDzx, DzDxi_over_J_sol, n);
+    UP(h->d_inv_s_dump, inv_s_solid, n); UP(h->d_inv_s_f, inv_s_fluid, nf);
+    return 0;
+}
+static int snapshot_nvars(const axb_handle_s *h) {
+    const bool mono = h->order == 0;
+    if (h->dump_type == AXB_DUMP_STRAIN_ONLY) return mono ? 4 : 6;
+    if (h->dump_type == AXB_DUMP_FULLFIELDS) return mono ? 6 : 9;
+    return 3;
+}
+static size_t snapshot_npoints(const axb_handle_s *h) {
+    if (h->dump_type == AXB_DUMP_FULLFIELDS)
+        return (size_t)(h->iend - h->ibeg + 1) * (h->jend - h->jbeg + 1) * ((size_t)h->nel_s + h->nel_f);
+    return (size_t)h->npt_s_kwf + h->npt_f_kwf;
+}
+int axb_snapshot_layout(axb_handle h, int32_t *npoints, int32_t *nvars) {
+    *npoints = (int32_t)snapshot_npoints(h); *nvars = snapshot_nvars(h);
+    return 0;
+}
+
 int axb_set_halo(axb_handle h, int32_t domain, int32_t nmsg, const int32_t *list_peer,
                  const int32_t *sizemsg, const int32_t *glocal_index_msg, int32_t maxmsg,
                  int32_t num_comm_gll, const int32_t *glob2el) {
@@ -921,7 +960,8 @@ int axb_finalize_setup(axb_handle h) {
     if (dzeros(h, h->d_recdump, (size_t)3 * std::max(h->num_rec, 1) * h->nseismo_max)) return 1;
     if (h->strain_it > 0 && h->have_kwf) {
         h->nstrain_max = h->niter / h->strain_it + 1;
-        if (dzeros(h, h->d_snap, (size_t)(h->npt_s_kwf + h->npt_f_kwf) * h->nstrain_max * 3)) return 1;
+        if (h->dump_type != AXB_DUMP_DISPL_ONLY && !h->dDse) return fail("axb_set_dump: planes missing");
+        if (dzeros(h, h->d_snap, snapshot_npoints(h) * h->nstrain_max * snapshot_nvars(h))) return 1;
     }
     if (dzeros(h, h->d_counters, 4)) return 1;
     if (dzeros(h, h->d_dyn, 4)) return 1;
@@ -935,7 +975,9 @@ int axb_finalize_setup(axb_handle h) {
         bool lean = true;
 #endif
         if (const char *ev = getenv("AXB_LEAN")) lean = atoi(ev) != 0;
-        h->lean = lean && h->scheme == AXB_NEWMARK2 && !h->gamma_s && !h->gamma_f && !h->dump_energy;
+        // ... and not with fullfields dumps (velo and dchi of the step are dumped)
+        h->lean = lean && h->scheme == AXB_NEWMARK2 && !h->gamma_s && !h->gamma_f && !h->dump_energy &&
+                  !(h->dump_type == AXB_DUMP_FULLFIELDS && h->strain_it > 0 && h->have_kwf);
         h->lean_state = false;
         bool graph = true;
         if (const char *ev = getenv("AXB_GRAPH")) graph = atoi(ev) != 0;
@@ -1369,6 +1411,25 @@ static void launch_dumps(axb_handle_s *h) {
 }
 static void launch_wavefield_dump(axb_handle_s *h) {
     CLS(h, 6);
+    if (h->have_kwf && h->strain_it > 0 && h->iter % h->strain_it == 0 && h->istrain < h->nstrain_max &&
+        h->dump_type != AXB_DUMP_DISPL_ONLY) {
+        // compute_strain [+ dump_velo_global] (axb_dump_fields.cuh)
+        FieldDumpArgs a;
+        std::memset(&a, 0, sizeof a);
+        a.nel_s = h->nel_s; a.nel_f = h->nel_f; a.order = h->order; a.dump_type = h->dump_type;
+        a.ibeg = h->ibeg; a.iend = h->iend; a.jbeg = h->jbeg; a.jend = h->jend;
+        a.nstrain_max = h->nstrain_max; a.istrain = h->istrain;
+        a.kwf_mask = h->d_kwf_mask; a.kwf_map = h->d_kwf_map; a.axis_s = h->d_axis_s; a.axis_f = h->d_axis_f;
+        a.disp = h->disp; a.velo = h->velo; a.cs = h->css; a.chi = h->chi; a.dchi = h->dchi;
+        a.Dse = h->dDse; a.Dze = h->dDze; a.Dsx = h->dDsx; a.Dzx = h->dDzx; a.inv_s = h->d_inv_s_dump;
+        a.Dse_f = h->d_Dse_f; a.Dze_f = h->d_Dze_f; a.Dsx_f = h->d_Dsx_f; a.Dzx_f = h->d_Dzx_f;
+        a.inv_s_f = h->d_inv_s_f; a.inv_rho = h->d_inv_rho;
+        a.snap = h->d_snap; a.npts = snapshot_npoints(h);
+        if (h->nel_s) LAUNCH(h, k_dump_fields_solid, std::max(1, std::min(cdiv(h->nel_s, 8), h->sms * 8)), 256, h->G, a);
+        if (h->nel_f) LAUNCH(h, k_dump_fields_fluid, h->grid_f, 256, h->G, a);
+        h->istrain++;
+        return;
+    }
     if (h->have_kwf && h->strain_it > 0 && h->iter % h->strain_it == 0 && h->istrain < h->nstrain_max) {
         DumpArgs a;
         a.nel_s = h->nel_s; a.nel_f = h->nel_f; a.order = h->order; a.strain_it = h->strain_it;
@@ -1665,9 +1726,9 @@ int axb_fetch_energy(axb_handle h, int32_t first, int32_t n, float *out) {
 }
 int axb_fetch_snapshots(axb_handle h, int32_t first, int32_t nsnap, float *out) {
     if (use(h)) return 1;
-    const size_t npts = (size_t)h->npt_s_kwf + h->npt_f_kwf;
+    const size_t npts = snapshot_npoints(h);
     if (first < 0 || nsnap < 0 || first + nsnap > h->istrain) return fail("snapshot range");
-    for (int v = 0; v < 3; v++)
+    for (int v = 0; v < snapshot_nvars(h); v++)
         CK(cudaMemcpyAsync(out + npts * (size_t)nsnap * v,
                            h->d_snap + npts * (first + (size_t)h->nstrain_max * v),
                            sizeof(float) * npts * nsnap, cudaMemcpyDeviceToHost, h->stream));

@@ -713,3 +713,4 @@ __global__ void __launch_bounds__(256) k_energy_fluid(const __grid_constant__ En
 }
 
 }  // namespace axb
+#include "axb_dump_fields.cuh"

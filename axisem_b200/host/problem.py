@@ -79,6 +79,8 @@ class Problem:
     unassem_mass_lam_fluid: Optional[np.ndarray] = None   # (:812-815)
     fluid_src: bool = False            # source inside the fluid (have_src in the fluid: add_source_fl)
     kwf: Optional[Dict[str, np.ndarray]] = None
+    dump_type: str = "displ_only"      # data_io%dump_type: displ_only | strain_only | fullfields
+    dump_block: tuple = (0, 4, 0, 4)   # ibeg, iend, jbeg, jend (fullfields; parameters.F90:400-403)
 
     @property
     def num_rec(self):
@@ -195,7 +197,8 @@ def build_problem(spec: MeshSpec, source: Optional[SourceParams] = None, *, rank
                   time_scheme: str = "newmark2", niter: int = 100, seis_it: int = 1,
                   strain_it: int = 0, courant: float = 0.6, deltat: Optional[float] = None,
                   rec_colat_deg=None, dump: bool = False, energy: bool = False, chunk_cols: int = 32,
-                  threads: Optional[int] = None) -> Problem:
+                  threads: Optional[int] = None, dump_type: str = "displ_only",
+                  dump_block=(0, 4, 0, 4)) -> Problem:
     assert time_scheme in TIME_SCHEMES
     source = source or SourceParams()
     src_type = source.src_type1
@@ -290,6 +293,8 @@ def build_problem(spec: MeshSpec, source: Optional[SourceParams] = None, *, rank
         rec_index=rec["index"])
     if dump:
         prob.kwf = kwf_maps(mesh)
+        prob.dump_type = dump_type
+        prob.dump_block = tuple(int(v) for v in dump_block)
     prob.unassem_mass_rho_solid, prob.unassem_mass_lam_fluid = um_s, um_f
     return prob
 

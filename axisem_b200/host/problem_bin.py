@@ -120,6 +120,18 @@ def problem_records(p):
         add("data_matr%inv_rho_fluid", p.inv_rho_fluid, f32)
         for k in ("DsDeta", "DzDeta", "DsDxi", "DzDxi"):
             add(f"data_pointwise%{k}_over_J_flu", pf[k + "_over_J"], f32)
+        dump_type = getattr(p, "dump_type", "displ_only")
+        add("data_io%dump_type", {"displ_only": 0, "strain_only": 1, "fullfields": 2}[dump_type], i32)
+        if dump_type != "displ_only":
+            ib, ie, jb, je = getattr(p, "dump_block", (0, 4, 0, 4))
+            for n_, v_ in (("ibeg", ib), ("iend", ie), ("jbeg", jb), ("jend", je)):
+                add("data_io%" + n_, int(v_), i32)
+            add("data_pointwise%inv_s_fluid", pf["inv_s"], f32)
+            if not (p.anel and not bool(p.att["coarse_grained"])):       # (not written above already)
+                for k in ("DsDeta", "DzDeta", "DsDxi", "DzDxi"):
+                    add(f"data_pointwise%{k}_over_J_sol", p.pw_solid[k + "_over_J"], f32)
+            if not p.anel:
+                add("data_pointwise%inv_s_solid", p.pw_solid["inv_s"], f32)
     for dom, hs in (("solid", m.halo_solid), ("fluid", m.halo_fluid)):
         add(f"data_comm%sizerecv_{dom}", int(hs.nmsg), i32)
         if hs.nmsg:

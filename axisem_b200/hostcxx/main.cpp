@@ -21,10 +21,10 @@ namespace {
 
 struct FileSink : axisem::OutputSink {
     struct Rank {
-        int num_rec = 0, nseis = 0, nsnap = 0;
+        int num_rec = 0, nseis = 0, nsnap = 0, nvars = 3;
         size_t npoints = 0;
         std::vector<float> seis;                 // (3, num_rec, nseis)
-        std::vector<std::vector<float>> snap;    // chunks of (npoints, n, 3)
+        std::vector<std::vector<float>> snap;    // chunks of (npoints, n, nvars)
         std::vector<int> snap_n;
     };
     std::map<int, Rank> ranks;
@@ -35,11 +35,12 @@ struct FileSink : axisem::OutputSink {
         r.seis.insert(r.seis.end(), v, v + (size_t)3 * num_rec * n);
         r.nseis += n;
     }
-    void snapshots(int rank, size_t npoints, int first, int n, const float *v) override {
+    void snapshots(int rank, size_t npoints, int nvars, int first, int n, const float *v) override {
         Rank &r = ranks[rank];
         r.npoints = npoints;
+        r.nvars = nvars;
         if (first != r.nsnap) throw axisem::SolverError("snapshot chunks out of order");
-        r.snap.emplace_back(v, v + npoints * n * 3);
+        r.snap.emplace_back(v, v + npoints * n * nvars);
         r.snap_n.push_back(n);
         r.nsnap += n;
     }
@@ -71,12 +72,12 @@ struct FileSink : axisem::OutputSink {
                 std::fclose(f);
             }
             if (r.nsnap) {
-                // reassemble oneddumpvar(npoints, nsnap, 3) from the buffered chunks
-                std::vector<float> all(r.npoints * r.nsnap * 3);
+                // reassemble oneddumpvar(npoints, nsnap, nvars) from the buffered chunks
+                std::vector<float> all(r.npoints * r.nsnap * r.nvars);
                 int off = 0;
                 for (size_t c = 0; c < r.snap.size(); c++) {
                     const int n = r.snap_n[c];
-                    for (int v = 0; v < 3; v++)
+                    for (int v = 0; v < r.nvars; v++)
                         std::memcpy(&all[(size_t)v * r.npoints * r.nsnap + (size_t)off * r.npoints],
                                     &r.snap[c][(size_t)v * r.npoints * n], sizeof(float) * r.npoints * n);
                     off += n;

@@ -96,6 +96,12 @@ axb_handle hand_over(const Modules &m, int device) {
                         m.f("data_matr%inv_rho_fluid"), m.f("data_pointwise%DsDeta_over_J_flu"),
                         m.f("data_pointwise%DzDeta_over_J_flu"), m.f("data_pointwise%DsDxi_over_J_flu"),
                         m.f("data_pointwise%DzDxi_over_J_flu")));
+    if (m.int_of("data_io%dump_wavefields", 0) && m.int_of("data_io%dump_type", 0) != 0)
+        CK(AXB(set_dump)(h, m.int_of("data_io%dump_type"), m.int_of("data_io%ibeg"), m.int_of("data_io%iend"),
+                         m.int_of("data_io%jbeg"), m.int_of("data_io%jend"),
+                         m.f("data_pointwise%DsDeta_over_J_sol"), m.f("data_pointwise%DzDeta_over_J_sol"),
+                         m.f("data_pointwise%DsDxi_over_J_sol"), m.f("data_pointwise%DzDxi_over_J_sol"),
+                         m.f("data_pointwise%inv_s_solid"), m.f("data_pointwise%inv_s_fluid")));
     const char *dom[2] = {"solid", "fluid"};
     for (int d = 0; d < 2; d++) {
         const std::string s = dom[d];
@@ -165,10 +171,12 @@ TimeLoopResult time_loop(const std::vector<Modules> &ranks, const TimeLoopOption
         const int have = AXB(nstrain)(H.h[r]);
         const int cnt = have - snap_done[r];
         if (cnt <= 0 || (!force && cnt < opt.nc_dumpbuffersize)) return;
-        const size_t np = (size_t)ranks[r].int_of("data_mesh%npoint_solid_kwf") + ranks[r].int_of("data_mesh%npoint_fluid_kwf");
-        buf.resize(np * cnt * 3);
+        int32_t np32 = 0, nvars = 3;
+        CK(AXB(snapshot_layout)(H.h[r], &np32, &nvars));
+        const size_t np = (size_t)np32;
+        buf.resize(np * cnt * nvars);
         CK(AXB(fetch_snapshots)(H.h[r], snap_done[r], cnt, buf.data()));
-        if (sink) sink->snapshots(ranks[r].int_of("data_proc%mynum"), np, snap_done[r], cnt, buf.data());
+        if (sink) sink->snapshots(ranks[r].int_of("data_proc%mynum"), np, nvars, snap_done[r], cnt, buf.data());
         snap_done[r] = have;
     };
 

@@ -28,8 +28,9 @@ public:
     virtual ~OutputSink() {}
     // recdumpvar(3, num_rec, first+1 : first+n) of rank `rank`
     virtual void seismograms(int rank, int num_rec, int first, int n, const float *recdumpvar) = 0;
-    // oneddumpvar(npoints, first+1 : first+n, 3)
-    virtual void snapshots(int rank, size_t npoints, int first, int n, const float *oneddumpvar) = 0;
+    // oneddumpvar(npoints, first+1 : first+n, nvars); nvars = nvar/2 of nc_routines.F90:943-1050
+    // (3 for displ_only, 6 (4) for strain_only, 9 (6) for fullfields)
+    virtual void snapshots(int rank, size_t npoints, int nvars, int first, int n, const float *oneddumpvar) = 0;
     // dump_energy: (4, n) sums of this rank for iter 0..n-1 (time_evol_wave.F90:1424-1526; the
     // writer applies psum over ranks and two*pi)
     virtual void energy(int /*rank*/, int /*n*/, const float * /*sums*/) {}

@@ -181,6 +181,28 @@ int AXB(set_kwf)(axb_handle h, const int32_t *kwf_mask, const int32_t *mapping_i
                  const float *DzDeta_over_J_flu, const float *DsDxi_over_J_flu,
                  const float *DzDxi_over_J_flu);
 
+/* dump_type of the wavefield dumps (data_io.f90; SOLVER/inparam_advanced KERNEL_DUMPTYPE):
+ * displ_only (default; dump_disp_global), strain_only and fullfields.  The latter two replace
+ * compute_strain (time_evol_wave.F90:1264-1410) and, for fullfields, dump_velo_global
+ * (wavefields_io.f90:932-1015), evaluated on the device every strain_it steps:
+ *   strain_only: 6 (monopole: 4) fields on the kwf point set of axb_set_kwf (kwf_mapping_sol/flu,
+ *                wavefields_io.f90:743-783);
+ *   fullfields:  the same fields + 3 (2) velocity fields on the block ibeg:iend x jbeg:jend of
+ *                every element, packed in Fortran order (i, j, element), solid then fluid.
+ * Needs the pointwise-derivative planes of the solid (data_pointwise: D*D*_over_J_sol), inv_s_solid
+ * and inv_s_fluid, all (0:4,0:4,nel); the fluid planes and inv_rho_fluid come from axb_set_kwf,
+ * which must be called too.  Before axb_finalize_setup.  Not restated: the zeroing of the
+ * source elements for src_dump_type == 'mask' — the reference never assigns that variable. */
+enum { AXB_DUMP_DISPL_ONLY = 0, AXB_DUMP_STRAIN_ONLY = 1, AXB_DUMP_FULLFIELDS = 2 };
+int AXB(set_dump)(axb_handle h, int32_t dump_type, int32_t ibeg, int32_t iend, int32_t jbeg, int32_t jend,
+                  const float *DsDeta_over_J_sol, const float *DzDeta_over_J_sol,
+                  const float *DsDxi_over_J_sol, const float *DzDxi_over_J_sol,
+                  const float *inv_s_solid, const float *inv_s_fluid);
+/* shape of the snapshot buffer: npoints (npts_sol + npts_flu) and nvars = nvar/2 of
+ * nc_routines.F90:943-1050, in that order: displ_only (s, p, z); strain_only (strain_dsus, _dsuz,
+ * _dpup, [_dsup, _dzup,] straintrace); fullfields: the same followed by velo_s, [velo_p,] velo_z */
+int AXB(snapshot_layout)(axb_handle h, int32_t *npoints, int32_t *nvars);
+
 /* data_comm.f90:36-71.  glocal_index_msg is (maxmsg, nmsg) Fortran order; send and
  * receive lists coincide (get_mesh.f90:303-310).  glob2el is (num_comm_gll,3) =
  * (ipol, jpol, iel). */
@@ -251,7 +273,8 @@ int64_t AXB(gpu_launches)(axb_handle h); /* kernels launched by this handle (0: 
 /* recdumpvar slice: out(3, num_rec, nsamples) Fortran order, samples first..first+n-1
  * (0-based; sample 0 is the dump at iter 0).  nc_dump_rec, nc_routines.F90:530-540 */
 int AXB(fetch_seismograms)(axb_handle h, int32_t first, int32_t nsamples, float *out);
-/* oneddumpvar slice: out(npoints, nsnap, 3) with var order (s, p, z); nc_routines.F90:248,275 */
+/* oneddumpvar slice: out(npoints, nsnap, nvars), shape and variable order as axb_snapshot_layout
+ * reports (displ_only: 3 variables s, p, z); nc_routines.F90:248,275 */
 int AXB(fetch_snapshots)(axb_handle h, int32_t first, int32_t nsnap, float *out);
 
 /* energy samples first..first+n-1 (0-based; sample k belongs to iter k): out(4, n) =

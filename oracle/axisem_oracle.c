@@ -128,8 +128,11 @@ struct axb_handle_s {
     float *um_rho_s, *um_lam_f;   /* unassem_mass_rho_solid, unassem_mass_lam_fluid */
     float *energy;       /* (4, niter + 1) */
     int nseismo_max;
-    float *snapdump;     /* (npoints, nstrain_max, 3) */
+    float *snapdump;     /* (npoints, nstrain_max, nvars) */
     int nstrain_max;
+    /* dump_type strain_only / fullfields (axo_set_dump) */
+    int dump_type, ibeg, iend, jbeg, jend;
+    float *dDse, *dDze, *dDsx, *dDzx, *d_inv_s, *d_inv_s_f;   /* data_pointwise planes of the dumps */
     int finalized;
     struct axb_handle_s **group;
     int ngroup;
@@ -334,6 +337,40 @@ int axo_set_kwf(axb_handle h, const int32_t *kwf_mask, const int32_t *mapping_ij
     return 0;
 }
 
+/* dump_type of the wavefield dumps (data_io.f90; parameters.F90:400-403 for ibeg..jend) */
+int axo_set_dump(axb_handle h, int32_t dump_type, int32_t ibeg, int32_t iend, int32_t jbeg, int32_t jend,
+                 const float *DsDeta_over_J_sol, const float *DzDeta_over_J_sol,
+                 const float *DsDxi_over_J_sol, const float *DzDxi_over_J_sol,
+                 const float *inv_s_solid, const float *inv_s_fluid) {
+    size_t n = (size_t)NPT * h->nel_s, nf = (size_t)NPT * h->nel_f;
+    if (dump_type < AXB_DUMP_DISPL_ONLY || dump_type > AXB_DUMP_FULLFIELDS) return fail("unknown dump_type");
+    if (ibeg < 0 || iend > 4 || ibeg > iend || jbeg < 0 || jend > 4 || jbeg > jend) return fail("bad ibeg..jend");
+    h->dump_type = dump_type; h->ibeg = ibeg; h->iend = iend; h->jbeg = jbeg; h->jend = jend;
+    if (dump_type == AXB_DUMP_DISPL_ONLY) return 0;
+    if (!DsDeta_over_J_sol || !DzDeta_over_J_sol || !DsDxi_over_J_sol || !DzDxi_over_J_sol || !inv_s_solid ||
+        (h->nel_f > 0 && !inv_s_fluid))
+        return fail("axo_set_dump: NULL plane");
+    h->dDse = dupf(DsDeta_over_J_sol, n); h->dDze = dupf(DzDeta_over_J_sol, n);
+    h->dDsx = dupf(DsDxi_over_J_sol, n); h->dDzx = dupf(DzDxi_over_J_sol, n);
+    h->d_inv_s = dupf(inv_s_solid, n); h->d_inv_s_f = dupf(inv_s_fluid, nf);
+    return 0;
+}
+static int snapshot_nvars(const axo_t *o) {
+    const int mono = o->src_order == AXB_MONOPOLE;
+    if (o->dump_type == AXB_DUMP_STRAIN_ONLY) return mono ? 4 : 6;
+    if (o->dump_type == AXB_DUMP_FULLFIELDS) return mono ? 6 : 9;
+    return 3;
+}
+static size_t snapshot_npoints(const axo_t *o) {
+    if (o->dump_type == AXB_DUMP_FULLFIELDS)
+        return (size_t)(o->iend - o->ibeg + 1) * (o->jend - o->jbeg + 1) * ((size_t)o->nel_s + o->nel_f);
+    return (size_t)o->npt_s_kwf + o->npt_f_kwf;
+}
+int axo_snapshot_layout(axb_handle h, int32_t *npoints, int32_t *nvars) {
+    *npoints = (int32_t)snapshot_npoints(h); *nvars = snapshot_nvars(h);
+    return 0;
+}
+
 int axo_set_halo(axb_handle h, int32_t domain, int32_t nmsg, const int32_t *list_peer,
                  const int32_t *sizemsg, const int32_t *glocal_index_msg, int32_t maxmsg,
                  int32_t num_comm_gll, const int32_t *glob2el) {
@@ -467,7 +504,8 @@ int axo_finalize_setup(axb_handle h) {
     if (h->dump_energy) h->energy = zerosf((size_t)4 * (h->niter + 1));
     if (h->strain_it > 0 && h->have_kwf) {
         h->nstrain_max = h->niter / h->strain_it + 1;
-        h->snapdump = zerosf((size_t)(h->npt_s_kwf + h->npt_f_kwf) * h->nstrain_max * 3);
+        if (h->dump_type != AXB_DUMP_DISPL_ONLY && !h->dDse) return fail("axo_set_dump: planes missing");
+        h->snapdump = zerosf(snapshot_npoints(h) * h->nstrain_max * snapshot_nvars(h));
     }
     h->iter = 0; h->iseismo = 0; h->istrain = 0; h->t = 0.0;
     h->finalized = 1;
@@ -1343,6 +1381,144 @@ static void dump_disp_global(axo_t *o) {
     o->istrain++;
 }
 
+/* ---- dump_type strain_only / fullfields ------------------------------------------------ */
+/* axisym_gradient_solid / _fluid of one element (pointwise_derivatives.f90:329-365, :509-544) */
+static void grad_el(const float *G1T, const float *G2T, const float *G2, int axial, const float *f,
+                    const float *dse, const float *dze, const float *dsx, const float *dzx,
+                    float *ds, float *dz) {
+    float m1[NPT], m2[NPT];
+    mxm_4(axial ? G1T : G2T, f, m1);
+    mxm_4(f, G2, m2);
+    FOR25 {
+        ds[q] = dze[q] * m1[q] + dzx[q] * m2[q];
+        dz[q] = dse[q] * m1[q] + dsx[q] * m2[q];
+    }
+}
+/* f_over_s_solid / f_over_s_fluid of one element (:130-178): f / s, on the axis the s-derivative */
+static void f_over_s_el(const float *G1T, const float *G2, int axial, const float *f, const float *inv_s,
+                        const float *dze, const float *dzx, float *out) {
+    FOR25 out[q] = inv_s[q] * f[q];
+    if (axial) {
+        float m1[NPT], m2[NPT];
+        mxm_4(G1T, f, m1);
+        mxm_4(f, G2, m2);
+        for (int j = 0; j < NP; j++) out[NP * j] = dze[NP * j] * m1[NP * j] + dzx[NP * j] * m2[NP * j];
+    }
+}
+/* where element-local point q of element e (domain offset eoff = 0 solid, nel_s fluid) goes in
+ * the dump buffer: kwf mapping for strain_only (wavefields_io.f90:743-783), the packed block
+ * ibeg:iend x jbeg:jend for fullfields (:811-812); -1 = not dumped */
+static long dump_slot(const axo_t *o, int fluid, int e, int q) {
+    if (o->dump_type == AXB_DUMP_STRAIN_ONLY) {
+        size_t pk = q + (size_t)NPT * ((size_t)e + (fluid ? o->nel_s : 0));
+        return o->kwf_mask[pk] ? (long)o->kwf_map[pk] - 1 : -1;
+    }
+    int i = q % NP, j = q / NP, ni = o->iend - o->ibeg + 1, nj = o->jend - o->jbeg + 1;
+    if (i < o->ibeg || i > o->iend || j < o->jbeg || j > o->jend) return -1;
+    long base = fluid ? (long)ni * nj * o->nel_s : 0;
+    return base + ((long)e * nj + (j - o->jbeg)) * ni + (i - o->ibeg);
+}
+/* compute_strain (time_evol_wave.F90:1264-1410) [+ dump_velo_global, wavefields_io.f90:932-1015,
+ * for fullfields].  Variable planes in the order of nc_routines.F90:976-1045. */
+static void compute_strain_dump(axo_t *o) {
+    const size_t cs = (size_t)NPT * o->nel_s;
+    const size_t npts = snapshot_npoints(o), vs = npts * o->nstrain_max;
+    float *base = o->snapdump + npts * o->istrain;
+    const int mono = o->src_order == AXB_MONOPOLE, di = o->src_order == AXB_DIPOLE;
+    const int full = o->dump_type == AXB_DUMP_FULLFIELDS;
+    const int V_DSUS = 0, V_DSUZ = 1, V_DPUP = 2, V_DSUP = 3, V_DZUP = 4, V_TR = mono ? 3 : 5;
+    const int V_VS = mono ? 4 : 6, V_VP = 7, V_VZ = mono ? 5 : 8;
+    const float two = 2.0f;
+    for (int e = 0; e < o->nel_s; e++) {
+        const float *u1 = EL(o->disp, e), *u2 = EL(o->disp + cs, e), *u3 = EL(o->disp + 2 * cs, e);
+        const float *dse = EL(o->dDse, e), *dze = EL(o->dDze, e), *dsx = EL(o->dDsx, e), *dzx = EL(o->dDzx, e);
+        const float *is = EL(o->d_inv_s, e);
+        const int ax = o->axis_s[e];
+        float T[NPT], g1[NPT], g2[NPT], hs[NPT], hz[NPT], buff[NPT], fs[NPT], fs3[NPT];
+        float E[6][NPT];
+        if (di) { FOR25 T[q] = u1[q] + u2[q]; grad_el(o->G1T, o->G2T, o->G2, ax, T, dse, dze, dsx, dzx, g1, g2); }
+        else grad_el(o->G1T, o->G2T, o->G2, ax, u1, dse, dze, dsx, dzx, g1, g2);
+        FOR25 E[V_DSUS][q] = g1[q];
+        grad_el(o->G1T, o->G2T, o->G2, ax, u3, dse, dze, dsx, dzx, hs, hz);
+        /* axisym_gradient_solid_add: grad(1) = old(2) + dsdf, grad(2) = old(1) + dzdf */
+        FOR25 { float o1 = g1[q], o2 = g2[q]; g1[q] = o2 + hs[q]; g2[q] = o1 + hz[q]; }
+        FOR25 { g1[q] = g1[q] / two; E[V_DSUZ][q] = g1[q]; }
+        if (mono) {
+            f_over_s_el(o->G1T, o->G2, ax, u1, is, dze, dzx, buff);
+            FOR25 { E[V_DPUP][q] = buff[q]; E[V_TR][q] = buff[q] + g2[q]; }
+        } else if (di) {
+            f_over_s_el(o->G1T, o->G2, ax, u2, is, dze, dzx, fs);
+            FOR25 { buff[q] = two * fs[q]; E[V_DPUP][q] = buff[q]; E[V_TR][q] = buff[q] + g2[q]; }
+            FOR25 T[q] = u1[q] - u2[q];
+            grad_el(o->G1T, o->G2T, o->G2, ax, T, dse, dze, dsx, dzx, hs, hz);
+            f_over_s_el(o->G1T, o->G2, ax, u3, is, dze, dzx, fs3);
+            FOR25 {
+                E[V_DSUP][q] = -fs[q] - hs[q] / two;
+                E[V_DZUP][q] = -(fs3[q] + hz[q]) / two;
+            }
+        } else {
+            FOR25 T[q] = u1[q] - two * u2[q];
+            f_over_s_el(o->G1T, o->G2, ax, T, is, dze, dzx, buff);
+            FOR25 { E[V_DPUP][q] = buff[q]; E[V_TR][q] = buff[q] + g2[q]; }
+            grad_el(o->G1T, o->G2T, o->G2, ax, u2, dse, dze, dsx, dzx, hs, hz);
+            FOR25 T[q] = u1[q] + u2[q] / two;
+            f_over_s_el(o->G1T, o->G2, ax, T, is, dze, dzx, fs);
+            f_over_s_el(o->G1T, o->G2, ax, u3, is, dze, dzx, fs3);
+            FOR25 {
+                E[V_DSUP][q] = -fs[q] - hs[q] / two;
+                E[V_DZUP][q] = -fs3[q] - hz[q] / two;
+            }
+        }
+        const float *v1 = EL(o->velo, e), *v2 = EL(o->velo + cs, e), *v3 = EL(o->velo + 2 * cs, e);
+        FOR25 {
+            long ct = dump_slot(o, 0, e, q);
+            if (ct < 0) continue;
+            for (int v = 0; v < (mono ? 4 : 6); v++) base[ct + vs * v] = E[v][q];
+            if (full) {
+                if (di) { base[ct + vs * V_VS] = v1[q] + v2[q]; base[ct + vs * V_VP] = v1[q] - v2[q]; }
+                else { base[ct + vs * V_VS] = v1[q]; if (!mono) base[ct + vs * V_VP] = v2[q]; }
+                base[ct + vs * V_VZ] = v3[q];
+            }
+        }
+    }
+    for (int e = 0; e < o->nel_f; e++) {
+        const float *dse = EL(o->Dse_f, e), *dze = EL(o->Dze_f, e), *dsx = EL(o->Dsx_f, e), *dzx = EL(o->Dzx_f, e);
+        const float *is = EL(o->d_inv_s_f, e), *ir = EL(o->inv_rho_fluid, e);
+        const int ax = o->axis_f[e];
+        float us[NPT], uz[NPT], g1[NPT], g2[NPT], hs[NPT], hz[NPT], fs[NPT], fz[NPT], ws[NPT], wz[NPT];
+        float E[6][NPT];
+        grad_el(o->G1T, o->G2T, o->G2, ax, EL(o->chi, e), dse, dze, dsx, dzx, us, uz);
+        FOR25 { us[q] = us[q] * ir[q]; uz[q] = uz[q] * ir[q]; }
+        grad_el(o->G1T, o->G2T, o->G2, ax, us, dse, dze, dsx, dzx, g1, g2);
+        FOR25 E[V_DSUS][q] = g1[q];
+        grad_el(o->G1T, o->G2T, o->G2, ax, uz, dse, dze, dsx, dzx, hs, hz);
+        FOR25 { float o1 = g1[q], o2 = g2[q]; g1[q] = o2 + hs[q]; g2[q] = o1 + hz[q]; }
+        FOR25 { g1[q] = g1[q] / two; E[V_DSUZ][q] = g1[q]; }
+        f_over_s_el(o->G1T, o->G2, ax, us, is, dze, dzx, fs);
+        FOR25 { E[V_DPUP][q] = fs[q]; E[V_TR][q] = fs[q] + g2[q]; }
+        if (!mono) {
+            f_over_s_el(o->G1T, o->G2, ax, uz, is, dze, dzx, fz);
+            if (di) FOR25 { E[V_DSUP][q] = (-fs[q]) / two; E[V_DZUP][q] = fz[q] / two; }
+            else FOR25 { E[V_DSUP][q] = -fs[q]; E[V_DZUP][q] = -fz[q]; }
+        }
+        if (full) grad_el(o->G1T, o->G2T, o->G2, ax, EL(o->dchi, e), dse, dze, dsx, dzx, ws, wz);
+        FOR25 {
+            long ct = dump_slot(o, 1, e, q);
+            if (ct < 0) continue;
+            for (int v = 0; v < (mono ? 4 : 6); v++) base[ct + vs * v] = E[v][q];
+            if (full) {
+                /* wavefields_io.f90:992-993 reads the s component at first index jbeg:jend where
+                 * it means ibeg:iend: the value stored for point i is that of i - ibeg + jbeg */
+                int i = q % NP, j = q / NP, iq = i - o->ibeg + o->jbeg;
+                base[ct + vs * V_VS] = ir[q] * ws[iq + NP * j];
+                if (!mono) base[ct + vs * V_VP] = 0.0f;
+                base[ct + vs * V_VZ] = ir[q] * wz[q];
+            }
+        }
+    }
+    o->istrain++;
+}
+
 /* time_evol_wave.F90:1104-1251, the parts on the hot path */
 static void solid_stiffness(axo_t *o, float *acc, const float *u);
 /* time_evol_wave.F90:1424-1526.  sum() is taken in array order with a real(4) accumulator;
@@ -1386,8 +1562,10 @@ static void energy(axo_t *o, int iter) {
 static void dump_stuff(axo_t *o, int iter) {
     if (o->dump_energy) energy(o, iter);
     if (o->num_rec > 0 && iter % o->seis_it == 0 && o->iseismo < o->nseismo_max) sample_receivers(o);
-    if (o->strain_it > 0 && o->have_kwf && iter % o->strain_it == 0 && o->istrain < o->nstrain_max)
-        dump_disp_global(o);
+    if (o->strain_it > 0 && o->have_kwf && iter % o->strain_it == 0 && o->istrain < o->nstrain_max) {
+        if (o->dump_type == AXB_DUMP_DISPL_ONLY) dump_disp_global(o);
+        else compute_strain_dump(o);
+    }
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -1826,9 +2004,9 @@ int axo_fetch_energy(axb_handle h, int32_t first, int32_t n, float *out) {
     return 0;
 }
 int axo_fetch_snapshots(axb_handle h, int32_t first, int32_t nsnap, float *out) {
-    size_t npts = (size_t)h->npt_s_kwf + h->npt_f_kwf;
+    size_t npts = snapshot_npoints(h);
     if (first < 0 || first + nsnap > h->istrain) return fail("snapshot range");
-    for (int v = 0; v < 3; v++)
+    for (int v = 0; v < snapshot_nvars(h); v++)
         for (int s = 0; s < nsnap; s++)
             memcpy(out + npts * (s + (size_t)nsnap * v),
                    h->snapdump + npts * ((first + s) + (size_t)h->nstrain_max * v), sizeof(float) * npts);
