@@ -1,8 +1,19 @@
-// axisem_b200_postproc — solver output -> seismograms in the receiver's component system.
-//   axisem_b200_postproc --src mtr [--amplitude 1e20 --magnitude 1e20] --sys enz [--conv T0 DECAY DT]
-//                        --stations st.txt --seis RUN.rank0000.seis.f32 --out traces.f32
-// stations file: one line per receiver of the .seis file, "colat_deg lon_deg"; .seis is
-// recdumpvar(3, num_rec, nseismo) as axisem_b200_solver writes it; out is (num_rec, 3, nseismo).
+// axisem_b200_postproc — solver output -> seismograms in the receiver's component system
+// (the job of SOLVER/UTILS/post_processing.F90 for the files axisem_b200_solver writes).
+//
+//   single simulation (simtype 'single'):
+//     axisem_b200_postproc --src mtr [--amplitude 1e20 --magnitude 1e20] --seis RUN.rank0000.seis.f32 ...
+//   full moment tensor (simtype 'moment'): the four basis runs and the event's CMTSOLUTION
+//     axisem_b200_postproc --cmt CMTSOLUTION --run mrr 1e20 MZZ.seis.f32 --run mtt_p_mpp 1e20 MXX.seis.f32
+//                          --run mtr 1e20 MXZ.seis.f32 --run mtp 1e20 MXY.seis.f32 ...
+//   common:  --stations st.txt --out traces.f32 [--sys enz|sph|cyl|xyz|src] [--srccolat DEG --srclon DEG]
+//            [--conv T0 DECAY DT]          zero-phase unit-area Gaussian (comparison with dirac_0 traces)
+//            [--stf-conv T0 DT gauss_0|gauss_1]   the reference's causal convolve_with_stf
+//
+// stations file: one line per receiver of the .seis files, "colat_deg lon_deg" in the solver's
+// frame (source at the north pole), as receiver_pts.dat of the reference; .seis is
+// recdumpvar(3, num_rec, nseismo); out is (num_rec, 3, nseismo), components in the reference's
+// order (enz: N E Z; sph: theta phi r; cyl: s phi z).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -13,25 +24,51 @@
 
 #include "postprocess.hpp"
 
+namespace {
+struct Run { std::string type; double magnitude; std::string file; std::vector<float> raw; };
+
+std::vector<float> read_f32(const std::string &path) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("cannot open " + path);
+    std::fseek(f, 0, SEEK_END);
+    const long nb = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    std::vector<float> v((size_t)nb / 4);
+    if (std::fread(v.data(), 4, v.size(), f) != v.size()) { std::fclose(f); throw std::runtime_error("short read of " + path); }
+    std::fclose(f);
+    return v;
+}
+}  // namespace
+
 int main(int argc, char **argv) {
-    std::string src, sys = "enz", stations, seis, out;
-    double amplitude = 1e20, magnitude = 1e20, t_0 = 0, decay = 3.5, dt = 0;
+    std::string sys = "enz", stations, out, cmt, stf_name;
+    std::vector<Run> runs;
+    std::string src, seis;
+    double amplitude = 1e20, magnitude = 1e20, t_0 = 0, decay = 3.5, dt = 0, stf_t0 = 0, stf_dt = 0;
+    axisem::SourceLocation loc;
     for (int k = 1; k < argc; k++) {
         const std::string a = argv[k];
         auto val = [&]() -> const char * { if (k + 1 >= argc) { std::fprintf(stderr, "%s needs a value\n", a.c_str()); std::exit(2); } return argv[++k]; };
         if (a == "--src") src = val();
+        else if (a == "--seis") seis = val();
+        else if (a == "--run") { Run r; r.type = val(); r.magnitude = std::atof(val()); r.file = val(); runs.push_back(r); }
+        else if (a == "--cmt") cmt = val();
         else if (a == "--sys") sys = val();
         else if (a == "--stations") stations = val();
-        else if (a == "--seis") seis = val();
         else if (a == "--out") out = val();
         else if (a == "--amplitude") amplitude = std::atof(val());
         else if (a == "--magnitude") magnitude = std::atof(val());
+        else if (a == "--srccolat") loc.colat = std::atof(val()) * M_PI / 180.0;
+        else if (a == "--srclon") loc.lon = std::atof(val()) * M_PI / 180.0;
         else if (a == "--conv") { t_0 = std::atof(val()); decay = std::atof(val()); dt = std::atof(val()); }
+        else if (a == "--stf-conv") { stf_t0 = std::atof(val()); stf_dt = std::atof(val()); stf_name = val(); }
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
-    if (src.empty() || stations.empty() || seis.empty() || out.empty()) {
-        std::fprintf(stderr, "usage: axisem_b200_postproc --src TYPE --stations FILE --seis FILE --out FILE [--sys enz|sph|cyl] "
-                             "[--amplitude A --magnitude M] [--conv T0 DECAY DT]\n");
+    if (!src.empty() && !seis.empty()) { Run r; r.type = src; r.magnitude = magnitude; r.file = seis; runs.push_back(r); }
+    if (runs.empty() || runs.size() > 4 || stations.empty() || out.empty()) {
+        std::fprintf(stderr, "usage: axisem_b200_postproc (--src TYPE --seis FILE | --cmt CMTSOLUTION --run TYPE MAGNITUDE FILE ...) "
+                             "--stations FILE --out FILE [--sys enz|sph|cyl|xyz|src] [--srccolat DEG --srclon DEG] "
+                             "[--amplitude A --magnitude M] [--conv T0 DECAY DT] [--stf-conv T0 DT gauss_0|gauss_1]\n");
         return 2;
     }
     try {
@@ -44,31 +81,38 @@ int main(int argc, char **argv) {
             std::fclose(f);
         }
         const size_t nrec = colat.size();
-        std::vector<float> raw;
-        {
-            FILE *f = std::fopen(seis.c_str(), "rb");
-            if (!f) throw std::runtime_error("cannot open " + seis);
-            std::fseek(f, 0, SEEK_END);
-            const long nb = std::ftell(f);
-            std::fseek(f, 0, SEEK_SET);
-            raw.resize((size_t)nb / 4);
-            if (std::fread(raw.data(), 4, raw.size(), f) != raw.size()) throw std::runtime_error("short read");
-            std::fclose(f);
+        size_t ns = 0;
+        for (Run &r : runs) {
+            r.raw = read_f32(r.file);
+            if (nrec == 0 || r.raw.size() % (3 * nrec) != 0)
+                throw std::runtime_error(r.file + " does not hold 3 x num_rec x n values");
+            if (ns && r.raw.size() / (3 * nrec) != ns) throw std::runtime_error("runs differ in length");
+            ns = r.raw.size() / (3 * nrec);
         }
-        if (nrec == 0 || raw.size() % (3 * nrec) != 0) throw std::runtime_error("seismogram file does not hold 3 x num_rec x n values");
-        const size_t ns = raw.size() / (3 * nrec);
         double Mij[6];
-        axisem::single_simulation_moment(src, amplitude, Mij);
-        std::vector<float> res(nrec * 3 * ns), spz(3 * ns), rot(3 * ns);
+        if (!cmt.empty()) axisem::moment_from_cmtsolution(cmt, Mij);
+        else if (runs.size() == 1) axisem::single_simulation_moment(runs[0].type, amplitude, Mij);
+        else throw std::runtime_error("several runs need the event's moment tensor (--cmt)");
+        std::vector<float> res(nrec * 3 * ns), one(3 * ns), sum, fil(3 * ns);
         for (size_t r = 0; r < nrec; r++) {
-            double f[3];
-            axisem::radiation_prefactor(src, Mij, magnitude, lon[r], f);
-            for (size_t k = 0; k < ns; k++)
-                for (int c = 0; c < 3; c++) spz[3 * k + c] = (float)(f[c] * raw[c + 3 * (r + nrec * k)]);
-            axisem::rotate_receiver_comp(sys, colat[r], ns, spz.data(), rot.data());
+            sum.assign(3 * ns, 0.0f);
+            for (const Run &run : runs) {
+                double f[3];
+                axisem::radiation_prefactor(run.type, Mij, run.magnitude, lon[r], f);
+                for (size_t k = 0; k < ns; k++)
+                    for (int c = 0; c < 3; c++) one[3 * k + c] = run.raw[c + 3 * (r + nrec * k)];
+                axisem::sum_individual_wavefields(sum, one.data(), ns, f);
+            }
+            if (stf_t0 > 0) {
+                axisem::convolve_with_stf(stf_t0, stf_dt, stf_name, ns, sum.data(), fil.data());
+                sum = fil;
+            }
+            double th_orig, ph_orig;
+            axisem::receiver_location(loc, colat[r], lon[r], th_orig, ph_orig);
+            axisem::rotate_receiver_comp(sys, loc, colat[r], lon[r], th_orig, ph_orig, ns, sum.data());
             for (int c = 0; c < 3; c++) {
                 std::vector<float> tr(ns);
-                for (size_t k = 0; k < ns; k++) tr[k] = rot[3 * k + c];
+                for (size_t k = 0; k < ns; k++) tr[k] = sum[3 * k + c];
                 if (t_0 > 0) axisem::convolve_gauss(tr, dt, t_0, decay);
                 for (size_t k = 0; k < ns; k++) res[(r * 3 + c) * ns + k] = tr[k];
             }
@@ -77,7 +121,7 @@ int main(int argc, char **argv) {
         if (!f) throw std::runtime_error("cannot write " + out);
         std::fwrite(res.data(), 4, res.size(), f);
         std::fclose(f);
-        std::printf("%zu receivers x 3 (%s) x %zu samples\n", nrec, sys.c_str(), ns);
+        std::printf("%zu receivers x 3 (%s) x %zu samples, %zu run(s)\n", nrec, sys.c_str(), ns, runs.size());
     } catch (const std::exception &e) {
         std::fprintf(stderr, "ERROR: %s\n", e.what());
         return 1;

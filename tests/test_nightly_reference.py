@@ -117,7 +117,7 @@ def test_native_postprocessing_of_the_same_run(native_oracle_run):
     if not os.path.exists(exe):
         subprocess.check_call(["bash", os.path.join(root, "axisem_b200", "hostcxx", "build.sh")])
     s = _native_seismograms(tmp, probs, colat.size)
-    want = to_enz("mtr", s, colat, lon)                       # (station, E/N/Z, sample)
+    want = to_enz("mtr", s, colat, lon)[:, [1, 0, 2], :]      # (station, N/E/Z, sample): the reference's order
     got = np.zeros_like(want)
     for r, p in enumerate(probs):
         if not p.num_rec:
