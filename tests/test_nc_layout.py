@@ -1,0 +1,103 @@
+"""The output database layout (axisem_b200/host/nc_layout.py) against the definitions of the
+reference's `nc_define_outputfile`, extracted from its Fortran into
+tests/golden/nc_schema_reference.json, and the data of a (CPU oracle) run against what went in."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from axisem_b200.host import SourceParams, build_problem, nc_layout
+from tests.util import small_spec
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+XTYPE = {"NF90_FLOAT": "f4", "NF90_DOUBLE": "f8", "NF90_INT": "i4", "NF90_CHAR": "S1"}
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return json.load(open(os.path.join(HERE, "golden", "nc_schema_reference.json")))
+
+
+@pytest.mark.parametrize("dump_type", ["displ_only", "strain_only", "fullfields"])
+@pytest.mark.parametrize("monopole", [True, False])
+def test_schema_is_the_references(ref, dump_type, monopole):
+    sch = nc_layout.schema(nrec=5, nseismo=11, niter=40, dump_wavefields=True, dump_type=dump_type, monopole=monopole,
+                           npoints_global=123, nstrain=4, nelem_kwf_global=9, anel=True)
+    assert list(sch["groups"]) == ref["groups"]
+    lens = {"nseismo": 11, "niter": 40, "3": 3, "40": 40, "nrec": 5, "nstrain": 4, "npoints_global": 123,
+            "nelem_kwf_global": 9, "4": 4, "npol+1": 5}
+    for name, d in ref["dimensions"].items():
+        holder = sch["dimensions"] if d["group"] == "" else sch["groups"][d["group"]]["dimensions"]
+        if d["group"] == "Mesh" and dump_type != "displ_only":
+            assert name not in holder                       # defined inside `if displ_only` in the reference
+            continue
+        assert holder[name] == lens[d["len"]], name
+    snap_names = ref["snapshot_variables"][dump_type][0 if monopole else 1]
+    assert snap_names == nc_layout.SNAP_VARS[(dump_type, monopole)]
+    mesh_displ_only = {"midpoint_mesh", "eltype", "axis", "fem_mesh", "sem_mesh", "mp_mesh_S", "mp_mesh_Z", "G0", "G1",
+                       "G2", "gll", "glj"}
+    seen = 0
+    for v in ref["variables"]:
+        vars_ = sch["variables"] if v["group"] == "" else sch["groups"][v["group"]]["variables"]
+        names = snap_names if v["name"].startswith("trim(") else [v["name"]]
+        if v["group"] == "Mesh" and v["name"] in mesh_displ_only and dump_type != "displ_only":
+            assert v["name"] not in vars_
+            continue
+        for n in names:
+            assert n in vars_, (v["group"], n)
+            assert vars_[n]["dtype"] == XTYPE[v["xtype"]], n
+            assert vars_[n]["dims"] == v["dims_fortran"][::-1], n      # netCDF order is the reverse of the Fortran dimids
+            seen += 1
+    total = sum(len(g["variables"]) for g in sch["groups"].values()) + len(sch["variables"])
+    assert seen == total                                     # nothing in the layout that the reference does not define
+
+
+def test_database_of_a_two_rank_run(ref, tmp_path):
+    """Two theta-slices through the oracle with a displ_only dump: the directory holds every
+    variable of the schema, displacement(receivers, components, time) is the recdumpvar of the
+    ranks, the snapshot variables are the ranks' oneddumpvar blocks side by side, sem_mesh indexes
+    mesh_S / mesh_Z consistently, and every global attribute of the reference is there."""
+    from axisem_b200.capi import connect_local, run_group
+    from oracle import oracle
+    n, colat = 24, np.linspace(10, 170, 9)
+    probs = [build_problem(small_spec(), SourceParams(src_type2="mtr", t_0=4.0), niter=n, dump=True, strain_it=6,
+                           seis_it=2, rank=r, nranks=2, rec_colat_deg=colat, anel=True) for r in range(2)]
+    lib = oracle.load()
+    loops = [oracle.make_loop(p) for p in probs]
+    connect_local(lib, loops)
+    run_group(lib, loops, n)
+    seis = [L.seismograms() for L in loops]
+    snaps = [L.snapshots() for L in loops]
+    out = str(tmp_path / "run.ncdir")
+    sch = nc_layout.write_database(out, probs, seis, snaps, colat_deg=colat)
+    for gname, g in sch["groups"].items():
+        for v in g["variables"]:
+            assert os.path.exists(os.path.join(out, gname, v + ".bin")), (gname, v)
+    disp = nc_layout.read_variable(out, "Seismograms", "displacement")
+    assert disp.shape == (9, 3, n // 2 + 1)
+    for p, s in zip(probs, seis):
+        assert np.array_equal(disp[p.rec_index], s.transpose(1, 2, 0))
+    assert np.abs(disp).max() > 0
+    ds = nc_layout.read_variable(out, "Snapshots", "disp_s")
+    np0 = snaps[0].shape[2]
+    assert ds.shape == (n // 6 + 1, np0 + snaps[1].shape[2])
+    assert np.array_equal(ds[:, :np0], snaps[0][0]) and np.array_equal(ds[:, np0:], snaps[1][0])
+    # mesh: the GLL points of an element, through sem_mesh, are where its geometry says they are
+    S, Z = (nc_layout.read_variable(out, "Mesh", k) for k in ("mesh_S", "mesh_Z"))
+    sem = nc_layout.read_variable(out, "Mesh", "sem_mesh")
+    fem = nc_layout.read_variable(out, "Mesh", "fem_mesh")
+    mid = nc_layout.read_variable(out, "Mesh", "midpoint_mesh")
+    from axisem_b200.host.mesh import element_coords
+    m0 = probs[0].mesh
+    _, _, _, s_el, z_el, *_ = element_coords(m0.solid, m0.basis)
+    assert np.allclose(S[sem[:m0.nel_solid]], s_el) and np.allclose(Z[sem[:m0.nel_solid]], z_el)
+    assert np.array_equal(fem[:, 0], sem[:, 0, 0]) and np.array_equal(fem[:, 2], sem[:, 4, 4])
+    assert np.array_equal(mid, sem[:, 2, 2])
+    assert np.allclose(nc_layout.read_variable(out, "Mesh", "mp_mesh_S"), S[mid])
+    r = np.hypot(S, Z)
+    vp = nc_layout.read_variable(out, "Mesh", "mesh_vp")
+    assert r.max() == pytest.approx(6371e3) and 1e3 < vp.min() and vp.max() < 14e3
+    have = set(json.load(open(os.path.join(out, "schema.json")))["attributes"])
+    want = {n for n, _ in ref["global_attributes"]}
+    assert want <= have, want - have
