@@ -56,7 +56,7 @@ def control_nodes(mesh):
 
 
 def write_meshdb(mesh, path: str, *, period: float = 50.0, courant: float = 0.6, dt: float = 0.1,
-                 bkgrdmodel: str = "prem_iso"):
+                 bkgrdmodel: str = "prem_iso", eltype=None):
     b, spec = mesh.basis, mesh.spec
     npol = spec.npol
     ns, nf = mesh.nel_solid, mesh.nel_fluid
@@ -82,7 +82,10 @@ def write_meshdb(mesh, path: str, *, period: float = 50.0, courant: float = 0.6,
     for e in range(nelem):
         u.rec(_arr(lnods[e], "<i4"))
     u.rec(_i(mesh.nglob_solid + mesh.nglob_fluid))              # nglob of the rank
-    u.rec(b"".join(b"curved" for _ in range(nelem)))            # eltype, character(len=6)
+    if eltype is None:
+        u.rec(b"".join(b"curved" for _ in range(nelem)))        # eltype, character(len=6)
+    else:
+        u.rec(b"".join(bytes(t).ljust(6)[:6] for t in eltype))  # (solid elements first, then fluid)
     u.rec(_arr(np.zeros(nelem), "<i4"))                         # coarsing, logical
     u.rec(_arr(np.arange(1, ns + 1), "<i4"))                    # ielsolid
     u.rec(_arr(np.arange(ns + 1, nelem + 1), "<i4"))            # ielfluid
@@ -96,8 +99,9 @@ def write_meshdb(mesh, path: str, *, period: float = 50.0, courant: float = 0.6,
     u.rec(bkgrdmodel.encode())
     u.rec(b"none  ")                                             # override_ext_q, character(len=6)
     u.rec(_d(router), _i(1 if nf else 0))
+    solid_dom = [0 if l.fluid else 1 for l in spec.layers][::-1]
     for k in range(ndisc):
-        u.rec(_d(discs[k]), _i(1), _i(0))
+        u.rec(_d(discs[k]), _i(solid_dom[k]), _i(0))
     u.rec(_d(float(spec.layers[0].r_bot), 0.0, 0.0, 0.0))        # rmin, minh_ic, maxh_ic, maxh_icb
     u.rec(_d(0.0, 0.0))
     u.rec(_d(0.0, 0.0))

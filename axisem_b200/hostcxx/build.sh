@@ -8,11 +8,13 @@ CXX="${CXX:-g++}"
 OUT="${OUT:-$HERE/../axisem_b200_solver}"
 "$CXX" -O2 -std=c++17 -Wall -Wextra -I"$ROOT/include" -o "$OUT" \
     "$HERE/main.cpp" "$HERE/time_loop.cpp" "$HERE/modules.cpp" "$HERE/meshdb.cpp" \
+    "$HERE/precomp.cpp" "$HERE/mapping.cpp" "$HERE/background_models.cpp" \
     -L"$HERE/.." -laxisem_b200 -Wl,-rpath,'$ORIGIN'
 echo "built $OUT"
 # mesher database -> module variables (no device code)
 "$CXX" -O2 -std=c++17 -Wall -Wextra -I"$ROOT/include" -o "$HERE/../axisem_b200_meshdb2axbp" \
-    "$HERE/meshdb2axbp.cpp" "$HERE/meshdb.cpp" "$HERE/modules.cpp" "$HERE/spectral.cpp"
+    "$HERE/meshdb2axbp.cpp" "$HERE/meshdb.cpp" "$HERE/modules.cpp" "$HERE/spectral.cpp" \
+    "$HERE/precomp.cpp" "$HERE/mapping.cpp" "$HERE/background_models.cpp"
 echo "built $HERE/../axisem_b200_meshdb2axbp"
 # spectral basis and background models (the first pieces of the native pre-processing)
 "$CXX" -O2 -std=c++17 -Wall -Wextra -o "$HERE/../axisem_b200_hosttool" \
@@ -21,3 +23,7 @@ echo "built $HERE/../axisem_b200_hosttool"
 # post-processing of the solver output (radiation factors, rotation, STF convolution)
 "$CXX" -O2 -std=c++17 -Wall -Wextra -o "$HERE/../axisem_b200_postproc" "$HERE/postproc_main.cpp" "$HERE/postprocess.cpp"
 echo "built $HERE/../axisem_b200_postproc"
+# the native pre-computation as a stand-alone step: MESHER databases -> complete containers
+"$CXX" -O2 -std=c++17 -Wall -Wextra -o "$HERE/../axisem_b200_precomp" "$HERE/precomp_main.cpp" "$HERE/precomp.cpp" \
+    "$HERE/mapping.cpp" "$HERE/background_models.cpp" "$HERE/meshdb.cpp" "$HERE/modules.cpp"
+echo "built $HERE/../axisem_b200_precomp"

@@ -16,6 +16,7 @@
 
 #include "meshdb.hpp"
 #include "time_loop.hpp"
+#include "precomp.hpp"
 
 namespace {
 
@@ -94,7 +95,11 @@ struct FileSink : axisem::OutputSink {
 void usage() {
     std::fprintf(stderr,
                  "usage: axisem_b200_solver [--steps N] [--devices D] [--dumpbuffer B] [--quiet] --out PREFIX "
-                 "rank0.axbp[+meshdb.dat0000] [rank1.axbp[+meshdb.dat0001] ...]\n");
+                 "rank0.axbp[+meshdb.dat0000] [rank1.axbp[+meshdb.dat0001] ...]\n"
+                 "   or: axisem_b200_solver --out PREFIX [--model prem_iso|prem_ani] [--src TYPE] [--depth KM] [--period T0]\n"
+                 "          [--niter N] [--dt DT] [--seis-it K] [--strain-it K] [--attenuation cg4|full] [--scheme NAME]\n"
+                 "          [--receivers COLAT,COLAT,...] [--energy]  meshdb.dat0000 [meshdb.dat0001 ...]\n"
+                 "       (the second form pre-computes everything from the MESHER's databases, no other input)\n");
 }
 
 }  // namespace
@@ -103,6 +108,7 @@ int main(int argc, char **argv) {
     axisem::TimeLoopOptions opt;
     std::string prefix;
     std::vector<std::string> files;
+    axisem::PrecompOptions pre;
     for (int k = 1; k < argc; k++) {
         const std::string a = argv[k];
         auto need = [&](const char *what) -> const char * {
@@ -114,13 +120,45 @@ int main(int argc, char **argv) {
         else if (a == "--dumpbuffer") opt.nc_dumpbuffersize = std::max(1, std::atoi(need("--dumpbuffer")));
         else if (a == "--quiet") opt.verbose = false;
         else if (a == "--out") prefix = need("--out");
+        else if (a == "--model") pre.model = need("--model");
+        else if (a == "--src") pre.src_type2 = need("--src");
+        else if (a == "--depth") pre.src_depth = 1e3 * std::atof(need("--depth"));
+        else if (a == "--period") pre.t_0 = std::atof(need("--period"));
+        else if (a == "--niter") pre.niter = std::atoi(need("--niter"));
+        else if (a == "--dt") pre.deltat = std::atof(need("--dt"));
+        else if (a == "--seis-it") pre.seis_it = std::atoi(need("--seis-it"));
+        else if (a == "--strain-it") { pre.strain_it = std::atoi(need("--strain-it")); pre.dump_wavefields = pre.strain_it > 0; }
+        else if (a == "--scheme") pre.time_scheme = need("--scheme");
+        else if (a == "--energy") pre.dump_energy = true;
+        else if (a == "--attenuation") { pre.attenuation = true; pre.att.coarse_grained = std::string(need("--attenuation")) != "full"; }
+        else if (a == "--receivers") {
+            std::string v = need("--receivers");
+            size_t pos = 0;
+            while (pos < v.size()) {
+                size_t c = v.find(',', pos);
+                if (c == std::string::npos) c = v.size();
+                pre.rec_colat_deg.push_back(std::atof(v.substr(pos, c - pos).c_str()));
+                pos = c + 1;
+            }
+        }
         else if (a == "-h" || a == "--help") { usage(); return 0; }
         else files.push_back(a);
     }
     if (files.empty() || prefix.empty()) { usage(); return 2; }
     try {
         std::vector<axisem::Modules> ranks;
+        const bool from_meshdb = files[0].find(".axbp") == std::string::npos;
+        if (from_meshdb) {
+            // MESHER databases only: everything else is computed here (precomp.hpp)
+            for (size_t r = 0; r < files.size(); r++) ranks.push_back(axisem::read_meshdb(files[r], (int)r));
+            axisem::precompute(ranks, pre);
+            const axisem::PrecompChecks c = axisem::precompute_checks(ranks);
+            if (opt.verbose)
+                std::printf("pre-computation: mass = volume %.10f (solid+fluid over sphere-hollow), S/F boundary term %.10f for %d boundaries\n",
+                            (c.solid_volume + c.fluid_volume) / (c.sphere_volume - c.hollow_volume), c.bdry_sum, c.n_sf_boundaries);
+        }
         for (const std::string &f : files) {
+            if (from_meshdb) break;
             // "terms.axbp+meshdb.datNNNN": mesh-level variables straight from the MESHER's database
             const size_t plus = f.find('+');
             axisem::Modules m = axisem::Modules::read(f.substr(0, plus));

@@ -1,0 +1,178 @@
+"""The native pre-computation (axisem_b200/hostcxx/precomp.cpp + mapping.cpp): from the MESHER's
+databases to the complete time-loop inputs with no Python in between — SURVEY.md section 8(f)
+item 1, second half (def_precomp_terms, get_model, analytic_mapping, attenuation set-up, source,
+receivers).
+
+  * every array it produces against the Python builder's (axisem_b200/host/precomp.py, the
+    restatement the parity tests rest on): to 1 ulp of real(4) wherever the value is significant,
+    noise-level otherwise (planes that cancel analytically for concentric elements);
+  * the reference's own self-checks: mass = volume (def_grid.f90:1188) and the S/F boundary
+    term = 2 per boundary (def_precomp_terms.f90:2743);
+  * the element mappings of all four element types against finite differences and their defining
+    geometry, and a database whose inner layer is re-typed linear / semino / semiso;
+  * the solver started from databases alone gives the seismograms of the Python-built problem.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from axisem_b200.host import AttenuationModel, SourceParams, build_problem, prem_mesh_spec
+from axisem_b200.host.meshdb_io import read_axbprob, write_meshdb
+from axisem_b200.host.problem_bin import problem_records
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "axisem_b200", "axisem_b200_precomp")
+COLAT = [10.0, 47.0, 93.0, 131.0, 170.0]
+
+
+@pytest.fixture(scope="module")
+def exe():
+    if not os.path.exists(EXE):
+        subprocess.check_call(["bash", os.path.join(ROOT, "axisem_b200", "hostcxx", "build.sh")])
+    return EXE
+
+
+def _run(exe, tmp, probs, src, anel, ani, extra=()):
+    files = []
+    for r, p in enumerate(probs):
+        f = os.path.join(tmp, f"meshdb.dat{r:04d}")
+        write_meshdb(p.mesh, f, dt=p.deltat, bkgrdmodel="prem_ani" if ani else "prem_iso")
+        files.append(f)
+    cmd = [exe, "--out", os.path.join(tmp, "pre"), "--src", src, "--period", "40", "--niter", str(probs[0].niter),
+           "--strain-it", "10", "--energy", "--receivers", ",".join(map(str, COLAT))] + list(extra)
+    if anel != "none":
+        cmd += ["--attenuation", anel]
+    out = subprocess.run(cmd + files, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    checks = dict(line.split() for line in out.stdout.strip().splitlines())
+    return [read_axbprob(os.path.join(tmp, f"pre.rank{r:04d}.axbp")) for r in range(len(probs))], checks, files
+
+
+@pytest.mark.parametrize("src,ani,anel,nranks", [("explosion", False, "none", 1), ("mtr", False, "none", 2),
+                                                 ("mtp", True, "cg4", 2), ("mtr", True, "full", 4),
+                                                 ("explosion", True, "cg4", 2)])
+def test_native_precomputation_equals_the_python_builder(exe, tmp_path, src, ani, anel, nranks):
+    spec = prem_mesh_spec(ntheta=16, nr_target=18, anisotropic=ani)
+    att = AttenuationModel(coarse_grained=(anel == "cg4")) if anel != "none" else None
+    probs = [build_problem(spec, SourceParams(src_type2=src, t_0=40.0), anel=anel != "none", att=att, niter=30, rank=r,
+                           nranks=nranks, rec_colat_deg=COLAT, dump=True, strain_it=10, energy=True)
+             for r in range(nranks)]
+    got, checks, _ = _run(exe, str(tmp_path), probs, src, anel, ani)
+    # the reference's self-checks
+    assert abs(float(checks["mass_over_volume"]) - 1.0) < 1e-9          # mass (rho = 1) = volume of the shell
+    assert int(checks["n_sf_boundaries"]) == 2
+    assert abs(float(checks["bdry_sum"]) - 2.0 * 2) < 1e-9              # int_0^pi sin = 2 per boundary
+    nrec = 0
+    for p, g in zip(probs, got):
+        recs = {n: np.ascontiguousarray(a, dtype=d) for n, a, d in problem_records(p)}
+        # scale of a family of planes: terms that cancel analytically are compared against it
+        fam = {}
+        for n, a in recs.items():
+            if a.dtype == np.float32 and a.size:
+                key = (n.split("%")[0], a.shape[-2:] if a.ndim >= 2 else ())
+                fam[key] = max(fam.get(key, 0.0), float(np.abs(a).max()))
+        for n, a in recs.items():
+            assert n in g, n
+            b = g[n]
+            assert a.size == b.size, (n, a.shape, b.shape)
+            a, b = a.reshape(-1), b.reshape(-1)
+            if a.dtype == np.int32:
+                assert np.array_equal(a, b), n
+            elif a.dtype == np.float64:
+                assert np.allclose(a, b, rtol=1e-13, atol=0), n
+            else:
+                key = (n.split("%")[0], recs[n].shape[-2:] if recs[n].ndim >= 2 else ())
+                scale = fam[key]
+                big = np.abs(a) > 1e-6 * scale
+                ulp = np.abs(a.view(np.int32).astype(np.int64) - b.astype(np.float32).view(np.int32).astype(np.int64))
+                assert (ulp[big] <= 1).all(), (n, int(ulp[big].max()))
+                assert np.abs(a - b)[~big].max(initial=0.0) <= 1e-12 * scale, n
+        nrec += int(g["data_mesh%num_rec"])
+    assert nrec == len(COLAT)
+
+
+def test_element_mappings(exe, tmp_path):
+    """curved / linear / semino / semiso through the tool's --mapping-check: corners hit the
+    control nodes, derivatives agree with central differences, the straight side of a semi element
+    is straight and its curved side lies on the ellipse through its end nodes."""
+    out = subprocess.run([exe, "--mapping-check"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr + out.stdout
+    vals = dict(line.split()[:2] for line in out.stdout.strip().splitlines())
+    for k in ("curved", "linear", "semino", "semiso"):
+        assert float(vals[k + "_corner_err"]) < 1e-6, (k, vals)              # metres
+        assert float(vals[k + "_derivative_err"]) < 1e-6, (k, vals)          # relative
+    assert float(vals["semino_line_err"]) < 1e-6 and float(vals["semiso_line_err"]) < 1e-6
+    assert float(vals["semino_ellipse_err"]) < 1e-9 and float(vals["semiso_ellipse_err"]) < 1e-9
+
+
+def test_database_with_other_element_types(exe, tmp_path):
+    """The innermost solid layer re-typed (linear: 8-node serendipity through the true arc mid-points;
+    semiso: elliptic bottom, straight top; semino on the row above: straight bottom, elliptic top),
+    as the mesher does around its inner cube: the reader takes the types from the database, the
+    mappings are dispatched per element, and mass = volume still holds to the accuracy the straight
+    sides and the quadrature allow (the two straight-sided rows cut the same lens in and out)."""
+    spec = prem_mesh_spec(ntheta=16, nr_target=18)
+    prob = build_problem(spec, SourceParams(src_type2="explosion", t_0=40.0), niter=10, rec_colat_deg=COLAT)
+    f = str(tmp_path / "meshdb.dat0000")
+    m = prob.mesh
+    ir0 = int(m.solid.ir.min())
+    eltype = np.array([b"curved"] * (m.nel_solid + m.nel_fluid))
+    eltype[:m.nel_solid][m.solid.ir == ir0] = b"linear"
+    write_meshdb(m, f, dt=prob.deltat, eltype=eltype)
+    out = subprocess.run([exe, "--out", str(tmp_path / "lin"), "--niter", "10", f], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    c = dict(line.split() for line in out.stdout.strip().splitlines())
+    # the parabola through three points of an arc of 11 degrees leaves a relative area error of ~1e-6
+    assert abs(float(c["mass_over_volume"]) - 1.0) < 1e-5
+    g = read_axbprob(str(tmp_path / "lin.rank0000.axbp"))
+    ref = {n: np.asarray(a) for n, a, d in problem_records(prob)}
+    lin = (m.solid.ir == ir0)
+    a, b = ref["data_matr%M21s"].reshape(-1, 25), g["data_matr%M21s"].reshape(-1, 25)
+    assert np.array_equal(a[~lin], b[~lin])                        # untouched elements: identical
+    assert not np.array_equal(a[lin], b[lin]) and np.allclose(a[lin], b[lin], rtol=2e-2)
+    # semiso below semino: straight interface between two rows
+    eltype[:] = b"curved"
+    eltype[:m.nel_solid][m.solid.ir == ir0] = b"semiso"
+    eltype[:m.nel_solid][m.solid.ir == ir0 + 1] = b"semino"
+    write_meshdb(m, f, dt=prob.deltat, eltype=eltype)
+    out = subprocess.run([exe, "--out", str(tmp_path / "semi"), "--niter", "10", f], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    c = dict(line.split() for line in out.stdout.strip().splitlines())
+    # what semiso loses semino gains; what remains is the GLL quadrature of the two distorted rows
+    assert abs(float(c["mass_over_volume"]) - 1.0) < 2e-5
+
+
+def test_solver_from_databases_alone(exe, tmp_path):
+    """axisem_b200_solver (here: its CPU twin linked against the oracle) started from the mesher's
+    databases only gives the seismograms of the run set up through Python."""
+    from axisem_b200.capi import connect_local, run_group
+    from oracle import oracle
+    nranks, n = 2, 60
+    spec = prem_mesh_spec(ntheta=16, nr_target=18, anisotropic=True)
+    probs = [build_problem(spec, SourceParams(src_type2="mtr", t_0=3.0), anel=True, niter=n, rank=r, nranks=nranks,
+                           rec_colat_deg=COLAT) for r in range(nranks)]
+    files = []
+    for r, p in enumerate(probs):
+        f = str(tmp_path / f"meshdb.dat{r:04d}")
+        write_meshdb(p.mesh, f, dt=p.deltat, bkgrdmodel="prem_ani")
+        files.append(f)
+    run = subprocess.run([oracle.build_host(), "--quiet", "--out", str(tmp_path / "run"), "--src", "mtr", "--period", "3",
+                          "--niter", str(n), "--attenuation", "cg4", "--receivers", ",".join(map(str, COLAT))] + files,
+                         capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr
+    lib = oracle.load()
+    loops = [oracle.make_loop(p) for p in probs]
+    connect_local(lib, loops)
+    run_group(lib, loops, n)
+    seen = 0
+    for r, (p, L) in enumerate(zip(probs, loops)):
+        if not p.num_rec:
+            continue
+        raw = np.fromfile(tmp_path / f"run.rank{r:04d}.seis.f32", dtype=np.float32).reshape(-1, p.num_rec, 3)
+        ref = L.seismograms()
+        assert raw.shape == ref.shape and np.abs(ref).max() > 0
+        assert np.abs(raw - ref).max() <= 2e-6 * np.abs(ref).max()
+        seen += p.num_rec
+    assert seen == len(COLAT)
