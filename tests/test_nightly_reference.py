@@ -129,8 +129,10 @@ def test_native_postprocessing_of_the_same_run(native_oracle_run):
                               str(tmp / f"run.rank{r:04d}.seis.f32"), "--out", str(out)], capture_output=True, text=True)
         assert run.returncode == 0, run.stderr
         got[p.rec_index] = np.fromfile(out, dtype=np.float32).reshape(p.num_rec, 3, -1)
-    scale = np.abs(want).max(axis=2, keepdims=True)
-    assert np.all(np.abs(got - want) <= 3e-7 * scale + 1e-30)
+    # the reference recovers the receiver's longitude through acos((x + 1e-11) / (|xy| + 1e-11))
+    # (post_processing.F90:214-224), good to ~5e-6 rad near phi = 0: that bounds the agreement
+    scale = np.abs(want).max(axis=(1, 2), keepdims=True)
+    assert np.all(np.abs(got - want) <= 1e-5 * scale + 1e-30)
     # Gaussian convolution of the tool against numpy's
     k = int(probs[0].rec_index[0]) if probs[0].num_rec else 0
     src_rank = next(r for r, p in enumerate(probs) if p.num_rec)
