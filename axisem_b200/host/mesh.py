@@ -155,6 +155,9 @@ class LocalMesh:
     nranks: int
     it0: int
     it1: int
+    nranks_r: int               # radial blocks (rank = theta_block * nranks_r + radial_block)
+    ir0: int
+    ir1: int
     solid: ElementSet
     fluid: ElementSet
     nel_solid: int
@@ -205,41 +208,66 @@ def element_coords(es: ElementSet, basis: SpectralBasis):
 
 
 def _domain_numbering(spec: MeshSpec, es: ElementSet, it0: int, fluid: bool):
-    """igloc (1-based, rank-local) and a mesh-global id for every element-local point."""
+    """igloc (1-based, rank-local), the rank's radial node range (first node, count) and a
+    mesh-global id for every element-local point.  The local numbers run over the radial nodes
+    the rank's elements of this domain touch (the whole column for theta-only slices)."""
     nrn = spec.nrnode_fluid if fluid else spec.nrnode_solid
     nel = es.nel
     if nel == 0:
-        return np.zeros(0, np.int32), 0, np.zeros(0, np.int64)
+        return np.zeros(0, np.int32), (0, 0), np.zeros(0, np.int64)
     i = np.arange(NP1)
     ip = np.where(es.north[:, None], i[None, :], 4 - i[None, :])          # (nel,5) theta
     jp = ip                                                                 # same flip in r
     tnode = 4 * es.it[:, None] + ip                                         # global
     rnode = spec.rbase[es.ir][:, None] + jp
     gid = tnode[:, None, :] * nrn + rnode[:, :, None]                       # (nel,j,i)
-    loc = (tnode - 4 * it0)[:, None, :] * nrn + rnode[:, :, None] + 1
-    return loc.reshape(-1).astype(np.int32), None, gid.reshape(-1)
+    r0 = int(spec.rbase[es.ir].min())
+    nloc = int(spec.rbase[es.ir].max()) + 4 - r0 + 1
+    loc = (tnode - 4 * it0)[:, None, :] * nloc + (rnode[:, :, None] - r0) + 1
+    return loc.reshape(-1).astype(np.int32), (r0, nloc), gid.reshape(-1)
+
+
+def radial_blocks(spec: MeshSpec, nranks_r: int):
+    """ir ranges of a radial decomposition into nranks_r blocks of about equal element counts
+    (MESHER/parallelization.f90:157-165 cuts in radius as well); a cut never falls on a solid/fluid
+    boundary, so that every S/F boundary pair stays inside one rank."""
+    cuts = [0]
+    for k in range(1, nranks_r):
+        c = int(round(k * spec.nr / nranks_r))
+        while 0 < c < spec.nr and spec.fluid_ir[c - 1] != spec.fluid_ir[c]:
+            c += 1
+        assert cuts[-1] < c < spec.nr, "too many radial blocks for this mesh"
+        cuts.append(c)
+    cuts.append(spec.nr)
+    return [(cuts[k], cuts[k + 1]) for k in range(nranks_r)]
 
 
 def build_rank(spec: MeshSpec, rank: int = 0, nranks: int = 1,
-               basis: Optional[SpectralBasis] = None) -> LocalMesh:
-    """The piece of the mesh owned by `rank` of a theta-only decomposition
-    (MESHER/parallelization.f90:68-112 gives equal element counts per slice)."""
+               basis: Optional[SpectralBasis] = None, nranks_r: int = 1) -> LocalMesh:
+    """The piece of the mesh owned by `rank` of a theta (x radius) decomposition
+    (MESHER/parallelization.f90:68-112 gives equal element counts per slice, :157-165 the radial
+    cuts).  rank = theta_block * nranks_r + radial_block; up to eight neighbours per rank."""
     basis = basis or SpectralBasis(spec.npol)
-    assert spec.ntheta % nranks == 0, "ntheta must be divisible by the number of slices"
-    ncol = spec.ntheta // nranks
-    it0, it1 = rank * ncol, (rank + 1) * ncol
+    assert nranks % nranks_r == 0
+    nth = nranks // nranks_r
+    assert spec.ntheta % nth == 0, "ntheta must be divisible by the number of theta slices"
+    bt, br = divmod(rank, nranks_r)
+    ncol = spec.ntheta // nth
+    it0, it1 = bt * ncol, (bt + 1) * ncol
+    blocks = radial_blocks(spec, nranks_r)
+    ir0, ir1 = blocks[br]
     cols = np.arange(it0, it1)
-    IT, IR = np.meshgrid(cols, np.arange(spec.nr), indexing="ij")          # ir fastest
+    IT, IR = np.meshgrid(cols, np.arange(ir0, ir1), indexing="ij")         # ir fastest
     IT = IT.reshape(-1)
     IR = IR.reshape(-1)
     fl = spec.fluid_ir[IR]
     solid = make_elements(spec, IT[~fl], IR[~fl])
     fluid = make_elements(spec, IT[fl], IR[fl])
 
-    ig_s, _, gid_s = _domain_numbering(spec, solid, it0, False)
-    ig_f, _, gid_f = _domain_numbering(spec, fluid, it0, True)
-    nglob_s = (4 * ncol + 1) * spec.nrnode_solid
-    nglob_f = (4 * ncol + 1) * spec.nrnode_fluid
+    ig_s, (r0_s, nloc_s), gid_s = _domain_numbering(spec, solid, it0, False)
+    ig_f, (r0_f, nloc_f), gid_f = _domain_numbering(spec, fluid, it0, True)
+    nglob_s = (4 * ncol + 1) * nloc_s
+    nglob_f = (4 * ncol + 1) * nloc_f
 
     # local element index by (it, ir)
     idx_s = -np.ones((ncol, spec.nr), dtype=np.int64)
@@ -249,7 +277,7 @@ def build_rank(spec: MeshSpec, rank: int = 0, nranks: int = 1,
 
     # ---- solid/fluid boundary pairs (data_mesh.f90:106-110) ------------------------
     bs, bf, js, jf, above = [], [], [], [], []
-    for ir in range(spec.nr - 1):
+    for ir in range(ir0, ir1 - 1):
         lo_f, hi_f = spec.fluid_ir[ir], spec.fluid_ir[ir + 1]
         if lo_f == hi_f:
             continue
@@ -273,45 +301,62 @@ def build_rank(spec: MeshSpec, rank: int = 0, nranks: int = 1,
     nel_bdry = len(bs)
 
     # ---- halo ---------------------------------------------------------------------
-    def halo(es: ElementSet, idx, nrn, igloc):
+    def halo(es: ElementSet, idx, fluid, r0, nloc, igloc):
+        """Messages to the (up to eight) neighbouring blocks: the shared column of radial nodes
+        for theta neighbours, the shared row of theta nodes for radial neighbours (only where the
+        elements across the cut belong to the same domain, i.e. share nodes), the single corner
+        node for diagonal ones.  Lists are ordered by node index, the same on both sides."""
         h = HaloSide()
-        if nrn == 0 or nranks == 1:
+        if es.nel == 0 or nranks == 1:
             return h
+        dom = spec.fluid_ir == fluid
+        # is the node row at the bottom / top of this block shared with the block below / above?
+        row_shared = {-1: br > 0 and dom[ir0 - 1] and dom[ir0], 1: br < nranks_r - 1 and dom[ir1 - 1] and dom[ir1]}
+        rloc_row = {-1: int(spec.rbase[ir0]) - r0 if dom[ir0] else -1,
+                    1: int(spec.rbase[ir1 - 1]) + 4 - r0 if dom[ir1 - 1] else -1}
+        tloc_col = {-1: 0, 1: 4 * ncol}
         peers, lists = [], []
-        g2e = []
-        for side, peer in ((0, rank - 1), (1, rank + 1)):
-            if peer < 0 or peer >= nranks:
-                continue
-            tloc = 0 if side == 0 else 4 * ncol
-            peers.append(peer)
-            lists.append(tloc * nrn + np.arange(nrn) + 1)
-            c = 0 if side == 0 else ncol - 1
-            north = (it0 + c) < spec.ntheta // 2
-            # local ipol sitting on the shared column
-            want = 0 if side == 0 else 4
-            ipol = want if north else 4 - want
-            els = idx[c, :]
-            els = els[els >= 0]
-            for e in els:
-                for j in range(NP1):
-                    g2e.append((ipol, j, e + 1))
+        for dt in (-1, 0, 1):
+            for dr in (-1, 0, 1):
+                if (dt, dr) == (0, 0) or not (0 <= bt + dt < nth) or not (0 <= br + dr < nranks_r):
+                    continue
+                if dr != 0 and not row_shared[dr]:
+                    continue
+                peer = (bt + dt) * nranks_r + (br + dr)
+                if dr == 0:
+                    # the peer has the same radial block: the whole column of this domain's nodes
+                    ids = tloc_col[dt] * nloc + np.arange(nloc) + 1
+                elif dt == 0:
+                    ids = np.arange(4 * ncol + 1) * nloc + rloc_row[dr] + 1
+                else:
+                    ids = np.array([tloc_col[dt] * nloc + rloc_row[dr] + 1])
+                # nodes of the column that no element of this rank touches (another domain's gap) are not sent
+                ids = ids[np.isin(ids, igloc)]
+                if ids.size:
+                    peers.append(peer)
+                    lists.append(ids)
         h.nmsg = len(peers)
+        if h.nmsg == 0:
+            return h
         h.list_peer = np.array(peers, dtype=np.int32)
         h.sizemsg = np.array([len(l) for l in lists], dtype=np.int32)
         m = max(len(l) for l in lists)
         h.glocal_index_msg = np.zeros((h.nmsg, m), dtype=np.int32)
         for k, l in enumerate(lists):
             h.glocal_index_msg[k, :len(l)] = l
-        g2e = np.array(sorted(g2e, key=lambda t: (t[2], t[1], t[0])), dtype=np.int32)
-        h.glob2el = g2e.reshape(-1, 3)
+        # glob2el (def_grid.f90:95-180): element-local points, in memory order, whose number is sent
+        sent = np.unique(np.concatenate(lists))
+        hit = np.nonzero(np.isin(igloc, sent))[0]
+        e, q = hit // NPT, hit % NPT
+        h.glob2el = np.stack([q % NP1, q // NP1, e + 1], axis=1).astype(np.int32)
         h.num_comm_gll = h.glob2el.shape[0]
         return h
 
-    halo_s = halo(solid, idx_s, spec.nrnode_solid, ig_s)
-    halo_f = halo(fluid, idx_f, spec.nrnode_fluid, ig_f)
+    halo_s = halo(solid, idx_s, False, r0_s, nloc_s, ig_s)
+    halo_f = halo(fluid, idx_f, True, r0_f, nloc_f, ig_f)
 
     return LocalMesh(
-        spec=spec, basis=basis, rank=rank, nranks=nranks, it0=it0, it1=it1,
+        spec=spec, basis=basis, rank=rank, nranks=nranks, it0=it0, it1=it1, nranks_r=nranks_r, ir0=ir0, ir1=ir1,
         solid=solid, fluid=fluid, nel_solid=solid.nel, nel_fluid=fluid.nel,
         igloc_solid=ig_s, igloc_fluid=ig_f, nglob_solid=nglob_s, nglob_fluid=nglob_f,
         axis_solid=solid.axis.astype(np.int32), axis_fluid=fluid.axis.astype(np.int32),
@@ -334,11 +379,13 @@ def surface_receivers(mesh: LocalMesh, colat_deg) -> Dict[str, np.ndarray]:
     top = np.nonzero(es.ir == spec.nr - 1)[0]
     xi, th, *_ = element_coords(es, mesh.basis)
     rec, keep = [], []
+    if top.size == 0:                # a radial block below the surface holds no receivers
+        return {"recfile_el": np.zeros((0, 3), dtype=np.int32), "index": np.zeros(0, dtype=np.int64)}
     colat = np.deg2rad(np.atleast_1d(np.asarray(colat_deg, dtype=np.float64)))
     lo = spec.theta_edges[mesh.it0]
     hi = spec.theta_edges[mesh.it1]
     for k, c in enumerate(colat):
-        owner_ok = (lo <= c < hi) or (mesh.rank == mesh.nranks - 1 and c == hi)
+        owner_ok = (lo <= c < hi) or (mesh.it1 == spec.ntheta and c == hi)
         if not owner_ok:
             continue
         d = np.abs(th[top, :] - c)

@@ -198,12 +198,12 @@ def build_problem(spec: MeshSpec, source: Optional[SourceParams] = None, *, rank
                   strain_it: int = 0, courant: float = 0.6, deltat: Optional[float] = None,
                   rec_colat_deg=None, dump: bool = False, energy: bool = False, chunk_cols: int = 32,
                   threads: Optional[int] = None, dump_type: str = "displ_only",
-                  dump_block=(0, 4, 0, 4)) -> Problem:
+                  dump_block=(0, 4, 0, 4), nranks_r: int = 1) -> Problem:
     assert time_scheme in TIME_SCHEMES
     source = source or SourceParams()
     src_type = source.src_type1
     basis = SpectralBasis(spec.npol)
-    mesh = build_rank(spec, rank, nranks, basis)
+    mesh = build_rank(spec, rank, nranks, basis, nranks_r)
     if deltat is None:
         deltat = stable_timestep(spec, basis, courant)
         if time_scheme != "newmark2":
@@ -264,6 +264,37 @@ def build_problem(spec: MeshSpec, source: Optional[SourceParams] = None, *, rank
     else:
         inv_mass_fluid = np.zeros((0, 5, 5))
     del parts
+    if nranks_r > 1:
+        # the arrays above cover whole columns (the mass matrix is assembled over them); keep this
+        # rank's radial block
+        IT, IR = np.meshgrid(cols, np.arange(spec.nr), indexing="ij")
+        IR = IR.reshape(-1)
+        fl = spec.fluid_ir[IR]
+        sel_s = (IR[~fl] >= mesh.ir0) & (IR[~fl] < mesh.ir1)
+        sel_f = (IR[fl] >= mesh.ir0) & (IR[fl] < mesh.ir1)
+        n_s, n_f = sel_s.size, sel_f.size
+
+        def cut(a, sel, n):
+            return a[sel] if isinstance(a, np.ndarray) and a.ndim >= 1 and a.shape[0] == n else a
+
+        solid = {k: cut(v, sel_s, n_s) for k, v in solid.items()}
+        pw_s = {k: cut(v, sel_s, n_s) for k, v in pw_s.items()}
+        if att_d is not None:
+            att_d = {k: cut(v, sel_s, n_s) for k, v in att_d.items()}
+        inv_mass_rho = inv_mass_rho[sel_s]
+        if um_s is not None:
+            um_s = um_s[sel_s]
+        if has_fluid:
+            fluid = {k: cut(v, sel_f, n_f) for k, v in fluid.items()}
+            pw_f = {k: cut(v, sel_f, n_f) for k, v in pw_f.items()}
+            inv_rho_fluid, fsm, inv_mass_fluid = inv_rho_fluid[sel_f], fsm[sel_f], inv_mass_fluid[sel_f]
+            if um_f is not None:
+                um_f = um_f[sel_f]
+        if mesh.nel_fluid == 0:
+            fluid, pw_f = {}, {k: np.zeros((0, 5, 5), np.float32) for k in pw_s}
+            inv_rho_fluid = fsm = np.zeros((0, 5, 5), np.float32)
+            inv_mass_fluid = np.zeros((0, 5, 5))
+        assert inv_mass_rho.shape[0] == mesh.nel_solid
 
     if mesh.nel_bdry:
         bidx = mesh.bdry_solid_el - 1

@@ -72,16 +72,25 @@ def compute_source_terms(mesh: LocalMesh, p: SourceParams, pw: Dict[str, np.ndar
     src1 = p.src_type1
     st = np.zeros((3, 8, 5, 5), dtype=np.float32)
     ielsrc = np.zeros(8, dtype=np.int32)
-    if mesh.rank != 0:
-        return 0, ielsrc, st
     spec, es, b = mesh.spec, mesh.solid, mesh.basis
     zsrc = spec.router - p.depth
-    # find_srcloc (source.f90:454-476): on-axis GLL point closest in z
+    # find_srcloc (source.f90:454-476): on-axis GLL point closest in z, over all ranks
     cand = np.nonzero(es.axis & es.north)[0]
     eta = b.eta
+    if mesh.it0 != 0 or cand.size == 0:
+        return 0, ielsrc, st
     r = 0.5 * ((1 - eta)[None, :] * es.r_a[cand, None] + (1 + eta)[None, :] * es.r_b[cand, None])
     d = np.abs(r - zsrc)
     dmin = d.min()
+    sol = np.nonzero(~spec.fluid_ir)[0]
+    r_all = 0.5 * ((1 - eta)[None, :] * spec.r_edges[sol, None] + (1 + eta)[None, :] * spec.r_edges[sol + 1, None])
+    if dmin > np.abs(r_all - zsrc).min() * (1 + 1e-12) + 1e-6:
+        return 0, ielsrc, st                                   # another radial block holds the source
+    jh = np.argwhere(d <= dmin * (1 + 1e-12) + 1e-6)
+    for a, j in jh:
+        e = cand[a]
+        on_cut = (es.ir[e] == mesh.ir0 and j == 0 and mesh.ir0 > 0) or (es.ir[e] == mesh.ir1 - 1 and j == 4 and mesh.ir1 < spec.nr)
+        assert not (mesh.nranks_r > 1 and on_cut), "source on a radial cut: move the source or the cut"
     hits = np.argwhere(d <= dmin * (1 + 1e-12) + 1e-6)
     srcs = [(cand[a], 0, j) for a, j in hits][:2]          # (iel, ipol, jpol)
     # work only on the elements that share a global point with a source element

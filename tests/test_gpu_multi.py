@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, src, n, ndev, out_dir, strict):
+def _worker(rank, world, port, src, n, ndev, out_dir, strict, nranks_r=1):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -31,7 +31,7 @@ def _worker(rank, world, port, src, n, ndev, out_dir, strict):
     from tests.util import make_problem
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        prob = make_problem(src, anel=True, ntheta=16, nr=18, niter=n, rank=rank, nranks=world)
+        prob = make_problem(src, anel=True, ntheta=16, nr=18, niter=n, rank=rank, nranks=world, nranks_r=nranks_r)
         loop = solver.time_loop(prob, device=rank % ndev, strict=strict)
         connect_ranks(loop, rank, world)
         loop.run(n)
@@ -43,9 +43,12 @@ def _worker(rank, world, port, src, n, ndev, out_dir, strict):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("world,src,strict", [(2, "mtr", True), (4, "explosion", True), (8, "mtr", True),
-                                              (2, "mtr", False), (8, "mtr", False)])
-def test_process_per_rank_ipc_halo_matches_oracle(world, src, strict, tmp_path):
+@pytest.mark.parametrize("world,src,strict,nranks_r", [(2, "mtr", True, 1), (4, "explosion", True, 1), (8, "mtr", True, 1),
+                                                       (2, "mtr", False, 1), (8, "mtr", False, 1),
+                                                       (4, "mtr", True, 2), (8, "mtr", False, 2)])
+def test_process_per_rank_ipc_halo_matches_oracle(world, src, strict, nranks_r, tmp_path):
+    """nranks_r = 2: theta x r blocks, up to 5 neighbours per rank here and corner points shared
+    by four ranks."""
     import torch
     import torch.multiprocessing as mp
     from axisem_b200.capi import connect_local, run_group
@@ -55,8 +58,8 @@ def test_process_per_rank_ipc_halo_matches_oracle(world, src, strict, tmp_path):
     if world == 8 and ndev < 8:
         pytest.skip("the 8-rank case wants 8 distinct devices (peer stores over NVLink)")
     n = 30 if ndev >= world else 8          # sharing one GPU time-slices the spinning waits
-    mp.spawn(_worker, args=(world, _free_port(), src, n, ndev, str(tmp_path), strict), nprocs=world, join=True)
-    probs = [make_problem(src, anel=True, ntheta=16, nr=18, niter=n, rank=r, nranks=world) for r in range(world)]
+    mp.spawn(_worker, args=(world, _free_port(), src, n, ndev, str(tmp_path), strict, nranks_r), nprocs=world, join=True)
+    probs = [make_problem(src, anel=True, ntheta=16, nr=18, niter=n, rank=r, nranks=world, nranks_r=nranks_r) for r in range(world)]
     ol = [oracle.make_loop(p) for p in probs]
     olib = oracle.load()
     connect_local(olib, ol)

@@ -211,6 +211,44 @@ def test_two_slices_loopback_matches_oracle_and_one_slice(src):
     assert rel_l2(s2, s1) <= 1e-5
 
 
+@pytest.mark.parametrize("nranks,nranks_r,strict", [(4, 2, True), (6, 3, True), (8, 2, True), (8, 2, False)])
+def test_theta_r_blocks_loopback(nranks, nranks_r, strict):
+    """theta x r decomposition (up to 8 neighbours, corner points shared by four ranks): the ranks
+    on one GPU over the direct-pointer halo == the oracle with the same blocks, and == the
+    undivided run within the summation-order tolerance."""
+    from axisem_b200 import solver
+    from axisem_b200.capi import connect_local, run_group
+    from oracle import oracle
+    n = 60
+    probs = [make_problem("mtr", anel=True, niter=n, rank=r, nranks=nranks, nranks_r=nranks_r, t_0=3.0)
+             for r in range(nranks)]
+    lib, gl = solver.time_loop_group(probs, strict=strict)
+    olib = oracle.load()
+    ol = [oracle.make_loop(p) for p in probs]
+    connect_local(olib, ol)
+    run_group(lib, gl, n)
+    for l in gl:
+        l.synchronize()
+    run_group(olib, ol, n)
+    for g, o in zip(gl, ol):
+        for f in ("disp", "velo", "chi", "dchi"):
+            if strict:
+                assert np.array_equal(g.get(f), o.get(f)), f
+            elif o.get(f).size and np.abs(o.get(f)).max() > 0:
+                assert rel_l2(g.get(f), o.get(f)) <= 1e-5, f
+        if strict:
+            assert np.array_equal(g.seismograms(), o.seismograms())
+    one = make_problem("mtr", anel=True, niter=n, t_0=3.0)
+    G1 = solver.time_loop(one, strict=strict)
+    G1.run(n)
+    s1 = G1.seismograms()
+    s2 = np.zeros_like(s1)
+    for p, g in zip(probs, gl):
+        if p.num_rec:
+            s2[:, p.rec_index, :] = g.seismograms()
+    assert np.abs(s1).max() > 0 and rel_l2(s2, s1) <= 1e-5
+
+
 @pytest.mark.parametrize("src", ["vertforce", "thetaforce", "mrr", "mpr", "mtt_m_mpp"])
 def test_other_source_types(src):
     """The remaining src_type(2) values (source.f90:985-1168); vertforce/thetaforce are what the
