@@ -230,14 +230,20 @@ def test_theta_r_blocks_loopback(nranks, nranks_r, strict):
     for l in gl:
         l.synchronize()
     run_group(olib, ol, n)
+    err = {f: 0.0 for f in ("disp", "velo", "chi", "dchi")}
+    ref = dict(err)
     for g, o in zip(gl, ol):
-        for f in ("disp", "velo", "chi", "dchi"):
+        for f in err:
             if strict:
                 assert np.array_equal(g.get(f), o.get(f)), f
-            elif o.get(f).size and np.abs(o.get(f)).max() > 0:
-                assert rel_l2(g.get(f), o.get(f)) <= 1e-5, f
+            err[f] += float(np.sum((g.get(f).astype(np.float64) - o.get(f)) ** 2))
+            ref[f] += float(np.sum(o.get(f).astype(np.float64) ** 2))
         if strict:
             assert np.array_equal(g.seismograms(), o.seismograms())
+    for f in err:
+        # product build: the tolerance on the whole field (blocks the wave has not reached hold
+        # only its 1e-30 tail, which has no relative accuracy of its own)
+        assert ref["disp"] > 0 and np.sqrt(err[f]) <= 1e-5 * np.sqrt(ref[f]), f   # (the fluid is still at rest)
     one = make_problem("mtr", anel=True, niter=n, t_0=3.0)
     G1 = solver.time_loop(one, strict=strict)
     G1.run(n)

@@ -1,9 +1,10 @@
 #!/bin/bash
-# A/B of the run-time variants on the bench workload (short runs, one JSON line each)
+# A/B of the run-time variants on the bench workload (short runs, one JSON line each);
+# AB_FLAGS: extra bench.py flags (e.g. "--full-memvars --ntheta 1792")
 mkdir -p gpurun_out
 run() { # name, env...
     local name=$1; shift
-    env "$@" timeout 300 python bench.py --steps 30 --warmup 5 --repeats 3 --no-cpu-baseline --no-e2e --no-check \
+    env "$@" timeout 300 python bench.py --steps 30 --warmup 5 --repeats 3 --no-cpu-baseline --no-e2e --no-check ${AB_FLAGS:-} \
         > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
     python - "$name" <<'PY'
 import json,sys
