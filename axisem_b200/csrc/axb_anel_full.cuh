@@ -21,7 +21,13 @@
 
 namespace axb {
 
-constexpr int TEA = 8;                    // elements per CTA
+#ifndef AXB_ANEL_MINB
+#define AXB_ANEL_MINB 4                   // resident CTAs per SM the register budget is set for
+#endif
+#ifndef AXB_ANEL_TEA
+#define AXB_ANEL_TEA 5                    // 125 points on 128 lanes; 8 (200 on 224) measured 9 % slower
+#endif
+constexpr int TEA = AXB_ANEL_TEA;         // elements per CTA
 constexpr int TPA = TEA * NPT;            // points per CTA
 constexpr int ANEL_THREADS = (TPA + 31) / 32 * 32;
 
@@ -42,8 +48,12 @@ struct AnelFullArgs {
     float *src_tr_tm1;                    // (25, nel)
 };
 
-template <int ORDER>
-__global__ void __launch_bounds__(ANEL_THREADS)
+// NSLS > 0: the number of SLS at compile time — the 6 x NSLS memory variables of the point are
+// loaded once, all loads in flight together, and stay in registers from the K term to the update
+// (the run-time version read them twice, one dependent round trip per SLS: ncu showed 18 warps
+// per issue waiting on the long scoreboard at 26 % issue utilisation).  NSLS = 0: any n_sls.
+template <int ORDER, int NSLS>
+__global__ void __launch_bounds__(ANEL_THREADS, NSLS > 0 ? AXB_ANEL_MINB : 1)
 k_anel_full(const __grid_constant__ GMat G, const __grid_constant__ AnelFullArgs a) {
     __shared__ GMat sG;
     __shared__ float sU[3][TPA];          // u1, u2, u3
@@ -59,7 +69,8 @@ k_anel_full(const __grid_constant__ GMat G, const __grid_constant__ AnelFullArgs
     const int e25 = el * NPT;
     const size_t p = (size_t)NPT * e + q;
     const bool ax = pt && a.axis[e] != 0;
-    const int n_sls = a.n_sls;
+    constexpr bool CT = NSLS > 0;
+    const int n_sls = CT ? NSLS : a.n_sls;
 
     float g2t_row[NP], g2_col[NP], g2_row[NP], g2t_col[NP], gat_row[NP], ga_row[NP], g0[NP];
 #pragma unroll
@@ -86,18 +97,46 @@ k_anel_full(const __grid_constant__ GMat G, const __grid_constant__ AnelFullArgs
         if (ORDER == 2) { sT[0][t] = u1 - 2 * u2; sT[1][t] = u2 - 2 * u1; }
     }
     const float *mv = a.memvar + (size_t)NPT * 6 * n_sls * e + q;    // mv[25 * (v + 6 j)]
+    float mreg[CT ? NSLS : 1][6];
+    // everything the update needs from HBM, requested before the first barrier
+    float dzdeta = 0.f, dzdxi = 0.f, dsdeta = 0.f, dsdxi = 0.f, is = 0.f, dmu = 0.f, dka = 0.f, tr_old = 0.f;
+    float dev_old[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (CT && pt) {
+#pragma unroll
+        for (int s = 0; s < (CT ? NSLS : 1); s++)
+#pragma unroll
+            for (int v = 0; v < 6; v++)
+                mreg[s][v] = (ORDER == 0 && (v == 3 || v == 5)) ? 0.f : mv[NPT * (v + 6 * s)];
+    }
+    if (a.do_update && pt) {
+        dzdeta = a.Dze[p]; dzdxi = a.Dzx[p]; dsdeta = a.Dse[p]; dsdxi = a.Dsx[p];
+        is = a.inv_s[p]; dmu = a.dmu[p]; dka = a.dka[p];
+        tr_old = a.src_tr_tm1[p];
+#pragma unroll
+        for (int v = 0; v < 6; v++) dev_old[v] = a.src_dev_tm1[(size_t)NPT * 6 * e + q + NPT * v];
+    }
 
     // ---------------------------------------------------------------- anelastic K term ----
     float r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f, r5 = 0.f, r6 = 0.f;
     float yl = 0.f;
     if (a.do_stiff) {
         if (pt) {
-            for (int s = 0; s < n_sls; s++) {
-                const float *m = mv + NPT * 6 * s;
-                r1 = r1 + m[0]; r2 = r2 + m[NPT]; r3 = r3 + m[2 * NPT];
-                if (ORDER != 0) r4 = r4 + m[3 * NPT];
-                r5 = r5 + m[4 * NPT];
-                if (ORDER != 0) r6 = r6 + m[5 * NPT];
+            if (CT) {
+#pragma unroll
+                for (int s = 0; s < (CT ? NSLS : 1); s++) {
+                    r1 = r1 + mreg[s][0]; r2 = r2 + mreg[s][1]; r3 = r3 + mreg[s][2];
+                    if (ORDER != 0) r4 = r4 + mreg[s][3];
+                    r5 = r5 + mreg[s][4];
+                    if (ORDER != 0) r6 = r6 + mreg[s][5];
+                }
+            } else {
+                for (int s = 0; s < n_sls; s++) {
+                    const float *m = mv + NPT * 6 * s;
+                    r1 = r1 + m[0]; r2 = r2 + m[NPT]; r3 = r3 + m[2 * NPT];
+                    if (ORDER != 0) r4 = r4 + m[3 * NPT];
+                    r5 = r5 + m[4 * NPT];
+                    if (ORDER != 0) r6 = r6 + m[5 * NPT];
+                }
             }
             const float vse = a.Vse[p], vsx = a.Vsx[p], vze = a.Vze[p], vzx = a.Vzx[p];
             yl = a.Y[p];
@@ -200,8 +239,6 @@ k_anel_full(const __grid_constant__ GMat G, const __grid_constant__ AnelFullArgs
     if (!a.do_update || !pt) return;
 
     // ---------------------------------------------- strain (compute_strain_att_el_4) ----
-    const float dzdeta = a.Dze[p], dzdxi = a.Dzx[p], dsdeta = a.Dse[p], dsdxi = a.Dsx[p];
-    const float is = a.inv_s[p];
     const int xi0 = e25 + 5 * j, et0 = e25 + i;
     // axisym_gradient_solid_el_4 of the plane f
 #define AXB_GRAD(f, ds, dz)                                                               \
@@ -246,7 +283,6 @@ k_anel_full(const __grid_constant__ GMat G, const __grid_constant__ AnelFullArgs
     // ------------------------------------ memory variables (time_step_memvars_4) ----
     float trace = g1 + g2;
     trace = trace + g3;
-    const float dmu = a.dmu[p], dka = a.dka[p];
     const double third = 1.0 / 3.0;
     const double dm2 = f2d(dmu * 2);
     float src[6];
@@ -259,14 +295,15 @@ k_anel_full(const __grid_constant__ GMat G, const __grid_constant__ AnelFullArgs
     const float src_tr = dka * trace;
     float *dev_tm1 = a.src_dev_tm1 + (size_t)NPT * 6 * e + q;
     float *tr_tm1 = a.src_tr_tm1 + p;
-    const double d_tr_t = f2d(src_tr), d_tr_tm1 = f2d(*tr_tm1);
+    const double d_tr_t = f2d(src_tr), d_tr_tm1 = f2d(tr_old);
     double d_t[6], d_tm1[6];
 #pragma unroll
-    for (int v = 0; v < 6; v++) { d_t[v] = f2d(src[v]); d_tm1[v] = f2d(dev_tm1[NPT * v]); }
+    for (int v = 0; v < 6; v++) { d_t[v] = f2d(src[v]); d_tm1[v] = f2d(dev_old[v]); }
     const double2 *c_mu = a.c_mu_tab + (size_t)n_sls * a.qidx_mu[e];
     const double2 *c_ka = a.c_ka_tab + (size_t)n_sls * a.qidx_ka[e];
     float *mvw = a.memvar + (size_t)NPT * 6 * n_sls * e + q;
-    for (int s = 0; s < n_sls; s++) {
+#pragma unroll
+    for (int s = 0; s < (CT ? NSLS : n_sls); s++) {
         const double2 cm = c_mu[s], ck = c_ka[s];
         const double ew = a.exp_w[s];
         const double tr_buf = rnd32(ck.x * d_tr_t + ck.y * d_tr_tm1);
@@ -275,8 +312,9 @@ k_anel_full(const __grid_constant__ GMat G, const __grid_constant__ AnelFullArgs
         for (int v = 0; v < 6; v++) {
             if (ORDER == 0 && (v == 3 || v == 5)) continue;
             const double dev_buf = rnd32(cm.x * d_t[v] + cm.y * d_tm1[v]);
-            if (v < 3) m[NPT * v] = d2f(ew * f2d(m[NPT * v]) + dev_buf + tr_buf);
-            else m[NPT * v] = d2f(ew * f2d(m[NPT * v]) + dev_buf);
+            const float old = CT ? mreg[CT ? s : 0][v] : m[NPT * v];
+            if (v < 3) m[NPT * v] = d2f(ew * f2d(old) + dev_buf + tr_buf);
+            else m[NPT * v] = d2f(ew * f2d(old) + dev_buf);
         }
     }
     *tr_tm1 = src_tr;

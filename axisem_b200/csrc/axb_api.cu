@@ -1231,9 +1231,15 @@ static void launch_anel_full(axb_handle_s *h, int do_stiff, int do_update, int m
     for (int k = 0; k < 8; k++) a.exp_w[k] = k < h->n_sls ? h->exp_w_h[k] : 0.0;
     a.memvar = h->memvar; a.src_dev_tm1 = h->src_dev_tm1; a.src_tr_tm1 = h->src_tr_tm1;
     const int grid = cdiv(h->nel_s, TEA);
-    if (h->order == 0) LAUNCH(h, k_anel_full<0>, grid, ANEL_THREADS, h->G, a);
-    else if (h->order == 1) LAUNCH(h, k_anel_full<1>, grid, ANEL_THREADS, h->G, a);
-    else LAUNCH(h, k_anel_full<2>, grid, ANEL_THREADS, h->G, a);
+    if (h->n_sls == 5) {
+        if (h->order == 0) LAUNCH(h, (k_anel_full<0, 5>), grid, ANEL_THREADS, h->G, a);
+        else if (h->order == 1) LAUNCH(h, (k_anel_full<1, 5>), grid, ANEL_THREADS, h->G, a);
+        else LAUNCH(h, (k_anel_full<2, 5>), grid, ANEL_THREADS, h->G, a);
+    } else {
+        if (h->order == 0) LAUNCH(h, (k_anel_full<0, 0>), grid, ANEL_THREADS, h->G, a);
+        else if (h->order == 1) LAUNCH(h, (k_anel_full<1, 0>), grid, ANEL_THREADS, h->G, a);
+        else LAUNCH(h, (k_anel_full<2, 0>), grid, ANEL_THREADS, h->G, a);
+    }
 }
 // S_A of one (sub)step: predictor/drift + K u, with the anelastic work fused (coarse-grained)
 // or in the kernel behind it (all 25 points).  anel: 0 none, 1 K term only, 2 K term + update

@@ -22,6 +22,7 @@ for v in "$@"; do
     nolean) run nolean AXB_LEAN=0 ;;
     noahead) run noahead AXB_CORR_AHEAD=0 ;;
     classic) run classic AXB_LEAN=0 AXB_GRAPH=0 ;;
+    nograph) run nograph AXB_GRAPH=0 ;;
     *) run "$v" AXB_LIBRARY="$PWD/axisem_b200/libaxisem_b200_$v.so" ;;
     esac
 done
