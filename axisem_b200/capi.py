@@ -62,7 +62,7 @@ OPS = {"solid_stiffness": 0, "anel_stiffness": 1, "fluid_stiffness": 2, "pdistsu
 # every symbol include/axisem_b200.h declares
 SYMBOLS = ["last_error", "create", "destroy", "set_mesh", "set_solid_terms", "set_fluid_terms",
            "set_mass", "set_energy", "set_sponge", "set_sf_boundary", "set_attenuation", "set_source",
-           "set_stf_values", "set_stf_params", "set_receivers", "set_kwf", "set_dump", "snapshot_layout", "set_halo", "set_time",
+           "set_stf_values", "set_stf_params", "set_receivers", "set_kwf", "set_dump", "snapshot_layout", "set_xdmf", "xdmf_count", "fetch_xdmf", "set_halo", "set_time",
            "finalize_setup", "set_stream", "synchronize", "connect_local", "ipc_blob_bytes", "ipc_export", "ipc_import", "run", "run_group",
            "profile", "get_profile", "iter", "nseismo", "nstrain", "gpu_launches", "fetch_seismograms",
            "fetch_snapshots", "fetch_energy", "get_state", "set_state", "apply_op"]
@@ -222,6 +222,17 @@ class TimeLoop:
                               C.c_int32(je), _fp(ps["DsDeta_over_J"], k), _fp(ps["DzDeta_over_J"], k),
                               _fp(ps["DsDxi_over_J"], k), _fp(ps["DzDxi_over_J"], k), _fp(ps["inv_s"], k),
                               _fp(p.pw_fluid.get("inv_s"), k)))
+        x = getattr(p, "xdmf", None)
+        if x is not None:
+            ps, pf = p.pw_solid, p.pw_fluid
+            ck(fn["set_xdmf"](h, C.c_int32(x["snap_it"]), C.c_int32(x["i_arr"].size), C.c_int32(x["j_arr"].size),
+                              _ip(x["i_arr"], k), _ip(x["j_arr"], k), _ip(x["plotting_mask"], k),
+                              _ip(x["mapping_ijel_iplot"], k), C.c_int32(x["npoint_plot"]),
+                              _fp(ps["DsDeta_over_J"], k), _fp(ps["DzDeta_over_J"], k), _fp(ps["DsDxi_over_J"], k),
+                              _fp(ps["DzDxi_over_J"], k), _fp(ps["inv_s"], k),
+                              _fp(pf.get("DsDeta_over_J"), k), _fp(pf.get("DzDeta_over_J"), k),
+                              _fp(pf.get("DsDxi_over_J"), k), _fp(pf.get("DzDxi_over_J"), k),
+                              _fp(pf.get("inv_s"), k), _fp(p.inv_rho_fluid, k)))
         for dom, hs in ((0, m.halo_solid), (1, m.halo_fluid)):
             if hs.nmsg:
                 maxmsg = hs.glocal_index_msg.shape[1]
@@ -297,6 +308,16 @@ class TimeLoop:
         if n > 0:
             self.lib.check(self.lib.fn["fetch_snapshots"](
                 self.h, C.c_int32(first), C.c_int32(n), out.ctypes.data_as(_F)))
+        return out
+
+    def xdmf_snapshots(self, first: int = 0, n: Optional[int] = None) -> np.ndarray:
+        """(5, nsnap, npoint_plot): u_s, u_p, u_z, straintrace, curlinplane (axb_fetch_xdmf)."""
+        cnt = C.c_int32()
+        self.lib.check(self.lib.fn["xdmf_count"](self.h, C.byref(cnt)))
+        n = cnt.value - first if n is None else n
+        out = np.zeros((5, n, self.prob.xdmf["npoint_plot"]), dtype=np.float32)
+        if n > 0:
+            self.lib.check(self.lib.fn["fetch_xdmf"](self.h, C.c_int32(first), C.c_int32(n), out.ctypes.data_as(_F)))
         return out
 
     def energy(self, first: int = 0, n: Optional[int] = None) -> np.ndarray:

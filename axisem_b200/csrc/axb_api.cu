@@ -134,6 +134,13 @@ struct axb_handle_s {
     int *d_kwf_mask = nullptr, *d_kwf_map = nullptr;
     float *d_inv_rho = nullptr, *d_Dse_f = nullptr, *d_Dze_f = nullptr, *d_Dsx_f = nullptr, *d_Dzx_f = nullptr;
     float *d_snap = nullptr;
+    // xdmf snapshots (axb_set_xdmf)
+    bool have_xdmf = false;
+    int snap_it = 0, isnap = 0, nsnap_max = 0, npoint_plot = 0;
+    int *d_xmap = nullptr;
+    float *d_xsnap = nullptr;
+    float *xs_Dse = nullptr, *xs_Dze = nullptr, *xs_Dsx = nullptr, *xs_Dzx = nullptr, *xs_inv_s = nullptr;
+    float *xf_Dse = nullptr, *xf_Dze = nullptr, *xf_Dsx = nullptr, *xf_Dzx = nullptr, *xf_inv_s = nullptr, *xf_inv_rho = nullptr;
     // dump_type strain_only / fullfields (axb_set_dump)
     int dump_type = AXB_DUMP_DISPL_ONLY, ibeg = 0, iend = 4, jbeg = 0, jend = 4;
     float *dDse = nullptr, *dDze = nullptr, *dDsx = nullptr, *dDzx = nullptr, *d_inv_s_dump = nullptr, *d_inv_s_f = nullptr;
@@ -796,6 +803,62 @@ int axb_set_dump(axb_handle h, int32_t dump_type, int32_t ibeg, int32_t iend, in
     UP(h->d_inv_s_dump, inv_s_solid, n); UP(h->d_inv_s_f, inv_s_fluid, nf);
     return 0;
 }
+// xdmf snapshots: the host's plot-point maps (dump_xdmf_grid, meshes_io.F90:110-437) become one
+// entry per element-local point, visited as xdmf_mapping does (wavefields_io.f90:690-738: the
+// corners of the plot cells, so nothing is plotted with fewer than two rows or columns)
+int axb_set_xdmf(axb_handle h, int32_t snap_it, int32_t i_n_xdmf, int32_t j_n_xdmf,
+                 const int32_t *i_arr_xdmf, const int32_t *j_arr_xdmf,
+                 const int32_t *plotting_mask, const int32_t *mapping_ijel_iplot, int32_t npoint_plot,
+                 const float *DsDeta_over_J_sol, const float *DzDeta_over_J_sol,
+                 const float *DsDxi_over_J_sol, const float *DzDxi_over_J_sol, const float *inv_s_solid,
+                 const float *DsDeta_over_J_flu, const float *DzDeta_over_J_flu,
+                 const float *DsDxi_over_J_flu, const float *DzDxi_over_J_flu, const float *inv_s_fluid,
+                 const float *inv_rho_fluid) {
+    if (use(h)) return 1;
+    if (snap_it < 1) return fail("axb_set_xdmf: snap_it must be positive");
+    if (i_n_xdmf < 1 || i_n_xdmf > NP || j_n_xdmf < 1 || j_n_xdmf > NP) return fail("axb_set_xdmf: bad i_n_xdmf / j_n_xdmf");
+    for (int k = 0; k < i_n_xdmf; k++) if (i_arr_xdmf[k] < 0 || i_arr_xdmf[k] >= NP) return fail("axb_set_xdmf: i_arr_xdmf out of range");
+    for (int k = 0; k < j_n_xdmf; k++) if (j_arr_xdmf[k] < 0 || j_arr_xdmf[k] >= NP) return fail("axb_set_xdmf: j_arr_xdmf out of range");
+    if (!DsDeta_over_J_sol || !DzDeta_over_J_sol || !DsDxi_over_J_sol || !DzDxi_over_J_sol || !inv_s_solid)
+        return fail("axb_set_xdmf: NULL solid plane");
+    if (h->nel_f > 0 && (!DsDeta_over_J_flu || !DzDeta_over_J_flu || !DsDxi_over_J_flu || !DzDxi_over_J_flu ||
+                         !inv_s_fluid || !inv_rho_fluid))
+        return fail("axb_set_xdmf: NULL fluid plane");
+    const int nelem = h->nel_s + h->nel_f;
+    std::vector<int> xmap((size_t)NPT * std::max(nelem, 1), 0);
+    for (int el = 0; el < nelem; el++)
+        for (int j = 0; j < j_n_xdmf; j++)
+            for (int i = 0; i < i_n_xdmf; i++) {
+                const size_t k = i + (size_t)i_n_xdmf * (j + (size_t)j_n_xdmf * el);
+                if (!plotting_mask[k] || i_n_xdmf < 2 || j_n_xdmf < 2) continue;
+                if (mapping_ijel_iplot[k] < 1 || mapping_ijel_iplot[k] > npoint_plot)
+                    return fail("axb_set_xdmf: mapping_ijel_iplot out of range");
+                xmap[i_arr_xdmf[i] + NP * j_arr_xdmf[j] + (size_t)NPT * el] = mapping_ijel_iplot[k];
+            }
+    h->have_xdmf = true; h->snap_it = snap_it; h->npoint_plot = npoint_plot;
+    UP(h->d_xmap, xmap.data(), xmap.size());
+    const size_t n = (size_t)NPT * h->nel_s, nf = (size_t)NPT * h->nel_f;
+    UP(h->xs_Dse, DsDeta_over_J_sol, n); UP(h->xs_Dze, DzDeta_over_J_sol, n);
+    UP(h->xs_Dsx, DsDxi_over_J_sol, n); UP(h->xs_Dzx, DzDxi_over_J_sol, n); UP(h->xs_inv_s, inv_s_solid, n);
+    if (h->nel_f > 0) {
+        UP(h->xf_Dse, DsDeta_over_J_flu, nf); UP(h->xf_Dze, DzDeta_over_J_flu, nf);
+        UP(h->xf_Dsx, DsDxi_over_J_flu, nf); UP(h->xf_Dzx, DzDxi_over_J_flu, nf);
+        UP(h->xf_inv_s, inv_s_fluid, nf); UP(h->xf_inv_rho, inv_rho_fluid, nf);
+    }
+    return 0;
+}
+int axb_xdmf_count(axb_handle h, int32_t *nsnap) { *nsnap = h->isnap; return 0; }
+int axb_fetch_xdmf(axb_handle h, int32_t first, int32_t nsnap, float *out) {
+    if (use(h)) return 1;
+    if (!h->have_xdmf) return fail("xdmf snapshots not enabled (axb_set_xdmf)");
+    if (first < 0 || nsnap < 0 || first + nsnap > h->isnap) return fail("xdmf snapshot range");
+    const size_t npts = (size_t)h->npoint_plot;
+    for (int v = 0; v < 5; v++)
+        CK(cudaMemcpyAsync(out + npts * (size_t)nsnap * v, h->d_xsnap + npts * (first + (size_t)h->nsnap_max * v),
+                           sizeof(float) * npts * nsnap, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
 static int snapshot_nvars(const axb_handle_s *h) {
     const bool mono = h->order == 0;
     if (h->dump_type == AXB_DUMP_STRAIN_ONLY) return mono ? 4 : 6;
@@ -963,6 +1026,10 @@ int axb_finalize_setup(axb_handle h) {
         if (h->dump_type != AXB_DUMP_DISPL_ONLY && !h->dDse) return fail("axb_set_dump: planes missing");
         if (dzeros(h, h->d_snap, snapshot_npoints(h) * h->nstrain_max * snapshot_nvars(h))) return 1;
     }
+    if (h->have_xdmf) {
+        h->nsnap_max = h->niter / h->snap_it + 1;            // parameters.F90:946
+        if (dzeros(h, h->d_xsnap, (size_t)std::max(h->npoint_plot, 1) * h->nsnap_max * 5)) return 1;
+    }
     if (dzeros(h, h->d_counters, 4)) return 1;
     if (dzeros(h, h->d_dyn, 4)) return 1;
     {
@@ -1043,6 +1110,7 @@ int axb_finalize_setup(axb_handle h) {
         CK(cudaFuncSetAttribute(h->solid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_solid));
     }
     h->iter = h->iseismo = h->istrain = h->ienergy = 0;
+    h->isnap = 0;
     h->finalized = true;
     CK(cudaDeviceSynchronize());
     // host copies no longer needed
@@ -1417,6 +1485,23 @@ static void launch_dumps(axb_handle_s *h) {
 }
 static void launch_wavefield_dump(axb_handle_s *h) {
     CLS(h, 6);
+    if (h->have_xdmf && h->iter % h->snap_it == 0 && h->isnap < h->nsnap_max) {
+        // glob_snapshot_xdmf (time_evol_wave.F90:1167-1176)
+        FieldDumpArgs a;
+        std::memset(&a, 0, sizeof a);
+        a.nel_s = h->nel_s; a.nel_f = h->nel_f; a.order = h->order; a.dump_type = 3;
+        a.xmap = h->d_xmap; a.ibeg = 0; a.iend = 4; a.jbeg = 0; a.jend = 4;
+        a.nstrain_max = h->nsnap_max; a.istrain = h->isnap;
+        a.axis_s = h->d_axis_s; a.axis_f = h->d_axis_f;
+        a.disp = h->disp; a.velo = h->velo; a.cs = h->css; a.chi = h->chi; a.dchi = h->dchi;
+        a.Dse = h->xs_Dse; a.Dze = h->xs_Dze; a.Dsx = h->xs_Dsx; a.Dzx = h->xs_Dzx; a.inv_s = h->xs_inv_s;
+        a.Dse_f = h->xf_Dse; a.Dze_f = h->xf_Dze; a.Dsx_f = h->xf_Dsx; a.Dzx_f = h->xf_Dzx;
+        a.inv_s_f = h->xf_inv_s; a.inv_rho = h->xf_inv_rho;
+        a.snap = h->d_xsnap; a.npts = (size_t)h->npoint_plot;
+        if (h->nel_s) LAUNCH(h, k_dump_fields_solid, std::max(1, std::min(cdiv(h->nel_s, 8), h->sms * 8)), 256, h->G, a);
+        if (h->nel_f) LAUNCH(h, k_dump_fields_fluid, h->grid_f, 256, h->G, a);
+        h->isnap++;
+    }
     if (h->have_kwf && h->strain_it > 0 && h->iter % h->strain_it == 0 && h->istrain < h->nstrain_max &&
         h->dump_type != AXB_DUMP_DISPL_ONLY) {
         // compute_strain [+ dump_velo_global] (axb_dump_fields.cuh)

@@ -8,12 +8,18 @@
 // ibeg:iend x jbeg:jend of every element for fullfields.  Runs every strain_it steps only, so the
 // mapping is the simple one: a warp per element, lane q = point (i, j), the 5x5 contractions of
 // pointwise_derivatives.f90:329-365 by shuffles (k ascending, as mxm does).
+//
+// dump_type 3 = the xdmf snapshots of glob_snapshot_xdmf (wavefields_io.f90:119-203): u_s, u_p,
+// u_z, calc_straintrace (:630-686) and calc_curlinplane (:601-627) at the plot points of
+// dump_xdmf_grid (meshes_io.F90:110-437; `xmap` = mapping_ijel_iplot where plotting_mask is set,
+// per element-local point, fluid elements first).
 #pragma once
 
 namespace axb {
 
 struct FieldDumpArgs {
-    int nel_s, nel_f, order, dump_type;      // dump_type 1 strain_only, 2 fullfields
+    int nel_s, nel_f, order, dump_type;      // dump_type 1 strain_only, 2 fullfields, 3 xdmf
+    const int *xmap;                         // xdmf: plot point (1-based) of (q, element), 0 = none
     int ibeg, iend, jbeg, jend;
     int nstrain_max, istrain;
     const int *kwf_mask, *kwf_map;
@@ -46,6 +52,7 @@ __device__ __forceinline__ float lane_f_over_s(float f, bool ax, const LaneG &L,
     return (ax && i == 0) ? dze * m1 + dzx * m2 : fs;
 }
 __device__ __forceinline__ long dump_slot(const FieldDumpArgs &a, bool fluid, int e, int q) {
+    if (a.dump_type == 3) return (long)a.xmap[q + (size_t)NPT * ((size_t)e + (fluid ? 0 : a.nel_f))] - 1;
     if (a.dump_type == 1) {
         const size_t pk = q + (size_t)NPT * ((size_t)e + (fluid ? a.nel_s : 0));
         return a.kwf_mask[pk] ? (long)a.kwf_map[pk] - 1 : -1;
@@ -108,6 +115,12 @@ k_dump_fields_solid(const __grid_constant__ GMat G, const __grid_constant__ Fiel
         if (!active) continue;
         const long ct = dump_slot(a, false, e, q);
         if (ct < 0) continue;
+        if (a.dump_type == 3) {
+            base[ct] = di ? u1 + u2 : u1; base[ct + vs] = di ? u1 - u2 : u2; base[ct + 2 * vs] = u3;
+            base[ct + 3 * vs] = E_tr;
+            base[ct + 4 * vs] = g.dz - h3.ds;        // d_z u_s - d_s u_z
+            continue;
+        }
         base[ct] = E_dsus; base[ct + vs] = E_dsuz; base[ct + 2 * vs] = E_dpup;
         if (!mono) { base[ct + 3 * vs] = E_dsup; base[ct + 4 * vs] = E_dzup; }
         base[ct + V_TR * vs] = E_tr;
@@ -163,6 +176,11 @@ k_dump_fields_fluid(const __grid_constant__ GMat G, const __grid_constant__ Fiel
         if (!active) continue;
         const long ct = dump_slot(a, true, e, q);
         if (ct < 0) continue;
+        if (a.dump_type == 3) {
+            base[ct] = us; base[ct + vs] = 0.f; base[ct + 2 * vs] = uz;
+            base[ct + 3 * vs] = fs + g2; base[ct + 4 * vs] = 0.f;
+            continue;
+        }
         base[ct] = E_dsus; base[ct + vs] = g1; base[ct + 2 * vs] = fs;
         if (!mono) {
             base[ct + 3 * vs] = di ? (-fs) / two : -fs;

@@ -81,6 +81,7 @@ class Problem:
     kwf: Optional[Dict[str, np.ndarray]] = None
     dump_type: str = "displ_only"      # data_io%dump_type: displ_only | strain_only | fullfields
     dump_block: tuple = (0, 4, 0, 4)   # ibeg, iend, jbeg, jend (fullfields; parameters.F90:400-403)
+    xdmf: Optional[Dict] = None        # dump_xdmf: the maps of host/xdmf.py:xdmf_maps + "snap_it"
 
     @property
     def num_rec(self):
@@ -198,7 +199,8 @@ def build_problem(spec: MeshSpec, source: Optional[SourceParams] = None, *, rank
                   strain_it: int = 0, courant: float = 0.6, deltat: Optional[float] = None,
                   rec_colat_deg=None, dump: bool = False, energy: bool = False, chunk_cols: int = 32,
                   threads: Optional[int] = None, dump_type: str = "displ_only",
-                  dump_block=(0, 4, 0, 4), nranks_r: int = 1) -> Problem:
+                  dump_block=(0, 4, 0, 4), nranks_r: int = 1, snap_it: int = 0,
+                  xdmf_opts: Optional[Dict] = None) -> Problem:
     assert time_scheme in TIME_SCHEMES
     source = source or SourceParams()
     src_type = source.src_type1
@@ -326,6 +328,11 @@ def build_problem(spec: MeshSpec, source: Optional[SourceParams] = None, *, rank
         prob.kwf = kwf_maps(mesh)
         prob.dump_type = dump_type
         prob.dump_block = tuple(int(v) for v in dump_block)
+    if snap_it > 0:
+        # SAVE_SNAPSHOTS with SNAPSHOTS_FORMAT xdmf: snap_it = floor(snap_dt / deltat) (parameters.F90:944)
+        from .xdmf import xdmf_maps
+        prob.xdmf = xdmf_maps(mesh, **(xdmf_opts or {}))
+        prob.xdmf["snap_it"] = int(snap_it)
     prob.unassem_mass_rho_solid, prob.unassem_mass_lam_fluid = um_s, um_f
     return prob
 

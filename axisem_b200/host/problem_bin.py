@@ -132,6 +132,26 @@ def problem_records(p):
                     add(f"data_pointwise%{k}_over_J_sol", p.pw_solid[k + "_over_J"], f32)
             if not p.anel:
                 add("data_pointwise%inv_s_solid", p.pw_solid["inv_s"], f32)
+    x = getattr(p, "xdmf", None)
+    add("data_io%dump_xdmf", int(x is not None), i32)
+    if x is not None:
+        add("data_time%snap_it", int(x["snap_it"]), i32)
+        add("data_io%i_arr_xdmf", x["i_arr"], i32)
+        add("data_io%j_arr_xdmf", x["j_arr"], i32)
+        add("data_mesh%plotting_mask", x["plotting_mask"], i32)
+        add("data_mesh%mapping_ijel_iplot", x["mapping_ijel_iplot"], i32)
+        add("data_mesh%npoint_plot", int(x["npoint_plot"]), i32)
+        have = set(n_ for n_, _, _ in r)
+        for k in ("DsDeta", "DzDeta", "DsDxi", "DzDxi"):
+            for dom_, pw_ in (("sol", p.pw_solid), ("flu", p.pw_fluid)):
+                if f"data_pointwise%{k}_over_J_{dom_}" not in have and k + "_over_J" in pw_:
+                    add(f"data_pointwise%{k}_over_J_{dom_}", pw_[k + "_over_J"], f32)
+        if "data_pointwise%inv_s_solid" not in have:
+            add("data_pointwise%inv_s_solid", p.pw_solid["inv_s"], f32)
+        if "data_pointwise%inv_s_fluid" not in have and "inv_s" in p.pw_fluid:
+            add("data_pointwise%inv_s_fluid", p.pw_fluid["inv_s"], f32)
+        if "data_matr%inv_rho_fluid" not in have:
+            add("data_matr%inv_rho_fluid", p.inv_rho_fluid, f32)
     for dom, hs in (("solid", m.halo_solid), ("fluid", m.halo_fluid)):
         add(f"data_comm%sizerecv_{dom}", int(hs.nmsg), i32)
         if hs.nmsg:

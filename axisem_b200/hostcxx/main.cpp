@@ -5,6 +5,7 @@
 // reference hands to its NetCDF writers as raw real(4) files:
 //   PREFIX.rankNNNN.seis.f32   recdumpvar(3, num_rec, nseismo)      (nc_routines.F90:530-540)
 //   PREFIX.rankNNNN.snap.f32   oneddumpvar(npoints, nstrain, 3)     (nc_routines.F90:248,275)
+//   PREFIX.rankNNNN.xdmf.f32   xdmf snapshot fields (npoint_plot, nsnap, 5)   (wavefields_io.f90:195-199)
 //   PREFIX.info                key = value summary
 #include <algorithm>
 #include <cstdio>
@@ -47,6 +48,8 @@ struct FileSink : axisem::OutputSink {
     }
     std::map<int, std::vector<float>> en;
     void energy(int rank, int n, const float *v) override { en[rank].assign(v, v + (size_t)4 * n); }
+    std::map<int, std::vector<float>> xd;
+    void xdmf(int rank, size_t npoint_plot, int n, const float *v) override { xd[rank].assign(v, v + npoint_plot * n * 5); }
     void write(const std::string &prefix) const {
         if (!en.empty()) {
             // energy.dat of the reference: t-less table  epot+..., summed over ranks, times two*pi
@@ -60,6 +63,16 @@ struct FileSink : axisem::OutputSink {
                 std::fprintf(f, "%zu %.6e %.6e %.6e %.6e %.6e\n", k, tp * s[0], tp * s[1], tp * s[2], tp * s[3],
                              0.5 * tp * (s[0] + s[1] + s[2] + s[3]));
             }
+            std::fclose(f);
+        }
+        for (const auto &kv : xd) {
+            // (npoint_plot, nsnap, 5): u_s, u_p, u_z, straintrace, curlinplane — host/xdmf.py:write_xdmf
+            // turns it into the reference's xdmf_snap_*.dat + xdmf_xml_NNNN.xdmf
+            char app[32];
+            std::snprintf(app, sizeof app, ".rank%04d", kv.first);
+            FILE *f = std::fopen((prefix + app + ".xdmf.f32").c_str(), "wb");
+            if (!f) throw axisem::SolverError("cannot write " + prefix + app + ".xdmf.f32");
+            std::fwrite(kv.second.data(), sizeof(float), kv.second.size(), f);
             std::fclose(f);
         }
         for (const auto &kv : ranks) {

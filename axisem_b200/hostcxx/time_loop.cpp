@@ -102,6 +102,18 @@ axb_handle hand_over(const Modules &m, int device) {
                          m.f("data_pointwise%DsDeta_over_J_sol"), m.f("data_pointwise%DzDeta_over_J_sol"),
                          m.f("data_pointwise%DsDxi_over_J_sol"), m.f("data_pointwise%DzDxi_over_J_sol"),
                          m.f("data_pointwise%inv_s_solid"), m.f("data_pointwise%inv_s_fluid")));
+    if (m.int_of("data_io%dump_xdmf", 0)) {
+        const Array &ia = m.at("data_io%i_arr_xdmf"), &ja = m.at("data_io%j_arr_xdmf");
+        const bool fl = m.int_of("data_mesh%nel_fluid") > 0;
+        CK(AXB(set_xdmf)(h, m.int_of("data_time%snap_it"), (int32_t)ia.count(), (int32_t)ja.count(), ia.i32(), ja.i32(),
+                         I("data_mesh%plotting_mask"), I("data_mesh%mapping_ijel_iplot"), m.int_of("data_mesh%npoint_plot"),
+                         m.f("data_pointwise%DsDeta_over_J_sol"), m.f("data_pointwise%DzDeta_over_J_sol"),
+                         m.f("data_pointwise%DsDxi_over_J_sol"), m.f("data_pointwise%DzDxi_over_J_sol"),
+                         m.f("data_pointwise%inv_s_solid"),
+                         fl ? m.f("data_pointwise%DsDeta_over_J_flu") : nullptr, fl ? m.f("data_pointwise%DzDeta_over_J_flu") : nullptr,
+                         fl ? m.f("data_pointwise%DsDxi_over_J_flu") : nullptr, fl ? m.f("data_pointwise%DzDxi_over_J_flu") : nullptr,
+                         fl ? m.f("data_pointwise%inv_s_fluid") : nullptr, fl ? m.f("data_matr%inv_rho_fluid") : nullptr));
+    }
     const char *dom[2] = {"solid", "fluid"};
     for (int d = 0; d < 2; d++) {
         const std::string s = dom[d];
@@ -214,6 +226,17 @@ TimeLoopResult time_loop(const std::vector<Modules> &ranks, const TimeLoopOption
                 buf.resize((size_t)4 * (iter + 1));
                 CK(AXB(fetch_energy)(H.h[r], 0, iter + 1, buf.data()));
                 sink->energy(ranks[r].int_of("data_proc%mynum"), iter + 1, buf.data());
+            }
+
+    if (sink)
+        for (int r = 0; r < n; r++)
+            if (ranks[r].int_of("data_io%dump_xdmf", 0)) {
+                int32_t cnt = 0;
+                CK(AXB(xdmf_count)(H.h[r], &cnt));
+                const size_t np = (size_t)ranks[r].int_of("data_mesh%npoint_plot");
+                buf.resize(std::max<size_t>(np * cnt * 5, 1));
+                if (cnt > 0) CK(AXB(fetch_xdmf)(H.h[r], 0, cnt, buf.data()));
+                sink->xdmf(ranks[r].int_of("data_proc%mynum"), np, cnt, buf.data());
             }
 
     TimeLoopResult res;

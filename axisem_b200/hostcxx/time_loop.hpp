@@ -31,6 +31,9 @@ public:
     // oneddumpvar(npoints, first+1 : first+n, nvars); nvars = nvar/2 of nc_routines.F90:943-1050
     // (3 for displ_only, 6 (4) for strain_only, 9 (6) for fullfields)
     virtual void snapshots(int rank, size_t npoints, int nvars, int first, int n, const float *oneddumpvar) = 0;
+    // xdmf snapshots (glob_snapshot_xdmf, wavefields_io.f90:195-199): (npoint_plot, n, 5) = u_s, u_p,
+    // u_z, straintrace, curlinplane of all n snapshots of the run
+    virtual void xdmf(int rank, size_t npoint_plot, int n, const float *fields) { (void)rank; (void)npoint_plot; (void)n; (void)fields; }
     // dump_energy: (4, n) sums of this rank for iter 0..n-1 (time_evol_wave.F90:1424-1526; the
     // writer applies psum over ranks and two*pi)
     virtual void energy(int /*rank*/, int /*n*/, const float * /*sums*/) {}

@@ -203,6 +203,33 @@ int AXB(set_dump)(axb_handle h, int32_t dump_type, int32_t ibeg, int32_t iend, i
  * _dpup, [_dsup, _dzup,] straintrace); fullfields: the same followed by velo_s, [velo_p,] velo_z */
 int AXB(snapshot_layout)(axb_handle h, int32_t *npoints, int32_t *nvars);
 
+/* XDMF snapshots (data_io.f90:36, 67-70: dump_xdmf, i_arr_xdmf, j_arr_xdmf; inparam_advanced
+ * XDMF_GLL_I / XDMF_GLL_J / XDMF_RMIN.. XDMF_COLAT_MAX).  The plot-point maps are the host's
+ * (dump_xdmf_grid, meshes_io.F90:110-437): plotting_mask and mapping_ijel_iplot are
+ * (i_n_xdmf, j_n_xdmf, nelem) Fortran order with the FLUID elements first (iel = 1..nel_fluid,
+ * then nel_fluid + 1..nelem), mapping 1-based into the npoint_plot plot points; i_arr_xdmf /
+ * j_arr_xdmf hold the GLL indices (0..npol) of the rows / columns that are plotted.  Every
+ * snap_it steps, the first time at iter 0 (dump_stuff, time_evol_wave.F90:1167-1176), the loop
+ * forms what glob_snapshot_xdmf (wavefields_io.f90:119-203) hands to its writers: the
+ * displacement in (s, phi, z) — 1/rho grad(chi) in the fluid — calc_straintrace (:630-686) and
+ * calc_curlinplane (:601-627).  The derivative planes are those of data_pointwise
+ * (DsDeta_over_J_sol, ..., inv_s_solid; *_flu, inv_s_fluid, inv_rho_fluid); fluid planes may be
+ * NULL when nel_fluid = 0.  Call before axb_finalize_setup. */
+int AXB(set_xdmf)(axb_handle h, int32_t snap_it, int32_t i_n_xdmf, int32_t j_n_xdmf,
+                  const int32_t *i_arr_xdmf, const int32_t *j_arr_xdmf,
+                  const int32_t *plotting_mask, const int32_t *mapping_ijel_iplot, int32_t npoint_plot,
+                  const float *DsDeta_over_J_sol, const float *DzDeta_over_J_sol,
+                  const float *DsDxi_over_J_sol, const float *DzDxi_over_J_sol, const float *inv_s_solid,
+                  const float *DsDeta_over_J_flu, const float *DzDeta_over_J_flu,
+                  const float *DsDxi_over_J_flu, const float *DzDxi_over_J_flu, const float *inv_s_fluid,
+                  const float *inv_rho_fluid);
+/* number of xdmf snapshots taken so far (isnap of the reference) */
+int AXB(xdmf_count)(axb_handle h, int32_t *nsnap);
+/* out(npoint_plot, nsnap, 5): u_s, u_p, u_z, straintrace, curlinplane of snapshots
+ * first..first+nsnap-1 (0-based) — the records of xdmf_snap_{s,p,z,trace,curlip}_NNNN.dat
+ * (wavefields_io.f90:195-199; u_p is not written for monopole sources, it is zero here) */
+int AXB(fetch_xdmf)(axb_handle h, int32_t first, int32_t nsnap, float *out);
+
 /* data_comm.f90:36-71.  glocal_index_msg is (maxmsg, nmsg) Fortran order; send and
  * receive lists coincide (get_mesh.f90:303-310).  glob2el is (num_comm_gll,3) =
  * (ipol, jpol, iel). */

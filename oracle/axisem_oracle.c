@@ -133,6 +133,12 @@ struct axb_handle_s {
     /* dump_type strain_only / fullfields (axo_set_dump) */
     int dump_type, ibeg, iend, jbeg, jend;
     float *dDse, *dDze, *dDsx, *dDzx, *d_inv_s, *d_inv_s_f;   /* data_pointwise planes of the dumps */
+    /* xdmf snapshots (axo_set_xdmf) */
+    int have_xdmf, snap_it, isnap, nsnap_max, x_in, x_jn, npoint_plot;
+    int *x_iarr, *x_jarr, *x_mask, *x_map;
+    float *xs_Dse, *xs_Dze, *xs_Dsx, *xs_Dzx, *xs_inv_s;        /* solid planes */
+    float *xf_Dse, *xf_Dze, *xf_Dsx, *xf_Dzx, *xf_inv_s, *xf_inv_rho;
+    float *xsnap;        /* (npoint_plot, nsnap_max, 5) */
     int finalized;
     struct axb_handle_s **group;
     int ngroup;
@@ -187,6 +193,9 @@ int axo_destroy(axb_handle h) {
     free(h->chi); free(h->dchi); free(h->ddchi0); free(h->ddchi1);
     free(h->memvar); free(h->src_dev_tm1); free(h->src_tr_tm1);
     free(h->gvec_s); free(h->gvec_f); free(h->recdump); free(h->snapdump);
+    free(h->x_iarr); free(h->x_jarr); free(h->x_mask); free(h->x_map); free(h->xsnap);
+    free(h->xs_Dse); free(h->xs_Dze); free(h->xs_Dsx); free(h->xs_Dzx); free(h->xs_inv_s);
+    free(h->xf_Dse); free(h->xf_Dze); free(h->xf_Dsx); free(h->xf_Dzx); free(h->xf_inv_s); free(h->xf_inv_rho);
     if (h->shm_base) { munmap(h->shm_base, h->shm_bytes); shm_unlink(h->shm_name); }
     free(h);
     return 0;
@@ -353,6 +362,52 @@ int axo_set_dump(axb_handle h, int32_t dump_type, int32_t ibeg, int32_t iend, in
     h->dDse = dupf(DsDeta_over_J_sol, n); h->dDze = dupf(DzDeta_over_J_sol, n);
     h->dDsx = dupf(DsDxi_over_J_sol, n); h->dDzx = dupf(DzDxi_over_J_sol, n);
     h->d_inv_s = dupf(inv_s_solid, n); h->d_inv_s_f = dupf(inv_s_fluid, nf);
+    return 0;
+}
+/* xdmf snapshots: the maps of dump_xdmf_grid (meshes_io.F90:110-437), fluid elements first */
+int axo_set_xdmf(axb_handle h, int32_t snap_it, int32_t i_n_xdmf, int32_t j_n_xdmf,
+                 const int32_t *i_arr_xdmf, const int32_t *j_arr_xdmf,
+                 const int32_t *plotting_mask, const int32_t *mapping_ijel_iplot, int32_t npoint_plot,
+                 const float *DsDeta_over_J_sol, const float *DzDeta_over_J_sol,
+                 const float *DsDxi_over_J_sol, const float *DzDxi_over_J_sol, const float *inv_s_solid,
+                 const float *DsDeta_over_J_flu, const float *DzDeta_over_J_flu,
+                 const float *DsDxi_over_J_flu, const float *DzDxi_over_J_flu, const float *inv_s_fluid,
+                 const float *inv_rho_fluid) {
+    size_t n = (size_t)NPT * h->nel_s, nf = (size_t)NPT * h->nel_f;
+    size_t nm = (size_t)i_n_xdmf * j_n_xdmf * (h->nel_s + h->nel_f);
+    if (snap_it < 1) return fail("axo_set_xdmf: snap_it must be positive");
+    if (i_n_xdmf < 1 || i_n_xdmf > NP || j_n_xdmf < 1 || j_n_xdmf > NP) return fail("axo_set_xdmf: bad i_n_xdmf / j_n_xdmf");
+    for (int k = 0; k < i_n_xdmf; k++) if (i_arr_xdmf[k] < 0 || i_arr_xdmf[k] >= NP) return fail("axo_set_xdmf: i_arr_xdmf out of range");
+    for (int k = 0; k < j_n_xdmf; k++) if (j_arr_xdmf[k] < 0 || j_arr_xdmf[k] >= NP) return fail("axo_set_xdmf: j_arr_xdmf out of range");
+    if (!DsDeta_over_J_sol || !DzDeta_over_J_sol || !DsDxi_over_J_sol || !DzDxi_over_J_sol || !inv_s_solid)
+        return fail("axo_set_xdmf: NULL solid plane");
+    if (h->nel_f > 0 && (!DsDeta_over_J_flu || !DzDeta_over_J_flu || !DsDxi_over_J_flu || !DzDxi_over_J_flu ||
+                         !inv_s_fluid || !inv_rho_fluid))
+        return fail("axo_set_xdmf: NULL fluid plane");
+    for (size_t k = 0; k < nm; k++)
+        if (plotting_mask[k] && (mapping_ijel_iplot[k] < 1 || mapping_ijel_iplot[k] > npoint_plot))
+            return fail("axo_set_xdmf: mapping_ijel_iplot out of range");
+    h->have_xdmf = 1; h->snap_it = snap_it; h->x_in = i_n_xdmf; h->x_jn = j_n_xdmf; h->npoint_plot = npoint_plot;
+    h->x_iarr = dupi(i_arr_xdmf, i_n_xdmf); h->x_jarr = dupi(j_arr_xdmf, j_n_xdmf);
+    h->x_mask = dupi(plotting_mask, nm); h->x_map = dupi(mapping_ijel_iplot, nm);
+    h->xs_Dse = dupf(DsDeta_over_J_sol, n); h->xs_Dze = dupf(DzDeta_over_J_sol, n);
+    h->xs_Dsx = dupf(DsDxi_over_J_sol, n); h->xs_Dzx = dupf(DzDxi_over_J_sol, n); h->xs_inv_s = dupf(inv_s_solid, n);
+    if (h->nel_f > 0) {
+        h->xf_Dse = dupf(DsDeta_over_J_flu, nf); h->xf_Dze = dupf(DzDeta_over_J_flu, nf);
+        h->xf_Dsx = dupf(DsDxi_over_J_flu, nf); h->xf_Dzx = dupf(DzDxi_over_J_flu, nf);
+        h->xf_inv_s = dupf(inv_s_fluid, nf); h->xf_inv_rho = dupf(inv_rho_fluid, nf);
+    }
+    return 0;
+}
+int axo_xdmf_count(axb_handle h, int32_t *nsnap) { *nsnap = h->isnap; return 0; }
+int axo_fetch_xdmf(axb_handle h, int32_t first, int32_t nsnap, float *out) {
+    size_t npts = (size_t)h->npoint_plot;
+    if (!h->have_xdmf) return fail("xdmf snapshots not enabled (axo_set_xdmf)");
+    if (first < 0 || nsnap < 0 || first + nsnap > h->isnap) return fail("xdmf snapshot range");
+    for (int v = 0; v < 5; v++)
+        for (int s = 0; s < nsnap; s++)
+            memcpy(out + npts * (s + (size_t)nsnap * v),
+                   h->xsnap + npts * ((first + s) + (size_t)h->nsnap_max * v), sizeof(float) * npts);
     return 0;
 }
 static int snapshot_nvars(const axo_t *o) {
@@ -1519,6 +1574,74 @@ static void compute_strain_dump(axo_t *o) {
     o->istrain++;
 }
 
+/* xdmf_mapping (wavefields_io.f90:690-738) of one element: the corners of the plot cells, in
+ * the reference's loop order, where plotting_mask says this element owns the plot point */
+static void xdmf_map_el(const axo_t *o, int iel, const float *v, float *plane) {
+    const int in = o->x_in, jn = o->x_jn;
+    const int *mask = o->x_mask + (size_t)in * jn * iel, *map = o->x_map + (size_t)in * jn * iel;
+    for (int i = 0; i < in - 1; i++) {
+        const int ipol = o->x_iarr[i], ipol1 = o->x_iarr[i + 1];
+        for (int j = 0; j < jn - 1; j++) {
+            const int jpol = o->x_jarr[j], jpol1 = o->x_jarr[j + 1];
+            if (mask[i + in * j]) plane[map[i + in * j] - 1] = v[ipol + NP * jpol];
+            if (mask[i + 1 + in * j]) plane[map[i + 1 + in * j] - 1] = v[ipol1 + NP * jpol];
+            if (mask[i + 1 + in * (j + 1)]) plane[map[i + 1 + in * (j + 1)] - 1] = v[ipol1 + NP * jpol1];
+            if (mask[i + in * (j + 1)]) plane[map[i + in * (j + 1)] - 1] = v[ipol + NP * jpol1];
+        }
+    }
+}
+/* glob_snapshot_xdmf (wavefields_io.f90:119-203) with calc_straintrace (:630-686) and
+ * calc_curlinplane (:601-627): planes u_s, u_p, u_z, straintrace, curlinplane */
+static void glob_snapshot_xdmf(axo_t *o) {
+    const size_t cs = (size_t)NPT * o->nel_s;
+    const size_t npts = (size_t)o->npoint_plot;
+    const int mono = o->src_order == AXB_MONOPOLE, di = o->src_order == AXB_DIPOLE;
+    const float two_rk = 2.0f;
+    if (!o->xsnap) {
+        o->nsnap_max = o->niter / o->snap_it + 1;        /* parameters.F90:946 */
+        o->xsnap = zerosf(npts * o->nsnap_max * 5);
+    }
+    float *P[5];
+    for (int v = 0; v < 5; v++) P[v] = o->xsnap + npts * (o->isnap + (size_t)o->nsnap_max * v);
+    for (int e = 0; e < o->nel_f; e++) {
+        const float *dse = EL(o->xf_Dse, e), *dze = EL(o->xf_Dze, e), *dsx = EL(o->xf_Dsx, e), *dzx = EL(o->xf_Dzx, e);
+        const float *is = EL(o->xf_inv_s, e), *ir = EL(o->xf_inv_rho, e);
+        const int ax = o->axis_f[e];
+        float us[NPT], uz[NPT], g1[NPT], g2[NPT], hs[NPT], hz[NPT], fs[NPT], zero[NPT], tr[NPT];
+        grad_el(o->G1T, o->G2T, o->G2, ax, EL(o->chi, e), dse, dze, dsx, dzx, us, uz);
+        FOR25 { us[q] = us[q] * ir[q]; uz[q] = uz[q] * ir[q]; zero[q] = 0.0f; }
+        grad_el(o->G1T, o->G2T, o->G2, ax, us, dse, dze, dsx, dzx, g1, g2);     /* 1: dsus, 2: dzus */
+        grad_el(o->G1T, o->G2T, o->G2, ax, uz, dse, dze, dsx, dzx, hs, hz);
+        /* axisym_gradient_fluid_add: grad(2) = dsus + dzuz */
+        FOR25 g2[q] = g1[q] + hz[q];
+        f_over_s_el(o->G1T, o->G2, ax, us, is, dze, dzx, fs);
+        FOR25 tr[q] = fs[q] + g2[q];
+        xdmf_map_el(o, e, us, P[0]); xdmf_map_el(o, e, zero, P[1]); xdmf_map_el(o, e, uz, P[2]);
+        xdmf_map_el(o, e, tr, P[3]); xdmf_map_el(o, e, zero, P[4]);
+    }
+    for (int e = 0; e < o->nel_s; e++) {
+        const float *u1 = EL(o->disp, e), *u2 = EL(o->disp + cs, e), *u3 = EL(o->disp + 2 * cs, e);
+        const float *dse = EL(o->xs_Dse, e), *dze = EL(o->xs_Dze, e), *dsx = EL(o->xs_Dsx, e), *dzx = EL(o->xs_Dzx, e);
+        const float *is = EL(o->xs_inv_s, e);
+        const int ax = o->axis_s[e];
+        float S[NPT], Pp[NPT], T[NPT], g1[NPT], g2[NPT], hs[NPT], hz[NPT], buff[NPT], tr[NPT], curl[NPT];
+        /* f_sol_spz: the (+, -) pair of a dipole source becomes (s, phi) */
+        if (di) FOR25 { S[q] = u1[q] + u2[q]; Pp[q] = u1[q] - u2[q]; }
+        else FOR25 { S[q] = u1[q]; Pp[q] = u2[q]; }
+        grad_el(o->G1T, o->G2T, o->G2, ax, S, dse, dze, dsx, dzx, g1, g2);      /* 1: dsus, 2: dzus */
+        grad_el(o->G1T, o->G2T, o->G2, ax, u3, dse, dze, dsx, dzx, hs, hz);     /* 1: dsuz, 2: dzuz */
+        FOR25 curl[q] = g2[q] - hs[q];
+        if (mono) f_over_s_el(o->G1T, o->G2, ax, u1, is, dze, dzx, buff);
+        else if (di) { f_over_s_el(o->G1T, o->G2, ax, u2, is, dze, dzx, buff); FOR25 buff[q] = two_rk * buff[q]; }
+        else { FOR25 T[q] = u1[q] - two_rk * u2[q]; f_over_s_el(o->G1T, o->G2, ax, T, is, dze, dzx, buff); }
+        FOR25 tr[q] = buff[q] + (g1[q] + hz[q]);
+        const int iel = o->nel_f + e;
+        xdmf_map_el(o, iel, S, P[0]); xdmf_map_el(o, iel, Pp, P[1]); xdmf_map_el(o, iel, u3, P[2]);
+        xdmf_map_el(o, iel, tr, P[3]); xdmf_map_el(o, iel, curl, P[4]);
+    }
+    o->isnap++;
+}
+
 /* time_evol_wave.F90:1104-1251, the parts on the hot path */
 static void solid_stiffness(axo_t *o, float *acc, const float *u);
 /* time_evol_wave.F90:1424-1526.  sum() is taken in array order with a real(4) accumulator;
@@ -1566,6 +1689,8 @@ static void dump_stuff(axo_t *o, int iter) {
         if (o->dump_type == AXB_DUMP_DISPL_ONLY) dump_disp_global(o);
         else compute_strain_dump(o);
     }
+    /* time_evol_wave.F90:1167-1176 */
+    if (o->have_xdmf && iter % o->snap_it == 0 && (!o->xsnap || o->isnap < o->nsnap_max)) glob_snapshot_xdmf(o);
 }
 
 /* ------------------------------------------------------------------------------------ */
