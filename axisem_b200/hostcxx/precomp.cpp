@@ -787,6 +787,7 @@ void precompute(std::vector<Modules> &ranks, const PrecompOptions &opt) {
         }
         // ---- wavefield-dump point set (meshes_io.F90:489-640: first visit wins, solid then fluid) -------
         m.put("data_io%dump_wavefields", scalar_i(opt.dump_wavefields && opt.strain_it > 0));
+        m.put("data_io%dump_xdmf", scalar_i(0));      // the xdmf plot maps (dump_xdmf_grid) are built by host/xdmf.py
         if (opt.dump_wavefields && opt.strain_it > 0) {
             const size_t n = (size_t)NPT * (nel_s + nel_f);
             std::vector<int32_t> mask(n, 0), map(n, 0);
