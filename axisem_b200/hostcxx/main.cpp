@@ -111,7 +111,7 @@ void usage() {
                  "rank0.axbp[+meshdb.dat0000] [rank1.axbp[+meshdb.dat0001] ...]\n"
                  "   or: axisem_b200_solver --out PREFIX [--model prem_iso|prem_ani] [--src TYPE] [--depth KM] [--period T0]\n"
                  "          [--niter N] [--dt DT] [--seis-it K] [--strain-it K] [--attenuation cg4|full] [--scheme NAME]\n"
-                 "          [--receivers COLAT,COLAT,...] [--energy]  meshdb.dat0000 [meshdb.dat0001 ...]\n"
+                 "          [--receivers COLAT,COLAT,...] [--energy] [--snap-it K]  meshdb.dat0000 [meshdb.dat0001 ...]\n"
                  "       (the second form pre-computes everything from the MESHER's databases, no other input)\n");
 }
 
@@ -143,6 +143,7 @@ int main(int argc, char **argv) {
         else if (a == "--strain-it") { pre.strain_it = std::atoi(need("--strain-it")); pre.dump_wavefields = pre.strain_it > 0; }
         else if (a == "--scheme") pre.time_scheme = need("--scheme");
         else if (a == "--energy") pre.dump_energy = true;
+        else if (a == "--snap-it") pre.snap_it = std::atoi(need("--snap-it"));
         else if (a == "--attenuation") { pre.attenuation = true; pre.att.coarse_grained = std::string(need("--attenuation")) != "full"; }
         else if (a == "--receivers") {
             std::string v = need("--receivers");

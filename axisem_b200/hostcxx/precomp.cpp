@@ -787,7 +787,76 @@ void precompute(std::vector<Modules> &ranks, const PrecompOptions &opt) {
         }
         // ---- wavefield-dump point set (meshes_io.F90:489-640: first visit wins, solid then fluid) -------
         m.put("data_io%dump_wavefields", scalar_i(opt.dump_wavefields && opt.strain_it > 0));
-        m.put("data_io%dump_xdmf", scalar_i(0));      // the xdmf plot maps (dump_xdmf_grid) are built by host/xdmf.py
+        // ---- xdmf plot points (dump_xdmf_grid, meshes_io.F90:110-437): elements with a corner inside the
+        // plot region, their (i_arr, j_arr) points de-duplicated by global number, fluid elements first ----
+        m.put("data_io%dump_xdmf", scalar_i(opt.snap_it > 0));
+        if (opt.snap_it > 0) {
+            const int in = (int)opt.xdmf_gll_i.size(), jn = (int)opt.xdmf_gll_j.size();
+            const int nelem = nel_f + nel_s;
+            std::vector<int32_t> mask((size_t)in * jn * nelem, 0), map((size_t)in * jn * nelem, 0);
+            std::vector<char> in_range(nelem, 0);
+            int nin = 0;
+            for (int d = 0; d < 2; d++) {
+                const Geometry &G = d ? g : f;                 // d = 0: fluid
+                const int nel = d ? nel_s : nel_f, off = d ? nel_f : 0;
+                for (int e = 0; e < nel; e++) {
+                    double rmin = 1e300, rmax = -1e300, tmin = 1e300, tmax = -1e300;
+                    for (int q : {0, NP - 1, NPT - NP, NPT - 1}) {
+                        const size_t p = (size_t)NPT * e + q;
+                        const double th = std::atan2(G.s[p], G.z[p]);
+                        rmin = std::min(rmin, G.r[p]); rmax = std::max(rmax, G.r[p]);
+                        tmin = std::min(tmin, th); tmax = std::max(tmax, th);
+                    }
+                    if (rmin < opt.xdmf_rmax && rmax > opt.xdmf_rmin && tmin < opt.xdmf_thetamax && tmax > opt.xdmf_thetamin) {
+                        in_range[off + e] = 1;
+                        nin++;
+                    }
+                }
+            }
+            const int nelem_plot = nin * (in - 1) * (jn - 1);
+            std::map<int64_t, int32_t> seen;
+            std::vector<double> points;
+            for (int d = 0; d < 2; d++) {
+                const Geometry &G = d ? g : f;
+                const int nel = d ? nel_s : nel_f, off = d ? nel_f : 0;
+                const int32_t *ig = m.i(d ? "data_mesh%igloc_solid" : "data_mesh%igloc_fluid");
+                const int64_t gofs = d ? m.int_of("data_mesh%nglob_fluid") : 0;
+                for (int e = 0; e < nel; e++) {
+                    if (!in_range[off + e]) continue;
+                    for (int i = 0; i < in; i++)
+                        for (int j = 0; j < jn; j++) {
+                            const size_t p = (size_t)NPT * e + opt.xdmf_gll_i[i] + NP * opt.xdmf_gll_j[j];
+                            const size_t k = i + (size_t)in * (j + (size_t)jn * (off + e));
+                            auto it = seen.find(ig[p] + gofs);
+                            if (it == seen.end()) {
+                                it = seen.emplace(ig[p] + gofs, (int32_t)seen.size() + 1).first;
+                                mask[k] = 1;
+                                points.push_back(G.s[p]);
+                                points.push_back(G.z[p]);
+                            }
+                            map[k] = it->second;
+                        }
+                }
+            }
+            std::vector<int32_t> grid;
+            grid.reserve((size_t)4 * nelem_plot);
+            for (int el = 0; el < nelem; el++) {
+                if (!in_range[el]) continue;
+                auto at = [&](int i, int j) { return map[i + (size_t)in * (j + (size_t)jn * el)] - 1; };
+                for (int i = 0; i < in - 1; i++)
+                    for (int j = 0; j < jn - 1; j++)
+                        for (int32_t c : {at(i, j), at(i + 1, j), at(i + 1, j + 1), at(i, j + 1)}) grid.push_back(c);
+            }
+            m.put("data_time%snap_it", scalar_i(opt.snap_it));
+            m.put("data_io%i_arr_xdmf", i32_of(std::vector<int32_t>(opt.xdmf_gll_i.begin(), opt.xdmf_gll_i.end()), {(uint64_t)in}));
+            m.put("data_io%j_arr_xdmf", i32_of(std::vector<int32_t>(opt.xdmf_gll_j.begin(), opt.xdmf_gll_j.end()), {(uint64_t)jn}));
+            m.put("data_mesh%plotting_mask", i32_of(mask, {(uint64_t)nelem, (uint64_t)jn, (uint64_t)in}));
+            m.put("data_mesh%mapping_ijel_iplot", i32_of(map, {(uint64_t)nelem, (uint64_t)jn, (uint64_t)in}));
+            m.put("data_mesh%npoint_plot", scalar_i((int32_t)seen.size()));
+            m.put("data_mesh%nelem_plot", scalar_i(nelem_plot));
+            m.put("data_mesh%xdmf_points", f32_of(points, {(uint64_t)seen.size(), 2}));
+            m.put("data_mesh%xdmf_grid", i32_of(grid, {(uint64_t)nelem_plot, 4}));
+        }
         if (opt.dump_wavefields && opt.strain_it > 0) {
             const size_t n = (size_t)NPT * (nel_s + nel_f);
             std::vector<int32_t> mask(n, 0), map(n, 0);

@@ -15,6 +15,7 @@
 //   source                    source.f90:206-233, 454-476, 587-660, 921-1226 (on-axis point source)
 //   receivers                 seismograms.f90:235-639 (nearest surface GLL point)
 //   wavefield-dump point set  meshes_io.F90:489-640
+//   xdmf plot points and grid meshes_io.F90:110-437 (dump_xdmf_grid)
 // Every array is stored under the reference's `<module>%<variable>` name in Fortran memory order,
 // i.e. exactly what axisem_b200/hostcxx/time_loop.cpp hands to the C ABI.
 #pragma once
@@ -49,6 +50,11 @@ struct PrecompOptions {
     bool dump_wavefields = false;
     bool dump_energy = false;
     std::vector<double> rec_colat_deg;  // receivers on the surface
+    // xdmf snapshots (SAVE_SNAPSHOTS with SNAPSHOTS_FORMAT xdmf): snap_it = floor(SNAPSHOT_DT / deltat),
+    // XDMF_GLL_I / _J, XDMF_RMIN / RMAX [m], XDMF_COLAT_MIN / MAX [rad] (parameters.F90:424-431, 572-594, 944)
+    int snap_it = 0;
+    std::vector<int> xdmf_gll_i = {0, 2, 4}, xdmf_gll_j = {0, 2, 4};
+    double xdmf_rmin = 0.0, xdmf_rmax = 7.0e6, xdmf_thetamin = 0.0, xdmf_thetamax = 3.14159265358979323846;
 };
 
 // `ranks`: read_meshdb results of all ranks of the run, in rank order (mass matrices are

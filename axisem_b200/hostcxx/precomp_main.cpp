@@ -82,6 +82,12 @@ int main(int argc, char **argv) {
         else if (a == "--strain-it") { pre.strain_it = std::atoi(need()); pre.dump_wavefields = pre.strain_it > 0; }
         else if (a == "--scheme") pre.time_scheme = need();
         else if (a == "--energy") pre.dump_energy = true;
+        else if (a == "--snap-it") pre.snap_it = std::atoi(need());
+        else if (a == "--xdmf-region") {     // RMIN_KM RMAX_KM COLAT_MIN_DEG COLAT_MAX_DEG
+            pre.xdmf_rmin = 1e3 * std::atof(need()); pre.xdmf_rmax = 1e3 * std::atof(need());
+            pre.xdmf_thetamin = std::atof(need()) * 3.14159265358979323846 / 180.0;
+            pre.xdmf_thetamax = std::atof(need()) * 3.14159265358979323846 / 180.0;
+        }
         else if (a == "--attenuation") { pre.attenuation = true; pre.att.coarse_grained = std::string(need()) != "full"; }
         else if (a == "--receivers") {
             const std::string v = need();

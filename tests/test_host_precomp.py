@@ -179,3 +179,43 @@ def test_solver_from_databases_alone(exe, tmp_path):
         assert np.abs(raw - ref).max() <= 2e-6 * np.abs(ref).max()
         seen += p.num_rec
     assert seen == len(COLAT)
+
+
+def test_native_xdmf_plot_maps_equal_the_python_builder(exe, tmp_path):
+    """dump_xdmf_grid (meshes_io.F90:110-437) in the native pre-computation: masks, mapping, plot
+    points and the quadrilateral grid, on two slices with a restricted plot region; and the solver
+    started from the databases writes the snapshots of the run set up through Python."""
+    from oracle import oracle
+    nranks, n = 2, 12
+    spec = prem_mesh_spec(ntheta=16, nr_target=18)
+    opts = dict(rmin=3.0e6, rmax=6.2e6, thetamin=0.0, thetamax=2.0)
+    probs = [build_problem(spec, SourceParams(src_type2="mtr", t_0=40.0), niter=n, rank=r, nranks=nranks,
+                           rec_colat_deg=COLAT, snap_it=5, xdmf_opts=opts) for r in range(nranks)]
+    got, _, files = _run(exe, str(tmp_path), probs, "mtr", "none", False,
+                         extra=["--snap-it", "5", "--xdmf-region", "3000", "6200", "0", str(np.degrees(2.0))])
+    for p, g in zip(probs, got):
+        x = p.xdmf
+        assert int(g["data_io%dump_xdmf"]) == 1 and int(g["data_time%snap_it"]) == 5
+        assert int(g["data_mesh%npoint_plot"]) == x["npoint_plot"] and int(g["data_mesh%nelem_plot"]) == x["nelem_plot"]
+        assert np.array_equal(g["data_mesh%plotting_mask"].reshape(x["plotting_mask"].shape), x["plotting_mask"])
+        assert np.array_equal(g["data_mesh%mapping_ijel_iplot"].reshape(x["mapping_ijel_iplot"].shape), x["mapping_ijel_iplot"])
+        assert np.array_equal(g["data_mesh%xdmf_grid"].reshape(-1, 4), x["grid"])
+        pts = g["data_mesh%xdmf_points"].reshape(-1, 2)
+        assert np.abs(pts - x["points"]).max() <= 1e-6 * 6.4e6
+    run = subprocess.run([oracle.build_host(), "--quiet", "--out", str(tmp_path / "run"), "--src", "mtr", "--period", "40",
+                          "--niter", str(n), "--snap-it", "5", "--receivers", ",".join(map(str, COLAT))] + files,
+                         capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr
+    full = [build_problem(spec, SourceParams(src_type2="mtr", t_0=40.0), niter=n, rank=r, nranks=nranks,
+                          rec_colat_deg=COLAT, snap_it=5) for r in range(nranks)]
+    from axisem_b200.capi import connect_local, run_group
+    lib = oracle.load()
+    loops = [oracle.make_loop(p) for p in full]
+    connect_local(lib, loops)
+    run_group(lib, loops, n)
+    for r, L in enumerate(loops):
+        want = L.xdmf_snapshots()
+        raw = np.fromfile(tmp_path / f"run.rank{r:04d}.xdmf.f32", dtype=np.float32).reshape(want.shape)
+        assert want.shape[1] == 3
+        scale = np.abs(want).max(axis=(1, 2), keepdims=True) + 1e-30
+        assert (np.abs(raw - want) / scale).max() <= 1e-5
