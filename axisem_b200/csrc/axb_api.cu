@@ -45,14 +45,12 @@ struct Halo {
     // device
     int nentries = 0;
     int *d_start = nullptr, *d_addr = nullptr, *d_dst_msg = nullptr, *d_dst_slot = nullptr;
-    // receive slab (owned): [parity 2][nc][nslots] floats, then flags
-    float *recv = nullptr;
-    int *flags = nullptr;                     // [MAXMSG] one per message (written by the peer)
-    int *d_done = nullptr;                    // block counter of k_halo_pack
+    // receive slab (owned): [parity 2][nc][nslots] words {value, exchange number}, written by
+    // the neighbours (axb_kernels.cuh: halo_read / k_halo_pack)
+    int2 *recv = nullptr;
     // where my messages go (peer memory)
-    float *peer_recv[MAXMSG] = {nullptr};
+    int2 *peer_recv[MAXMSG] = {nullptr};
     int peer_nslots[MAXMSG] = {0}, peer_offset[MAXMSG] = {0};
-    int *peer_flag[MAXMSG] = {nullptr};
     int seq = 0;                              // exchanges done
 };
 
@@ -934,8 +932,6 @@ int axb_finalize_setup(axb_handle h) {
         Halo &H = h->halo[d];
         if (H.nmsg == 0) continue;
         if (dzeros(h, H.recv, (size_t)2 * H.nc * H.nslots)) return 1;
-        if (dzeros(h, H.flags, MAXMSG)) return 1;
-        if (dzeros(h, H.d_done, 1)) return 1;
     }
     if (build_asm(h, h->nel_s, h->nglob_s, h->igloc_s, h->halo[0], h->d_asm_cp_s, h->d_asm_grp_s)) return 1;
     if (build_asm(h, h->nel_f, h->nglob_f, h->igloc_f, h->halo[1], h->d_asm_cp_f, h->d_asm_grp_f)) return 1;
@@ -1121,13 +1117,11 @@ int axb_finalize_setup(axb_handle h) {
 
 // --------------------------------------------------------------------------------------
 // halo wiring
-static int wire(axb_handle_s *me, int d, int m, float *peer_recv, int *peer_flags, int peer_nslots,
-                int peer_offset, int peer_msg_index) {
+static int wire(axb_handle_s *me, int d, int m, int2 *peer_recv, int peer_nslots, int peer_offset) {
     Halo &H = me->halo[d];
     H.peer_recv[m] = peer_recv;
     H.peer_nslots[m] = peer_nslots;
     H.peer_offset[m] = peer_offset;
-    H.peer_flag[m] = peer_flags + peer_msg_index;
     return 0;
 }
 
@@ -1158,16 +1152,16 @@ int axb_connect_local(axb_handle *hs, int32_t n) {
                 int mm = -1;
                 for (int q = 0; q < Hp.nmsg; q++) if (Hp.peer[q] == hs[a]->rank) mm = q;
                 if (mm < 0 || Hp.size[mm] != H.size[m]) return fail("halo lists inconsistent between ranks");
-                wire(hs[a], d, m, Hp.recv, Hp.flags, Hp.nslots, Hp.offset[mm], mm);
+                wire(hs[a], d, m, Hp.recv, Hp.nslots, Hp.offset[mm]);
             }
         }
     return 0;
 }
 
-// IPC blob: [0..63] memhandle solid slab, [64..127] flags solid, [128..191] fluid slab,
-// [192..255] flags fluid, then per domain: nmsg, nslots, (peer, size, offset) x MAXMSG
+// IPC blob: memhandles of the solid and of the fluid receive slab, then per domain: nmsg,
+// nslots, (peer, size, offset) x MAXMSG
 struct IpcBlob {
-    cudaIpcMemHandle_t recv[2], flags[2];
+    cudaIpcMemHandle_t recv[2];
     int rank, nmsg[2], nslots[2];
     int peer[2][MAXMSG], size[2][MAXMSG], offset[2][MAXMSG];
 };
@@ -1186,10 +1180,7 @@ int axb_ipc_export(axb_handle h, void *blob, int32_t blob_bytes) {
         Halo &H = h->halo[d];
         b.nmsg[d] = H.nmsg; b.nslots[d] = H.nslots;
         for (int m = 0; m < H.nmsg; m++) { b.peer[d][m] = H.peer[m]; b.size[d][m] = H.size[m]; b.offset[d][m] = H.offset[m]; }
-        if (H.nmsg) {
-            CK(cudaIpcGetMemHandle(&b.recv[d], H.recv));
-            CK(cudaIpcGetMemHandle(&b.flags[d], H.flags));
-        }
+        if (H.nmsg) CK(cudaIpcGetMemHandle(&b.recv[d], H.recv));
     }
     std::memcpy(blob, &b, sizeof b);
     return 0;
@@ -1208,12 +1199,10 @@ int axb_ipc_import(axb_handle h, int32_t peer_rank, const void *blob, int32_t bl
             int mm = -1;
             for (int q = 0; q < b.nmsg[d]; q++) if (b.peer[d][q] == h->rank) mm = q;
             if (mm < 0 || b.size[d][mm] != H.size[m]) return fail("halo lists inconsistent between ranks");
-            void *pr = nullptr, *pf = nullptr;
+            void *pr = nullptr;
             CK(cudaIpcOpenMemHandle(&pr, b.recv[d], cudaIpcMemLazyEnablePeerAccess));
-            CK(cudaIpcOpenMemHandle(&pf, b.flags[d], cudaIpcMemLazyEnablePeerAccess));
             h->ipc_opened.push_back(pr);
-            h->ipc_opened.push_back(pf);
-            wire(h, d, m, (float *)pr, (int *)pf, b.nslots[d], b.offset[d][mm], mm);
+            wire(h, d, m, (int2 *)pr, b.nslots[d], b.offset[d][mm]);
         }
     }
     return 0;
@@ -1240,16 +1229,13 @@ static void prof_mark(axb_handle_s *h, bool begin) {
     } while (0)
 #define CLS(h, c) (h)->prof_cls = (c)
 
-static bool halo_wait_kernel() {
-    static const bool v = [] { const char *e = getenv("AXB_HALO_WAIT_KERNEL"); return e && atoi(e) != 0; }();
-    return v;
-}
 // dyn: the kernel is being captured into the step graph and takes the exchange number from
 // the device-resident counters (value = dyn[DYN_SEQ] + 1)
 static HaloArrival halo_arrival(const axb_handle_s *h, const Halo &H, bool dyn) {
     HaloArrival r;
-    r.flags = (H.nmsg == 0 || halo_wait_kernel()) ? nullptr : H.flags;
+    std::memset(&r, 0, sizeof r);
     r.nmsg = H.nmsg; r.value = dyn ? 1 : H.seq;
+    for (int m = 0; m < H.nmsg; m++) r.off[m] = H.offset[m];
     r.abort = h->d_counters + 2; r.timeout_ns = h->halo_timeout_ns;
     r.dyn = dyn ? h->d_dyn : nullptr;
     return r;
@@ -1406,34 +1392,22 @@ static int halo_send(axb_handle_s *h, int d, const float *vec, size_t cs, bool d
     std::memset(&a, 0, sizeof a);
     a.nentries = H.nentries; a.nc = H.nc; a.start = H.d_start; a.addr = H.d_addr; a.vec = vec; a.cs = cs;
     a.dst_msg = H.d_dst_msg; a.dst_slot = H.d_dst_slot;
-    a.done = H.d_done; a.nflag = H.nmsg; a.value = H.seq + 1;
+    a.value = H.seq + 1;
     for (int m = 0; m < H.nmsg; m++) {
         if (!H.peer_recv[m]) return fail("halo peers not connected (axb_connect_local / axb_ipc_import)");
         a.dst_base[m] = H.peer_recv[m] + H.peer_offset[m];
         a.dst_cs[m] = H.peer_nslots[m];
-        a.flag[m] = H.peer_flag[m];
     }
     a.parity = parity;
     a.dyn = dyn ? h->d_dyn : nullptr;
-    // pack + signal in one launch: the last block raises the neighbours' arrival counters
+    // every word carries its own arrival flag: no fence, no signal launch
     LAUNCH(h, k_halo_pack, std::max(1, cdiv((long long)a.nentries * a.nc, 128)), 128, a);
     if (!dyn) H.seq++;
     return 0;
 }
-// phase 2: wait until every neighbour's message of this exchange has landed.  By default the
-// wait lives inside the corrector (only the threads of cut points spin, the rest of the
-// kernel overlaps the exchange); AXB_HALO_WAIT_KERNEL=1 puts a one-warp wait kernel in front.
-static void halo_wait(axb_handle_s *h, int d) {
-    Halo &H = h->halo[d];
-    if (H.nmsg == 0 || !halo_wait_kernel()) return;
-    CLS(h, 5);
-    FlagArgs f;
-    std::memset(&f, 0, sizeof f);
-    f.n = H.nmsg; f.value = H.seq;
-    f.abort = h->d_counters + 2; f.timeout_ns = h->halo_timeout_ns;
-    for (int m = 0; m < H.nmsg; m++) f.flag[m] = H.flags + m;
-    LAUNCH(h, k_halo_wait, 1, 32, f);
-}
+// phase 2 (WAITALL) has no launch of its own: the threads of cut points inside the correctors
+// spin on the words they need (halo_read), the rest of the kernel overlaps the exchange.
+static void halo_wait(axb_handle_s *, int) {}
 // energy (time_evol_wave.F90:1424-1526) of the state after step `iter`.  K u and K dchi go
 // to acc1 / ddchi1, which are dead between steps.
 static void launch_energy(axb_handle_s *h) {
@@ -1708,8 +1682,7 @@ int axb_run_group(axb_handle *hs, int32_t n, int32_t nsteps) {
         to_lean(hs[i]);
     }
     // one handle, Newmark, no per-kernel events: the step is replayed from its CUDA graph
-    const bool graph = n == 1 && hs[0]->use_graph && hs[0]->scheme == AXB_NEWMARK2 && !hs[0]->prof &&
-                       !halo_wait_kernel();
+    const bool graph = n == 1 && hs[0]->use_graph && hs[0]->scheme == AXB_NEWMARK2 && !hs[0]->prof;
     if (graph && ensure_step_graph(hs[0])) return 1;
     for (int s = 0; s < nsteps; s++) {
         if (graph && hs[0]->step_graph) {

@@ -142,17 +142,20 @@ __device__ __forceinline__ int edge_slot(int q) {
     return ((INTERIOR >> q) & 1u) ? -1 : slot;
 }
 
-// Arrival counters of the current halo exchange (one per message, raised by the peer GPU
-// after its partial sums have landed in this rank's receive slab).  Only the threads of cut
-// points look at them, so the rest of a corrector overlaps the exchange (the reference
-// overlaps it with the next stiffness call, time_evol_wave.F90:386-427).
+// Halo receive side.  Every value a neighbour GPU delivers travels as one 8-byte word
+// {value bits, exchange number} written with a single store into this rank's receive slab (the
+// "LL" protocol of collective libraries): the word is its own arrival flag, so the sender needs
+// no fence, no block counter and no separate flag store, and the receiver needs no fence between
+// flag and data.  Only the threads of cut points read the slab, spinning on their own words, so
+// the rest of a corrector overlaps the exchange (the reference overlaps it with the next
+// stiffness call, time_evol_wave.F90:386-427).
 // A neighbour that never delivers (a dead peer process, a rank that was not stepped) must not
 // hang the GPU: the spin is bounded by `timeout_ns`, and the first thread to give up raises
 // the handle's abort flag, which every later wait honours at once.  axb_synchronize reports it
 // the way the reference's pcheck stops a run (commpi.F90:64-111).
 struct HaloArrival {
-    const volatile int *flags;   // null: a k_halo_wait launch has already waited
-    int nmsg, value;
+    int nmsg, value;             // value: exchange number the words of this exchange carry
+    int off[8];                  // first slot of each message (to name the late message)
     volatile int *abort;         // counters[2]: 0 fine, m + 1 = message m timed out
     unsigned long long timeout_ns;
     const int *dyn;              // graph replay: value = dyn[DYN_SEQ] + value
@@ -165,23 +168,54 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __forceinline__ bool wait_flag(const volatile int *flag, int value, volatile int *abort,
-                                          unsigned long long timeout_ns, int msg) {
-    if (*flag >= value) return true;
-    const unsigned long long t0 = global_ns();
-    while (*flag < value) {
-        if (*abort) return false;
-        if (global_ns() - t0 > timeout_ns) { *abort = msg + 1; __threadfence(); return false; }
-        __nanosleep(100);
-    }
-    return true;
+__device__ __forceinline__ int2 ld_volatile_v2(const int2 *p) {
+    int2 w;
+    asm volatile("ld.volatile.global.v2.s32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(p));
+    return w;
 }
-__device__ __forceinline__ void halo_arrived(const HaloArrival &h) {
-    if (!h.flags) return;
-    const int value = h.dyn ? h.dyn[DYN_SEQ] + h.value : h.value;
-    for (int m = 0; m < h.nmsg; m++)
-        if (!wait_flag(h.flags + m, value, h.abort, h.timeout_ns, m)) break;
-    __threadfence_system();
+__device__ __forceinline__ void st_volatile_v2(int2 *p, int x, int y) {
+    asm volatile("st.volatile.global.v2.s32 [%0], {%1, %2};" ::"l"(p), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ int halo_expected(const HaloArrival &h) {
+    return h.dyn ? h.dyn[DYN_SEQ] + h.value : h.value;
+}
+// raise the abort flag for the message that owns `slot`
+__device__ __forceinline__ void halo_give_up(const HaloArrival &h, int slot) {
+    int m = 0;
+    while (m + 1 < h.nmsg && slot >= h.off[m + 1]) m++;
+    *h.abort = m + 1;
+    __threadfence();
+}
+// the NC values (one per field component, component stride cs) in slot `slot` of the slab once the
+// neighbour's words of exchange `want` are there; component 1 is skipped for SKIP1 (monopole)
+template <int NC, bool SKIP1>
+__device__ __forceinline__ void halo_read(const int2 *slab, size_t cs, int slot, int want, const HaloArrival &h,
+                                          float (&out)[NC]) {
+    int2 w[NC];
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        if (SKIP1 && c == 1) { w[c] = make_int2(0, want); continue; }
+        w[c] = ld_volatile_v2(slab + cs * c + slot);
+        ok = ok && w[c].y == want;
+    }
+    if (!ok) {
+        const unsigned long long t0 = global_ns();
+        while (true) {
+            ok = true;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                if (SKIP1 && c == 1) continue;
+                w[c] = ld_volatile_v2(slab + cs * c + slot);
+                ok = ok && w[c].y == want;
+            }
+            if (ok || *h.abort) break;
+            if (global_ns() - t0 > h.timeout_ns) { halo_give_up(h, slot); break; }
+            __nanosleep(100);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) out[c] = ok ? __int_as_float(w[c].x) : 0.f;
 }
 
 }  // namespace axb
@@ -201,13 +235,13 @@ struct FluidCorrArgs {
     const float *chi;
     const float *inv_mass_fluid, *gamma;   // gamma may be null
     AsmTable T;
-    const float *recv; size_t recv_cs;   // both parities: [2][nc][recv_cs]; recv_parity picks one
+    const int2 *recv; size_t recv_cs;    // both parities: [2][nc][recv_cs] words; recv_parity picks one
     int recv_parity;
     HaloArrival arrival;
     int assemble_only;
 };
 // the receive slab of the current exchange (graph replay: parity from the device counter)
-__device__ __forceinline__ const float *recv_slab(const float *recv, size_t cs, int nc, int parity, const int *dyn) {
+__device__ __forceinline__ const int2 *recv_slab(const int2 *recv, size_t cs, int nc, int parity, const int *dyn) {
     if (dyn) parity = dyn[DYN_SEQ] & 1;
     return recv + (size_t)parity * nc * cs;
 }
@@ -239,10 +273,15 @@ __global__ void __launch_bounds__(256, AXB_FCORR_MINB) k_fluid_corrector(const _
             const int nloc = a.T.grp[g], nrem = a.T.grp[g + 1];
             float s = 0.0f;
             for (int m = 0; m < nloc; m++) s = s + a.ddchi1[a.T.grp[g + 2 + m]];
-            if (nrem > 0) halo_arrived(a.arrival);
-            // peer-written data: read at L2 (the slab is reused every second exchange)
-            const float *recv = recv_slab(a.recv, a.recv_cs, 1, a.recv_parity, a.arrival.dyn);
-            for (int m = 0; m < nrem; m++) s = s + __ldcg(recv + a.T.grp[g + 2 + nloc + m]);
+            if (nrem > 0) {
+                const int2 *recv = recv_slab(a.recv, a.recv_cs, 1, a.recv_parity, a.arrival.dyn);
+                const int want = halo_expected(a.arrival);
+                for (int m = 0; m < nrem; m++) {
+                    float r[1];
+                    halo_read<1, false>(recv, 0, a.T.grp[g + 2 + nloc + m], want, a.arrival, r);
+                    s = s + r[0];
+                }
+            }
             v = s;
         }
     }
@@ -317,7 +356,7 @@ struct SolidCorrArgs {
     const float *disp;
     const float *inv_mass_rho, *gamma;
     AsmTable T;
-    const float *recv; size_t recv_cs;   // both parities: [2][3][recv_cs]
+    const int2 *recv; size_t recv_cs;    // both parities: [2][3][recv_cs] words
     int recv_parity;
     HaloArrival arrival;
     const int *dyn;           // graph replay: iter = dyn[DYN_ITER]
@@ -333,6 +372,35 @@ struct SolidCorrArgs {
     int stf_stride, stf_off;  // index = iter*stride + off
     int assemble_only;
 };
+
+// Assembled value of a point whose copies do not fit the int4 entry: more than four local copies,
+// or partial sums of neighbour ranks (cut points).  A fraction of a percent of the points; the
+// corrector forms it before it requests anything else, so that nothing but the point's address is
+// live across the spin (at 40 registers anything more spills in the common path).
+template <int ORDER>
+__device__ __forceinline__ float3 solid_group_sum(const SolidCorrArgs &a, int g) {
+    const size_t cs = a.cs;
+    const int nloc = a.T.grp[g], nrem = a.T.grp[g + 1];
+    float s[3] = {0.f, 0.f, 0.f};
+    for (int m = 0; m < nloc; m++) {
+        const int ad = a.T.grp[g + 2 + m];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            if (!(ORDER == 0 && c == 1)) s[c] = s[c] + a.acc1[ad + cs * c];
+    }
+    if (nrem > 0) {
+        const int2 *recv = recv_slab(a.recv, a.recv_cs, 3, a.recv_parity, a.arrival.dyn);
+        const int want = halo_expected(a.arrival);
+        for (int m = 0; m < nrem; m++) {
+            float r[3];
+            halo_read<3, ORDER == 0>(recv, a.recv_cs, a.T.grp[g + 2 + nloc + m], want, a.arrival, r);
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                if (!(ORDER == 0 && c == 1)) s[c] = s[c] + r[c];
+        }
+    }
+    return make_float3(s[0], s[1], s[2]);
+}
 
 // S_B: pdistsum_solid + source + mass inversion + sponge + velocity update.
 // Replaces commun.F90:69-171 (+commpi.F90:453-500) and time_evol_wave.F90:466-494 / :689-715.
@@ -363,6 +431,8 @@ k_solid_corrector(const __grid_constant__ SolidCorrArgs a) {
             if (MODE != 4) prefetch_l2(a.inv_mass_rho + pn);
         }
     }
+    float3 grp_sum = make_float3(0.f, 0.f, 0.f);
+    if (cp.x == -2) grp_sum = solid_group_sum<ORDER>(a, cp.y);
     // every other input of this point is requested up front (the stores below would otherwise
     // order the per-component loads behind them)
     constexpr bool upd = MODE != 4;
@@ -394,25 +464,7 @@ k_solid_corrector(const __grid_constant__ SolidCorrArgs a) {
             v[c] = s;
         }
     } else if (cp.x == -2) {
-        const int g = cp.y;
-        const int nloc = a.T.grp[g], nrem = a.T.grp[g + 1];
-        float s[3] = {0.f, 0.f, 0.f};
-        for (int m = 0; m < nloc; m++) {
-            const int ad = a.T.grp[g + 2 + m];
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-                if (!(ORDER == 0 && c == 1)) s[c] = s[c] + a.acc1[ad + cs * c];
-        }
-        if (nrem > 0) halo_arrived(a.arrival);
-        const float *recv = recv_slab(a.recv, a.recv_cs, 3, a.recv_parity, a.arrival.dyn);
-        for (int m = 0; m < nrem; m++) {
-            const int sl = a.T.grp[g + 2 + nloc + m];
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-                if (!(ORDER == 0 && c == 1)) s[c] = s[c] + __ldcg(recv + sl + a.recv_cs * c);
-        }
-#pragma unroll
-        for (int c = 0; c < 3; c++) v[c] = s[c];
+        v[0] = grp_sum.x; v[1] = grp_sum.y; v[2] = grp_sum.z;
     }
     if (MODE == 4) {
         // op test: stage the assembled field in acc0 (acc1 must stay intact while other
@@ -479,47 +531,26 @@ struct PackArgs {
     const float *vec; size_t cs;
     const int *dst_msg;       // message index of each entry
     const int *dst_slot;      // slot inside the peer's slab
-    float *dst_base[8];       // per message: peer slab base (parity 0)
+    int2 *dst_base[8];        // per message: peer slab base (parity 0), words {value, exchange number}
     size_t dst_cs[8];         // per message: component stride of the peer slab (= its slot count)
     int parity;               // which half of the peers' slabs this exchange writes
-    // signal: the last block to finish raises the peers' arrival counters
-    int *done;                // local block counter (zero between launches)
-    int nflag, value;
-    volatile int *flag[8];
+    int value;                // exchange number the words carry
     const int *dyn;           // graph replay: parity = dyn[DYN_SEQ] & 1, value = dyn[DYN_SEQ] + 1
 };
+// feed_buffer + ISEND (commpi.F90:371-452): one thread per (send entry, component) sums the local
+// copies of the cut point and stores {sum, exchange number} into the neighbour's slab
 __global__ void k_halo_pack(const __grid_constant__ PackArgs a) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nentries * a.nc) return;
     const int seq = a.dyn ? a.dyn[DYN_SEQ] : 0;
     const int parity = a.dyn ? (seq & 1) : a.parity;
-    if (t < a.nentries * a.nc) {
-        const int en = t % a.nentries, c = t / a.nentries;
-        float s = 0.0f;
-        for (int m = a.start[en]; m < a.start[en + 1]; m++) s = s + a.vec[a.addr[m] + a.cs * c];
-        const int msg = a.dst_msg[en];
-        a.dst_base[msg][(size_t)parity * a.nc * a.dst_cs[msg] + a.dst_slot[en] + a.dst_cs[msg] * c] = s;
-    }
-    // release: the block's peer stores are ordered before the flag by one system-scope fence
-    // behind the barrier (fence cumulativity), not by one fence per thread
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        const int prev = atomicAdd(a.done, 1);
-        if (prev == (int)gridDim.x - 1) {
-            *a.done = 0;
-            __threadfence_system();
-            const int value = a.dyn ? seq + 1 : a.value;
-            for (int m = 0; m < a.nflag; m++) *a.flag[m] = value;
-        }
-    }
-}
-struct FlagArgs { int n; volatile int *flag[8]; int value; volatile int *abort; unsigned long long timeout_ns; };
-// stand-alone wait (AXB_HALO_WAIT_KERNEL=1): one warp spins on the arrival counters
-__global__ void k_halo_wait(const __grid_constant__ FlagArgs a) {
-    if (threadIdx.x < a.n) {
-        wait_flag(a.flag[threadIdx.x], a.value, a.abort, a.timeout_ns, threadIdx.x);
-        __threadfence_system();
-    }
+    const int value = a.dyn ? seq + 1 : a.value;
+    const int en = t % a.nentries, c = t / a.nentries;
+    float s = 0.0f;
+    for (int m = a.start[en]; m < a.start[en + 1]; m++) s = s + a.vec[a.addr[m] + a.cs * c];
+    const int msg = a.dst_msg[en];
+    st_volatile_v2(a.dst_base[msg] + (size_t)parity * a.nc * a.dst_cs[msg] + a.dst_slot[en] + a.dst_cs[msg] * c,
+                   __float_as_int(s), value);
 }
 
 // ---------------------------------------------------------------------------------------
