@@ -254,13 +254,13 @@ int AXB(finalize_setup)(axb_handle h);
 /* Multi-rank runs: every rank's handle must be connected to its peers before axb_run.
  * In-process (oracle, single-process multi-GPU): axb_connect_local with all handles.
  * One process per GPU: every rank exports one opaque blob of AXB_IPC_BLOB_BYTES bytes
- * (CUDA IPC handles of its receive slabs and arrival counters plus its message lists;
+ * (CUDA IPC handles of its receive slabs plus its message lists;
  * axb_ipc_blob_bytes() returns the same number at run time), the blobs travel once over any
  * channel (MPI_Allgather in the Fortran host, torch.distributed here), and each rank imports
  * the blobs of the ranks its halo lists name.  A smaller buffer is rejected with an error.
  * The mappings an import opens are closed by axb_destroy.
  *
- * A neighbour that never delivers does not hang the GPU: every wait on an arrival counter is
+ * A neighbour that never delivers does not hang the GPU: every wait for a neighbour's value is
  * bounded (10 s; AXB_HALO_TIMEOUT_MS overrides), the rank then raises its abort flag and
  * axb_synchronize fails with "HALO EXCHANGE TIMED OUT ..." — the counterpart of the
  * reference's pcheck, which stops all ranks when one fails (commpi.F90:64-111). */
