@@ -1382,7 +1382,7 @@ static void launch_bdry2solid(axb_handle_s *h) {
     a.uflu = h->ddchi0; a.acc1 = h->acc1; a.cs = h->css;
     LAUNCH(h, k_bdry2solid, cdiv(h->nel_bdry * NP, 128), 128, a);
 }
-// phase 1 of pdistsum_*: pack partial sums into the neighbours' slabs and raise their flags
+// phase 1 of pdistsum_*: pack the partial sums of the cut points into the neighbours' slabs
 static int halo_send(axb_handle_s *h, int d, const float *vec, size_t cs, bool dyn = false) {
     Halo &H = h->halo[d];
     if (H.nmsg == 0) return 0;
