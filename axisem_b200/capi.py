@@ -52,7 +52,10 @@ class Attenuation(C.Structure):
 
 SCHEMES = {"newmark2": 0, "symplec4": 1, "ML_SO4m5": 2, "ML_SO6m7": 3, "KL_O8m17": 4,
            "SS_35o10": 5}
-STF_TYPES = {"gauss_0": 0, "gauss_1": 1, "gauss_2": 2}
+# sub-stages per step (symplectic_coefficients, time_evol_wave.F90:749-967)
+NSTAGES = {"symplec4": 4, "ML_SO4m5": 5, "ML_SO6m7": 7, "KL_O8m17": 17, "SS_35o10": 35}
+# stf_type codes of include/axisem_b200.h (dirac_1 is a Newmark-only alias of dirac_0: compute_stf_t has no case for it)
+STF_TYPES = {"gauss_0": 0, "gauss_1": 1, "gauss_2": 2, "errorf": 3, "dirac_0": 4, "quheavi": 5, "dirac_1": 4}
 FIELDS = {"disp": 0, "velo": 1, "acc0": 2, "acc1": 3, "chi": 4, "dchi": 5, "ddchi0": 6,
           "ddchi1": 7, "memvar": 8, "src_dev_tm1": 9, "src_tr_tm1": 10}
 DUMP_TYPES = {"displ_only": 0, "strain_only": 1, "fullfields": 2}
@@ -62,7 +65,7 @@ OPS = {"solid_stiffness": 0, "anel_stiffness": 1, "fluid_stiffness": 2, "pdistsu
 # every symbol include/axisem_b200.h declares
 SYMBOLS = ["last_error", "create", "destroy", "set_mesh", "set_solid_terms", "set_fluid_terms",
            "set_mass", "set_energy", "set_sponge", "set_sf_boundary", "set_attenuation", "set_source",
-           "set_stf_values", "set_stf_params", "set_receivers", "set_kwf", "set_dump", "snapshot_layout", "set_xdmf", "xdmf_count", "fetch_xdmf", "set_halo", "set_time",
+           "set_stf_values", "set_stf_params", "get_stf_symp", "set_receivers", "set_kwf", "set_dump", "snapshot_layout", "set_xdmf", "xdmf_count", "fetch_xdmf", "set_halo", "set_time",
            "finalize_setup", "set_stream", "synchronize", "connect_local", "ipc_blob_bytes", "ipc_export", "ipc_import", "run", "run_group",
            "profile", "get_profile", "iter", "nseismo", "nstrain", "gpu_launches", "fetch_seismograms",
            "fetch_snapshots", "fetch_energy", "get_state", "set_state", "apply_op"]
@@ -200,7 +203,8 @@ class TimeLoop:
         ck(fn["set_source"](h, C.c_int32(int(getattr(p, "fluid_src", False))), C.c_int32(p.nelsrc), _ip(p.ielsrc, k),
                             _fp(p.source_term_el, k), _fp(p.stf, k), C.c_int32(p.stf.size)))
         s = p.source
-        shift = float(np.ceil(s.shift_fact * s.t_0 / p.deltat) * p.deltat)
+        from .host.source import stf_shift
+        shift = stf_shift(s, p.deltat)
         ck(fn["set_stf_params"](h, C.c_int32(STF_TYPES[s.stf_type]), C.c_double(s.decay),
                                 C.c_double(s.t_0), C.c_double(shift), C.c_double(s.magnitude)))
         # recfile_el(num_rec,3) Fortran order
@@ -270,6 +274,13 @@ class TimeLoop:
         v = np.ascontiguousarray(values, dtype=np.float32)
         self.lib.check(self.lib.fn["set_stf_values"](self.h, C.c_int32(first_iter),
                                                      C.c_int32(v.size), v.ctypes.data_as(_F)))
+
+    def stf_symp(self, first_iter: int, n: int) -> np.ndarray:
+        """(n, nstages): the source time function at the sub-stages of steps first_iter+1.. as the
+        symplectic loop applies it."""
+        out = np.zeros((n, NSTAGES[self.prob.time_scheme]), dtype=np.float32)
+        self.lib.check(self.lib.fn["get_stf_symp"](self.h, C.c_int32(first_iter), C.c_int32(n), out.ctypes.data_as(_F)))
+        return out
 
     def set_stream(self, cuda_stream: int):
         self.lib.check(self.lib.fn["set_stream"](self.h, C.c_void_p(cuda_stream)))

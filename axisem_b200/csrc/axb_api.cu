@@ -302,16 +302,41 @@ int symplectic_coefficients(axb_handle_s *o) {
     return 0;
 }
 
-// compute_stf_t (source.f90:206-233)
-double stf_t(const axb_handle_s *o, double t) {
-    const double a = o->decay / o->t_0, x = a * (t - o->shift);
-    const double pi = 3.1415926535898;
-    switch (o->stf_type) {
-    case AXB_STF_GAUSS_0: return std::exp(-(x * x)) * o->magnitude * a / std::sqrt(pi);
-    case AXB_STF_GAUSS_1: return -2.0 * a * a * (t - o->shift) * std::exp(-(x * x))
-                                 / (a * std::sqrt(2.0) * std::exp(-0.5)) * o->magnitude;
-    default: return a * a * (2.0 * a * a * (t - o->shift) * (t - o->shift) - 1.0)
-                    * std::exp(-(x * x)) / (2.0 * a * a * std::exp(-1.5)) * o->magnitude;
+// the reference's own error function (source.f90:662-692; coefficients are default-real literals)
+double erf_nr(double x) {
+    static const float c[10] = {-1.26551223f, 1.00002368f, 0.37409196f, 0.09678418f, -0.18628806f,
+                                0.27886807f, -1.13520398f, 1.48851587f, -0.82215223f, 0.17087277f};
+    const double z = std::fabs(x), t = 1.0 / (1.0 + 0.5 * z);
+    double poly = (double)c[9];
+    for (int k = 8; k >= 0; k--) poly = t * poly + (double)c[k];
+    double erfcc = t * std::exp(-z * z + poly);
+    if (x < 0.0) erfcc = 2.0 - erfcc;
+    return 1.0 - erfcc;
+}
+// compute_stf_t (source.f90:206-233) on the nstages sub-stage times `t` of one step.  The smooth
+// types are point-wise; delta_src_t (:890-904) is a hat function switched by the FIRST sub-stage
+// time of the step, quasiheavi_t (:908-917) sets the sub-stages seis_it..nstages (an index, not a
+// time) to the magnitude.
+void stf_t(const axb_handle_s *o, int n, const double *t, double *out) {
+    const double a = o->decay / o->t_0, pi = 3.1415926535898, dt = o->deltat, sh = o->shift;
+    for (int k = 0; k < n; k++) {
+        const double x = a * (t[k] - sh);
+        switch (o->stf_type) {
+        case AXB_STF_GAUSS_0: out[k] = std::exp(-(x * x)) * o->magnitude * a / std::sqrt(pi); break;
+        case AXB_STF_GAUSS_1: out[k] = -2.0 * a * a * (t[k] - sh) * std::exp(-(x * x))
+                                       / (a * std::sqrt(2.0) * std::exp(-0.5)) * o->magnitude; break;
+        case AXB_STF_GAUSS_2: out[k] = a * a * (2.0 * a * a * (t[k] - sh) * (t[k] - sh) - 1.0)
+                                       * std::exp(-(x * x)) / (2.0 * a * a * std::exp(-1.5)) * o->magnitude; break;
+        case AXB_STF_ERRORF: out[k] = (erf_nr(x) * 0.5 + 0.5) * o->magnitude; break;
+        case AXB_STF_QUHEAVI: out[k] = (k + 1 >= o->seis_it) ? o->magnitude : 0.0; break;
+        default: out[k] = 0.0; break;
+        }
+    }
+    if (o->stf_type == AXB_STF_DIRAC_0) {
+        if (t[0] > sh - dt && t[0] <= sh)
+            for (int k = 0; k < n; k++) out[k] = (t[k] - t[0]) / dt * o->magnitude / dt;
+        if (t[0] >= sh && t[0] < sh + dt)
+            for (int k = 0; k < n; k++) out[k] = (1.0 - (t[k] - t[0]) / dt) * o->magnitude / dt;
     }
 }
 
@@ -743,8 +768,9 @@ int axb_set_source(axb_handle h, int32_t fluid_src, int32_t nelsrc, const int32_
 
 int axb_set_stf_params(axb_handle h, int32_t stf_type, double decay, double t_0,
                        double shift_fact, double magnitude) {
-    if (stf_type != AXB_STF_GAUSS_0 && stf_type != AXB_STF_GAUSS_1 && stf_type != AXB_STF_GAUSS_2)
-        return fail("axb_set_stf_params: stf_type must be gauss_0, gauss_1 or gauss_2 (compute_stf_t, source.f90:206-233)");
+    if (stf_type < AXB_STF_GAUSS_0 || stf_type > AXB_STF_QUHEAVI)
+        return fail("axb_set_stf_params: source time function non existant (compute_stf_t, source.f90:206-233: "
+                    "gauss_0, gauss_1, gauss_2, errorf, dirac_0, quheavi)");
     if (!(t_0 > 0)) return fail("axb_set_stf_params: t_0 must be positive");
     h->stf_type = stf_type; h->decay = decay; h->t_0 = t_0; h->shift = shift_fact;
     h->magnitude = magnitude;
@@ -1005,11 +1031,12 @@ int axb_finalize_setup(axb_handle h) {
         // stf at the sub-stage times of every step: subdt = t - deltat + coeff
         // (time_evol_wave.F90:592-593, :689), t accumulated as in :586
         std::vector<float> tab((size_t)h->nstages * std::max(h->niter, 1));
-        double t = 0.0;
+        double t = 0.0, subdt[40], stf_symp[40];
         for (int it = 0; it < h->niter; it++) {
             t += h->deltat;
-            for (int k = 0; k < h->nstages; k++)
-                tab[(size_t)it * h->nstages + k] = (float)stf_t(h, t - h->deltat + h->coeff[k]);
+            for (int k = 0; k < h->nstages; k++) subdt[k] = t - h->deltat + h->coeff[k];
+            stf_t(h, h->nstages, subdt, stf_symp);
+            for (int k = 0; k < h->nstages; k++) tab[(size_t)it * h->nstages + k] = (float)stf_symp[k];
         }
         UP(h->d_stf_symp, tab.data(), tab.size());
     } else if (h->nelsrc > 0 && (!h->d_stf || h->niter_stf < h->niter)) {
@@ -1761,6 +1788,16 @@ int axb_set_stf_values(axb_handle h, int32_t first_iter, int32_t n, const float 
     }
     CK(cudaMemcpyAsync(h->d_stf + first_iter, values, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int axb_get_stf_symp(axb_handle h, int32_t first_iter, int32_t n, float *out) {
+    if (use(h)) return 1;
+    if (h->scheme == AXB_NEWMARK2 || !h->d_stf_symp) return fail("axb_get_stf_symp: symplectic schemes only, after axb_finalize_setup");
+    if (first_iter < 0 || n < 0 || first_iter + n > h->niter) return fail("stf range");
+    if (n == 0) return 0;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out, h->d_stf_symp + (size_t)first_iter * h->nstages, sizeof(float) * (size_t)n * h->nstages, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -19,6 +19,8 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 
+from .source import stf_shift
+
 SNAP_VARS = {   # nc_varnamelist, nc_routines.F90:943-1045
     ("displ_only", True): ["disp_s", "disp_z"],
     ("displ_only", False): ["disp_s", "disp_p", "disp_z"],
@@ -103,7 +105,7 @@ def global_attributes(prob, *, nseismo: int, nstrain: int, deltat_coarse: float,
                       srccolat: float = 0.0, srclon: float = 0.0, simtype: str = "single") -> Dict:
     """parameters.F90:1480-1552 (build provenance strings are this repository's)."""
     s = prob.source
-    shift = float(np.ceil(s.shift_fact * s.t_0 / prob.deltat) * prob.deltat)
+    shift = stf_shift(s, prob.deltat)
     seis_dt = prob.deltat * prob.seis_it
     spec = prob.mesh.spec
     a = {

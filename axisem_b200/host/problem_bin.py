@@ -18,6 +18,7 @@ import struct
 import numpy as np
 
 from ..capi import SCHEMES, SOLID_FIELDS, STF_TYPES, fortran_matrix
+from .source import stf_shift
 
 _DT = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.int32): 2}
 
@@ -105,7 +106,7 @@ def problem_records(p):
     add("data_source%stf_type", STF_TYPES[s.stf_type], i32)
     add("data_source%decay", float(s.decay), f64)
     add("data_source%t_0", float(s.t_0), f64)
-    add("data_source%shift_fact", float(np.ceil(s.shift_fact * s.t_0 / p.deltat) * p.deltat), f64)
+    add("data_source%shift_fact", stf_shift(s, p.deltat), f64)
     add("data_source%magnitude", float(s.magnitude), f64)
     add("data_mesh%num_rec", int(p.num_rec), i32)
     add("data_mesh%recfile_el", np.ascontiguousarray(p.recfile_el.T), i32)

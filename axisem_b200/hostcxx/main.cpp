@@ -110,6 +110,7 @@ void usage() {
                  "usage: axisem_b200_solver [--steps N] [--devices D] [--dumpbuffer B] [--quiet] --out PREFIX "
                  "rank0.axbp[+meshdb.dat0000] [rank1.axbp[+meshdb.dat0001] ...]\n"
                  "   or: axisem_b200_solver --out PREFIX [--model prem_iso|prem_ani] [--src TYPE] [--depth KM] [--period T0]\n"
+                 "          [--stf gauss_0|gauss_1|gauss_2|errorf|dirac_0|quheavi] [--discrete-choice gaussi|1dirac|...] [--shift SECONDS]\n"
                  "          [--niter N] [--dt DT] [--seis-it K] [--strain-it K] [--attenuation cg4|full] [--scheme NAME]\n"
                  "          [--receivers COLAT,COLAT,...] [--energy] [--snap-it K]  meshdb.dat0000 [meshdb.dat0001 ...]\n"
                  "       (the second form pre-computes everything from the MESHER's databases, no other input)\n");
@@ -137,6 +138,9 @@ int main(int argc, char **argv) {
         else if (a == "--src") pre.src_type2 = need("--src");
         else if (a == "--depth") pre.src_depth = 1e3 * std::atof(need("--depth"));
         else if (a == "--period") pre.t_0 = std::atof(need("--period"));
+        else if (a == "--stf") pre.stf_type = need("--stf");
+        else if (a == "--discrete-choice") pre.discrete_choice = need("--discrete-choice");
+        else if (a == "--shift") pre.shift_seconds = std::atof(need("--shift"));
         else if (a == "--niter") pre.niter = std::atoi(need("--niter"));
         else if (a == "--dt") pre.deltat = std::atof(need("--dt"));
         else if (a == "--seis-it") pre.seis_it = std::atoi(need("--seis-it"));

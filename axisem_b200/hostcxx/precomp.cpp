@@ -377,14 +377,82 @@ void assemble(std::vector<Modules> &ranks, const std::string &dom, std::vector<s
     }
 }
 
-// compute_stf / compute_stf_t (source.f90:206-233, 587-660)
+// shift_fact of the reference in seconds
+double stf_shift(const PrecompOptions &o, double deltat) {
+    return o.shift_seconds >= 0.0 ? o.shift_seconds : std::ceil(o.shift_fact * o.t_0 / deltat) * deltat;
+}
+
+// the reference's own error function (Numerical Recipes erfc, source.f90:662-692; the coefficients
+// are default-real literals)
+double erf_nr(double x) {
+    static const float c[10] = {-1.26551223f, 1.00002368f, 0.37409196f, 0.09678418f, -0.18628806f,
+                                0.27886807f, -1.13520398f, 1.48851587f, -0.82215223f, 0.17087277f};
+    const double z = std::fabs(x), t = 1.0 / (1.0 + 0.5 * z);
+    double poly = (double)c[9];
+    for (int k = 8; k >= 0; k--) poly = t * poly + (double)c[k];
+    double erfcc = t * std::exp(-z * z + poly);
+    if (x < 0.0) erfcc = 2.0 - erfcc;
+    return 1.0 - erfcc;
+}
+
+// the smooth source time functions: gauss, gauss_d, gauss_dd, errorf (source.f90:587-660)
 double stf_at(const PrecompOptions &o, double t, double deltat) {
-    const double shift = std::ceil(o.shift_fact * o.t_0 / deltat) * deltat, a = o.decay / o.t_0, x = a * (t - shift);
+    const double shift = stf_shift(o, deltat), a = o.decay / o.t_0, x = a * (t - shift);
     if (o.stf_type == "gauss_0") return std::exp(-x * x) * o.magnitude * a / std::sqrt(PI);
     if (o.stf_type == "gauss_1") return -2.0 * a * a * (t - shift) * std::exp(-x * x) / (a * std::sqrt(2.0) * std::exp(-0.5)) * o.magnitude;
     if (o.stf_type == "gauss_2")
         return a * a * (2.0 * a * a * (t - shift) * (t - shift) - 1.0) * std::exp(-x * x) / (2.0 * a * a * std::exp(-1.5)) * o.magnitude;
-    throw SolverError("unknown stf_type " + o.stf_type);
+    if (o.stf_type == "errorf") return (erf_nr(x) * 0.5 + 0.5) * o.magnitude;
+    throw SolverError("source time function non existant: " + o.stf_type);
+}
+
+// delta_src (source.f90:696-814): the discrete Dirac of `discrete_choice`, normalised to unit integral,
+// times the magnitude; quheavi: its running integral
+std::vector<float> delta_src(const PrecompOptions &o, int niter, double deltat) {
+    const double gpi = 3.1415926535898;                       // global_parameters.f90
+    const double a = (double)(float)o.t_0;                    // discrete_dirac_halfwidth (realkind)
+    const double shift = (double)(float)stf_shift(o, deltat); // shift_fact_discrete_dirac (realkind)
+    const std::string &c = o.discrete_choice;
+    std::vector<double> signal(niter, 0.0);
+    for (int i = 1; i <= niter; i++) {
+        double t = (double)i * deltat, v;
+        if (c == "cauchy") v = 1.0 / a * std::exp(-std::fabs((t - shift) / a));
+        else if (c == "caulor") v = 1.0 / gpi * a / (a * a + (t - shift) * (t - shift));
+        else if (c == "sincfc") {
+            if (t == shift) t = 0.00001 + shift;
+            v = 1.0 / (a * gpi) * std::sin((-shift + t) / a) / ((-shift + t) / a);
+        } else if (c == "gaussi") v = 1.0 / (a * std::sqrt(gpi)) * std::exp(-((t - shift) / a) * ((t - shift) / a));
+        else if (c == "triang") v = std::fabs(t - shift) <= a / 2.0 ? 2.0 / a - 4.0 / (a * a) * std::fabs(t - shift) : 0.0;
+        else if (c == "1dirac") v = i == (int)(shift / deltat) ? 1.0 : 0.0;
+        else throw SolverError("do not know discrete Dirac " + c);
+        signal[i - 1] = v;
+    }
+    double sum = 0.0;
+    for (double v : signal) sum += v;
+    const double integral = sum * deltat;
+    std::vector<float> stf(niter);
+    for (int i = 0; i < niter; i++) stf[i] = (float)((double)(float)(signal[i] / integral) * o.magnitude);
+    if (o.stf_type == "quheavi") {
+        double acc = 0.0;
+        for (int i = 0; i < niter; i++) { acc += (double)stf[i] * deltat; stf[i] = (float)acc; }
+    }
+    return stf;
+}
+
+// compute_stf (source.f90:144-202)
+std::vector<float> compute_stf(const PrecompOptions &o, int niter, double deltat) {
+    if (o.stf_type == "dirac_0" || o.stf_type == "dirac_1" || o.stf_type == "quheavi") return delta_src(o, niter, deltat);
+    std::vector<float> stf(niter);
+    for (int k = 0; k < niter; k++) stf[k] = (float)stf_at(o, (double)(float)((k + 1) * deltat), deltat);
+    return stf;
+}
+
+int stf_code(const std::string &s) {       // include/axisem_b200.h
+    static const std::map<std::string, int> codes = {{"gauss_0", 0}, {"gauss_1", 1}, {"gauss_2", 2}, {"errorf", 3},
+                                                     {"dirac_0", 4}, {"dirac_1", 4}, {"quheavi", 5}};
+    const auto it = codes.find(s);
+    if (it == codes.end()) throw SolverError("source time function non existant: " + s);
+    return it->second;
 }
 
 const std::map<std::string, std::string> SRC_POLE = {
@@ -748,14 +816,13 @@ void precompute(std::vector<Modules> &ranks, const PrecompOptions &opt) {
             m.put("data_source%ielsrc", i32_of(ielsrc, {8}));
             m.put("data_source%source_term_el", make(Array::F32, {3, 8, NP, NP}, st.data()));
             std::vector<float> stf(std::max(opt.niter, 1), 0.0f);
-            if (opt.time_scheme == "newmark2")
-                for (int k = 0; k < opt.niter; k++) stf[k] = (float)stf_at(opt, (double)(float)((k + 1) * deltat), deltat);
+            if (opt.time_scheme == "newmark2" && opt.niter > 0) stf = compute_stf(opt, opt.niter, deltat);
+            else if (opt.stf_type == "dirac_1") throw SolverError("source time function non existant for the symplectic schemes: dirac_1");
             m.put("data_source%stf", make(Array::F32, {(uint64_t)stf.size()}, stf.data()));
-            const int stf_code = opt.stf_type == "gauss_0" ? 0 : (opt.stf_type == "gauss_1" ? 1 : 2);
-            m.put("data_source%stf_type", scalar_i(stf_code));
+            m.put("data_source%stf_type", scalar_i(stf_code(opt.stf_type)));
             m.put("data_source%decay", scalar_d(opt.decay));
             m.put("data_source%t_0", scalar_d(opt.t_0));
-            m.put("data_source%shift_fact", scalar_d(std::ceil(opt.shift_fact * opt.t_0 / deltat) * deltat));
+            m.put("data_source%shift_fact", scalar_d(stf_shift(opt, deltat)));
             m.put("data_source%magnitude", scalar_d(opt.magnitude));
         }
         // ---- receivers: nearest surface GLL point to each colatitude, owned by the rank that holds it ---

@@ -41,7 +41,9 @@ struct PrecompOptions {
     std::string model;                  // "" = the database's bkgrdmodel (prem_iso | prem_ani)
     std::string src_type2 = "explosion";
     double src_depth = 100.0e3, magnitude = 1.0e20, t_0 = 50.0, decay = 3.5, shift_fact = 1.5;
-    std::string stf_type = "gauss_0";
+    std::string stf_type = "gauss_0";     // gauss_0|gauss_1|gauss_2|errorf|dirac_0|dirac_1|quheavi (source.f90:152-171)
+    std::string discrete_choice = "gaussi"; // delta_src's approximation of the Dirac (parameters.F90:995-999)
+    double shift_seconds = -1.0;          // >= 0: shift_fact in seconds as the caller fixed it; else from shift_fact * t_0
     std::string time_scheme = "newmark2";
     int niter = 100, seis_it = 1, strain_it = 0;
     double deltat = 0.0;                // 0 = the mesher's (times 1.5 for the symplectic schemes)

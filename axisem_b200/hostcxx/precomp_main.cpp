@@ -76,6 +76,10 @@ int main(int argc, char **argv) {
         else if (a == "--src") pre.src_type2 = need();
         else if (a == "--depth") pre.src_depth = 1e3 * std::atof(need());
         else if (a == "--period") pre.t_0 = std::atof(need());
+        else if (a == "--stf") pre.stf_type = need();
+        else if (a == "--discrete-choice") pre.discrete_choice = need();
+        else if (a == "--shift") pre.shift_seconds = std::atof(need());
+        else if (a == "--magnitude") pre.magnitude = std::atof(need());
         else if (a == "--niter") pre.niter = std::atoi(need());
         else if (a == "--dt") pre.deltat = std::atof(need());
         else if (a == "--seis-it") pre.seis_it = std::atoi(need());

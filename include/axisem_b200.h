@@ -55,8 +55,13 @@ enum {
     AXB_KL_O8M17 = 4, AXB_SS_35O10 = 5
 };
 
-/* stf_type for the point-wise STF of the symplectic schemes (SOLVER/source.f90:206-233) */
-enum { AXB_STF_GAUSS_0 = 0, AXB_STF_GAUSS_1 = 1, AXB_STF_GAUSS_2 = 2 };
+/* stf_type for the point-wise STF of the symplectic schemes: every case of compute_stf_t
+ * (SOLVER/source.f90:206-233; gauss_t :818, gauss_d_t :835, gauss_dd_t :853, errorf_t :873,
+ * delta_src_t :890, quasiheavi_t :908) */
+enum {
+    AXB_STF_GAUSS_0 = 0, AXB_STF_GAUSS_1 = 1, AXB_STF_GAUSS_2 = 2,
+    AXB_STF_ERRORF = 3, AXB_STF_DIRAC_0 = 4, AXB_STF_QUHEAVI = 5
+};
 
 enum { AXB_DOMAIN_SOLID = 0, AXB_DOMAIN_FLUID = 1 };
 
@@ -168,6 +173,11 @@ int AXB(set_stf_values)(axb_handle h, int32_t first_iter, int32_t n, const float
 /* point-wise STF for the symplectic schemes, compute_stf_t (source.f90:206-233) */
 int AXB(set_stf_params)(axb_handle h, int32_t stf_type, double decay, double t_0,
                         double shift_fact, double magnitude);
+
+/* out(nstages, n): stf_symp of steps first_iter+1 .. first_iter+n (0-based first_iter) as the
+ * symplectic loop applies it, real(stf_symp(i), kind=realkind) (time_evol_wave.F90:592-593, :689);
+ * valid after axb_finalize_setup of a symplectic scheme */
+int AXB(get_stf_symp)(axb_handle h, int32_t first_iter, int32_t n, float *out);
 
 /* recfile_el(num_rec,3) = (iel, ipol, jpol), data_mesh.f90:138 */
 int AXB(set_receivers)(axb_handle h, int32_t num_rec, const int32_t *recfile_el);

@@ -1777,16 +1777,60 @@ static void newmark_part3(axo_t *o) {
     dump_stuff(o, o->iter);
 }
 
-/* source.f90:206-233 + gauss_t etc.: point-wise STF */
-static double stf_t(const axo_t *o, double t) {
-    double a = o->decay / o->t_0, x = a * (t - o->shift_fact);
-    const double pi = 3.1415926535898;
+/* source.f90:662-692: the reference's erf (Numerical Recipes erfc; default-real literals) */
+static double erf_nr(double x) {
+    static const float c[10] = {-1.26551223f, 1.00002368f, 0.37409196f, 0.09678418f, -0.18628806f,
+                                0.27886807f, -1.13520398f, 1.48851587f, -0.82215223f, 0.17087277f};
+    double z = fabs(x), t = 1.0 / (1.0 + 0.5 * z), poly = (double)c[9], erfcc;
+    for (int k = 8; k >= 0; k--) poly = t * poly + (double)c[k];
+    erfcc = t * exp(-z * z + poly);
+    if (x < 0.0) erfcc = 2.0 - erfcc;
+    return 1.0 - erfcc;
+}
+
+/* compute_stf_t, source.f90:206-233: gauss_t :818-831, gauss_d_t :835-849, gauss_dd_t :853-869,
+ * errorf_t :873-886, delta_src_t :890-904 (whole-array assignments switched by t(1)),
+ * quasiheavi_t :908-917 (stf_t(seis_it:nstf_t) = magnitude) */
+static void compute_stf_t(const axo_t *o, int nstf_t, const double *t, double *stf_t) {
+    const double a = o->decay / o->t_0, pi = 3.1415926535898;
+    int i;
     switch (o->stf_type) {
-    case AXB_STF_GAUSS_0: return exp(-(x * x)) * o->magnitude * a / sqrt(pi);
-    case AXB_STF_GAUSS_1: return -2.0 * a * a * (t - o->shift_fact) * exp(-(x * x))
-                                 / (a * sqrt(2.0) * exp(-0.5)) * o->magnitude;
-    default: return a * a * (2.0 * a * a * (t - o->shift_fact) * (t - o->shift_fact) - 1.0)
-                    * exp(-(x * x)) / (2.0 * a * a * exp(-1.5)) * o->magnitude;
+    case AXB_STF_GAUSS_0:
+        for (i = 0; i < nstf_t; i++) {
+            double x = a * (t[i] - o->shift_fact);
+            stf_t[i] = exp(-(x * x)) * o->magnitude * a / sqrt(pi);
+        }
+        break;
+    case AXB_STF_GAUSS_1:
+        for (i = 0; i < nstf_t; i++) {
+            double x = a * (t[i] - o->shift_fact);
+            stf_t[i] = -2.0 * a * a * (t[i] - o->shift_fact) * exp(-(x * x)) / (a * sqrt(2.0) * exp(-0.5)) * o->magnitude;
+        }
+        break;
+    case AXB_STF_GAUSS_2:
+        for (i = 0; i < nstf_t; i++) {
+            double x = a * (t[i] - o->shift_fact);
+            stf_t[i] = a * a * (2.0 * a * a * (t[i] - o->shift_fact) * (t[i] - o->shift_fact) - 1.0)
+                       * exp(-(x * x)) / (2.0 * a * a * exp(-1.5)) * o->magnitude;
+        }
+        break;
+    case AXB_STF_ERRORF:
+        for (i = 0; i < nstf_t; i++) stf_t[i] = (erf_nr(a * (t[i] - o->shift_fact)) * 0.5 + 0.5) * o->magnitude;
+        break;
+    case AXB_STF_DIRAC_0:
+        for (i = 0; i < nstf_t; i++) stf_t[i] = 0.0;
+        if (t[0] > (o->shift_fact - o->deltat) && t[0] <= o->shift_fact)
+            for (i = 0; i < nstf_t; i++) stf_t[i] = (t[i] - t[0]) / o->deltat * o->magnitude / o->deltat;
+        if (t[0] >= o->shift_fact && t[0] < (o->shift_fact + o->deltat))
+            for (i = 0; i < nstf_t; i++) stf_t[i] = (1. - (t[i] - t[0]) / o->deltat) * o->magnitude / o->deltat;
+        break;
+    case AXB_STF_QUHEAVI:
+        for (i = 0; i < nstf_t; i++) stf_t[i] = 0.0;
+        for (i = (o->seis_it > 1 ? o->seis_it : 1); i <= nstf_t; i++) stf_t[i - 1] = o->magnitude;
+        break;
+    default:
+        fprintf(stderr, " source time function non existant: %d\n", o->stf_type);
+        abort();
     }
 }
 
@@ -1978,7 +2022,9 @@ static int run_ipc(axo_t *o, int nsteps) {
         } else {
             double stf_symp[40];
             o->t += o->deltat;
-            for (int k = 0; k < o->nstages; k++) stf_symp[k] = stf_t(o, o->t - o->deltat + o->coeff[k]);
+            double subdt[40];
+            for (int k = 0; k < o->nstages; k++) subdt[k] = o->t - o->deltat + o->coeff[k];
+            compute_stf_t(o, o->nstages, subdt, stf_symp);
             for (int k = 0; k < o->nstages; k++) {
                 symp_part1(o, k);
                 if (exchange_ipc(o, AXB_DOMAIN_FLUID)) return 1;
@@ -2014,7 +2060,9 @@ static void *rank_worker(void *arg) {
         } else {
             double stf_symp[40];
             o->t += o->deltat;
-            for (int k = 0; k < o->nstages; k++) stf_symp[k] = stf_t(o, o->t - o->deltat + o->coeff[k]);
+            double subdt[40];
+            for (int k = 0; k < o->nstages; k++) subdt[k] = o->t - o->deltat + o->coeff[k];
+            compute_stf_t(o, o->nstages, subdt, stf_symp);
             for (int k = 0; k < o->nstages; k++) {
                 symp_part1(o, k);
                 pthread_barrier_wait(w->bar);
@@ -2071,8 +2119,9 @@ int axo_run_group(axb_handle *hs, int32_t n, int32_t nsteps) {
         } else {
             double stf_symp[40];
             for (int i = 0; i < n; i++) hs[i]->t += hs[i]->deltat;
-            for (int k = 0; k < hs[0]->nstages; k++)
-                stf_symp[k] = stf_t(hs[0], hs[0]->t - hs[0]->deltat + hs[0]->coeff[k]);
+            double subdt[40];
+            for (int k = 0; k < hs[0]->nstages; k++) subdt[k] = hs[0]->t - hs[0]->deltat + hs[0]->coeff[k];
+            compute_stf_t(hs[0], hs[0]->nstages, subdt, stf_symp);
             for (int k = 0; k < hs[0]->nstages; k++) {
                 PAR_RANKS for (int i = 0; i < n; i++) { set_ftz(); symp_part1(hs[i], k); }
                 for (int i = 0; i < n; i++) if (exchange(hs[i], AXB_DOMAIN_FLUID)) return 1;
@@ -2103,6 +2152,19 @@ int axo_run(axb_handle h, int32_t nsteps) {
 int axo_set_stf_values(axb_handle h, int32_t first, int32_t n, const float *v) {
     if (first < 0 || first + n > h->niter_stf) return fail("stf range");
     memcpy(h->stf + first, v, sizeof(float) * n);
+    return 0;
+}
+int axo_get_stf_symp(axb_handle h, int32_t first, int32_t n, float *out) {
+    double t = 0.0, subdt[40], stf_symp[40];
+    if (h->scheme == AXB_NEWMARK2 || h->nstages <= 0) return fail("axo_get_stf_symp: symplectic schemes only, after finalize_setup");
+    if (first < 0 || n < 0 || first + n > h->niter) return fail("stf range");
+    for (int it = 0; it < first + n; it++) {          /* t accumulated as in time_evol_wave.F90:586 */
+        t += h->deltat;
+        if (it < first) continue;
+        for (int k = 0; k < h->nstages; k++) subdt[k] = t - h->deltat + h->coeff[k];
+        compute_stf_t(h, h->nstages, subdt, stf_symp);
+        for (int k = 0; k < h->nstages; k++) out[(size_t)(it - first) * h->nstages + k] = (float)stf_symp[k];
+    }
     return 0;
 }
 int axo_profile(axb_handle h, int32_t e) { (void)h; (void)e; return 0; }

@@ -180,6 +180,27 @@ def test_symplectic_time_loop(scheme):
     assert np.array_equal(G.seismograms(), O.seismograms())
 
 
+@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("stf", ["errorf", "dirac_0", "quheavi", "gauss_1"])
+def test_symplectic_source_time_functions(stf, strict):
+    """every case of compute_stf_t (source.f90:206-233) drives the symplectic loop: the table of
+    sub-stage samples and the wavefield it excites, from rest, against the oracle."""
+    n = 40
+    kw = {"stf_type": stf, "magnitude": 1.0e20}
+    if stf in ("dirac_0", "quheavi"):
+        kw["shift_seconds"] = 2.0
+    prob = make_problem("mtr", anel=True, niter=n, scheme="symplec4", t_0=4.0, seis_it=2, source_kw=kw)
+    G, O = _pair(prob, strict)
+    assert np.array_equal(G.stf_symp(0, n), O.stf_symp(0, n))
+    assert np.abs(G.stf_symp(0, n)).max() > 0
+    for L in (G, O):
+        L.run(n)
+    assert np.abs(O.get("disp")).max() > 0
+    for f in ("disp", "velo", "chi", "dchi", "memvar"):
+        _cmp(f, G.get(f), O.get(f), strict, 1e-5)
+    _cmp("seismograms", G.seismograms(), O.seismograms(), strict, 1e-5)
+
+
 @pytest.mark.parametrize("src", ["explosion", "mtr"])
 def test_two_slices_loopback_matches_oracle_and_one_slice(src):
     """theta-slice decomposition: 2 ranks on one GPU (direct-pointer halo) == 2-rank oracle

@@ -219,3 +219,31 @@ def test_native_xdmf_plot_maps_equal_the_python_builder(exe, tmp_path):
         assert want.shape[1] == 3
         scale = np.abs(want).max(axis=(1, 2), keepdims=True) + 1e-30
         assert (np.abs(raw - want) / scale).max() <= 1e-5
+
+
+@pytest.mark.parametrize("stf,choice", [("gauss_1", "gaussi"), ("gauss_2", "gaussi"), ("errorf", "gaussi"),
+                                        ("dirac_0", "gaussi"), ("dirac_0", "1dirac"), ("dirac_1", "triang"),
+                                        ("dirac_0", "cauchy"), ("dirac_0", "caulor"), ("dirac_0", "sincfc"),
+                                        ("quheavi", "gaussi"), ("quheavi", "1dirac")])
+def test_native_source_time_functions(exe, tmp_path, stf, choice):
+    """compute_stf of the C++ host (every SOURCE_FUNCTION of the reference, every discrete Dirac of
+    delta_src) equals the numpy restatement sample by sample; the stf_type code and the shift that
+    the symplectic loop would use travel with it."""
+    from axisem_b200.capi import STF_TYPES
+    from axisem_b200.host.source import stf_shift
+    spec = prem_mesh_spec(ntheta=16, nr_target=18)
+    shift = 7.0 if stf in ("dirac_0", "dirac_1", "quheavi") else None
+    src = SourceParams(src_type2="explosion", t_0=4.0 if shift else 40.0, stf_type=stf, discrete_choice=choice, shift_seconds=shift)
+    prob = build_problem(spec, src, niter=300, rec_colat_deg=COLAT, dump=True, strain_it=10, energy=True)
+    extra = ["--stf", stf, "--discrete-choice", choice, "--period", str(src.t_0), "--niter", "300"]
+    if shift:
+        extra += ["--shift", str(shift)]
+    got, _, _ = _run(exe, str(tmp_path), [prob], "explosion", "none", False, extra)
+    a, b = prob.stf, got[0]["data_source%stf"].astype(np.float32).reshape(-1)
+    assert a.shape == b.shape and np.abs(a).max() > 0
+    ulp = np.abs(a.view(np.int32).astype(np.int64) - b.view(np.int32).astype(np.int64))
+    big = np.abs(a) > 1e-6 * np.abs(a).max()
+    assert (ulp[big] <= 1).all(), int(ulp[big].max())
+    assert np.abs(a - b)[~big].max(initial=0.0) <= 1e-12 * np.abs(a).max()
+    assert int(got[0]["data_source%stf_type"]) == STF_TYPES[stf]
+    assert float(got[0]["data_source%shift_fact"]) == stf_shift(src, prob.deltat)

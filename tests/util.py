@@ -11,10 +11,10 @@ def small_spec(ntheta=16, nr=18, anisotropic=False):
 
 def make_problem(src="explosion", anel=False, ntheta=16, nr=18, niter=40, rank=0, nranks=1,
                  scheme="newmark2", anisotropic=False, dump=False, strain_it=0, t_0=40.0,
-                 seis_it=1, coarse_grained=True, nranks_r=1):
+                 seis_it=1, coarse_grained=True, nranks_r=1, source_kw=None):
     spec = small_spec(ntheta, nr, anisotropic)
     att = AttenuationModel(coarse_grained=coarse_grained) if anel else None
-    return build_problem(spec, SourceParams(src_type2=src, t_0=t_0), anel=anel, att=att, niter=niter,
+    return build_problem(spec, SourceParams(src_type2=src, t_0=t_0, **(source_kw or {})), anel=anel, att=att, niter=niter,
                          rank=rank, nranks=nranks, time_scheme=scheme, dump=dump,
                          strain_it=strain_it, seis_it=seis_it, nranks_r=nranks_r)
 
