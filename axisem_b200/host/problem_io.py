@@ -22,7 +22,7 @@ _PROB_ARRAYS = ["inv_mass_rho", "inv_mass_fluid", "fluid_free_surface_mask", "in
                 "solid_absorbing_gamma", "fluid_absorbing_gamma"]
 _PROB_SCALARS = ["src_type", "src_order", "time_scheme", "deltat", "niter", "seis_it", "strain_it",
                  "anel", "nelsrc"]
-_SRC_FIELDS = ["src_type2", "depth", "magnitude", "stf_type", "t_0", "decay", "shift_fact"]
+_SRC_FIELDS = ["src_type2", "depth", "magnitude", "stf_type", "t_0", "decay", "shift_fact", "shift_seconds", "discrete_choice"]
 _DICTS = ["solid", "fluid", "pw_solid", "pw_fluid", "att", "kwf"]
 
 

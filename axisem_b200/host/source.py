@@ -49,8 +49,9 @@ class SourceParams:
 
 def stf_shift(p: SourceParams, deltat: float) -> float:
     """shift_fact of the reference in seconds."""
-    if p.shift_seconds is not None:
-        return float(p.shift_seconds)
+    fixed = getattr(p, "shift_seconds", None)      # containers written before the field existed
+    if fixed is not None:
+        return float(fixed)
     return float(np.ceil(p.shift_fact * p.t_0 / deltat) * deltat)
 
 
