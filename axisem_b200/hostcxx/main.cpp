@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "background_models.hpp"
 #include "meshdb.hpp"
 #include "time_loop.hpp"
 #include "precomp.hpp"
@@ -109,7 +110,7 @@ void usage() {
     std::fprintf(stderr,
                  "usage: axisem_b200_solver [--steps N] [--devices D] [--dumpbuffer B] [--quiet] --out PREFIX "
                  "rank0.axbp[+meshdb.dat0000] [rank1.axbp[+meshdb.dat0001] ...]\n"
-                 "   or: axisem_b200_solver --out PREFIX [--model prem_iso|prem_ani] [--src TYPE] [--depth KM] [--period T0]\n"
+                 "   or: axisem_b200_solver --out PREFIX [--model NAME | --ext-model FILE.bm] [--src TYPE] [--depth KM] [--period T0]\n"
                  "          [--stf gauss_0|gauss_1|gauss_2|errorf|dirac_0|quheavi] [--discrete-choice gaussi|1dirac|...] [--shift SECONDS]\n"
                  "          [--niter N] [--dt DT] [--seis-it K] [--strain-it K] [--attenuation cg4|full] [--scheme NAME]\n"
                  "          [--receivers COLAT,COLAT,...] [--energy] [--snap-it K]  meshdb.dat0000 [meshdb.dat0001 ...]\n"
@@ -135,6 +136,11 @@ int main(int argc, char **argv) {
         else if (a == "--quiet") opt.verbose = false;
         else if (a == "--out") prefix = need("--out");
         else if (a == "--model") pre.model = need("--model");
+        else if (a == "--ext-model") {
+            try { axisem::set_external_model(axisem::read_external_model(need("--ext-model"))); }
+            catch (const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
+            pre.model = "external";
+        }
         else if (a == "--src") pre.src_type2 = need("--src");
         else if (a == "--depth") pre.src_depth = 1e3 * std::atof(need("--depth"));
         else if (a == "--period") pre.t_0 = std::atof(need("--period"));

@@ -134,8 +134,10 @@ Material material(const std::string &model, const Geometry &g) {
             M.phi[p] = v.vpv * v.vpv / (v.vph * v.vph);
             M.eta[p] = v.eta;
             M.vp[p] = std::max(v.vph, v.vpv);
-            M.qmu[e] = v.qmu;
-            M.qka[e] = v.qkappa;
+            if (q == NP * (NP / 2 - 1) + NP / 2 - 1) {      // Q_mu_1d at (npol/2 - 1, npol/2 - 1), get_model.F90:236-242
+                M.qmu[e] = v.qmu;
+                M.qka[e] = v.qkappa;
+            }
         }
     }
     return M;

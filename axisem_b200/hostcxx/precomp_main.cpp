@@ -1,5 +1,5 @@
 // axisem_b200_precomp — MESHER databases -> complete time-loop inputs (module variables), natively.
-//   axisem_b200_precomp --out PREFIX [--model prem_iso|prem_ani] [--src TYPE] [--depth KM] [--period T0]
+//   axisem_b200_precomp --out PREFIX [--model NAME | --ext-model FILE.bm] [--src TYPE] [--depth KM] [--period T0]
 //        [--niter N] [--dt DT] [--seis-it K] [--strain-it K] [--attenuation cg4|full] [--scheme NAME]
 //        [--receivers COLAT,...] [--energy] meshdb.dat0000 [meshdb.dat0001 ...]
 // writes PREFIX.rankNNNN.axbp (what axisem_b200_solver takes) and prints the reference's
@@ -11,6 +11,7 @@
 
 #include <cmath>
 
+#include "background_models.hpp"
 #include "mapping.hpp"
 #include "meshdb.hpp"
 #include "precomp.hpp"
@@ -63,6 +64,48 @@ static int mapping_check() {
     return 0;
 }
 
+// prints "r_km idom rho vpv vsv vph vsh eta qmu qka" per radius, and the model's discontinuities first
+int model_eval(const std::string &name, const std::string &list) {
+    try {
+        if (name == "external") {
+            const axisem::ExternalModel &E = axisem::external_model();
+            std::printf("ndisc %d anelastic %d anisotropic %d name %s\n", E.ndisc(), (int)E.anelastic, (int)E.anisotropic, E.name.c_str());
+            for (int k = 1; k <= E.ndisc(); k++) std::printf("discont %d %.6f fluid %d\n", k, E.discont(k) / 1000.0, (int)E.fluid(k));
+        } else {
+            const auto &d = axisem::model_domains(name);
+            std::printf("ndisc %d anelastic %d anisotropic %d name %s\n", (int)d.size(), (int)axisem::model_is_anelastic(name),
+                        (int)axisem::model_is_ani(name), name.c_str());
+            for (size_t k = 0; k < d.size(); k++) std::printf("discont %d %.6f fluid %d\n", (int)k + 1, d[k].r_top_km, (int)d[k].fluid);
+        }
+        size_t pos = 0;
+        while (pos < list.size()) {
+            size_t c = list.find(',', pos);
+            if (c == std::string::npos) c = list.size();
+            std::string tok = list.substr(pos, c - pos);
+            pos = c + 1;
+            bool upper = false;
+            if (!tok.empty() && tok.back() == '+') { upper = true; tok.pop_back(); }
+            const double r = 1000.0 * std::atof(tok.c_str());
+            int idom;
+            if (name == "external") {
+                const axisem::ExternalModel &E = axisem::external_model();
+                idom = E.ndisc();
+                for (int k = 1; k <= E.ndisc(); k++) {      // from the surface: first domain that holds r
+                    const double bot = k < E.ndisc() ? E.discont(k + 1) : 0.0;
+                    if (r <= E.discont(k) && (upper ? r >= bot : r > bot)) { idom = k; break; }
+                }
+            } else idom = axisem::model_domain_of(name, r, upper);
+            const axisem::ModelValues v = axisem::model_evaluate(name, r, idom);
+            std::printf("%.6f %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", r / 1000.0, idom, v.rho, v.vpv, v.vsv, v.vph, v.vsh, v.eta,
+                        v.qmu, v.qkappa);
+        }
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "%s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
     axisem::PrecompOptions pre;
     std::string prefix;
@@ -73,6 +116,15 @@ int main(int argc, char **argv) {
         if (a == "--mapping-check") return mapping_check();
         else if (a == "--out") prefix = need();
         else if (a == "--model") pre.model = need();
+        else if (a == "--ext-model") {        // bkgrdmodel = 'external': the tabulated .bm file of the run
+            try { axisem::set_external_model(axisem::read_external_model(need())); }
+            catch (const std::exception &e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
+            pre.model = "external";
+        }
+        else if (a == "--model-eval") {       // NAME R_KM[+][,R_KM[+]...]: the model at these radii ('+': upper side of a discontinuity)
+            const std::string name = need(), v = need();
+            return model_eval(name, v);
+        }
         else if (a == "--src") pre.src_type2 = need();
         else if (a == "--depth") pre.src_depth = 1e3 * std::atof(need());
         else if (a == "--period") pre.t_0 = std::atof(need());

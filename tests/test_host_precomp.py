@@ -247,3 +247,40 @@ def test_native_source_time_functions(exe, tmp_path, stf, choice):
     assert np.abs(a - b)[~big].max(initial=0.0) <= 1e-12 * np.abs(a).max()
     assert int(got[0]["data_source%stf_type"]) == STF_TYPES[stf]
     assert float(got[0]["data_source%shift_fact"]) == stf_shift(src, prob.deltat)
+
+
+def test_external_background_model(exe, tmp_path):
+    """bkgrdmodel = 'external' (--ext-model FILE.bm): the reference's own tabulation of prem_ani
+    (TESTING/TEST04 model.bm, tests/golden/prem_ani_model_bm.npz) through read_ext_model / get_ext_disc
+    / interpolate gives the planes of the analytic prem_ani to the resolution of the table, with
+    attenuation (Q from the table's columns)."""
+    from .test_background_models import ANI_COLS, _fixture, _write_bm
+    spec = prem_mesh_spec(ntheta=16, nr_target=18, anisotropic=True)
+    att = AttenuationModel(coarse_grained=True)
+    prob = build_problem(spec, SourceParams(src_type2="mtr", t_0=40.0), anel=True, att=att, niter=30,
+                         rec_colat_deg=COLAT, dump=True, strain_it=10, energy=True)
+    ana, _, _ = _run(exe, str(tmp_path), [prob], "mtr", "cg4", True)
+    bm = str(tmp_path / "prem_ani.bm")
+    _write_bm(bm, _fixture()[0], ANI_COLS)
+    ext, checks, _ = _run(exe, str(tmp_path), [prob], "mtr", "cg4", True, ["--ext-model", bm])
+    assert abs(float(checks["mass_over_volume"]) - 1.0) < 1e-9
+    n = 0
+    for name, a in ana[0].items():
+        b = ext[0][name]
+        assert a.shape == b.shape, name
+        if a.dtype.kind in "iu" or not a.size:
+            assert np.array_equal(a, b), name
+            continue
+        a64, b64 = a.astype(np.float64).reshape(-1), b.astype(np.float64).reshape(-1)
+        scale = np.abs(a64).max()
+        if name.startswith(("data_matr%", "attenuation%")) and scale > 0:
+            assert np.abs(a64 - b64).max() <= 1e-3 * scale, (name, np.abs(a64 - b64).max() / scale)
+            n += 1
+        elif name.startswith(("data_mesh%", "data_spec%", "data_pointwise%", "data_source%", "data_comm%")):
+            if name != "data_mesh%bkgrdmodel":
+                assert np.allclose(a64, b64, rtol=1e-3, atol=1e-3 * scale), name
+    assert n > 30
+    # the planes do differ: the table is linear between its nodes
+    m = "data_matr%M11s"
+    assert not np.array_equal(ana[0][m], ext[0][m])
+    assert np.array_equal(ana[0]["data_matr%Q_mu"], ext[0]["data_matr%Q_mu"])     # piecewise constant: exact
