@@ -7,7 +7,7 @@ ROOT="$HERE/../.."
 CXX="${CXX:-g++}"
 OUT="${OUT:-$HERE/../axisem_b200_solver}"
 "$CXX" -O2 -std=c++17 -Wall -Wextra -I"$ROOT/include" -o "$OUT" \
-    "$HERE/main.cpp" "$HERE/time_loop.cpp" "$HERE/modules.cpp" "$HERE/meshdb.cpp" \
+    "$HERE/main.cpp" "$HERE/time_loop.cpp" "$HERE/modules.cpp" "$HERE/meshdb.cpp" "$HERE/receivers.cpp" \
     "$HERE/precomp.cpp" "$HERE/mapping.cpp" "$HERE/background_models.cpp" \
     -L"$HERE/.." -laxisem_b200 -Wl,-rpath,'$ORIGIN'
 echo "built $OUT"
@@ -24,6 +24,6 @@ echo "built $HERE/../axisem_b200_hosttool"
 "$CXX" -O2 -std=c++17 -Wall -Wextra -o "$HERE/../axisem_b200_postproc" "$HERE/postproc_main.cpp" "$HERE/postprocess.cpp"
 echo "built $HERE/../axisem_b200_postproc"
 # the native pre-computation as a stand-alone step: MESHER databases -> complete containers
-"$CXX" -O2 -std=c++17 -Wall -Wextra -o "$HERE/../axisem_b200_precomp" "$HERE/precomp_main.cpp" "$HERE/precomp.cpp" \
+"$CXX" -O2 -std=c++17 -Wall -Wextra -o "$HERE/../axisem_b200_precomp" "$HERE/precomp_main.cpp" "$HERE/precomp.cpp" "$HERE/receivers.cpp" \
     "$HERE/mapping.cpp" "$HERE/background_models.cpp" "$HERE/meshdb.cpp" "$HERE/modules.cpp"
 echo "built $HERE/../axisem_b200_precomp"

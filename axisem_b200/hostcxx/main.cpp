@@ -19,6 +19,7 @@
 #include "meshdb.hpp"
 #include "time_loop.hpp"
 #include "precomp.hpp"
+#include "receivers.hpp"
 
 namespace {
 
@@ -113,7 +114,7 @@ void usage() {
                  "   or: axisem_b200_solver --out PREFIX [--model NAME | --ext-model FILE.bm] [--src TYPE] [--depth KM] [--period T0]\n"
                  "          [--stf gauss_0|gauss_1|gauss_2|errorf|dirac_0|quheavi] [--discrete-choice gaussi|1dirac|...] [--shift SECONDS]\n"
                  "          [--niter N] [--dt DT] [--seis-it K] [--strain-it K] [--attenuation cg4|full] [--scheme NAME]\n"
-                 "          [--receivers COLAT,COLAT,...] [--energy] [--snap-it K]  meshdb.dat0000 [meshdb.dat0001 ...]\n"
+                 "          [--receivers COLAT,COLAT,... | --receivers-file receivers.dat | --stations STATIONS] [--src-lat DEG --src-lon DEG] [--energy] [--snap-it K]  meshdb.dat0000 [meshdb.dat0001 ...]\n"
                  "       (the second form pre-computes everything from the MESHER's databases, no other input)\n");
 }
 
@@ -124,6 +125,7 @@ int main(int argc, char **argv) {
     std::string prefix;
     std::vector<std::string> files;
     axisem::PrecompOptions pre;
+    axisem::ReceiverSetup recs;
     for (int k = 1; k < argc; k++) {
         const std::string a = argv[k];
         auto need = [&](const char *what) -> const char * {
@@ -144,6 +146,10 @@ int main(int argc, char **argv) {
         else if (a == "--src") pre.src_type2 = need("--src");
         else if (a == "--depth") pre.src_depth = 1e3 * std::atof(need("--depth"));
         else if (a == "--period") pre.t_0 = std::atof(need("--period"));
+        else if (a == "--receivers-file") recs.receivers_file = need("--receivers-file");
+        else if (a == "--stations") recs.stations_file = need("--stations");
+        else if (a == "--src-lat") recs.src_lat_deg = std::atof(need("--src-lat"));
+        else if (a == "--src-lon") recs.src_lon_deg = std::atof(need("--src-lon"));
         else if (a == "--stf") pre.stf_type = need("--stf");
         else if (a == "--discrete-choice") pre.discrete_choice = need("--discrete-choice");
         else if (a == "--shift") pre.shift_seconds = std::atof(need("--shift"));
@@ -175,7 +181,10 @@ int main(int argc, char **argv) {
         if (from_meshdb) {
             // MESHER databases only: everything else is computed here (precomp.hpp)
             for (size_t r = 0; r < files.size(); r++) ranks.push_back(axisem::read_meshdb(files[r], (int)r));
+            std::vector<double> rec_lon;
+            if (recs.given()) axisem::prepare_receivers(recs, prefix, pre.rec_colat_deg, rec_lon);
             axisem::precompute(ranks, pre);
+            if (recs.given()) axisem::write_receiver_pts(prefix + ".receiver_pts.dat", axisem::receiver_indices(ranks), axisem::receiver_colatitudes(ranks), rec_lon);
             const axisem::PrecompChecks c = axisem::precompute_checks(ranks);
             if (opt.verbose)
                 std::printf("pre-computation: mass = volume %.10f (solid+fluid over sphere-hollow), S/F boundary term %.10f for %d boundaries\n",

@@ -831,8 +831,12 @@ void precompute(std::vector<Modules> &ranks, const PrecompOptions &opt) {
         {
             std::vector<int32_t> rec;       // (num_rec, 3) Fortran order, filled later
             std::vector<std::array<int32_t, 3>> hits;
-            for (double cd : opt.rec_colat_deg) {
+            std::vector<int32_t> loc2glob;   // loc2globrec (1-based position in the receiver list)
+            std::vector<double> th_deg;      // recfile_th: colatitude of the grid point taken [deg]
+            for (size_t irec = 0; irec < opt.rec_colat_deg.size(); irec++) {
+                const double cd = opt.rec_colat_deg[irec];
                 const double c = cd * PI / 180.0;
+                double th_best = 0.0;
                 double best = 1e300;
                 size_t best_rank = nr;
                 std::array<int32_t, 3> at{0, 0, 0};
@@ -843,16 +847,18 @@ void precompute(std::vector<Modules> &ranks, const PrecompOptions &opt) {
                             const size_t p = (size_t)NPT * e + k;
                             if (std::fabs(G.r[p] - router) > 1e-3 * router * 1e-3) continue;
                             const double d = std::fabs(std::atan2(G.s[p], G.z[p]) - c);
-                            if (d < best - 1e-14) { best = d; best_rank = q; at = {e + 1, k % NP, k / NP}; }
+                            if (d < best - 1e-14) { best = d; best_rank = q; at = {e + 1, k % NP, k / NP}; th_best = std::atan2(G.s[p], G.z[p]); }
                         }
                 }
-                if (best_rank == r) hits.push_back(at);
+                if (best_rank == r) { hits.push_back(at); loc2glob.push_back((int32_t)irec + 1); th_deg.push_back(th_best * 180.0 / PI); }
             }
             const size_t nrec = hits.size();
             rec.resize(3 * nrec);
             for (size_t k = 0; k < nrec; k++) { rec[k] = hits[k][0]; rec[nrec + k] = hits[k][1]; rec[2 * nrec + k] = hits[k][2]; }
             m.put("data_mesh%num_rec", scalar_i((int32_t)nrec));
             m.put("data_mesh%recfile_el", i32_of(rec, {3, (uint64_t)nrec}));
+            m.put("data_mesh%loc2globrec", i32_of(loc2glob, {(uint64_t)nrec}));
+            m.put("data_mesh%recfile_th", make(Array::F64, {(uint64_t)nrec}, th_deg.data()));
         }
         // ---- wavefield-dump point set (meshes_io.F90:489-640: first visit wins, solid then fluid) -------
         m.put("data_io%dump_wavefields", scalar_i(opt.dump_wavefields && opt.strain_it > 0));
@@ -968,6 +974,25 @@ void precompute(std::vector<Modules> &ranks, const PrecompOptions &opt) {
             m.put("precomp%fluid_volume_over_2pi", scalar_d(vf));
         }
     }
+}
+
+std::vector<std::vector<int>> receiver_indices(const std::vector<Modules> &ranks) {
+    std::vector<std::vector<int>> out;
+    for (const Modules &m : ranks) {
+        const size_t n = (size_t)m.int_of("data_mesh%num_rec");
+        const int32_t *p = n ? m.i("data_mesh%loc2globrec") : nullptr;
+        out.emplace_back(p, p + n);
+    }
+    return out;
+}
+std::vector<std::vector<double>> receiver_colatitudes(const std::vector<Modules> &ranks) {
+    std::vector<std::vector<double>> out;
+    for (const Modules &m : ranks) {
+        const size_t n = (size_t)m.int_of("data_mesh%num_rec");
+        const double *p = n ? m.d("data_mesh%recfile_th") : nullptr;
+        out.emplace_back(p, p + n);
+    }
+    return out;
 }
 
 PrecompChecks precompute_checks(const std::vector<Modules> &ranks) {

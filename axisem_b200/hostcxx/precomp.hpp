@@ -59,6 +59,10 @@ struct PrecompOptions {
     double xdmf_rmin = 0.0, xdmf_rmax = 7.0e6, xdmf_thetamin = 0.0, xdmf_thetamax = 3.14159265358979323846;
 };
 
+// loc2globrec / recfile_th of every rank after precompute (for receiver_pts.dat)
+std::vector<std::vector<int>> receiver_indices(const std::vector<Modules> &ranks);
+std::vector<std::vector<double>> receiver_colatitudes(const std::vector<Modules> &ranks);
+
 // `ranks`: read_meshdb results of all ranks of the run, in rank order (mass matrices are
 // assembled across the cuts).  On return every Modules also holds the time-loop inputs.
 void precompute(std::vector<Modules> &ranks, const PrecompOptions &opt);

@@ -15,6 +15,7 @@
 #include "mapping.hpp"
 #include "meshdb.hpp"
 #include "precomp.hpp"
+#include "receivers.hpp"
 
 // --mapping-check: the four element mappings on one spherical-shell element (20-31 degrees,
 // 3000-3600 km): corners, derivatives against central differences, the defining geometry of the
@@ -108,6 +109,7 @@ int model_eval(const std::string &name, const std::string &list) {
 
 int main(int argc, char **argv) {
     axisem::PrecompOptions pre;
+    axisem::ReceiverSetup recs;
     std::string prefix;
     std::vector<std::string> files;
     for (int k = 1; k < argc; k++) {
@@ -125,6 +127,10 @@ int main(int argc, char **argv) {
             const std::string name = need(), v = need();
             return model_eval(name, v);
         }
+        else if (a == "--receivers-file") recs.receivers_file = need();      // receivers.dat (RECFILE_TYPE colatlon)
+        else if (a == "--stations") recs.stations_file = need();             // STATIONS (RECFILE_TYPE stations)
+        else if (a == "--src-lat") recs.src_lat_deg = std::atof(need());     // SOURCE_LAT / SOURCE_LON [deg]
+        else if (a == "--src-lon") recs.src_lon_deg = std::atof(need());
         else if (a == "--src") pre.src_type2 = need();
         else if (a == "--depth") pre.src_depth = 1e3 * std::atof(need());
         else if (a == "--period") pre.t_0 = std::atof(need());
@@ -163,7 +169,10 @@ int main(int argc, char **argv) {
     try {
         std::vector<axisem::Modules> ranks;
         for (size_t r = 0; r < files.size(); r++) ranks.push_back(axisem::read_meshdb(files[r], (int)r));
+        std::vector<double> rec_lon;
+        if (recs.given()) axisem::prepare_receivers(recs, prefix, pre.rec_colat_deg, rec_lon);
         axisem::precompute(ranks, pre);
+        if (recs.given()) axisem::write_receiver_pts(prefix + ".receiver_pts.dat", axisem::receiver_indices(ranks), axisem::receiver_colatitudes(ranks), rec_lon);
         const axisem::PrecompChecks c = axisem::precompute_checks(ranks);
         std::printf("mass_over_volume %.12f\nbdry_sum %.12f\nn_sf_boundaries %d\n",
                     (c.solid_volume + c.fluid_volume) / (c.sphere_volume - c.hollow_volume), c.bdry_sum, c.n_sf_boundaries);

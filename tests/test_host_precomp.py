@@ -284,3 +284,67 @@ def test_external_background_model(exe, tmp_path):
     m = "data_matr%M11s"
     assert not np.array_equal(ana[0][m], ext[0][m])
     assert np.array_equal(ana[0]["data_matr%Q_mu"], ext[0]["data_matr%Q_mu"])     # piecewise constant: exact
+
+
+def test_receiver_files_and_rotation(exe, tmp_path):
+    """prepare_from_recfile_seis on the native host: receivers.dat (colatlon) and STATIONS (stations,
+    repeated station + network dropped, longitudes <= 0 shifted), the rotation of rotations.f90 into
+    the frame with the source on the pole (epicentral distance = colatitude there; the post-processing's
+    receiver_location, restated from another file of the reference, maps it back), receiver_pts.dat and
+    the location of the closest surface points."""
+    spec = prem_mesh_spec(ntheta=16, nr_target=18)
+    probs = [build_problem(spec, SourceParams(src_type2="explosion", t_0=40.0), niter=10, rank=r, nranks=2,
+                           rec_colat_deg=COLAT, dump=True, strain_it=10, energy=True) for r in range(2)]
+    st = tmp_path / "STATIONS"
+    st.write_text("AAK II 42.639 74.494 1645.0 30.0\n"
+                  "ANMO IU 34.946 -106.457 1850.0 100.0\n"
+                  "AAK II 42.639 74.494 1645.0 30.0\n"          # the same station again: dropped
+                  "SPA IU -89.93 145.0 2927.0 0.0\n"
+                  "AAK KN 42.639 74.494 1645.0 30.0\n")         # same name, another network: kept
+    src_lat, src_lon = 36.5, 140.25
+    got, _, _ = _run(exe, str(tmp_path), probs, "explosion", "none", False,
+                     ["--stations", str(st), "--src-lat", str(src_lat), "--src-lon", str(src_lon)])
+    pre = str(tmp_path / "pre")
+    names = [l.split() for l in open(pre + ".receiver_names.dat").read().strip().splitlines()]
+    assert [n[0] for n in names] == ["AAK_II", "ANMO_IU", "SPA_IU", "AAK_KN"]
+    colat = np.array([float(n[1]) for n in names])
+    lon = np.array([float(n[2]) for n in names])
+    assert np.allclose(colat, [90 - 42.639, 90 - 34.946, 179.93, 90 - 42.639]) and np.allclose(lon, [74.494, 360 - 106.457, 145.0, 74.494])
+    rot = np.loadtxt(pre + ".receiver_rotated.dat")
+    # epicentral distance by the spherical law of cosines
+    sc, sl = np.radians(90 - src_lat), np.radians(src_lon)
+    rc, rl = np.radians(colat), np.radians(lon)
+    dist = np.degrees(np.arccos(np.cos(sc) * np.cos(rc) + np.sin(sc) * np.sin(rc) * np.cos(rl - sl)))
+    assert np.allclose(rot[:, 0], dist, atol=1e-6)
+    # back through the inverse rotation: x = R y with R = rot_mat of def_rot_matrix
+    R = np.array([[np.cos(sc) * np.cos(sl), -np.sin(sl), np.sin(sc) * np.cos(sl)],
+                  [np.cos(sc) * np.sin(sl), np.cos(sl), np.sin(sc) * np.sin(sl)],
+                  [-np.sin(sc), 0.0, np.cos(sc)]])
+    th, ph = np.radians(rot[:, 0]), np.radians(rot[:, 1])
+    x = R @ np.stack([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)])
+    x0 = np.stack([np.sin(rc) * np.cos(rl), np.sin(rc) * np.sin(rl), np.cos(rc)])
+    assert np.abs(x - x0).max() < 1e-6          # (the reference's + smallval_dble costs the longitude of a polar station 0.005 deg)
+    assert np.allclose((np.degrees(np.arctan2(x[1], x[0])) % 360.0)[[0, 1, 3]], lon[[0, 1, 3]], atol=1e-5)
+    # the grid points taken: each receiver on exactly one rank, within half a surface element of its distance
+    pts = np.loadtxt(pre + ".receiver_pts.dat")
+    assert pts.shape == (4, 3) and np.allclose(pts[:, 1], rot[:, 1])
+    assert np.abs(pts[:, 0] - rot[:, 0]).max() < 180.0 / 16 / 2
+    nrec = 0
+    for r, g in enumerate(got):
+        idx = g["data_mesh%loc2globrec"].reshape(-1) if int(g["data_mesh%num_rec"]) else np.zeros(0, int)
+        assert (pts[idx - 1, 2] == r).all()
+        assert np.allclose(g["data_mesh%recfile_th"].reshape(-1), pts[idx - 1, 0]) if idx.size else True
+        nrec += idx.size
+    assert nrec == 4
+    # receivers.dat: source on the pole (no rotation), names recfile_NNNN
+    rd = tmp_path / "receivers.dat"
+    rd.write_text("3\n10.0 0.0\n95.5 270.0\n171.0 12.5\n")
+    _run(exe, str(tmp_path), probs, "explosion", "none", False, ["--receivers-file", str(rd)])
+    names = [l.split() for l in open(pre + ".receiver_names.dat").read().strip().splitlines()]
+    assert [n[0] for n in names] == ["recfile_0001", "recfile_0002", "recfile_0003"]
+    assert np.allclose(np.loadtxt(pre + ".receiver_rotated.dat"), [[10.0, 0.0], [95.5, 270.0], [171.0, 12.5]])
+    # the reference's stops
+    rd.write_text("1\n10.0 -5.0\n")
+    files = [str(tmp_path / f"meshdb.dat{r:04d}") for r in range(2)]
+    out = subprocess.run([exe, "--out", pre, "--receivers-file", str(rd)] + files, capture_output=True, text=True)
+    assert out.returncode != 0 and "negative receiver longitudes" in out.stderr
