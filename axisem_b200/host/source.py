@@ -56,16 +56,17 @@ def stf_shift(p: SourceParams, deltat: float) -> float:
 
 
 def discrete_dirac_setup(period: float, deltat: float, seis_it: int, strain_it: int = 0,
-                         dump_wavefields: bool = False) -> Tuple[float, str, float]:
+                         dump_wavefields: bool = False, stf_type: str = "dirac_0") -> Tuple[float, str, float]:
     """(discrete_dirac_halfwidth, discrete_choice, shift_fact_discrete_dirac) for dirac_0 / quheavi as
     parameters.F90:975-1068 sets them: half width period / 8 (period / (2 deltat_coarse), at least
     15, where only seismograms are down-sampled), a Gaussian where anything is down-sampled and a
     one-sample spike otherwise, and the first shift beyond four half widths that is a whole number of
-    time steps, seismogram samples and wavefield samples."""
+    time steps, seismogram samples and wavefield samples.  (The narrower half width is taken for
+    dirac_0 only: the reference tests stf_type against 'queavi' there, parameters.F90:979.)"""
     seis_dt = deltat * seis_it
     deltat_coarse = deltat * (strain_it if dump_wavefields and strain_it > 0 else seis_it)
     pvh = 8
-    if not dump_wavefields and deltat_coarse > 1.9 * deltat:
+    if not dump_wavefields and stf_type == "dirac_0" and deltat_coarse > 1.9 * deltat:
         pvh = int(period / (2.0 * deltat_coarse))           # integer period_vs_discrete_halfwidth
         if pvh < 15:
             pvh = 15

@@ -83,6 +83,9 @@ def test_discrete_dirac_setup_follows_parameters_f90():
     assert shift > 4 * half and abs(shift / 2.0 - round(shift / 2.0)) < 1e-6
     half, choice, shift = discrete_dirac_setup(200.0, 0.5, seis_it=4)
     assert half == float(np.float32(200.0 / 50))
+    # ... for dirac_0 only (the reference compares with 'queavi' there): quheavi keeps period / 8
+    half, choice, _ = discrete_dirac_setup(200.0, 0.5, seis_it=4, stf_type="quheavi")
+    assert (half, choice) == (25.0, "gaussi")
     # wavefield dumps: Gaussian of half width period / 8, shift on the dump grid too
     half, choice, shift = discrete_dirac_setup(50.0, 0.5, seis_it=2, strain_it=8, dump_wavefields=True)
     assert (half, choice) == (6.25, "gaussi")
