@@ -7,7 +7,7 @@ ROOT="$HERE/../.."
 CXX="${CXX:-g++}"
 OUT="${OUT:-$HERE/../axisem_b200_solver}"
 "$CXX" -O2 -std=c++17 -Wall -Wextra -I"$ROOT/include" -o "$OUT" \
-    "$HERE/main.cpp" "$HERE/time_loop.cpp" "$HERE/modules.cpp" "$HERE/meshdb.cpp" "$HERE/receivers.cpp" \
+    "$HERE/main.cpp" "$HERE/time_loop.cpp" "$HERE/modules.cpp" "$HERE/meshdb.cpp" "$HERE/receivers.cpp" "$HERE/rundir.cpp" \
     "$HERE/precomp.cpp" "$HERE/mapping.cpp" "$HERE/background_models.cpp" \
     -L"$HERE/.." -laxisem_b200 -Wl,-rpath,'$ORIGIN'
 echo "built $OUT"
@@ -21,7 +21,7 @@ echo "built $HERE/../axisem_b200_meshdb2axbp"
     "$HERE/hosttool.cpp" "$HERE/spectral.cpp" "$HERE/background_models.cpp"
 echo "built $HERE/../axisem_b200_hosttool"
 # post-processing of the solver output (radiation factors, rotation, STF convolution)
-"$CXX" -O2 -std=c++17 -Wall -Wextra -o "$HERE/../axisem_b200_postproc" "$HERE/postproc_main.cpp" "$HERE/postprocess.cpp"
+"$CXX" -O2 -std=c++17 -Wall -Wextra -o "$HERE/../axisem_b200_postproc" "$HERE/postproc_main.cpp" "$HERE/postprocess.cpp" "$HERE/rundir.cpp"
 echo "built $HERE/../axisem_b200_postproc"
 # the native pre-computation as a stand-alone step: MESHER databases -> complete containers
 "$CXX" -O2 -std=c++17 -Wall -Wextra -o "$HERE/../axisem_b200_precomp" "$HERE/precomp_main.cpp" "$HERE/precomp.cpp" "$HERE/receivers.cpp" \

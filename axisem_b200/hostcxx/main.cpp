@@ -8,6 +8,7 @@
 //   PREFIX.rankNNNN.xdmf.f32   xdmf snapshot fields (npoint_plot, nsnap, 5)   (wavefields_io.f90:195-199)
 //   PREFIX.info                key = value summary
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +21,7 @@
 #include "time_loop.hpp"
 #include "precomp.hpp"
 #include "receivers.hpp"
+#include "rundir.hpp"
 
 namespace {
 
@@ -107,9 +109,107 @@ struct FileSink : axisem::OutputSink {
     }
 };
 
+// what the reference leaves in its run directory with USE_NETCDF false: simulation.info, Data/receiver_names.dat,
+// Data/receiver_pts.dat, Data/<receiver>_disp.dat, Data/stf*.dat — the input of its post-processing
+void write_rundir(const std::string &dir, const std::vector<axisem::Modules> &ranks, const axisem::PrecompOptions &pre,
+                  const axisem::ReceiverSetup &recs, const axisem::ReceiverList &rec_list, const std::vector<double> &rec_lon,
+                  const FileSink &sink, const axisem::TimeLoopResult &res) {
+    const double PI = 3.14159265358979323846;
+    axisem::make_directory(dir);
+    axisem::make_directory(dir + "/Data");
+    const axisem::Modules &m0 = ranks[0];
+    const auto loc2glob = axisem::receiver_indices(ranks);
+    const auto th = axisem::receiver_colatitudes(ranks);
+    size_t nrec = 0;
+    for (const auto &v : loc2glob) nrec += v.size();
+    // receivers of the run in the order of the list they came from
+    axisem::ReceiverList names = rec_list;
+    std::vector<double> lon = rec_lon;
+    if (names.size() == 0) {
+        for (size_t k = 0; k < nrec; k++) {
+            char b[32];
+            std::snprintf(b, sizeof b, "recfile_%04zu", k + 1);
+            names.name.push_back(b);
+            names.colat_deg.push_back(k < pre.rec_colat_deg.size() ? pre.rec_colat_deg[k] : 0.0);
+            names.lon_deg.push_back(0.0);
+        }
+        lon.assign(nrec, 0.0);
+    }
+    if (names.size() != nrec) throw axisem::SolverError("PROBLEM: sum of local receivers is different than global!");
+    axisem::write_receiver_names(dir + "/Data/receiver_names.dat", names);
+    axisem::write_receiver_pts(dir + "/Data/receiver_pts.dat", loc2glob, th, lon);
+    // seismograms of all ranks in list order
+    const int nseis = res.nseismo;
+    std::vector<float> seis((size_t)nseis * nrec * 3, 0.0f);
+    for (size_t r = 0; r < ranks.size(); r++) {
+        if (loc2glob[r].empty()) continue;
+        const auto it = sink.ranks.find(ranks[r].int_of("data_proc%mynum"));
+        if (it == sink.ranks.end() || it->second.nseis != nseis) throw axisem::SolverError("rundir: seismograms of a rank are missing");
+        const size_t nl = loc2glob[r].size();
+        for (int k = 0; k < nseis; k++)
+            for (size_t q = 0; q < nl; q++)
+                for (int c = 0; c < 3; c++)
+                    seis[((size_t)k * nrec + (loc2glob[r][q] - 1)) * 3 + c] = it->second.seis[((size_t)k * nl + q) * 3 + c];
+    }
+    const int src_order = m0.int_of("data_source%src_order");
+    axisem::write_disp_files(dir + "/Data", names.name, src_order == 0, nseis, seis);
+    // simulation.info
+    axisem::SimulationInfo s;
+    {
+        const axisem::Array &b = m0.at("data_mesh%bkgrdmodel");
+        for (size_t k = 0; k < b.count(); k++) s.bkgrdmodel.push_back((char)b.i32()[k]);
+        if (!pre.model.empty()) s.bkgrdmodel = pre.model;
+    }
+    s.deltat = m0.real_of("data_time%deltat");
+    s.niter = m0.int_of("data_time%niter");
+    s.src_type1 = src_order == 0 ? "monopole" : (src_order == 1 ? "dipole" : "quadpole");
+    s.src_type2 = pre.src_type2;
+    s.stf_type = pre.stf_type;
+    s.period = pre.t_0;
+    s.src_depth_km = pre.src_depth / 1000.0;
+    s.srccolat = (90.0 - recs.src_lat_deg) * PI / 180.0;
+    s.srclon = recs.src_lon_deg * PI / 180.0;
+    s.magnitude = pre.magnitude;
+    s.num_rec_tot = (int)nrec;
+    s.nseismo = nseis;
+    const int seis_it = m0.int_of("data_time%seis_it"), strain_it = m0.int_of("data_time%strain_it");
+    s.seis_dt = (double)(float)s.deltat * (double)(float)seis_it;        // real(deltat) * real(seis_it)
+    const bool dump = m0.int_of("data_io%dump_wavefields") != 0;
+    const double deltat_coarse = s.deltat * (dump ? strain_it : seis_it);
+    s.nstrain = dump ? res.nstrain : 0;
+    s.strain_dt = dump ? deltat_coarse : 0.0;
+    const int snap_it = m0.has("data_time%snap_it") ? m0.int_of("data_time%snap_it") : 0;
+    s.nsnap = snap_it > 0 ? s.niter / snap_it : 0;
+    s.snap_dt = snap_it > 0 ? s.deltat * snap_it : 0.0;
+    s.ibeg = 0; s.iend = 4;                                              // displ_only: the whole element (get_mesh.f90:91-96)
+    s.shift_fact = m0.real_of("data_source%shift_fact");
+    s.ishift_deltat = (int)std::lround(s.shift_fact / s.deltat);
+    s.ishift_seisdt = (int)std::lround(s.shift_fact / (s.deltat * seis_it));
+    s.ishift_straindt = (int)std::lround(s.shift_fact / deltat_coarse);
+    s.rec_file_type = recs.stations_file.empty() ? "colatlon" : "stations";
+    s.nproc = (int)ranks.size();
+    // the reference's nelem / nel_fluid are per rank (equal on all ranks): rank 0's
+    s.nelem = m0.int_of("data_mesh%nel_solid") + m0.int_of("data_mesh%nel_fluid");
+    s.nel_fluid = m0.int_of("data_mesh%nel_fluid");
+    axisem::write_simulation_info(dir + "/simulation.info", s);
+    // stf.dat, stf_seis.dat, stf_strain.dat (compute_stf, source.f90:186-199)
+    if (m0.has("data_source%stf")) {
+        const axisem::Array &a = m0.at("data_source%stf");
+        const char *fn[3] = {"/Data/stf.dat", "/Data/stf_seis.dat", "/Data/stf_strain.dat"};
+        const int every[3] = {1, seis_it, std::max(strain_it, 1)};
+        for (int q = 0; q < 3; q++) {
+            FILE *f = std::fopen((dir + fn[q]).c_str(), "w");
+            if (!f) throw axisem::SolverError("cannot write " + dir + fn[q]);
+            for (int i = 1; i <= s.niter && (size_t)i <= a.count(); i++)
+                if (i % every[q] == 0) std::fprintf(f, " %16.8E %16.8E\n", (double)((float)i * (float)s.deltat), (double)a.f32()[i - 1]);
+            std::fclose(f);
+        }
+    }
+}
+
 void usage() {
     std::fprintf(stderr,
-                 "usage: axisem_b200_solver [--steps N] [--devices D] [--dumpbuffer B] [--quiet] --out PREFIX "
+                 "usage: axisem_b200_solver [--steps N] [--devices D] [--dumpbuffer B] [--quiet] [--rundir DIR] --out PREFIX "
                  "rank0.axbp[+meshdb.dat0000] [rank1.axbp[+meshdb.dat0001] ...]\n"
                  "   or: axisem_b200_solver --out PREFIX [--model NAME | --ext-model FILE.bm] [--src TYPE] [--depth KM] [--period T0]\n"
                  "          [--stf gauss_0|gauss_1|gauss_2|errorf|dirac_0|quheavi] [--discrete-choice gaussi|1dirac|...] [--shift SECONDS]\n"
@@ -126,6 +226,7 @@ int main(int argc, char **argv) {
     std::vector<std::string> files;
     axisem::PrecompOptions pre;
     axisem::ReceiverSetup recs;
+    std::string rundir;
     for (int k = 1; k < argc; k++) {
         const std::string a = argv[k];
         auto need = [&](const char *what) -> const char * {
@@ -137,6 +238,7 @@ int main(int argc, char **argv) {
         else if (a == "--dumpbuffer") opt.nc_dumpbuffersize = std::max(1, std::atoi(need("--dumpbuffer")));
         else if (a == "--quiet") opt.verbose = false;
         else if (a == "--out") prefix = need("--out");
+        else if (a == "--rundir") rundir = need("--rundir");     // the reference's run directory (USE_NETCDF false): rundir.hpp
         else if (a == "--model") pre.model = need("--model");
         else if (a == "--ext-model") {
             try { axisem::set_external_model(axisem::read_external_model(need("--ext-model"))); }
@@ -177,12 +279,13 @@ int main(int argc, char **argv) {
     if (files.empty() || prefix.empty()) { usage(); return 2; }
     try {
         std::vector<axisem::Modules> ranks;
+        std::vector<double> rec_lon;
+        axisem::ReceiverList rec_list;
         const bool from_meshdb = files[0].find(".axbp") == std::string::npos;
         if (from_meshdb) {
             // MESHER databases only: everything else is computed here (precomp.hpp)
             for (size_t r = 0; r < files.size(); r++) ranks.push_back(axisem::read_meshdb(files[r], (int)r));
-            std::vector<double> rec_lon;
-            if (recs.given()) axisem::prepare_receivers(recs, prefix, pre.rec_colat_deg, rec_lon);
+            if (recs.given()) rec_list = axisem::prepare_receivers(recs, prefix, pre.rec_colat_deg, rec_lon);
             axisem::precompute(ranks, pre);
             if (recs.given()) axisem::write_receiver_pts(prefix + ".receiver_pts.dat", axisem::receiver_indices(ranks), axisem::receiver_colatitudes(ranks), rec_lon);
             const axisem::PrecompChecks c = axisem::precompute_checks(ranks);
@@ -210,6 +313,10 @@ int main(int argc, char **argv) {
             std::fprintf(f, "rank%04d = num_rec %d nseis %d npoints %zu nsnap %d\n", kv.first, kv.second.num_rec,
                          kv.second.nseis, kv.second.npoints, kv.second.nsnap);
         std::fclose(f);
+        if (!rundir.empty()) {
+            if (!from_meshdb) throw axisem::SolverError("--rundir needs the run described on the command line (the meshdb form)");
+            write_rundir(rundir, ranks, pre, recs, rec_list, rec_lon, sink, res);
+        }
         if (opt.verbose) std::printf("time loop done: %d steps, %.3f s\n", res.iter, res.seconds);
     } catch (const std::exception &e) {
         // the reference writes the message and stops (pcheck / stop)

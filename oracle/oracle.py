@@ -70,7 +70,7 @@ def build_host(force: bool = False) -> str:
              or os.path.getmtime(HOST_EXE) < max([os.path.getmtime(f) for f in srcs] + [os.path.getmtime(LIB)]))
     if force or stale:
         cpp = [os.path.join(src_dir, f) for f in ("main.cpp", "time_loop.cpp", "modules.cpp", "meshdb.cpp", "precomp.cpp", "mapping.cpp",
-                                                        "background_models.cpp", "receivers.cpp")]
+                                                        "background_models.cpp", "receivers.cpp", "rundir.cpp")]
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(HERE, "..", "include"),
                                "-DAXB_PREFIX=axo_", "-o", HOST_EXE] + cpp
                               + ["-L" + HERE, "-laxisem_oracle", "-Wl,-rpath," + HERE])

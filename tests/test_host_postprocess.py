@@ -155,3 +155,80 @@ def test_causal_stf_convolution(exe, tmp_path):
     assert np.abs(got[0, 0] - want).max() < 1e-6 * ker.max()
     assert np.abs(got[0, 1] - 2 * want).max() < 2e-6 * ker.max()
     assert abs(ker.sum() - 1.0) < 2e-3                         # unit area: amplitudes are preserved
+
+
+def _write_simdir(d, src1, src2, mag, raw, names, colat, lon, dt, shift, sc, sl):
+    """A run directory as the reference's solver leaves it with USE_NETCDF false (simulation.info in
+    the formats of parameters.F90:1410-1465, Data/receiver_names.dat, receiver_pts.dat, *_disp.dat)."""
+    os.makedirs(d / "Data")
+    ns, nrec = raw.shape[0], raw.shape[1]
+    A = lambda s: f"{s:>45s}"[:45]
+    f21 = lambda v, s: f"{v:22.7f}{A(s)}\n"
+    f22 = lambda v, s: f"{v:20d}{A(s)}\n"
+    f23 = lambda v, s: f"{v:>20s}{A(s)}\n"
+    txt = (f23("prem_iso", "background model") + f21(dt, "time step [s]") + f22(ns - 1, "number of time steps")
+           + f23(src1, "source type") + f23(src2, "source type") + f23("dirac_0", "source time function") + f23("moment", "simtype")
+           + f21(20.0, "dominant source period") + f21(24.4, "source depth [km]") + f21(sc, "Source colatitude")
+           + f21(sl, "Source longitude") + f"{mag:15.5E}{A('scalar source magnitude')}\n" + f22(nrec, "number of receivers")
+           + f22(ns, "length of seismogram [time samples]") + f21(dt, "seismogram sampling [s]") + f22(0, "number of strain dumps")
+           + f21(0.0, "strain dump sampling rate [s]") + f22(0, "number of snapshot dumps") + f21(0.0, "snapshot dump sampling rate [s]")
+           + f23("cyl", "receiver components ") + f22(0, "  ibeg: beginning gll index for wavefield dumps")
+           + f22(4, "iend: end gll index for wavefield dumps") + f21(shift, "source shift factor [s]")
+           + f22(round(shift / dt), "source shift factor for deltat") + f22(round(shift / dt), "source shift factor for seis_dt")
+           + f22(round(shift / dt), "source shift factor for deltat_coarse") + f23("stations", "receiver file type")
+           + f21(0.0, "receiver spacing (0 if not even)") + f"{'F':>20s}{A('use netcdf for wavefield output?')}\n"
+           + f22(100, "nelem") + f22(20, "nel_fluid") + f22(2, "nproc"))
+    (d / "simulation.info").write_text(txt)
+    (d / "Data" / "receiver_names.dat").write_text("".join(f" {n} {10.0 + k} {20.0 + k}\n" for k, n in enumerate(names)))
+    (d / "Data" / "receiver_pts.dat").write_text("".join(f" {float(np.rad2deg(c))!r} {float(np.rad2deg(l))!r} {k % 2}\n"
+                                                         for k, (c, l) in enumerate(zip(colat, lon))))
+    for k, n in enumerate(names):
+        cols = raw[:, k, :][:, [0, 2]] if src1 == "monopole" else raw[:, k, :]
+        np.savetxt(d / "Data" / f"{n}_disp.dat", cols, fmt="%16.8E")
+
+
+@pytest.mark.parametrize("sys", ["enz", "sph"])
+def test_run_directories_in_the_references_layout(exe, tmp_path, sys):
+    """--simdir: the four run directories of a moment-tensor source as the reference's solver (or
+    axisem_b200_solver --rundir) writes them give what the raw arrays give; --ascii-out writes the
+    processed traces the way post_processing.F90:410-425 does."""
+    rng = np.random.default_rng(11)
+    nrec, ns, dt, shift = 5, 48, 0.5, 4.0
+    sc, sl = np.deg2rad(37.5), np.deg2rad(143.0)
+    colat = np.deg2rad(rng.uniform(5, 175, nrec))
+    lon = np.deg2rad(rng.uniform(0, 360, nrec))
+    names = [f"ST{k:02d}_XX" for k in range(nrec)]
+    M_dyncm = np.array([1.2e26, -0.7e26, -0.5e26, 2.1e26, -1.4e26, 0.9e26])
+    cmt = tmp_path / "CMTSOLUTION"
+    cmt.write_text(" PDE 2011  3 11  5 46 23.00  38.3200  142.3700  24.4 7.2 9.0 TEST EVENT\n"
+                   "event name:     TEST\ntime shift:      0.0000\nhalf duration:   0.0000\n"
+                   "latitude:       52.5\nlongitude:     143.0\ndepth:          24.4\n"
+                   + "".join(f"{n}:      {v:.6e}\n" for n, v in zip(("Mrr", "Mtt", "Mpp", "Mrt", "Mrp", "Mtp"), M_dyncm)))
+    runs, args = [], []
+    for t, s1, mag, sub in (("mrr", "monopole", 1e20, "MZZ"), ("mtt_p_mpp", "monopole", 2e20, "MXX_P_MYY"),
+                            ("mtr", "dipole", 1e20, "MXZ_MYZ"), ("mtp", "quadpole", 0.5e20, "MXY_MXX_M_MYY")):
+        raw = rng.standard_normal((ns, nrec, 3)).astype(np.float32)
+        if s1 == "monopole":
+            raw[:, :, 1] = 0.0
+        _write_simdir(tmp_path / sub, s1, t, mag, raw, names, colat, lon, dt, shift, sc, sl)
+        runs.append((t, mag, raw))
+        args += ["--simdir", str(tmp_path / sub)]
+    out = tmp_path / "out.f32"
+    run = subprocess.run([exe, "--cmt", str(cmt), "--sys", sys, "--out", str(out), "--ascii-out", str(tmp_path / "POST")] + args,
+                         capture_output=True, text=True)
+    assert run.returncode == 0, run.stderr
+    got = np.fromfile(out, dtype=np.float32).reshape(nrec, 3, ns)
+    want = _expected(runs, M_dyncm / 1e7, colat, lon, sc, sl, sys)
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() <= 3e-6 * scale            # the source location came from simulation.info
+    comps = {"enz": "NEZ", "sph": "tpr"}[sys]
+    for k, n in enumerate(names):
+        for c in range(3):
+            tab = np.loadtxt(tmp_path / "POST" / "SEISMOGRAMS" / f"{n}_disp_post_mij_conv0000_{comps[c]}.dat")
+            assert tab.shape == (ns, 2)
+            assert np.allclose(tab[:, 0], np.arange(ns) * dt - shift) and np.abs(tab[:, 1] - got[k, c]).max() <= 1e-6 * scale
+    # a run with NetCDF output is refused, not half-read
+    info = (tmp_path / "MZZ" / "simulation.info").read_text().replace("                   F", "                   T")
+    (tmp_path / "MZZ" / "simulation.info").write_text(info)
+    run = subprocess.run([exe, "--simdir", str(tmp_path / "MZZ"), "--out", str(out)], capture_output=True, text=True)
+    assert run.returncode != 0 and "NetCDF" in run.stderr

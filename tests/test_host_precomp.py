@@ -348,3 +348,84 @@ def test_receiver_files_and_rotation(exe, tmp_path):
     files = [str(tmp_path / f"meshdb.dat{r:04d}") for r in range(2)]
     out = subprocess.run([exe, "--out", pre, "--receivers-file", str(rd)] + files, capture_output=True, text=True)
     assert out.returncode != 0 and "negative receiver longitudes" in out.stderr
+
+
+def _fortran_field(line, width):
+    return line[:width], line[width:]
+
+
+@pytest.mark.parametrize("src,nranks", [("mtr", 2), ("explosion", 1)])
+def test_solver_leaves_the_references_run_directory(exe, tmp_path, src, nranks):
+    """--rundir: what the reference leaves behind with USE_NETCDF false and its post-processing reads —
+    simulation.info in the formats of parameters.F90:1410-1465 (read back the way post_processing.F90:614-647
+    reads it), Data/receiver_names.dat, Data/receiver_pts.dat, and one <receiver>_disp.dat per station
+    with the samples of the run (two columns for a monopole, list order of the STATIONS file across ranks)."""
+    from axisem_b200.capi import connect_local, run_group
+    from oracle import oracle
+    n = 40
+    spec = prem_mesh_spec(ntheta=16, nr_target=18)
+    st = tmp_path / "STATIONS"
+    st.write_text("S170 XX -80.0 0.0 0.0 0.0\nS010 XX 80.0 0.0 0.0 0.0\nS093 YY -3.0 45.0 0.0 0.0\nS047 XX 43.0 200.0 0.0 0.0\n")
+    colat = [170.0, 10.0, 93.0, 47.0]
+    probs = [build_problem(spec, SourceParams(src_type2=src, t_0=3.0), niter=n, rank=r, nranks=nranks, seis_it=2,
+                           rec_colat_deg=colat) for r in range(nranks)]
+    files = []
+    for r, p in enumerate(probs):
+        f = str(tmp_path / f"meshdb.dat{r:04d}")
+        write_meshdb(p.mesh, f, dt=p.deltat, bkgrdmodel="prem_iso")
+        files.append(f)
+    rundir = tmp_path / "RUN"
+    run = subprocess.run([oracle.build_host(), "--quiet", "--out", str(tmp_path / "run"), "--rundir", str(rundir), "--src", src,
+                          "--period", "3", "--niter", str(n), "--seis-it", "2", "--stations", str(st)] + files,
+                         capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr
+    # ---- simulation.info: 32 lines, value in a 20 / 22 / 15 wide field, label right-justified in 45
+    lines = open(rundir / "simulation.info").read().splitlines()
+    assert len(lines) == 32
+    widths = [20, 22, 20, 20, 20, 20, 20, 22, 22, 22, 22, 15, 20, 20, 22, 20, 22, 20, 22, 20, 20, 20, 22, 20, 20, 20, 20, 22, 20, 20, 20, 20]
+    labels = ["background model", "time step [s]", "number of time steps", "source type", "source type", "source time function", "simtype",
+              "dominant source period", "source depth [km]", "Source colatitude", "Source longitude", "scalar source magnitude",
+              "number of receivers", "length of seismogram [time samples]", "seismogram sampling [s]", "number of strain dumps",
+              "strain dump sampling rate [s]", "number of snapshot dumps", "snapshot dump sampling rate [s]", "receiver components",
+              "ibeg: beginning gll index for wavefield dum",       # 47 characters through an a45 edit descriptor
+              "iend: end gll index for wavefield dumps", "source shift factor [s]",
+              "source shift factor for deltat", "source shift factor for seis_dt", "source shift factor for deltat_coarse",
+              "receiver file type", "receiver spacing (0 if not even)", "use netcdf for wavefield output?", "nelem", "nel_fluid", "nproc"]
+    vals = []
+    for line, w, lab in zip(lines, widths, labels):
+        assert len(line) == w + 45, line
+        v, l = _fortran_field(line, w)
+        assert l.strip() == lab, line
+        vals.append(v.split()[0])
+    p0 = probs[0]
+    assert vals[0] == "prem_iso" and float(vals[1]) == pytest.approx(p0.deltat, abs=1e-7) and int(vals[2]) == n
+    assert vals[3] == ("dipole" if src == "mtr" else "monopole") and vals[4] == src and vals[5] == "gauss_0" and vals[6] == "single"
+    assert float(vals[7]) == 3.0 and float(vals[8]) == 100.0 and float(vals[9]) == 0.0 and float(vals[10]) == 0.0
+    assert vals[11] == "1.00000E+20" and int(vals[12]) == 4 and int(vals[13]) == n // 2 + 1
+    assert float(vals[14]) == pytest.approx(2 * p0.deltat, abs=1e-6)
+    assert vals[19] == "cyl" and vals[26] == "stations" and vals[28] == "F" and int(vals[31]) == nranks
+    assert int(vals[29]) == p0.mesh.nel_solid + p0.mesh.nel_fluid and int(vals[30]) == p0.mesh.nel_fluid
+    shift = float(vals[22])
+    assert int(vals[23]) == round(shift / p0.deltat) and int(vals[24]) == round(shift / (2 * p0.deltat))
+    # ---- receivers
+    names = [l.split()[0] for l in open(rundir / "Data" / "receiver_names.dat").read().strip().splitlines()]
+    assert names == ["S170_XX", "S010_XX", "S093_YY", "S047_XX"]
+    pts = np.loadtxt(rundir / "Data" / "receiver_pts.dat")
+    assert pts.shape == (4, 3) and np.abs(pts[:, 0] - colat).max() < 180.0 / 16 / 2
+    # ---- seismograms: the run itself, per station
+    lib = oracle.load()
+    loops = [oracle.make_loop(p) for p in probs]
+    connect_local(lib, loops)
+    run_group(lib, loops, n)
+    ref = np.zeros((n // 2 + 1, 4, 3), np.float32)
+    for p, L in zip(probs, loops):
+        if p.num_rec:
+            ref[:, p.rec_index, :] = L.seismograms()
+    assert np.abs(ref).max() > 0
+    for k, name in enumerate(names):
+        tab = np.loadtxt(rundir / "Data" / f"{name}_disp.dat")
+        assert tab.shape == (n // 2 + 1, 2 if src == "explosion" else 3)
+        want = ref[:, k, :][:, [0, 2]] if src == "explosion" else ref[:, k, :]
+        assert np.abs(tab - want).max() <= 3e-6 * np.abs(ref).max() + 1e-8 * np.abs(want).max()
+    stf = np.loadtxt(rundir / "Data" / "stf_seis.dat")
+    assert stf.shape == (n // 2, 2) and np.allclose(stf[:, 1], p0.stf[1::2], rtol=1e-6)
