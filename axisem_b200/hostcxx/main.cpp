@@ -192,6 +192,19 @@ void write_rundir(const std::string &dir, const std::vector<axisem::Modules> &ra
     s.nelem = m0.int_of("data_mesh%nel_solid") + m0.int_of("data_mesh%nel_fluid");
     s.nel_fluid = m0.int_of("data_mesh%nel_fluid");
     axisem::write_simulation_info(dir + "/simulation.info", s);
+    // xdmf snapshots (SAVE_SNAPSHOTS with SNAPSHOTS_FORMAT xdmf): iter 0, snap_it, 2 snap_it ...
+    for (const axisem::Modules &m : ranks) {
+        const int rank = m.int_of("data_proc%mynum");
+        const auto it = sink.xd.find(rank);
+        if (it == sink.xd.end() || !m.has("data_mesh%npoint_plot")) continue;
+        const int npnt = m.int_of("data_mesh%npoint_plot"), nel = m.int_of("data_mesh%nelem_plot");
+        if (npnt <= 0) continue;
+        const int nsn = (int)(it->second.size() / ((size_t)5 * npnt));
+        std::vector<double> times(nsn);
+        for (int k = 0; k < nsn; k++) times[k] = (double)k * snap_it * s.deltat;
+        axisem::write_xdmf_files(dir + "/Data", rank, npnt, nel, m.at("data_mesh%xdmf_points").f32(), m.i("data_mesh%xdmf_grid"),
+                                 it->second.data(), nsn, times, src_order == 0);
+    }
     // stf.dat, stf_seis.dat, stf_strain.dat (compute_stf, source.f90:186-199)
     if (m0.has("data_source%stf")) {
         const axisem::Array &a = m0.at("data_source%stf");

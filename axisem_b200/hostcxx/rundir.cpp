@@ -3,6 +3,8 @@
 #include <sys/stat.h>
 
 #include <cerrno>
+#include <cstdarg>
+#include <vector>
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -128,6 +130,113 @@ std::vector<float> read_disp_files(const std::string &data_dir, const std::vecto
         }
     }
     return seis;
+}
+
+namespace {
+
+template <class T>
+void put_big_endian(const std::string &path, const T *v, size_t n) {
+    static_assert(sizeof(T) == 4, "4-byte items");
+    std::vector<unsigned char> b(4 * n);
+    for (size_t k = 0; k < n; k++) {
+        const unsigned char *p = reinterpret_cast<const unsigned char *>(&v[k]);
+        b[4 * k] = p[3]; b[4 * k + 1] = p[2]; b[4 * k + 2] = p[1]; b[4 * k + 3] = p[0];
+    }
+    FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::invalid_argument("cannot write " + path);
+    std::fwrite(b.data(), 1, b.size(), f);
+    std::fclose(f);
+}
+
+std::string fmt(const char *f, ...) __attribute__((format(printf, 1, 2)));
+std::string fmt(const char *f, ...) {
+    char b[512];
+    va_list ap;
+    va_start(ap, f);
+    std::vsnprintf(b, sizeof b, f, ap);
+    va_end(ap);
+    return b;
+}
+
+// the Attribute block of formats 734 / 735 (wavefields_io.f90:286-297)
+std::string hyperslab(const char *name, int npoint, int isnap0, int nsnap, const std::string &fname) {
+    return fmt("        <Attribute Name=\"%s\" AttributeType=\"Scalar\" Center=\"Node\">\n", name) +
+           fmt("            <DataItem ItemType=\"HyperSlab\" Dimensions=\"%10d\" Type=\"HyperSlab\">\n", npoint) +
+           "                <DataItem Dimensions=\"3 2\" Format=\"XML\">\n" +
+           fmt("                    %10d          0 \n", isnap0) +
+           "                             1          1 \n" +
+           fmt("                             1 %10d\n", npoint) +
+           "                </DataItem>\n" +
+           fmt("                <DataItem Dimensions=\"%10d%10d\" NumberType=\"Float\" Format=\"binary\" Endian=\"Big\">\n", nsnap, npoint) +
+           "                   " + fname + "\n" +
+           "                </DataItem>\n            </DataItem>\n        </Attribute>\n";
+}
+
+}  // namespace
+
+void write_xdmf_files(const std::string &dir, int rank, int npnt, int nel, const float *points, const int32_t *grid,
+                      const float *fields, int nsnap, const std::vector<double> &times, bool monopole) {
+    const std::string app = fmt("%04d", rank);
+    put_big_endian(dir + "/xdmf_points_" + app + ".dat", points, (size_t)2 * npnt);
+    put_big_endian(dir + "/xdmf_grid_" + app + ".dat", grid, (size_t)4 * nel);
+    const char *names[5] = {"s", "p", "z", "trace", "curlip"};
+    for (int v = 0; v < 5; v++) {
+        if (v == 1 && monopole) continue;                          // unit 13101 is not opened
+        put_big_endian(dir + "/xdmf_snap_" + names[v] + "_" + app + ".dat", fields + (size_t)v * nsnap * npnt, (size_t)nsnap * npnt);
+    }
+    const std::string head = "<?xml version=\"1.0\" ?>\n<!DOCTYPE Xdmf SYSTEM \"Xdmf.dtd\" []>\n"
+                             "<Xdmf xmlns:xi=\"http://www.w3.org/2003/XInclude\" Version=\"2.2\">\n<Domain>\n";
+    {
+        std::string s = head + "<Grid Name=\"CellsTime\" GridType=\"Collection\" CollectionType=\"Temporal\">\n"
+                               "  <Grid GridType=\"Uniform\">\n    <Time Value=\"0.000\" />\n" +
+                        fmt("    <Topology TopologyType=\"Quadrilateral\" NumberOfElements=\"%10d\">\n", nel) +
+                        fmt("      <DataItem Dimensions=\"%10d 4\" NumberType=\"Int\" Format=\"binary\" Endian=\"Big\">\n", nel) +
+                        "        xdmf_grid_" + app + ".dat\n      </DataItem>\n    </Topology>\n"
+                        "    <Geometry GeometryType=\"XY\">\n" +
+                        fmt("      <DataItem Dimensions=\"%10d 2\" NumberType=\"Float\" Format=\"binary\" Endian=\"Big\">\n", npnt) +
+                        "        xdmf_points_" + app + ".dat\n      </DataItem>\n    </Geometry>\n"
+                        "  </Grid>\n</Grid>\n</Domain>\n</Xdmf>\n";
+        std::ofstream f(dir + "/xdmf_meshonly_" + app + ".xdmf");
+        if (!f) throw std::invalid_argument("cannot write " + dir + "/xdmf_meshonly_" + app + ".xdmf");
+        f << s;
+    }
+    std::string xml = head + "\n" +
+                      fmt("<DataItem Name=\"grid\" Dimensions=\"%10d 4\" NumberType=\"Int\" Format=\"binary\" Endian=\"Big\">\n", nel) +
+                      "  xdmf_grid_" + app + ".dat\n</DataItem>\n" +
+                      fmt("<DataItem Name=\"points\" Dimensions=\"%10d 2\" NumberType=\"Float\" Format=\"binary\" Endian=\"Big\">\n", npnt) +
+                      "  xdmf_points_" + app + ".dat\n</DataItem>\n\n"
+                      "<Grid Name=\"CellsTime\" GridType=\"Collection\" CollectionType=\"Temporal\">\n\n";
+    const int ncomp = monopole ? 2 : 3;
+    const char *comps[3] = {"u_s", monopole ? "u_z" : "u_p", "u_z"};
+    const char *files[3] = {"s", monopole ? "z" : "p", "z"};
+    for (int k = 0; k < nsnap; k++) {
+        const std::string sn = fmt("%04d", k + 1);
+        xml += "    <Grid Name=\"" + sn + "\" GridType=\"Uniform\">\n" +
+               fmt("        <Time Value=\"%8.2f\" />\n", times[k]) +
+               fmt("        <Topology TopologyType=\"Quadrilateral\" NumberOfElements=\"%10d\">\n", nel) +
+               "            <DataItem Reference=\"XML\">\n                /Xdmf/Domain/DataItem[@Name=\"grid\"]\n"
+               "            </DataItem>\n        </Topology>\n        <Geometry GeometryType=\"XY\">\n"
+               "            <DataItem Reference=\"XML\">\n                /Xdmf/Domain/DataItem[@Name=\"points\"]\n"
+               "            </DataItem>\n        </Geometry>\n";
+        for (int c = 0; c < ncomp; c++) xml += hyperslab(comps[c], npnt, k, nsnap, std::string("xdmf_snap_") + files[c] + "_" + app + ".dat");
+        std::string terms, refs;
+        for (int c = 0; c < ncomp; c++) {
+            terms += fmt("%s$%d * $%d", c ? " + " : "", c, c);
+            refs += "                <DataItem Reference=\"XML\">\n"
+                    "                    /Xdmf/Domain/Grid[@Name=\"CellsTime\"]/Grid[@Name=\"" + sn + "\"]/Attribute[@Name=\"" + comps[c] +
+                    "\"]/DataItem[1]\n                </DataItem>\n";
+        }
+        xml += "        <Attribute Name=\"abs\" AttributeType=\"Scalar\" Center=\"Node\">\n"
+               "            <DataItem ItemType=\"Function\" Function=\"sqrt(" + terms + ")\" Dimensions=\"" + fmt("%10d", npnt) + "\">\n" + refs +
+               "            </DataItem>\n        </Attribute>\n";
+        xml += hyperslab("straintrace", npnt, k, nsnap, "xdmf_snap_trace_" + app + ".dat");
+        xml += hyperslab("curlinplane", npnt, k, nsnap, "xdmf_snap_curlip_" + app + ".dat");
+        xml += "    </Grid>\n\n";
+    }
+    xml += "</Grid>\n</Domain>\n</Xdmf>\n";
+    std::ofstream f(dir + "/xdmf_xml_" + app + ".xdmf");
+    if (!f) throw std::invalid_argument("cannot write " + dir + "/xdmf_xml_" + app + ".xdmf");
+    f << xml;
 }
 
 }  // namespace axisem

@@ -5,6 +5,7 @@
 // `Data/<receiver>_disp.dat` per receiver (compute_recfile_seis_bare, seismograms.f90:742-778: u_s, u_z for a
 // monopole, u_s, u_phi, u_z otherwise, one line per seismogram sample).
 #pragma once
+#include <cstdint>
 #include <string>
 #include <vector>
 
@@ -37,6 +38,14 @@ void write_disp_files(const std::string &data_dir, const std::vector<std::string
                       int nseis, const std::vector<float> &seis);
 // the way back (post_processing.F90:344-357): (nseis, nrec, 3), u_phi = 0 for a monopole
 std::vector<float> read_disp_files(const std::string &data_dir, const std::vector<std::string> &names, bool monopole, int nseis);
+
+// XDMF snapshots of one rank as the reference leaves them in Data/ (dump_xdmf_grid, meshes_io.F90:400-437;
+// glob_snapshot_xdmf formats 733-735 and finish_xdmf_xml, wavefields_io.f90:195-330): big-endian
+// xdmf_points_NNNN.dat, xdmf_grid_NNNN.dat, xdmf_snap_{s,p,z,trace,curlip}_NNNN.dat (no p file for a
+// monopole), xdmf_meshonly_NNNN.xdmf, xdmf_xml_NNNN.xdmf.  fields: (5, nsnap, npoint_plot) as
+// OutputSink::xdmf delivers them; times[k]: time of snapshot k
+void write_xdmf_files(const std::string &data_dir, int rank, int npoint_plot, int nelem_plot, const float *points,
+                      const int32_t *grid, const float *fields, int nsnap, const std::vector<double> &times, bool monopole);
 
 void make_directory(const std::string &path);      // mkdir -p of one level; no error if it exists
 

@@ -202,7 +202,8 @@ def test_native_xdmf_plot_maps_equal_the_python_builder(exe, tmp_path):
         assert np.array_equal(g["data_mesh%xdmf_grid"].reshape(-1, 4), x["grid"])
         pts = g["data_mesh%xdmf_points"].reshape(-1, 2)
         assert np.abs(pts - x["points"]).max() <= 1e-6 * 6.4e6
-    run = subprocess.run([oracle.build_host(), "--quiet", "--out", str(tmp_path / "run"), "--src", "mtr", "--period", "40",
+    run = subprocess.run([oracle.build_host(), "--quiet", "--out", str(tmp_path / "run"), "--rundir", str(tmp_path / "RUN"),
+                          "--src", "mtr", "--period", "40",
                           "--niter", str(n), "--snap-it", "5", "--receivers", ",".join(map(str, COLAT))] + files,
                          capture_output=True, text=True, timeout=600)
     assert run.returncode == 0, run.stderr
@@ -219,6 +220,22 @@ def test_native_xdmf_plot_maps_equal_the_python_builder(exe, tmp_path):
         assert want.shape[1] == 3
         scale = np.abs(want).max(axis=(1, 2), keepdims=True) + 1e-30
         assert (np.abs(raw - want) / scale).max() <= 1e-5
+        # --rundir: the native host writes the reference's Data/xdmf_* files itself — byte for byte what the
+        # Python writer (tests/test_xdmf.py holds it against the reference's formats) makes of the same arrays
+        from axisem_b200.host.xdmf import write_xdmf
+        x = full[r].xdmf                       # (this run plots the whole domain)
+        app = f"{r:04d}"
+        pts = np.fromfile(tmp_path / "RUN" / "Data" / f"xdmf_points_{app}.dat", dtype=">f4").reshape(-1, 2)
+        grd = np.fromfile(tmp_path / "RUN" / "Data" / f"xdmf_grid_{app}.dat", dtype=">i4").reshape(-1, 4)
+        assert pts.shape == x["points"].shape and np.abs(pts - x["points"]).max() <= 1e-6 * 6.4e6 and np.array_equal(grd, x["grid"])
+        maps = dict(npoint_plot=x["npoint_plot"], nelem_plot=x["nelem_plot"], points=pts, grid=grd)
+        ref = write_xdmf(str(tmp_path / f"py{r}"), r, maps, raw, [k * 5 * full[r].deltat for k in range(3)], monopole=False)
+        assert len(ref) == 9
+        for path in ref.values():
+            name = os.path.basename(path)
+            assert open(path, "rb").read() == open(tmp_path / "RUN" / "Data" / name, "rb").read(), name
+    info = open(tmp_path / "RUN" / "simulation.info").read().splitlines()
+    assert int(info[17].split()[0]) == n // 5 and float(info[18].split()[0]) == pytest.approx(5 * full[0].deltat, abs=1e-6)
 
 
 @pytest.mark.parametrize("stf,choice", [("gauss_1", "gaussi"), ("gauss_2", "gaussi"), ("errorf", "gaussi"),
