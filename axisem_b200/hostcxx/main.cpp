@@ -205,6 +205,31 @@ void write_rundir(const std::string &dir, const std::vector<axisem::Modules> &ra
         axisem::write_xdmf_files(dir + "/Data", rank, npnt, nel, m.at("data_mesh%xdmf_points").f32(), m.i("data_mesh%xdmf_grid"),
                                  it->second.data(), nsn, times, src_order == 0);
     }
+    // energy_sol.dat, energy_flu.dat, energy_glob.dat (SAVE_ENERGY; time_evol_wave.F90:103-110, 1514-1523)
+    if (!sink.en.empty()) {
+        const size_t n = sink.en.begin()->second.size() / 4;
+        bool have_fluid = false;
+        for (const axisem::Modules &m : ranks) have_fluid = have_fluid || m.int_of("data_mesh%nel_fluid") > 0;
+        FILE *fs = have_fluid ? std::fopen((dir + "/Data/energy_sol.dat").c_str(), "w") : nullptr;
+        FILE *ff = have_fluid ? std::fopen((dir + "/Data/energy_flu.dat").c_str(), "w") : nullptr;
+        FILE *fg = std::fopen((dir + "/Data/energy_glob.dat").c_str(), "w");
+        if (!fg || (have_fluid && (!fs || !ff))) throw axisem::SolverError("cannot write " + dir + "/Data/energy_*.dat");
+        double t = 0.0;
+        for (size_t k = 0; k < n; k++) {
+            double e[4] = {0, 0, 0, 0};       // epot_sol, ekin_sol, epot_flu, ekin_flu
+            for (const auto &kv : sink.en) for (int c = 0; c < 4; c++) e[c] += kv.second[4 * k + c];
+            for (double &v : e) v *= 2.0 * PI;
+            if (have_fluid) {
+                std::fprintf(fs, "%16.6E%16.6E%16.6E\n", t, e[1], e[0]);
+                std::fprintf(ff, "%16.6E%16.6E%16.6E\n", t, e[2], e[3]);
+            }
+            std::fprintf(fg, "%16.6E%16.6E%16.6E%16.6E\n", t, e[0] + e[2], e[1] + e[3], 0.5 * (e[0] + e[2] + e[1] + e[3]));
+            t += s.deltat;
+        }
+        if (fs) std::fclose(fs);
+        if (ff) std::fclose(ff);
+        std::fclose(fg);
+    }
     // stf.dat, stf_seis.dat, stf_strain.dat (compute_stf, source.f90:186-199)
     if (m0.has("data_source%stf")) {
         const axisem::Array &a = m0.at("data_source%stf");

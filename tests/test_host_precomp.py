@@ -446,3 +446,24 @@ def test_solver_leaves_the_references_run_directory(exe, tmp_path, src, nranks):
         assert np.abs(tab - want).max() <= 3e-6 * np.abs(ref).max() + 1e-8 * np.abs(want).max()
     stf = np.loadtxt(rundir / "Data" / "stf_seis.dat")
     assert stf.shape == (n // 2, 2) and np.allclose(stf[:, 1], p0.stf[1::2], rtol=1e-6)
+    # ---- SAVE_ENERGY: energy_sol / _flu / _glob.dat, one line per time step from t = 0, 1pe16.6 columns
+    run = subprocess.run([oracle.build_host(), "--quiet", "--out", str(tmp_path / "run"), "--rundir", str(rundir), "--src", src,
+                          "--period", "3", "--niter", str(n), "--seis-it", "2", "--stations", str(st), "--energy"] + files,
+                         capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr
+    eprobs = [build_problem(spec, SourceParams(src_type2=src, t_0=3.0), niter=n, rank=r, nranks=nranks, seis_it=2,
+                            rec_colat_deg=colat, energy=True) for r in range(nranks)]
+    loops = [oracle.make_loop(p) for p in eprobs]
+    connect_local(lib, loops)
+    run_group(lib, loops, n)
+    e = 2 * np.pi * sum(L.energy().astype(np.float64) for L in loops)          # (n + 1, 4): epot_s, ekin_s, epot_f, ekin_f
+    sol, flu, glob = (np.loadtxt(rundir / "Data" / f"energy_{k}.dat") for k in ("sol", "flu", "glob"))
+    line = open(rundir / "Data" / "energy_glob.dat").readline().rstrip("\n")
+    assert len(line) == 64 and sol.shape == (n + 1, 3) and glob.shape == (n + 1, 4)
+    tt = np.arange(n + 1) * p0.deltat
+    scale = np.abs(e).max()
+    assert np.allclose(sol[:, 0], tt, rtol=2e-6, atol=1e-9) and scale > 0
+    assert np.abs(sol[:, 1] - e[:, 1]).max() <= 3e-6 * scale and np.abs(sol[:, 2] - e[:, 0]).max() <= 3e-6 * scale
+    assert np.abs(flu[:, 1] - e[:, 2]).max() <= 3e-6 * scale and np.abs(flu[:, 2] - e[:, 3]).max() <= 3e-6 * scale
+    assert np.abs(glob[:, 1] - (e[:, 0] + e[:, 2])).max() <= 3e-6 * scale
+    assert np.abs(glob[:, 3] - 0.5 * e.sum(axis=1)).max() <= 3e-6 * scale
