@@ -1,0 +1,188 @@
+"""A conforming mesh with a lateral coarsening ("doubling") layer, written as a MESHER database — test
+fixture for the native reader and pre-computation (axisem_b200/hostcxx/meshdb.cpp, mapping.cpp,
+precomp.cpp) on a mesh that is not a theta x r grid.
+
+Shell r_min .. router, all solid (bkgrdmodel prem_iso_solid_light): `nth` columns above the layer, `nth`/2
+below it, and between them the 4-to-2 template the mesher's coarsening layers are made of — six elements
+per period with one circular and one straight side (eltype semino / semiso of analytic_semi_mapping.f90),
+straight diagonals in between:
+
+    y=1   T0----T1----T2----T3----T4        q1 [B0 P  T1 T0] semino   q4 [C  Q  T3 T2] semino
+          | q1  |  q3 |  q4 | q6  |         q2 [B0 B2 C  P ] semiso   q5 [B2 B4 Q  C ] semiso
+    y=.5  |     P-----C-----Q     |         q3 [P  C  T2 T1] semino   q6 [Q  B4 T4 T3] semino
+          |   /   q2  |  q5   \\   |
+    y=0   B0----------B2----------B4        (corners counter-clockwise from (xi, eta) = (-1, -1))
+
+The axis cuts the tiling along B2-C-T2, so that axial elements have their xi = -1 edge on it (GLJ points in
+xi on both sides of every shared xi-edge).  Southern elements are turned by 180 degrees (xi = -1 towards
+the south axis, eta = -1 on the larger radius) as in the mesher; that swaps semino and semiso.  Global
+numbers are topological: corners by node, edge points by the edge's end nodes, so nothing depends on
+coordinates agreeing to the last bit."""
+import struct
+
+import numpy as np
+
+TEMPLATE = [
+    ([(0, 0), (1, .5), (1, 1), (0, 1)], "semino"),
+    ([(0, 0), (2, 0), (2, .5), (1, .5)], "semiso"),
+    ([(1, .5), (2, .5), (2, 1), (1, 1)], "semino"),
+    ([(2, .5), (3, .5), (3, 1), (2, 1)], "semino"),
+    ([(2, 0), (4, 0), (3, .5), (2, .5)], "semiso"),
+    ([(3, .5), (4, 0), (4, 1), (3, 1)], "semino"),
+]
+
+
+def build(nth=16, r_coarse=(1221.5e3, 2350e3, 3480e3, 3630e3, 4115e3, 4600e3), r_dbl=(4600e3, 4900e3),
+          r_fine=(4900e3, 5250e3, 5600e3, 5701e3, 5771e3, 5971e3, 6151e3, 6371e3), doubling=True):
+    """-> dict with everything write_database() needs.  doubling=False: the same radial layering with `nth`
+    columns everywhere (the comparison mesh)."""
+    assert nth % 8 == 0
+    th_f = np.linspace(0.0, np.pi, nth + 1)
+    th_f[-1] = np.pi
+    els = []                                        # (corners [(th, r)] x 4, eltype, coarsing)
+
+    def regular(thetas, radii):
+        for r0, r1 in zip(radii[:-1], radii[1:]):
+            for t0, t1 in zip(thetas[:-1], thetas[1:]):
+                els.append(([(t0, r0), (t1, r0), (t1, r1), (t0, r1)], "curved", False))
+
+    if doubling:
+        regular(th_f[::2], r_coarse)
+        r0, r1 = r_dbl
+        for m in range(nth // 4 + 1):               # template x in [0, 4] on fine columns [4m - 2, 4m + 2]
+            for corners, kind in TEMPLATE:
+                cols = [4 * m - 2 + x for x, _ in corners]
+                if min(cols) < 0 or max(cols) > nth:
+                    continue
+                els.append(([(th_f[int(c)], r0 + y * (r1 - r0)) for c, (_, y) in zip(cols, corners)], kind, True))
+        regular(th_f, r_fine)
+    else:
+        regular(th_f, tuple(r_coarse) + tuple(r_fine))
+    nelem = len(els)
+    # orientation: southern elements turned by 180 degrees
+    corners, eltype, coarsing = [], [], []
+    for c, kind, co in els:
+        if np.mean([t for t, _ in c]) > 0.5 * np.pi:
+            c = [c[2], c[3], c[0], c[1]]
+            kind = {"semino": "semiso", "semiso": "semino"}.get(kind, kind)
+        corners.append(c)
+        eltype.append(kind)
+        coarsing.append(co)
+    # nodes
+    key = lambda t, r: (int(round(t / np.pi * 2 ** 24)), int(round(r * 16)))
+    node_id, node_tr = {}, []
+    for c in corners:
+        for t, r in c:
+            if key(t, r) not in node_id:
+                node_id[key(t, r)] = len(node_tr)
+                node_tr.append((t, r))
+    cn = np.array([[node_id[key(t, r)] for t, r in c] for c in corners])       # (nelem, 4)
+    # global numbers of the 25 points of each element
+    ig = np.zeros((nelem, 5, 5), dtype=np.int64)                                # [e, j, i]
+    nxt = [len(node_tr)]
+    edge_pts = {}
+
+    def edge(a, b):
+        """the three interior points of edge a -> b, in that direction"""
+        k = (min(a, b), max(a, b))
+        if k not in edge_pts:
+            edge_pts[k] = [nxt[0], nxt[0] + 1, nxt[0] + 2]
+            nxt[0] += 3
+        p = edge_pts[k]
+        return p if a < b else p[::-1]
+
+    for e in range(nelem):
+        c0, c1, c2, c3 = cn[e]
+        ig[e, 0, 0], ig[e, 0, 4], ig[e, 4, 4], ig[e, 4, 0] = c0, c1, c2, c3
+        ig[e, 0, 1:4] = edge(c0, c1)
+        ig[e, 4, 1:4] = edge(c3, c2)
+        ig[e, 1:4, 0] = edge(c0, c3)
+        ig[e, 1:4, 4] = edge(c1, c2)
+        ig[e, 1:4, 1:4] = np.arange(nxt[0], nxt[0] + 9).reshape(3, 3)
+        nxt[0] += 9
+    # compress to 1..nglob in order of first appearance
+    flat = ig.reshape(-1)
+    _, first, inv = np.unique(flat, return_index=True, return_inverse=True)
+    order = np.argsort(np.argsort(first))
+    igloc = (order[inv] + 1).astype(np.int32)
+    nglob = int(igloc.max())
+    # control nodes: corners and edge mid-points (on the circle where both ends share a radius and the edge
+    # is not one of the template's straight chords), not shared between elements
+    def sz(t, r):
+        s = 0.0 if (t == 0.0 or t == np.pi) else r * np.sin(t)
+        return s, r * np.cos(t)
+
+    crd = np.zeros((8 * nelem, 2))
+    for e, c in enumerate(corners):
+        for k in range(4):
+            (ta, ra), (tb, rb) = c[k], c[(k + 1) % 4]
+            crd[8 * e + 2 * k] = sz(ta, ra)
+            circ = ra == rb and (eltype[e] == "curved" or (k in (0, 2) and (eltype[e] == "semino") == (k == 2)))
+            if circ:
+                crd[8 * e + 2 * k + 1] = sz(0.5 * (ta + tb), ra)
+            else:
+                crd[8 * e + 2 * k + 1] = 0.5 * (np.array(sz(ta, ra)) + np.array(sz(tb, rb)))
+    lnods = np.arange(1, 8 * nelem + 1, dtype=np.int32).reshape(nelem, 8)
+    on_axis = lambda t: t == 0.0 or t == np.pi
+    ax_el = np.array([e + 1 for e, c in enumerate(corners) if on_axis(c[0][0]) and on_axis(c[3][0])], dtype=np.int32)
+    for e, c in enumerate(corners):                 # no element touches the axis with a corner only
+        n_ax = sum(on_axis(t) for t, _ in c)
+        assert n_ax in (0, 2) and (n_ax == 0 or e + 1 in ax_el), (e, c)
+    return dict(nelem=nelem, crd=crd, lnods=lnods, eltype=eltype, coarsing=np.array(coarsing), igloc=igloc, nglob=nglob,
+                ax_el=ax_el, corners=corners, router=float(r_fine[-1]), rmin=float(r_coarse[0]),
+                ndoubling=int(np.sum(coarsing)))
+
+
+def write_database(path, M, basis, *, bkgrdmodel="prem_iso_solid_light", dt=1.0, period=50.0,
+                   discont=(6371e3, 6151e3, 5971e3, 5771e3, 5701e3, 5600e3, 3630e3, 3480e3, 1221.5e3)):
+    """One rank, all solid: the record sequence of MESHER/pdb.f90:2205-2382 (see axisem_b200/host/meshdb_io.py)."""
+    f = open(path, "wb")
+
+    def rec(*parts):
+        payload = b"".join(parts)
+        m = struct.pack("<i", len(payload))
+        f.write(m + payload + m)
+
+    I = lambda *v: np.asarray(v, dtype="<i4").tobytes()
+    D = lambda *v: np.asarray(v, dtype="<f8").tobytes()
+    A = lambda a, dt_: np.ascontiguousarray(a, dtype=dt_).tobytes()
+    nelem, npol = M["nelem"], 4
+    for v in (1, npol, nelem, nelem * 25, nelem, 0, nelem * 25, 0, M["nglob"], 0, 0, len(discont), len(bkgrdmodel)):
+        rec(I(v))
+    for name in ("xi_k", "eta", "dxi", "wt", "wt_axial_k"):
+        rec(A(getattr(basis, name, np.zeros(npol + 1)), "<f8"))
+    rec(A(basis.G0, "<f4"))
+    for name in ("G1", "G1T", "G2", "G2T"):
+        rec(A(np.asarray(getattr(basis, name), dtype=np.float32).T, "<f4"))
+    rec(I(M["crd"].shape[0]))
+    rec(A(M["crd"][:, 0], "<f8"))
+    rec(A(M["crd"][:, 1], "<f8"))
+    for e in range(nelem):
+        rec(A(M["lnods"][e], "<i4"))
+    rec(I(M["nglob"]))
+    rec(b"".join(t.encode().ljust(6)[:6] for t in M["eltype"]))
+    rec(A(M["coarsing"].astype(np.int32), "<i4"))
+    rec(A(np.arange(1, nelem + 1), "<i4"))                    # ielsolid
+    rec(A(np.zeros(0), "<i4"))                                # ielfluid
+    rec(A(M["igloc"], "<i4"))
+    rec(A(np.zeros(0), "<i4"))
+    rec(I(0))                                                 # have_bdry_elem
+    rec(D(1.5, period, 0.6, dt))
+    rec(bkgrdmodel.encode())
+    rec(b"none  ")
+    rec(D(M["router"]), I(0))                                 # router, have_fluid
+    for r in discont:
+        rec(D(r), I(1), I(0))
+    rec(D(M["rmin"], 0.0, 0.0, 0.0))
+    rec(D(0.0, 0.0))
+    rec(D(0.0, 0.0))
+    for _ in range(2):
+        rec(D(0.0), I(1))
+        rec(D(0.0, 0.0))
+    ax = M["ax_el"]
+    rec(I(ax.size, ax.size, 0))
+    rec(A(ax, "<i4"))
+    rec(A(ax, "<i4"))
+    rec(A(np.zeros(0), "<i4"))
+    rec(I(0))                                                 # solid messaging: no neighbours
+    f.close()

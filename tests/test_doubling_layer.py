@@ -1,0 +1,114 @@
+"""A MESHER database that is not a theta x r grid: a conforming lateral coarsening ("doubling") layer of
+semino / semiso elements between a fine upper and a coarse lower shell (tests/doubling_mesh.py), through the
+whole native chain — database reader, element mappings, pre-computation, time loop.
+
+There is no second implementation to compare such a mesh with, so the checks are the reference's own
+invariants and a twin run: mass = volume (def_grid.f90:1188), a stable run whose total energy is constant
+once the source has acted (the diagnostic of time_evol_wave.F90:1424-1526 — symmetric positive operators on
+every element type), and seismograms equal, to discretisation accuracy, to those of the uncoarsened mesh
+with the same radial layering."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from axisem_b200.host.spectral import SpectralBasis
+
+from . import doubling_mesh as dm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PRECOMP = os.path.join(ROOT, "axisem_b200", "axisem_b200_precomp")
+PRODUCT_EXE = os.path.join(ROOT, "axisem_b200", "axisem_b200_solver")
+COLAT = "40,80,120,160"
+RUN = ["--src", "explosion", "--depth", "300", "--period", "250", "--seis-it", "4", "--receivers", COLAT]
+
+
+def _databases(tmp_path, nth=32):
+    b = SpectralBasis(4)
+    out = {}
+    for name, flag in (("dbl", True), ("reg", False)):
+        M = dm.build(nth=nth, doubling=flag)
+        path = str(tmp_path / f"{name}.dat0000")
+        dm.write_database(path, M, b, dt=0.5)
+        out[name] = (path, M)
+    return out
+
+
+def _traces(rundir, n=4):
+    return np.array([np.loadtxt(os.path.join(rundir, "Data", f"recfile_{k:04d}_disp.dat")) for k in range(1, n + 1)])
+
+
+def test_mesh_is_conforming():
+    M = dm.build(nth=32)
+    assert M["nelem"] == 7 * 32 + 48 + 5 * 16 and M["ndoubling"] == 48
+    assert sorted(set(M["eltype"])) == ["curved", "semino", "semiso"]
+    ig = M["igloc"].reshape(M["nelem"], 5, 5)
+    # every interior edge is shared by exactly two elements, point for point; boundary edges lie on r_min,
+    # router or the axis
+    edges = {}
+    for e in range(M["nelem"]):
+        for pts in (ig[e, 0, :], ig[e, 4, :], ig[e, :, 0], ig[e, :, 4]):
+            k = tuple(sorted((int(pts[0]), int(pts[4]))))
+            edges.setdefault(k, []).append((e, tuple(int(p) for p in pts)))
+    nbound = 0
+    for k, users in edges.items():
+        assert len(users) in (1, 2)
+        if len(users) == 2:
+            a, b = users[0][1], users[1][1]
+            assert a == b or a == b[::-1]
+        else:
+            nbound += 1
+    assert nbound == 32 + 16 + 2 * 14           # surface, inner surface, the two halves of the axis
+    # valence of the template's nodes: P and Q belong to three elements, C to four, and six meet where the
+    # diagonals of two periods reach the coarse row
+    val = np.bincount(np.concatenate([ig[:, 0, 0], ig[:, 0, 4], ig[:, 4, 0], ig[:, 4, 4]]))
+    assert set(val[val > 0]) == {1, 2, 3, 4, 6} and (val == 3).sum() == 16 and (val == 6).sum() == 8
+
+
+def test_native_chain_on_a_coarsening_layer(tmp_path):
+    from oracle import oracle
+    db = _databases(tmp_path)
+    for name, (path, M) in db.items():
+        out = subprocess.run([PRECOMP, "--out", str(tmp_path / f"pre_{name}"), "--niter", "10"] + RUN[:6] + [path],
+                             capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        checks = dict(line.split() for line in out.stdout.strip().splitlines())
+        assert abs(float(checks["mass_over_volume"]) - 1.0) < 1e-9, (name, checks)
+        assert int(checks["n_sf_boundaries"]) == 0
+    exe = oracle.build_host()
+    tr, en = {}, {}
+    for name, (path, M) in db.items():
+        r = subprocess.run([exe, "--quiet", "--out", str(tmp_path / f"run_{name}"), "--rundir", str(tmp_path / f"RUN_{name}"),
+                            "--niter", "4000", "--energy"] + RUN + [path], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr
+        tr[name] = _traces(tmp_path / f"RUN_{name}")
+        en[name] = np.loadtxt(tmp_path / f"RUN_{name}" / "Data" / "energy_glob.dat")
+    for name in db:
+        e = en[name]
+        late = e[e[:, 0] > 900.0, 3]                    # the source (250 s, centred on 375 s) has acted
+        assert late.min() > 0 and (late.max() - late.min()) / late.mean() < 1e-4, name
+    assert abs(en["dbl"][-1, 3] / en["reg"][-1, 3] - 1.0) < 1e-3          # the same energy went in
+    a, b = tr["dbl"], tr["reg"]
+    assert a.shape == b.shape == (4, 1001, 2) and np.abs(b).max() > 0
+    for k in range(4):
+        assert np.sqrt(((a[k] - b[k]) ** 2).sum() / (b[k] ** 2).sum()) < 0.03, k
+        assert np.corrcoef(a[k][:, 1], b[k][:, 1])[0, 1] > 0.999
+
+
+@pytest.mark.gpu
+def test_cuda_library_on_a_coarsening_layer(tmp_path):
+    """The device library on the unstructured database (assembly groups of valence 3 and 4 in the layer,
+    semino / semiso coefficient planes): the product host against its CPU twin linked to the oracle."""
+    from oracle import oracle
+    assert os.path.exists(PRODUCT_EXE), "axisem_b200_solver missing: run __graft_entry__.build()"
+    path, M = _databases(tmp_path)["dbl"]
+    got = {}
+    for name, exe in (("gpu", PRODUCT_EXE), ("cpu", oracle.build_host())):
+        r = subprocess.run([exe, "--quiet", "--out", str(tmp_path / name), "--niter", "2000", "--attenuation", "cg4"] + RUN + [path],
+                           capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr
+        got[name] = np.fromfile(tmp_path / f"{name}.rank0000.seis.f32", dtype=np.float32)
+    assert got["gpu"].shape == got["cpu"].shape and np.abs(got["cpu"]).max() > 0
+    d = got["gpu"].astype(np.float64) - got["cpu"]
+    assert np.sqrt((d ** 2).sum() / (got["cpu"].astype(np.float64) ** 2).sum()) <= 1e-5
