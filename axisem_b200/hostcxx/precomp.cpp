@@ -484,6 +484,8 @@ void precompute(std::vector<Modules> &ranks, const PrecompOptions &opt) {
             const Array &b = m.at("data_mesh%bkgrdmodel");
             for (size_t k = 0; k < b.count(); k++) model.push_back((char)b.i32()[k]);
         }
+        if (opt.attenuation && !model_is_anelastic(model))          // get_mesh.f90:142-150
+            throw SolverError("viscoelastic attenuation set, but backgroundmodel " + model + " is elastic only.");
         if (deltat <= 0) deltat = m.real_of("data_time%deltat") * (opt.time_scheme == "newmark2" ? 1.0 : 1.5);
         const Spectral sp{m.d("data_spec%eta"), m.d("data_spec%wt"), m.d("data_spec%xi_k"), m.d("data_spec%wt_axial_k")};
         gs[r] = element_geometry(m, false, sp);

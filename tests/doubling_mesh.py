@@ -2,7 +2,7 @@
 fixture for the native reader and pre-computation (axisem_b200/hostcxx/meshdb.cpp, mapping.cpp,
 precomp.cpp) on a mesh that is not a theta x r grid.
 
-Shell r_min .. router, all solid (bkgrdmodel prem_iso_solid_light): `nth` columns above the layer, `nth`/2
+Shell r_min .. router, all solid (the mantle of prem_iso_light above a free inner surface at the CMB): `nth` columns above the layer, `nth`/2
 below it, and between them the 4-to-2 template the mesher's coarsening layers are made of — six elements
 per period with one circular and one straight side (eltype semino / semiso of analytic_semi_mapping.f90),
 straight diagonals in between:
@@ -32,8 +32,8 @@ TEMPLATE = [
 ]
 
 
-def build(nth=16, r_coarse=(1221.5e3, 2350e3, 3480e3, 3630e3, 4115e3, 4600e3), r_dbl=(4600e3, 4900e3),
-          r_fine=(4900e3, 5250e3, 5600e3, 5701e3, 5771e3, 5971e3, 6151e3, 6371e3), doubling=True):
+def build(nth=16, r_coarse=(3480e3, 3630e3, 4115e3, 4600e3), r_dbl=(4600e3, 4900e3),
+          r_fine=(4900e3, 5250e3, 5600e3, 5701e3, 5771e3, 5971e3, 6151e3, 6291e3, 6371e3), doubling=True):
     """-> dict with everything write_database() needs.  doubling=False: the same radial layering with `nth`
     columns everywhere (the comparison mesh)."""
     assert nth % 8 == 0
@@ -133,8 +133,8 @@ def build(nth=16, r_coarse=(1221.5e3, 2350e3, 3480e3, 3630e3, 4115e3, 4600e3), r
                 ndoubling=int(np.sum(coarsing)))
 
 
-def write_database(path, M, basis, *, bkgrdmodel="prem_iso_solid_light", dt=1.0, period=50.0,
-                   discont=(6371e3, 6151e3, 5971e3, 5771e3, 5701e3, 5600e3, 3630e3, 3480e3, 1221.5e3)):
+def write_database(path, M, basis, *, bkgrdmodel="prem_iso_light", dt=1.0, period=50.0,
+                   discont=(6371e3, 6291e3, 6151e3, 5971e3, 5771e3, 5701e3, 5600e3, 3630e3, 3480e3, 1221.5e3)):
     """One rank, all solid: the record sequence of MESHER/pdb.f90:2205-2382 (see axisem_b200/host/meshdb_io.py)."""
     f = open(path, "wb")
 

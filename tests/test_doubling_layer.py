@@ -41,7 +41,7 @@ def _traces(rundir, n=4):
 
 def test_mesh_is_conforming():
     M = dm.build(nth=32)
-    assert M["nelem"] == 7 * 32 + 48 + 5 * 16 and M["ndoubling"] == 48
+    assert M["nelem"] == 8 * 32 + 48 + 3 * 16 and M["ndoubling"] == 48
     assert sorted(set(M["eltype"])) == ["curved", "semino", "semiso"]
     ig = M["igloc"].reshape(M["nelem"], 5, 5)
     # every interior edge is shared by exactly two elements, point for point; boundary edges lie on r_min,
@@ -59,7 +59,7 @@ def test_mesh_is_conforming():
             assert a == b or a == b[::-1]
         else:
             nbound += 1
-    assert nbound == 32 + 16 + 2 * 14           # surface, inner surface, the two halves of the axis
+    assert nbound == 32 + 16 + 2 * 13           # surface, inner surface, the two halves of the axis
     # valence of the template's nodes: P and Q belong to three elements, C to four, and six meet where the
     # diagonals of two periods reach the coarse row
     val = np.bincount(np.concatenate([ig[:, 0, 0], ig[:, 0, 4], ig[:, 4, 0], ig[:, 4, 4]]))
@@ -91,6 +91,10 @@ def test_native_chain_on_a_coarsening_layer(tmp_path):
     assert abs(en["dbl"][-1, 3] / en["reg"][-1, 3] - 1.0) < 1e-3          # the same energy went in
     a, b = tr["dbl"], tr["reg"]
     assert a.shape == b.shape == (4, 1001, 2) and np.abs(b).max() > 0
+    # attenuation needs an anelastic model (get_mesh.f90:142-150); prem_iso_light is one, its solid twin is not
+    out = subprocess.run([PRECOMP, "--out", str(tmp_path / "x"), "--model", "prem_iso_solid_light", "--attenuation", "cg4", "--niter", "10"]
+                         + RUN[:6] + [db["dbl"][0]], capture_output=True, text=True)
+    assert out.returncode != 0 and "elastic only" in out.stderr
     for k in range(4):
         assert np.sqrt(((a[k] - b[k]) ** 2).sum() / (b[k] ** 2).sum()) < 0.03, k
         assert np.corrcoef(a[k][:, 1], b[k][:, 1])[0, 1] > 0.999
