@@ -32,54 +32,73 @@ TEMPLATE = [
 ]
 
 
+def _sz(t, r):
+    s = 0.0 if (t == 0.0 or t == np.pi) else r * np.sin(t)
+    return (s, r * np.cos(t))
+
+
 def build(nth=16, r_coarse=(3480e3, 3630e3, 4115e3, 4600e3), r_dbl=(4600e3, 4900e3),
-          r_fine=(4900e3, 5250e3, 5600e3, 5701e3, 5771e3, 5971e3, 6151e3, 6291e3, 6371e3), doubling=True):
+          r_fine=(4900e3, 5250e3, 5600e3, 5701e3, 5771e3, 5971e3, 6151e3, 6291e3, 6371e3), doubling=True,
+          cube_halfwidth=None):
     """-> dict with everything write_database() needs.  doubling=False: the same radial layering with `nth`
-    columns everywhere (the comparison mesh)."""
+    columns everywhere (the comparison mesh).  cube_halfwidth = a: the sphere below r_coarse[0] is filled as
+    the mesher fills it — a half square [0, a] x [-a, a] of `linear` elements and, around it, one ring of
+    elements with a straight side on the square and a circular one on r_coarse[0] (semino / semiso)."""
     assert nth % 8 == 0
     th_f = np.linspace(0.0, np.pi, nth + 1)
     th_f[-1] = np.pi
-    els = []                                        # (corners [(th, r)] x 4, eltype, coarsing)
+    els = []                                        # (corners [(s, z)] x 4 counter-clockwise, eltype, coarsing, turn in the south)
 
     def regular(thetas, radii):
         for r0, r1 in zip(radii[:-1], radii[1:]):
             for t0, t1 in zip(thetas[:-1], thetas[1:]):
-                els.append(([(t0, r0), (t1, r0), (t1, r1), (t0, r1)], "curved", False))
+                els.append(([_sz(t0, r0), _sz(t1, r0), _sz(t1, r1), _sz(t0, r1)], "curved", False, True))
 
+    th_c = th_f[::2] if doubling else th_f
+    if cube_halfwidth:
+        a, nc = float(cube_halfwidth), (len(th_c) - 1) // 4
+        assert 4 * nc == len(th_c) - 1 and a * np.sqrt(2.0) < r_coarse[0]
+        h = a / nc
+        for jz in range(2 * nc):
+            for js in range(nc):
+                s0, s1, z0, z1 = js * h, (js + 1) * h, -a + jz * h, -a + (jz + 1) * h
+                els.append(([(s0, z0), (s1, z0), (s1, z1), (s0, z1)], "linear", False, False))
+        # the square's boundary from the north axis to the south axis, one node per column edge of the shell
+        bnd = [(k * h, a) for k in range(nc)] + [(a, a - k * h) for k in range(2 * nc)] + [(a - k * h, -a) for k in range(nc + 1)]
+        for k in range(4 * nc):
+            els.append(([bnd[k], bnd[k + 1], _sz(th_c[k + 1], r_coarse[0]), _sz(th_c[k], r_coarse[0])], "semino", False, True))
     if doubling:
-        regular(th_f[::2], r_coarse)
+        regular(th_c, r_coarse)
         r0, r1 = r_dbl
         for m in range(nth // 4 + 1):               # template x in [0, 4] on fine columns [4m - 2, 4m + 2]
             for corners, kind in TEMPLATE:
                 cols = [4 * m - 2 + x for x, _ in corners]
                 if min(cols) < 0 or max(cols) > nth:
                     continue
-                els.append(([(th_f[int(c)], r0 + y * (r1 - r0)) for c, (_, y) in zip(cols, corners)], kind, True))
+                els.append(([_sz(th_f[int(c)], r0 + y * (r1 - r0)) for c, (_, y) in zip(cols, corners)], kind, True, True))
         regular(th_f, r_fine)
     else:
         regular(th_f, tuple(r_coarse) + tuple(r_fine))
     nelem = len(els)
-    # orientation: southern elements turned by 180 degrees
+    # orientation: southern elements of the shell are turned by 180 degrees
     corners, eltype, coarsing = [], [], []
-    for c, kind, co in els:
-        if np.mean([t for t, _ in c]) > 0.5 * np.pi:
+    for c, kind, co, turn in els:
+        if turn and np.mean([z for _, z in c]) < 0.0:
             c = [c[2], c[3], c[0], c[1]]
             kind = {"semino": "semiso", "semiso": "semino"}.get(kind, kind)
         corners.append(c)
         eltype.append(kind)
         coarsing.append(co)
     # nodes
-    key = lambda t, r: (int(round(t / np.pi * 2 ** 24)), int(round(r * 16)))
-    node_id, node_tr = {}, []
+    key = lambda s_, z_: (int(round(s_ * 64)), int(round(z_ * 64)))
+    node_id = {}
     for c in corners:
-        for t, r in c:
-            if key(t, r) not in node_id:
-                node_id[key(t, r)] = len(node_tr)
-                node_tr.append((t, r))
-    cn = np.array([[node_id[key(t, r)] for t, r in c] for c in corners])       # (nelem, 4)
+        for s_, z_ in c:
+            node_id.setdefault(key(s_, z_), len(node_id))
+    cn = np.array([[node_id[key(s_, z_)] for s_, z_ in c] for c in corners])       # (nelem, 4)
     # global numbers of the 25 points of each element
     ig = np.zeros((nelem, 5, 5), dtype=np.int64)                                # [e, j, i]
-    nxt = [len(node_tr)]
+    nxt = [len(node_id)]
     edge_pts = {}
 
     def edge(a, b):
@@ -106,30 +125,28 @@ def build(nth=16, r_coarse=(3480e3, 3630e3, 4115e3, 4600e3), r_dbl=(4600e3, 4900
     order = np.argsort(np.argsort(first))
     igloc = (order[inv] + 1).astype(np.int32)
     nglob = int(igloc.max())
-    # control nodes: corners and edge mid-points (on the circle where both ends share a radius and the edge
-    # is not one of the template's straight chords), not shared between elements
-    def sz(t, r):
-        s = 0.0 if (t == 0.0 or t == np.pi) else r * np.sin(t)
-        return s, r * np.cos(t)
-
+    # control nodes: corners and edge mid-points (on the circle for the circular sides), not shared between elements
     crd = np.zeros((8 * nelem, 2))
     for e, c in enumerate(corners):
         for k in range(4):
-            (ta, ra), (tb, rb) = c[k], c[(k + 1) % 4]
-            crd[8 * e + 2 * k] = sz(ta, ra)
-            circ = ra == rb and (eltype[e] == "curved" or (k in (0, 2) and (eltype[e] == "semino") == (k == 2)))
-            if circ:
-                crd[8 * e + 2 * k + 1] = sz(0.5 * (ta + tb), ra)
-            else:
-                crd[8 * e + 2 * k + 1] = 0.5 * (np.array(sz(ta, ra)) + np.array(sz(tb, rb)))
+            pa, pb = np.array(c[k]), np.array(c[(k + 1) % 4])
+            ra, rb = np.hypot(*pa), np.hypot(*pb)
+            crd[8 * e + 2 * k] = pa
+            mid = 0.5 * (pa + pb)
+            circ = abs(ra - rb) < 1e-3 and ra > 0 and (eltype[e] == "curved" or (eltype[e] == "semino" and k == 2)
+                                                       or (eltype[e] == "semiso" and k == 0))
+            if circ and np.hypot(*mid) > 0:
+                mid = mid * (ra / np.hypot(*mid))
+                if pa[0] == 0.0 and pb[0] == 0.0:
+                    mid[0] = 0.0
+            crd[8 * e + 2 * k + 1] = mid
     lnods = np.arange(1, 8 * nelem + 1, dtype=np.int32).reshape(nelem, 8)
-    on_axis = lambda t: t == 0.0 or t == np.pi
-    ax_el = np.array([e + 1 for e, c in enumerate(corners) if on_axis(c[0][0]) and on_axis(c[3][0])], dtype=np.int32)
+    ax_el = np.array([e + 1 for e, c in enumerate(corners) if c[0][0] == 0.0 and c[3][0] == 0.0], dtype=np.int32)
     for e, c in enumerate(corners):                 # no element touches the axis with a corner only
-        n_ax = sum(on_axis(t) for t, _ in c)
+        n_ax = sum(s_ == 0.0 for s_, _ in c)
         assert n_ax in (0, 2) and (n_ax == 0 or e + 1 in ax_el), (e, c)
     return dict(nelem=nelem, crd=crd, lnods=lnods, eltype=eltype, coarsing=np.array(coarsing), igloc=igloc, nglob=nglob,
-                ax_el=ax_el, corners=corners, router=float(r_fine[-1]), rmin=float(r_coarse[0]),
+                ax_el=ax_el, corners=corners, router=float(r_fine[-1]), rmin=0.0 if cube_halfwidth else float(r_coarse[0]),
                 ndoubling=int(np.sum(coarsing)))
 
 

@@ -100,6 +100,69 @@ def test_native_chain_on_a_coarsening_layer(tmp_path):
         assert np.corrcoef(a[k][:, 1], b[k][:, 1])[0, 1] > 0.999
 
 
+# ---- the whole sphere: inner square of `linear` elements, a ring of semino / semiso elements around it ----
+RC = (1221.5e3, 2350e3, 3480e3, 3630e3, 4115e3, 4600e3)
+RF = (4900e3, 5250e3, 5600e3, 5701e3, 5771e3, 5971e3, 6151e3, 6371e3)
+DISC = (6371e3, 6151e3, 5971e3, 5771e3, 5701e3, 5600e3, 3630e3, 3480e3, 1221.5e3)
+
+
+def _sphere_database(tmp_path, name, cube):
+    M = dm.build(nth=32, r_coarse=RC, r_fine=RF, cube_halfwidth=cube)
+    path = str(tmp_path / f"{name}.dat0000")
+    dm.write_database(path, M, SpectralBasis(4), bkgrdmodel="prem_iso_solid_light", discont=DISC, dt=0.5)
+    return path, M
+
+
+def test_native_chain_on_a_full_sphere_with_inner_cube(tmp_path):
+    """No hollow centre: the mesher's central square of `linear` (8-node serendipity) elements and the ring
+    that joins it to the spherical shell, below a coarsening layer, in prem_iso_solid_light (all solid).
+    The volume of the whole sphere, a stable run with constant energy while the wavefield crosses the centre
+    several times, and — until anything has reached the inner core — the seismograms of the same mesh
+    with a free surface at the inner-core boundary instead."""
+    from oracle import oracle
+    runs = {"cube": _sphere_database(tmp_path, "cube", 500e3), "hollow": _sphere_database(tmp_path, "hollow", None)}
+    M = runs["cube"][1]
+    assert {t: M["eltype"].count(t) for t in set(M["eltype"])} == {"linear": 32, "semino": 32, "semiso": 32, "curved": 304}
+    assert M["ax_el"].size == 2 * (5 + 1 + 7) + 2 * 4 + 4          # shell + coarsening layer, ring, square
+    exe = oracle.build_host()
+    tr, en = {}, {}
+    for name, (path, _) in runs.items():
+        out = subprocess.run([PRECOMP, "--out", str(tmp_path / f"pre_{name}"), "--niter", "10"] + RUN[:6] + [path], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        checks = dict(line.split() for line in out.stdout.strip().splitlines())
+        assert abs(float(checks["mass_over_volume"]) - 1.0) < 1e-9, (name, checks)      # cube: the volume of the whole sphere
+        r = subprocess.run([exe, "--quiet", "--out", str(tmp_path / f"run_{name}"), "--rundir", str(tmp_path / f"RUN_{name}"),
+                            "--niter", "6000", "--energy", "--src", "explosion", "--depth", "300", "--period", "250", "--seis-it", "4",
+                            "--receivers", "40,80,120,178", path], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr
+        tr[name] = _traces(tmp_path / f"RUN_{name}")
+        en[name] = np.loadtxt(tmp_path / f"RUN_{name}" / "Data" / "energy_glob.dat")
+        late = en[name][en[name][:, 0] > 900.0, 3]
+        assert late.min() > 0 and (late.max() - late.min()) / late.mean() < 1e-4, name
+    assert abs(en["cube"][-1, 3] / en["hollow"][-1, 3] - 1.0) < 1e-3
+    a, b = tr["cube"], tr["hollow"]
+    t = np.arange(a.shape[1]) * 4 * 0.5
+    rel = lambda k, w: np.sqrt(((a[k][w] - b[k][w]) ** 2).sum() / (b[k][w] ** 2).sum())
+    assert rel(0, t < 700.0) < 1e-4 and rel(1, t < 1200.0) < 1e-3 and rel(2, t < 1200.0) < 1e-3      # mantle phases only
+    assert rel(3, t < 3000.0) > 0.05                                                                  # the centre is there
+
+
+@pytest.mark.gpu
+def test_cuda_library_on_a_full_sphere_with_inner_cube(tmp_path):
+    from oracle import oracle
+    assert os.path.exists(PRODUCT_EXE), "axisem_b200_solver missing: run __graft_entry__.build()"
+    path, _ = _sphere_database(tmp_path, "cube", 500e3)
+    got = {}
+    for name, exe in (("gpu", PRODUCT_EXE), ("cpu", oracle.build_host())):
+        r = subprocess.run([exe, "--quiet", "--out", str(tmp_path / name), "--niter", "3000", "--src", "mtr", "--depth", "300",
+                            "--period", "250", "--seis-it", "4", "--receivers", "40,80,120,178", path], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr
+        got[name] = np.fromfile(tmp_path / f"{name}.rank0000.seis.f32", dtype=np.float32)
+    assert got["gpu"].shape == got["cpu"].shape and np.abs(got["cpu"]).max() > 0
+    d = got["gpu"].astype(np.float64) - got["cpu"]
+    assert np.sqrt((d ** 2).sum() / (got["cpu"].astype(np.float64) ** 2).sum()) <= 1e-5
+
+
 @pytest.mark.gpu
 def test_cuda_library_on_a_coarsening_layer(tmp_path):
     """The device library on the unstructured database (assembly groups of valence 3 and 4 in the layer,
