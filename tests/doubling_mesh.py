@@ -79,6 +79,49 @@ def build(nth=16, r_coarse=(3480e3, 3630e3, 4115e3, 4600e3), r_dbl=(4600e3, 4900
         regular(th_f, r_fine)
     else:
         regular(th_f, tuple(r_coarse) + tuple(r_fine))
+    return _finish(els, router=float(r_fine[-1]), rmin=0.0 if cube_halfwidth else float(r_coarse[0]))
+
+
+def build_rows(rows, ncol_bottom, *, cube_halfwidth=None, fluid=None):
+    """The general form: `rows` from the bottom up, (r0, r1, 'R') a regular row, (r0, r1, 'D') a coarsening
+    row above which the number of columns is twice that below; `ncol_bottom` columns in the lowest row
+    (four per side element of the inner square when cube_halfwidth is given, which fills the sphere below
+    rows[0][0]).  fluid(r_mid) -> bool marks the fluid rows (regular rows only)."""
+    els = []
+    ncol = ncol_bottom
+    th = np.linspace(0.0, np.pi, ncol + 1)
+    th[-1] = np.pi
+    if cube_halfwidth:
+        a, nc = float(cube_halfwidth), ncol // 4
+        assert 4 * nc == ncol and a * np.sqrt(2.0) < rows[0][0]
+        h = a / nc
+        for jz in range(2 * nc):
+            for js in range(nc):
+                s0, s1, z0, z1 = js * h, (js + 1) * h, -a + jz * h, -a + (jz + 1) * h
+                els.append(([(s0, z0), (s1, z0), (s1, z1), (s0, z1)], "linear", False, False))
+        bnd = [(k * h, a) for k in range(nc)] + [(a, a - k * h) for k in range(2 * nc)] + [(a - k * h, -a) for k in range(nc + 1)]
+        for k in range(4 * nc):
+            els.append(([bnd[k], bnd[k + 1], _sz(th[k + 1], rows[0][0]), _sz(th[k], rows[0][0])], "semino", False, True))
+    for r0, r1, kind in rows:
+        if kind == "R":
+            for t0, t1 in zip(th[:-1], th[1:]):
+                els.append(([_sz(t0, r0), _sz(t1, r0), _sz(t1, r1), _sz(t0, r1)], "curved", False, True))
+        else:
+            assert ncol % 4 == 0
+            nth = 2 * ncol
+            th_f = np.linspace(0.0, np.pi, nth + 1)
+            th_f[-1] = np.pi
+            for m in range(nth // 4 + 1):
+                for corners, k2 in TEMPLATE:
+                    cols = [4 * m - 2 + x for x, _ in corners]
+                    if min(cols) < 0 or max(cols) > nth:
+                        continue
+                    els.append(([_sz(th_f[int(c)], r0 + y * (r1 - r0)) for c, (_, y) in zip(cols, corners)], k2, True, True))
+            ncol, th = nth, th_f
+    return _finish(els, router=float(rows[-1][1]), rmin=0.0 if cube_halfwidth else float(rows[0][0]), fluid=fluid)
+
+
+def _finish(els, router, rmin, fluid=None):
     nelem = len(els)
     # orientation: southern elements of the shell are turned by 180 degrees
     corners, eltype, coarsing = [], [], []
@@ -145,14 +188,51 @@ def build(nth=16, r_coarse=(3480e3, 3630e3, 4115e3, 4600e3), r_dbl=(4600e3, 4900
     for e, c in enumerate(corners):                 # no element touches the axis with a corner only
         n_ax = sum(s_ == 0.0 for s_, _ in c)
         assert n_ax in (0, 2) and (n_ax == 0 or e + 1 in ax_el), (e, c)
+    # ---- solid / fluid domains: global element order = solid elements first; numbers per domain; the
+    # boundary pairs with the j index of the shared edge on either side (data_mesh.f90:106-110)
+    dom = {}
+    if fluid is not None:
+        rmid = np.array([np.hypot(np.mean([p[0] for p in c]), np.mean([p[1] for p in c])) for c in corners])
+        is_f = np.array([bool(fluid(r)) for r in rmid])
+        perm = np.concatenate([np.nonzero(~is_f)[0], np.nonzero(is_f)[0]])
+        ns, nf = int((~is_f).sum()), int(is_f.sum())
+        corners = [corners[e] for e in perm]
+        eltype = [eltype[e] for e in perm]
+        coarsing = [coarsing[e] for e in perm]
+        crd = crd.reshape(nelem, 8, 2)[perm].reshape(-1, 2)
+        igr = ig[perm]
+
+        def compress(block):
+            flat_ = block.reshape(-1)
+            _, first_, inv_ = np.unique(flat_, return_index=True, return_inverse=True)
+            order_ = np.argsort(np.argsort(first_))
+            return (order_[inv_] + 1).astype(np.int32)
+
+        ig_s, ig_f = compress(igr[:ns]), compress(igr[ns:])
+        edge_users = {}
+        for e in range(nelem):
+            for jj, pts in ((0, igr[e, 0, :]), (4, igr[e, 4, :]), (-1, igr[e, :, 0]), (-2, igr[e, :, 4])):
+                edge_users.setdefault(tuple(sorted((int(pts[0]), int(pts[4])))), []).append((e, jj, [int(q) for q in pts]))
+        bs, bf, js, jf = [], [], [], []
+        for users in edge_users.values():
+            if len(users) == 2 and (users[0][0] < ns) != (users[1][0] < ns):
+                (es, j_s, ps), (ef, j_f, pf) = sorted(users)
+                assert j_s in (0, 4) and j_f in (0, 4) and ps == pf, "a solid/fluid boundary must be an eta = const edge with xi aligned"
+                bs.append(es + 1); bf.append(ef - ns + 1); js.append(j_s); jf.append(j_f)
+        ax_all = np.array([e + 1 for e, c in enumerate(corners) if c[0][0] == 0.0 and c[3][0] == 0.0], dtype=np.int32)
+        dom = dict(nel_solid=ns, nel_fluid=nf, igloc_solid=ig_s, igloc_fluid=ig_f, nglob_solid=int(ig_s.max()),
+                   nglob_fluid=int(ig_f.max()) if nf else 0, bdry_solid_el=np.array(bs, np.int32), bdry_fluid_el=np.array(bf, np.int32),
+                   bdry_jpol_solid=np.array(js, np.int32), bdry_jpol_fluid=np.array(jf, np.int32),
+                   ax_el_solid=ax_all[ax_all <= ns], ax_el_fluid=ax_all[ax_all > ns] - ns)
+        ax_el = ax_all
     return dict(nelem=nelem, crd=crd, lnods=lnods, eltype=eltype, coarsing=np.array(coarsing), igloc=igloc, nglob=nglob,
-                ax_el=ax_el, corners=corners, router=float(r_fine[-1]), rmin=0.0 if cube_halfwidth else float(r_coarse[0]),
-                ndoubling=int(np.sum(coarsing)))
+                ax_el=ax_el, corners=corners, router=router, rmin=rmin, ndoubling=int(np.sum(coarsing)), **dom)
 
 
 def write_database(path, M, basis, *, bkgrdmodel="prem_iso_light", dt=1.0, period=50.0,
-                   discont=(6371e3, 6291e3, 6151e3, 5971e3, 5771e3, 5701e3, 5600e3, 3630e3, 3480e3, 1221.5e3)):
-    """One rank, all solid: the record sequence of MESHER/pdb.f90:2205-2382 (see axisem_b200/host/meshdb_io.py)."""
+                   discont=(6371e3, 6291e3, 6151e3, 5971e3, 5771e3, 5701e3, 5600e3, 3630e3, 3480e3, 1221.5e3),
+                   solid_domain=None):
+    """One rank: the record sequence of MESHER/pdb.f90:2205-2382 (see axisem_b200/host/meshdb_io.py)."""
     f = open(path, "wb")
 
     def rec(*parts):
@@ -164,7 +244,11 @@ def write_database(path, M, basis, *, bkgrdmodel="prem_iso_light", dt=1.0, perio
     D = lambda *v: np.asarray(v, dtype="<f8").tobytes()
     A = lambda a, dt_: np.ascontiguousarray(a, dtype=dt_).tobytes()
     nelem, npol = M["nelem"], 4
-    for v in (1, npol, nelem, nelem * 25, nelem, 0, nelem * 25, 0, M["nglob"], 0, 0, len(discont), len(bkgrdmodel)):
+    ns, nf = M.get("nel_solid", nelem), M.get("nel_fluid", 0)
+    ig_s, ig_f = M.get("igloc_solid", M["igloc"]), M.get("igloc_fluid", np.zeros(0, np.int32))
+    ng_s, ng_f = M.get("nglob_solid", M["nglob"]), M.get("nglob_fluid", 0)
+    nb = len(M.get("bdry_solid_el", ()))
+    for v in (1, npol, nelem, nelem * 25, ns, nf, ns * 25, nf * 25, ng_s, ng_f, nb, len(discont), len(bkgrdmodel)):
         rec(I(v))
     for name in ("xi_k", "eta", "dxi", "wt", "wt_axial_k"):
         rec(A(getattr(basis, name, np.zeros(npol + 1)), "<f8"))
@@ -176,20 +260,25 @@ def write_database(path, M, basis, *, bkgrdmodel="prem_iso_light", dt=1.0, perio
     rec(A(M["crd"][:, 1], "<f8"))
     for e in range(nelem):
         rec(A(M["lnods"][e], "<i4"))
-    rec(I(M["nglob"]))
+    rec(I(ng_s + ng_f))
     rec(b"".join(t.encode().ljust(6)[:6] for t in M["eltype"]))
-    rec(A(M["coarsing"].astype(np.int32), "<i4"))
-    rec(A(np.arange(1, nelem + 1), "<i4"))                    # ielsolid
-    rec(A(np.zeros(0), "<i4"))                                # ielfluid
-    rec(A(M["igloc"], "<i4"))
-    rec(A(np.zeros(0), "<i4"))
-    rec(I(0))                                                 # have_bdry_elem
+    rec(A(np.asarray(M["coarsing"]).astype(np.int32), "<i4"))
+    rec(A(np.arange(1, ns + 1), "<i4"))                       # ielsolid
+    rec(A(np.arange(ns + 1, nelem + 1), "<i4"))               # ielfluid
+    rec(A(ig_s, "<i4"))
+    rec(A(ig_f, "<i4"))
+    rec(I(1 if nb else 0))                                    # have_bdry_elem
+    if nb:
+        for k in ("bdry_solid_el", "bdry_fluid_el", "bdry_jpol_solid", "bdry_jpol_fluid"):
+            rec(A(M[k], "<i4"))
     rec(D(1.5, period, 0.6, dt))
     rec(bkgrdmodel.encode())
     rec(b"none  ")
-    rec(D(M["router"]), I(0))                                 # router, have_fluid
-    for r in discont:
-        rec(D(r), I(1), I(0))
+    rec(D(M["router"]), I(1 if nf else 0))                    # router, have_fluid
+    if solid_domain is None:
+        solid_domain = [1] * len(discont)
+    for r, sd in zip(discont, solid_domain):
+        rec(D(r), I(sd), I(0))
     rec(D(M["rmin"], 0.0, 0.0, 0.0))
     rec(D(0.0, 0.0))
     rec(D(0.0, 0.0))
@@ -197,9 +286,12 @@ def write_database(path, M, basis, *, bkgrdmodel="prem_iso_light", dt=1.0, perio
         rec(D(0.0), I(1))
         rec(D(0.0, 0.0))
     ax = M["ax_el"]
-    rec(I(ax.size, ax.size, 0))
+    ax_s, ax_f = M.get("ax_el_solid", ax), M.get("ax_el_fluid", np.zeros(0, np.int32))
+    rec(I(ax.size, ax_s.size, ax_f.size))
     rec(A(ax, "<i4"))
-    rec(A(ax, "<i4"))
-    rec(A(np.zeros(0), "<i4"))
+    rec(A(ax_s, "<i4"))
+    rec(A(ax_f, "<i4"))
     rec(I(0))                                                 # solid messaging: no neighbours
+    if nf:
+        rec(I(0))                                             # fluid messaging
     f.close()
