@@ -139,7 +139,8 @@ void write_rundir(const std::string &dir, const std::vector<axisem::Modules> &ra
     axisem::write_receiver_names(dir + "/Data/receiver_names.dat", names);
     axisem::write_receiver_pts(dir + "/Data/receiver_pts.dat", loc2glob, th, lon);
     // seismograms of all ranks in list order
-    const int nseis = res.nseismo;
+    int nseis = res.nseismo;                       // (rank 0's count; a rank without receivers keeps none)
+    for (const auto &kv : sink.ranks) nseis = std::max(nseis, kv.second.nseis);
     std::vector<float> seis((size_t)nseis * nrec * 3, 0.0f);
     for (size_t r = 0; r < ranks.size(); r++) {
         if (loc2glob[r].empty()) continue;

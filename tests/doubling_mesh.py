@@ -220,13 +220,90 @@ def _finish(els, router, rmin, fluid=None):
                 assert j_s in (0, 4) and j_f in (0, 4) and ps == pf, "a solid/fluid boundary must be an eta = const edge with xi aligned"
                 bs.append(es + 1); bf.append(ef - ns + 1); js.append(j_s); jf.append(j_f)
         ax_all = np.array([e + 1 for e, c in enumerate(corners) if c[0][0] == 0.0 and c[3][0] == 0.0], dtype=np.int32)
+        ig = igr
         dom = dict(nel_solid=ns, nel_fluid=nf, igloc_solid=ig_s, igloc_fluid=ig_f, nglob_solid=int(ig_s.max()),
                    nglob_fluid=int(ig_f.max()) if nf else 0, bdry_solid_el=np.array(bs, np.int32), bdry_fluid_el=np.array(bf, np.int32),
                    bdry_jpol_solid=np.array(js, np.int32), bdry_jpol_fluid=np.array(jf, np.int32),
                    ax_el_solid=ax_all[ax_all <= ns], ax_el_fluid=ax_all[ax_all > ns] - ns)
         ax_el = ax_all
     return dict(nelem=nelem, crd=crd, lnods=lnods, eltype=eltype, coarsing=np.array(coarsing), igloc=igloc, nglob=nglob,
-                ax_el=ax_el, corners=corners, router=router, rmin=rmin, ndoubling=int(np.sum(coarsing)), **dom)
+                ax_el=ax_el, corners=corners, router=router, rmin=rmin, ndoubling=int(np.sum(coarsing)), topo=ig, **dom)
+
+
+def partition(M, nth_blocks, r_cuts=()):
+    """The mesher's domain decomposition of a mesh built above: theta blocks by the colatitude of the element
+    centroids, times radial blocks cut at `r_cuts` (never at a solid/fluid boundary) — one database per rank,
+    with its own element order (solid first), its own global numbers per domain, and the message lists of
+    data_comm.f90:36-71 towards every rank it shares points with (the same points in the same order on either
+    side; a point shared by three or four ranks travels in each pairwise message)."""
+    nelem = M["nelem"]
+    ns = M.get("nel_solid", nelem)
+    cent = np.array([[np.mean([p[0] for p in c]), np.mean([p[1] for p in c])] for c in M["corners"]])
+    th = np.arctan2(cent[:, 0], cent[:, 1])
+    rr = np.hypot(cent[:, 0], cent[:, 1])
+    tb = np.minimum((th / np.pi * nth_blocks).astype(int), nth_blocks - 1)
+    rb = np.searchsorted(np.asarray(r_cuts, dtype=float), rr)
+    nrb = len(r_cuts) + 1
+    rank = tb * nrb + rb
+    if "bdry_solid_el" in M:                      # a boundary pair lives on one rank
+        for es, ef in zip(M["bdry_solid_el"], M["bdry_fluid_el"]):
+            rank[ns + ef - 1] = rank[es - 1]
+    nranks = nth_blocks * nrb
+    topo = M["topo"].reshape(nelem, 25)
+    is_f = np.arange(nelem) >= ns
+    out, gids = [], []
+    for r in range(nranks):
+        E = np.nonzero(rank == r)[0]              # global order is solid first: so is this
+        Es, Ef = E[~is_f[E]], E[is_f[E]]
+        loc = {}
+
+        def compress(block):
+            flat_ = block.reshape(-1)
+            if flat_.size == 0:
+                return np.zeros(0, np.int32), np.zeros(0, np.int64)
+            u, first_, inv_ = np.unique(flat_, return_index=True, return_inverse=True)
+            order_ = np.argsort(np.argsort(first_))
+            gid = np.zeros(u.size, np.int64)
+            gid[order_] = u                       # gid[local - 1] = topological id
+            return (order_[inv_] + 1).astype(np.int32), gid
+
+        ig_s, gid_s = compress(topo[Es])
+        ig_f, gid_f = compress(topo[Ef])
+        gids.append((gid_s, gid_f))
+        new_of = {int(e): k for k, e in enumerate(E)}
+        ne = E.size
+        d = dict(nelem=ne, nel_solid=int(Es.size), nel_fluid=int(Ef.size), igloc_solid=ig_s, igloc_fluid=ig_f,
+                 nglob_solid=int(gid_s.size), nglob_fluid=int(gid_f.size), igloc=ig_s, nglob=int(gid_s.size),
+                 crd=M["crd"].reshape(nelem, 8, 2)[E].reshape(-1, 2), lnods=np.arange(1, 8 * ne + 1, dtype=np.int32).reshape(ne, 8),
+                 eltype=[M["eltype"][e] for e in E], coarsing=np.asarray(M["coarsing"])[E], router=M["router"], rmin=M["rmin"],
+                 nranks=nranks, rank=r, have_fluid=M.get("nel_fluid", 0) > 0)
+        ax = np.array([new_of[int(e) - 1] + 1 for e in M["ax_el"] if int(e) - 1 in new_of], dtype=np.int32)
+        d["ax_el"] = ax
+        d["ax_el_solid"] = ax[ax <= Es.size]
+        d["ax_el_fluid"] = ax[ax > Es.size] - Es.size
+        bs, bf, js, jf = [], [], [], []
+        if "bdry_solid_el" in M:
+            for es, ef, a_, b_ in zip(M["bdry_solid_el"], M["bdry_fluid_el"], M["bdry_jpol_solid"], M["bdry_jpol_fluid"]):
+                if int(es) - 1 in new_of:
+                    assert ns + int(ef) - 1 in new_of
+                    bs.append(new_of[int(es) - 1] + 1); bf.append(new_of[ns + int(ef) - 1] - Es.size + 1); js.append(a_); jf.append(b_)
+        d.update(bdry_solid_el=np.array(bs, np.int32), bdry_fluid_el=np.array(bf, np.int32),
+                 bdry_jpol_solid=np.array(js, np.int32), bdry_jpol_fluid=np.array(jf, np.int32))
+        out.append(d)
+    for r in range(nranks):
+        for dname, k in (("solid", 0), ("fluid", 1)):
+            peers, lists = [], []
+            mine = gids[r][k]
+            where = {int(g): i + 1 for i, g in enumerate(mine)}
+            for q in range(nranks):
+                if q == r:
+                    continue
+                shared = np.intersect1d(mine, gids[q][k])
+                if shared.size:
+                    peers.append(q)
+                    lists.append(np.array([where[int(g)] for g in shared], dtype=np.int32))
+            out[r]["halo_" + dname] = (np.array(peers, np.int32), lists)
+    return out
 
 
 def write_database(path, M, basis, *, bkgrdmodel="prem_iso_light", dt=1.0, period=50.0,
@@ -248,7 +325,7 @@ def write_database(path, M, basis, *, bkgrdmodel="prem_iso_light", dt=1.0, perio
     ig_s, ig_f = M.get("igloc_solid", M["igloc"]), M.get("igloc_fluid", np.zeros(0, np.int32))
     ng_s, ng_f = M.get("nglob_solid", M["nglob"]), M.get("nglob_fluid", 0)
     nb = len(M.get("bdry_solid_el", ()))
-    for v in (1, npol, nelem, nelem * 25, ns, nf, ns * 25, nf * 25, ng_s, ng_f, nb, len(discont), len(bkgrdmodel)):
+    for v in (M.get("nranks", 1), npol, nelem, nelem * 25, ns, nf, ns * 25, nf * 25, ng_s, ng_f, nb, len(discont), len(bkgrdmodel)):
         rec(I(v))
     for name in ("xi_k", "eta", "dxi", "wt", "wt_axial_k"):
         rec(A(getattr(basis, name, np.zeros(npol + 1)), "<f8"))
@@ -274,7 +351,8 @@ def write_database(path, M, basis, *, bkgrdmodel="prem_iso_light", dt=1.0, perio
     rec(D(1.5, period, 0.6, dt))
     rec(bkgrdmodel.encode())
     rec(b"none  ")
-    rec(D(M["router"]), I(1 if nf else 0))                    # router, have_fluid
+    have_fluid = bool(M.get("have_fluid", nf > 0))            # of the whole mesh
+    rec(D(M["router"]), I(1 if have_fluid else 0))            # router, have_fluid
     if solid_domain is None:
         solid_domain = [1] * len(discont)
     for r, sd in zip(discont, solid_domain):
@@ -291,7 +369,15 @@ def write_database(path, M, basis, *, bkgrdmodel="prem_iso_light", dt=1.0, perio
     rec(A(ax, "<i4"))
     rec(A(ax_s, "<i4"))
     rec(A(ax_f, "<i4"))
-    rec(I(0))                                                 # solid messaging: no neighbours
-    if nf:
-        rec(I(0))                                             # fluid messaging
+    for dname in ("solid", "fluid"):                          # messaging (pdb.f90:2330-2380)
+        if dname == "fluid" and not have_fluid:
+            break
+        peers, lists = M.get("halo_" + dname, (np.zeros(0, np.int32), []))
+        rec(I(len(peers)))
+        if len(peers):
+            rec(A(peers, "<i4"))
+            rec(A([len(l) for l in lists], "<i4"))
+            for l in lists:
+                for g in l:
+                    rec(I(int(g)))
     f.close()

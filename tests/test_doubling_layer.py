@@ -164,18 +164,89 @@ def test_cuda_library_on_a_full_sphere_with_inner_cube(tmp_path):
 
 
 @pytest.mark.gpu
-def test_cuda_library_on_a_coarsening_layer(tmp_path):
-    """The device library on the unstructured database (assembly groups of valence 3 and 4 in the layer,
-    semino / semiso coefficient planes): the product host against its CPU twin linked to the oracle."""
+@pytest.mark.parametrize("variant", [["--attenuation", "cg4"], ["--attenuation", "full"], ["--scheme", "symplec4"]],
+                         ids=["cg4", "full_memvars", "symplec4"])
+def test_cuda_library_on_a_coarsening_layer(tmp_path, variant):
+    """The device library on the unstructured database (assembly groups of valence 3, 4 and 6 in the layer,
+    semino / semiso coefficient planes): the product host against its CPU twin linked to the oracle — Newmark
+    with coarse-grained and with full memory variables, and the 4th-order symplectic loop."""
     from oracle import oracle
     assert os.path.exists(PRODUCT_EXE), "axisem_b200_solver missing: run __graft_entry__.build()"
     path, M = _databases(tmp_path)["dbl"]
     got = {}
     for name, exe in (("gpu", PRODUCT_EXE), ("cpu", oracle.build_host())):
-        r = subprocess.run([exe, "--quiet", "--out", str(tmp_path / name), "--niter", "2000", "--attenuation", "cg4"] + RUN + [path],
+        r = subprocess.run([exe, "--quiet", "--out", str(tmp_path / name), "--niter", "2000"] + variant + RUN + [path],
                            capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stderr
         got[name] = np.fromfile(tmp_path / f"{name}.rank0000.seis.f32", dtype=np.float32)
     assert got["gpu"].shape == got["cpu"].shape and np.abs(got["cpu"]).max() > 0
     d = got["gpu"].astype(np.float64) - got["cpu"]
     assert np.sqrt((d ** 2).sum() / (got["cpu"].astype(np.float64) ** 2).sum()) <= 1e-5
+
+
+# ---- the mesher's domain decomposition of such a mesh ----------------------------------------------------------
+EARTH_ROWS = [(1221.5e3, 2350e3, "R"), (2350e3, 3480e3, "R"), (3480e3, 3630e3, "R"), (3630e3, 4115e3, "R"), (4115e3, 4600e3, "R"),
+              (4600e3, 4900e3, "D"), (4900e3, 5250e3, "R"), (5250e3, 5600e3, "R"), (5600e3, 5701e3, "R"), (5701e3, 5771e3, "R"),
+              (5771e3, 5971e3, "R"), (5971e3, 6151e3, "R"), (6151e3, 6291e3, "R"), (6291e3, 6371e3, "R")]
+EARTH_DISC = (6371e3, 6291e3, 6151e3, 5971e3, 5771e3, 5701e3, 5600e3, 3630e3, 3480e3, 1221.5e3)
+EARTH_ARGS = ["--src", "mtr", "--depth", "300", "--period", "250", "--seis-it", "4", "--attenuation", "cg4", "--receivers", "40,80,120,178"]
+
+
+def _earth_databases(tmp_path, tag, nth_blocks, r_cuts):
+    F = dm.build_rows(EARTH_ROWS, 16, cube_halfwidth=500e3, fluid=lambda r: 1221.5e3 < r < 3480e3)
+    parts = dm.partition(F, nth_blocks, r_cuts)
+    files = []
+    for r, P in enumerate(parts):
+        files.append(str(tmp_path / f"{tag}.dat{r:04d}"))
+        dm.write_database(files[-1], P, SpectralBasis(4), bkgrdmodel="prem_iso_light", discont=EARTH_DISC,
+                          solid_domain=[1, 1, 1, 1, 1, 1, 1, 1, 0, 1], dt=0.5)
+    return files, parts
+
+
+def _seis_by_station(tmp_path, tag, exe, files, niter, extra=()):
+    r = subprocess.run([exe, "--quiet", "--out", str(tmp_path / f"run_{tag}"), "--rundir", str(tmp_path / f"RUN_{tag}"),
+                        "--niter", str(niter)] + list(extra) + EARTH_ARGS + files, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr
+    return _traces(tmp_path / f"RUN_{tag}")
+
+
+@pytest.mark.parametrize("nth_blocks,r_cuts", [(2, (5000e3,)), (3, ())], ids=["2x2_blocks", "3_slices"])
+def test_decomposed_whole_earth_equals_one_rank(tmp_path, nth_blocks, r_cuts):
+    """One database per rank of a whole Earth (inner square, fluid core, coarsening layer) cut into theta x r
+    blocks: every rank of the 2 x 2 case has three neighbours and one point belongs to all four; boundary
+    pairs stay on one rank; ranks without fluid, ranks without receivers.  The pre-computation assembles mass
+    and boundary terms across the cuts, and the dipole + attenuation run equals the undivided one to the
+    order of summation."""
+    from oracle import oracle
+    one, _ = _earth_databases(tmp_path, "one", 1, ())
+    files, parts = _earth_databases(tmp_path, "cut", nth_blocks, r_cuts)
+    assert len(files) == nth_blocks * (len(r_cuts) + 1)
+    if r_cuts:
+        assert all(len(P["halo_solid"][0]) == 3 for P in parts)
+        assert sorted(len(l) for l in parts[0]["halo_solid"][1])[0] == 1          # the point where the four blocks meet
+        assert any(P["nel_fluid"] == 0 for P in parts) and any(P["nel_fluid"] > 0 for P in parts)
+    for P in parts:
+        for q, l in zip(*P["halo_solid"]):                                         # symmetric lists
+            back = dict(zip(*[parts[q]["halo_solid"][0].tolist(), parts[q]["halo_solid"][1]]))
+            assert len(back[P["rank"]]) == len(l)
+    out = subprocess.run([PRECOMP, "--out", str(tmp_path / "pre"), "--niter", "10"] + EARTH_ARGS[:6] + files, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    checks = dict(line.split() for line in out.stdout.strip().splitlines())
+    assert abs(float(checks["mass_over_volume"]) - 1.0) < 1e-9 and abs(float(checks["bdry_sum"]) - 4.0) < 1e-9
+    exe = oracle.build_host()
+    a = _seis_by_station(tmp_path, "one", exe, one, 2000)
+    b = _seis_by_station(tmp_path, "cut", exe, files, 2000)
+    assert np.abs(a).max() > 0 and np.sqrt(((a - b) ** 2).sum() / (a ** 2).sum()) < 1e-5
+
+
+@pytest.mark.gpu
+def test_cuda_library_on_a_decomposed_whole_earth(tmp_path):
+    """Four theta x r blocks of the whole Earth as four handles on one device (halo words between
+    them), against the undivided run of the CPU twin."""
+    from oracle import oracle
+    assert os.path.exists(PRODUCT_EXE), "axisem_b200_solver missing: run __graft_entry__.build()"
+    one, _ = _earth_databases(tmp_path, "one", 1, ())
+    files, _ = _earth_databases(tmp_path, "cut", 2, (5000e3,))
+    a = _seis_by_station(tmp_path, "cpu", oracle.build_host(), one, 2000)
+    b = _seis_by_station(tmp_path, "gpu", PRODUCT_EXE, files, 2000, extra=["--devices", "1"])
+    assert np.abs(a).max() > 0 and np.sqrt(((a - b) ** 2).sum() / (a ** 2).sum()) < 1e-5

@@ -83,13 +83,22 @@ def test_explosion_on_a_whole_earth_against_the_references_traces(tmp_path):
     13 608 steps: a minute and a half on one core)."""
     from oracle import oracle
     path, _ = _database(tmp_path, 64)
-    cc, amp, _ = _run(oracle.build_host(), path, str(tmp_path / "run"), "explosion")
+    cc, amp, s = _run(oracle.build_host(), path, str(tmp_path / "run"), "explosion")
     assert cc.size == 40
     # measured: 0.9974 / 0.9995, amplitude 0.988 - 1.025 (median 1.005).  The hollow 224 x 60 mesh of
     # test_nightly_reference.py: 0.921 / 0.9985, 0.84 - 1.07; the reference's own traces against the
     # independent YSPEC solution it ships: 0.997 - 0.9996.
     assert cc.min() > 0.995 and np.median(cc) > 0.999
     assert 0.97 < amp.min() and amp.max() < 1.04 and abs(np.median(amp) - 1.0) < 0.01
+    # and against the independent YSPEC solution of this case that the reference ships (no attenuation, no
+    # gravity; N and Z): measured 0.920 / 0.9993 (hollow mesh: 0.920 / 0.9984), median amplitude ratio 1.003
+    names, lat, lon = stations()
+    colat = np.deg2rad(90.0 - lat)
+    shift = np.ceil(1.5 * T_0 / DT) * DT
+    t = np.arange(s.shape[0]) * max(1, int(0.8 / DT)) * DT - shift
+    res = compare("explosion", to_enz("explosion", s, colat, np.deg2rad(lon)), t, T_0, against="yspec")
+    big = res[:, :, 3] > 0.002 * res[:, :, 3].max()
+    assert np.median(res[:, :, 0][big]) > 0.999 and res[:, :, 0][big].min() > 0.9 and abs(np.median(res[:, :, 2][big]) - 1.0) < 0.01
 
 
 @pytest.mark.gpu
