@@ -152,6 +152,21 @@ def mesh_group(probs: Sequence) -> Dict[str, np.ndarray]:
     mid, eltype, axis, fem, sem, mps, mpz = [], [], [], [], [], [], []
     base = 0
     for p in probs:
+        nm = getattr(p, "nc_mesh", None)
+        if nm is not None:                 # a run set up by the native pre-computation: the arrays travel in its container
+            pts_s.append(nm["mesh_S"])
+            pts_z.append(nm["mesh_Z"])
+            for k in mat:
+                mat[k].append(nm["mesh_" + k])
+            mid.append(nm["midpoint_mesh"] + base)
+            eltype.append(nm["eltype"])
+            axis.append(nm["axis"])
+            fem.append(nm["fem_mesh"].reshape(-1, 4) + base)
+            sem.append(nm["sem_mesh"].reshape(-1, 5, 5) + base)
+            mps.append(nm["mp_mesh_S"])
+            mpz.append(nm["mp_mesh_Z"])
+            base += nm["mesh_S"].size
+            continue
         m, q = p.mesh, p.kwf
         npt = q["npoint_solid_kwf"] + q["npoint_fluid_kwf"]
         S, Z = np.zeros(npt), np.zeros(npt)
@@ -279,6 +294,57 @@ def write_database(outdir: str, probs: Sequence, seismograms: Sequence[np.ndarra
     with open(os.path.join(outdir, "schema.json"), "w") as f:
         json.dump(sch, f, indent=1, default=lambda o: o.item() if hasattr(o, "item") else str(o))
     return sch
+
+
+def native_problem(rec: Dict[str, np.ndarray], rec_offset: int = 0):
+    """What write_database needs of a rank, from the module-variable container the native pre-computation wrote
+    (axisem_b200_precomp, hostcxx/precomp.cpp; read with meshdb_io.read_axbprob)."""
+    from types import SimpleNamespace as NS
+    from ..capi import SCHEMES, STF_TYPES
+    from .source import SourceParams
+    i = lambda k, d=None: int(np.asarray(rec[k]).reshape(-1)[0]) if k in rec else d
+    f = lambda k: float(np.asarray(rec[k]).reshape(-1)[0])
+    text = lambda k: "".join(chr(int(c)) for c in np.asarray(rec[k]).reshape(-1))
+    order = i("data_source%src_order")
+    src = SourceParams(src_type2=text("data_source%src_type2"), depth=f("data_source%src_depth"), magnitude=f("data_source%magnitude"),
+                       stf_type=text("data_source%stf_name"), t_0=f("data_source%t_0"), decay=f("data_source%decay"),
+                       shift_seconds=f("data_source%shift_fact"))
+    assert STF_TYPES[src.stf_type] == i("data_source%stf_type")
+    basis = NS(G0=np.asarray(rec["data_spec%G0"], np.float64).reshape(-1),
+               G1=np.asarray(rec["data_spec%G1"], np.float64).reshape(5, 5).T, G2=np.asarray(rec["data_spec%G2"], np.float64).reshape(5, 5).T,
+               eta=np.asarray(rec["data_spec%eta"], np.float64).reshape(-1), xi_k=np.asarray(rec["data_spec%xi_k"], np.float64).reshape(-1))
+    mesh = NS(nel_solid=i("data_mesh%nel_solid"), nel_fluid=i("data_mesh%nel_fluid"), basis=basis,
+              spec=NS(router=f("data_mesh%router")))
+    dump = i("data_io%dump_wavefields", 0) != 0
+    kwf = dict(npoint_solid_kwf=i("data_mesh%npoint_solid_kwf"), npoint_fluid_kwf=i("data_mesh%npoint_fluid_kwf")) if dump else None
+    num_rec = i("data_mesh%num_rec")
+    scheme = {v: k for k, v in SCHEMES.items()}[i("data_time%time_scheme")]
+    p = NS(mesh=mesh, source=src, src_order=order, src_type=("monopole", "dipole", "quadpole")[order], time_scheme=scheme,
+           deltat=f("data_time%deltat"), niter=i("data_time%niter"), seis_it=i("data_time%seis_it"), strain_it=i("data_time%strain_it"),
+           stf=np.asarray(rec["data_source%stf"], np.float32).reshape(-1), anel=i("attenuation%anel_true", 0) != 0,
+           num_rec=num_rec, rec_index=(np.asarray(rec["data_mesh%loc2globrec"]).reshape(-1) - 1 if num_rec else np.zeros(0, int)),
+           kwf=kwf, dump_type="displ_only")
+    if dump:
+        p.nc_mesh = {k.split("%", 1)[1]: np.asarray(v) for k, v in rec.items() if k.startswith("nc_mesh%")}
+    return p
+
+
+def write_database_native(outdir: str, containers: Sequence[str], run_prefix: str, *, colat_deg=None, names=None,
+                          background_model: str = "prem_iso") -> Dict:
+    """The database directory of a run of the native chain: `containers` are the PREFIX.rankNNNN.axbp files
+    of axisem_b200_precomp, `run_prefix` the --out of axisem_b200_solver (RUN.rankNNNN.seis.f32 / .snap.f32)."""
+    from .meshdb_io import read_axbprob
+    probs = [native_problem(read_axbprob(c)) for c in containers]
+    seis, snaps = [], []
+    for r, p in enumerate(probs):
+        fs = f"{run_prefix}.rank{r:04d}.seis.f32"
+        seis.append(np.fromfile(fs, dtype=np.float32).reshape(-1, p.num_rec, 3) if p.num_rec else np.zeros((0, 0, 3), np.float32))
+        if p.kwf is not None:
+            npt = p.kwf["npoint_solid_kwf"] + p.kwf["npoint_fluid_kwf"]
+            snaps.append(np.fromfile(f"{run_prefix}.rank{r:04d}.snap.f32", dtype=np.float32).reshape(3, -1, npt))
+    if colat_deg is None:
+        colat_deg = np.asarray(read_axbprob(containers[0])["data_mesh%recfile_readth"], np.float64).reshape(-1)
+    return write_database(outdir, probs, seis, snaps or None, colat_deg=colat_deg, names=names, background_model=background_model)
 
 
 def read_variable(outdir: str, group: str, name: str) -> np.ndarray:

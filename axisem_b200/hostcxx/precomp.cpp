@@ -828,6 +828,12 @@ void precompute(std::vector<Modules> &ranks, const PrecompOptions &opt) {
             m.put("data_source%t_0", scalar_d(opt.t_0));
             m.put("data_source%shift_fact", scalar_d(stf_shift(opt, deltat)));
             m.put("data_source%magnitude", scalar_d(opt.magnitude));
+            {
+                std::vector<int32_t> chars(opt.src_type2.begin(), opt.src_type2.end()), stfc(opt.stf_type.begin(), opt.stf_type.end());
+                m.put("data_source%src_type2", i32_of(chars, {(uint64_t)chars.size()}));
+                m.put("data_source%stf_name", i32_of(stfc, {(uint64_t)stfc.size()}));
+                m.put("data_source%src_depth", scalar_d(opt.src_depth));
+            }
         }
         // ---- receivers: nearest surface GLL point to each colatitude, owned by the rank that holds it ---
         {
@@ -839,18 +845,25 @@ void precompute(std::vector<Modules> &ranks, const PrecompOptions &opt) {
                 const double cd = opt.rec_colat_deg[irec];
                 const double c = cd * PI / 180.0;
                 double th_best = 0.0;
+                // every rank finds its closest surface point (first one wins within the rank); of the ranks that
+                // reach the global minimum the one with the largest number takes the receiver (seismograms.f90:477-484)
                 double best = 1e300;
                 size_t best_rank = nr;
                 std::array<int32_t, 3> at{0, 0, 0};
                 for (size_t q = 0; q < nr; q++) {
                     const Geometry &G = gs[q];
+                    double mine = 1e300, th_mine = 0.0;
+                    std::array<int32_t, 3> at_mine{0, 0, 0};
                     for (int e = 0; e < G.nel; e++)
                         for (int k = 0; k < NPT; k++) {
                             const size_t p = (size_t)NPT * e + k;
                             if (std::fabs(G.r[p] - router) > 1e-3 * router * 1e-3) continue;
                             const double d = std::fabs(std::atan2(G.s[p], G.z[p]) - c);
-                            if (d < best - 1e-14) { best = d; best_rank = q; at = {e + 1, k % NP, k / NP}; th_best = std::atan2(G.s[p], G.z[p]); }
+                            if (d < mine - 1e-14) { mine = d; at_mine = {e + 1, k % NP, k / NP}; th_mine = std::atan2(G.s[p], G.z[p]); }
                         }
+                    if (mine < 1e299 && (mine < best - 1e-12 || std::fabs(mine - best) <= 1e-12)) {
+                        best = std::fmin(best, mine); best_rank = q; at = at_mine; th_best = th_mine;
+                    }
                 }
                 if (best_rank == r) { hits.push_back(at); loc2glob.push_back((int32_t)irec + 1); th_deg.push_back(th_best * 180.0 / PI); }
             }
@@ -861,6 +874,7 @@ void precompute(std::vector<Modules> &ranks, const PrecompOptions &opt) {
             m.put("data_mesh%recfile_el", i32_of(rec, {3, (uint64_t)nrec}));
             m.put("data_mesh%loc2globrec", i32_of(loc2glob, {(uint64_t)nrec}));
             m.put("data_mesh%recfile_th", make(Array::F64, {(uint64_t)nrec}, th_deg.data()));
+            m.put("data_mesh%recfile_readth", make(Array::F64, {(uint64_t)opt.rec_colat_deg.size()}, opt.rec_colat_deg.data()));   // all receivers of the run
         }
         // ---- wavefield-dump point set (meshes_io.F90:489-640: first visit wins, solid then fluid) -------
         m.put("data_io%dump_wavefields", scalar_i(opt.dump_wavefields && opt.strain_it > 0));
@@ -956,6 +970,57 @@ void precompute(std::vector<Modules> &ranks, const PrecompOptions &opt) {
             m.put("data_mesh%npoint_solid_kwf", scalar_i(counts[0]));
             m.put("data_mesh%npoint_fluid_kwf", scalar_i(counts[1]));
             m.put("data_io%dump_type", scalar_i(0));
+            // ---- the Mesh group of the output database (nc_routines.F90:668-823, meshes_io.F90:641-778):
+            // coordinates and the model at the dumped points, and per dumped element its mid-point, corner and
+            // GLL point numbers in that list (0-based within the rank)
+            const int npt = counts[0] + counts[1];
+            std::vector<double> S(npt, 0.0), Z(npt, 0.0);
+            std::vector<float> vp(npt, 0.f), vs(npt, 0.f), rho(npt, 0.f), lam(npt, 0.f), mu(npt, 0.f), xi(npt, 0.f), phi(npt, 0.f),
+                eta(npt, 0.f), qmu(npt, 0.f), qka(npt, 0.f);
+            const int nel = nel_s + nel_f;
+            std::vector<int32_t> mid(nel), elt(nel), axs(nel), fem((size_t)4 * nel), sem((size_t)NPT * nel);
+            std::vector<double> mps(nel), mpz(nel);
+            const int32_t *eltype = m.i("data_mesh%eltype");
+            for (int d = 0; d < 2; d++) {
+                const Geometry &G = d ? f : g;
+                const Material &M = d ? mf[r] : ms[r];
+                const int ne = d ? nel_f : nel_s;
+                const size_t off = d ? (size_t)NPT * nel_s : 0;
+                for (int e = 0; e < ne; e++) {
+                    for (int q = 0; q < NPT; q++) {
+                        const size_t p = (size_t)NPT * e + q;
+                        const int k = map[off + p] - 1;
+                        sem[off + p] = k;
+                        if (!mask[off + p]) continue;
+                        S[k] = G.s[p]; Z[k] = G.z[p];
+                        rho[k] = (float)M.rho[p]; lam[k] = (float)M.lam[p]; mu[k] = (float)M.mu[p];
+                        xi[k] = (float)M.xi[p]; phi[k] = (float)M.phi[p]; eta[k] = (float)M.eta[p];
+                        vp[k] = (float)std::sqrt((M.lam[p] + 2.0 * M.mu[p]) / M.rho[p]);
+                        vs[k] = (float)std::sqrt(M.mu[p] / M.rho[p]);
+                        qmu[k] = (float)M.qmu[e]; qka[k] = (float)M.qka[e];
+                    }
+                    const size_t ee = (d ? nel_s : 0) + e, p0 = off + (size_t)NPT * e;
+                    mid[ee] = map[p0 + 2 * NP + 2] - 1;
+                    elt[ee] = eltype[G.iel_glob[e]];
+                    axs[ee] = G.axis[e];
+                    fem[4 * ee] = map[p0] - 1; fem[4 * ee + 1] = map[p0 + NP - 1] - 1;
+                    fem[4 * ee + 2] = map[p0 + NPT - 1] - 1; fem[4 * ee + 3] = map[p0 + NPT - NP] - 1;
+                    mps[ee] = G.s[(size_t)NPT * e + 2 * NP + 2]; mpz[ee] = G.z[(size_t)NPT * e + 2 * NP + 2];
+                }
+            }
+            const uint64_t un = (uint64_t)npt, ue = (uint64_t)nel;
+            m.put("nc_mesh%mesh_S", make(Array::F64, {un}, S.data()));
+            m.put("nc_mesh%mesh_Z", make(Array::F64, {un}, Z.data()));
+            const std::pair<const char *, const std::vector<float> *> fl[] = {{"vp", &vp}, {"vs", &vs}, {"rho", &rho}, {"lambda", &lam},
+                {"mu", &mu}, {"xi", &xi}, {"phi", &phi}, {"eta", &eta}, {"Qmu", &qmu}, {"Qka", &qka}};
+            for (const auto &kv : fl) m.put(std::string("nc_mesh%mesh_") + kv.first, make(Array::F32, {un}, kv.second->data()));
+            m.put("nc_mesh%midpoint_mesh", i32_of(mid, {ue}));
+            m.put("nc_mesh%eltype", i32_of(elt, {ue}));
+            m.put("nc_mesh%axis", i32_of(axs, {ue}));
+            m.put("nc_mesh%fem_mesh", i32_of(fem, {ue, 4}));
+            m.put("nc_mesh%sem_mesh", i32_of(sem, {ue, NP, NP}));
+            m.put("nc_mesh%mp_mesh_S", make(Array::F64, {ue}, mps.data()));
+            m.put("nc_mesh%mp_mesh_Z", make(Array::F64, {ue}, mpz.data()));
         }
         // ---- time ------------------------------------------------------------------------------------------
         static const std::map<std::string, int> SCHEMES = {{"newmark2", 0}, {"symplec4", 1}, {"ML_SO4m5", 2},

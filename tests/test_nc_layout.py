@@ -101,3 +101,55 @@ def test_database_of_a_two_rank_run(ref, tmp_path):
     have = set(json.load(open(os.path.join(out, "schema.json")))["attributes"])
     want = {n for n, _ in ref["global_attributes"]}
     assert want <= have, want - have
+
+
+def test_database_of_a_native_run_equals_the_python_one(tmp_path):
+    """The same two-rank run set up twice — by the Python builder, and by the native chain (mesher-format
+    databases -> axisem_b200_precomp -> C++ host) — gives the same output database: every variable of every
+    group (coordinates, model, element tables, seismograms, snapshots) and the global attributes."""
+    import subprocess
+    from axisem_b200.capi import connect_local, run_group
+    from axisem_b200.host.meshdb_io import write_meshdb
+    from oracle import oracle
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n, colat = 24, np.linspace(10, 170, 9)
+    probs = [build_problem(small_spec(), SourceParams(src_type2="mtr", t_0=4.0), niter=n, dump=True, strain_it=6,
+                           seis_it=2, rank=r, nranks=2, rec_colat_deg=colat, anel=True) for r in range(2)]
+    lib = oracle.load()
+    loops = [oracle.make_loop(p) for p in probs]
+    connect_local(lib, loops)
+    run_group(lib, loops, n)
+    py = str(tmp_path / "py.ncdir")
+    nc_layout.write_database(py, probs, [L.seismograms() for L in loops], [L.snapshots() for L in loops], colat_deg=colat)
+    files = []
+    for r, p in enumerate(probs):
+        files.append(str(tmp_path / f"meshdb.dat{r:04d}"))
+        write_meshdb(p.mesh, files[-1], dt=p.deltat, bkgrdmodel="prem_iso")
+    pre = subprocess.run([os.path.join(root, "axisem_b200", "axisem_b200_precomp"), "--out", str(tmp_path / "pre"), "--src", "mtr",
+                          "--period", "4", "--niter", str(n), "--seis-it", "2", "--strain-it", "6", "--attenuation", "cg4",
+                          "--receivers", ",".join(map(str, colat))] + files, capture_output=True, text=True)
+    assert pre.returncode == 0, pre.stderr
+    cont = [str(tmp_path / f"pre.rank{r:04d}.axbp") for r in range(2)]
+    run = subprocess.run([oracle.build_host(), "--quiet", "--out", str(tmp_path / "run")] + cont, capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr
+    tool = subprocess.run([os.sys.executable, os.path.join(root, "tools", "native_to_nc_layout.py"), "--out", str(tmp_path / "nat.ncdir"),
+                           "--run", str(tmp_path / "run")] + cont, capture_output=True, text=True)
+    assert tool.returncode == 0, tool.stderr
+    nat = str(tmp_path / "nat.ncdir")
+    a, b = (json.load(open(os.path.join(d, "schema.json"))) for d in (py, nat))
+    assert a["dimensions"] == b["dimensions"] and a["groups"].keys() == b["groups"].keys()
+    for k, v in a["attributes"].items():
+        w = b["attributes"][k]
+        assert (v == pytest.approx(w, rel=1e-6) if isinstance(v, float) else v == w), (k, v, w)
+    nvar = 0
+    for gname, g in [("", a)] + list(a["groups"].items()):
+        for v in g["variables"]:
+            x, y = nc_layout.read_variable(py, gname, v), nc_layout.read_variable(nat, gname, v)
+            assert x.shape == y.shape, (gname, v)
+            if x.dtype.kind in "iuS":
+                assert np.array_equal(x, y), (gname, v)
+            else:
+                scale = np.abs(x).max()
+                assert np.abs(x.astype(np.float64) - y).max() <= 3e-6 * scale + 1e-30, (gname, v, np.abs(x.astype(np.float64) - y).max() / (scale + 1e-300))
+            nvar += 1
+    assert nvar > 40
