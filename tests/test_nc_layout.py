@@ -153,3 +153,63 @@ def test_database_of_a_native_run_equals_the_python_one(tmp_path):
                 assert np.abs(x.astype(np.float64) - y).max() <= 3e-6 * scale + 1e-30, (gname, v, np.abs(x.astype(np.float64) - y).max() / (scale + 1e-300))
             nvar += 1
     assert nvar > 40
+
+
+def test_database_of_a_native_run_on_a_whole_earth(tmp_path):
+    """The same tool on a mesh the Python builder cannot make: inner square, ring, fluid core, coarsening
+    layer, two ranks (tests/doubling_mesh.py).  The Mesh group carries the four element types, one point per
+    global number of either domain from the centre to the surface, and element tables that index it
+    consistently; with and without wavefield dumps."""
+    import subprocess
+    from oracle import oracle
+    from axisem_b200.host.spectral import SpectralBasis
+    from . import doubling_mesh as dm
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rows = [(1221.5e3, 2350e3, "R"), (2350e3, 3480e3, "R"), (3480e3, 3630e3, "R"), (3630e3, 4600e3, "R"), (4600e3, 4900e3, "D"),
+            (4900e3, 5600e3, "R"), (5600e3, 5701e3, "R"), (5701e3, 5771e3, "R"), (5771e3, 5971e3, "R"), (5971e3, 6151e3, "R"),
+            (6151e3, 6291e3, "R"), (6291e3, 6371e3, "R")]
+    F = dm.build_rows(rows, 16, cube_halfwidth=500e3, fluid=lambda r: 1221.5e3 < r < 3480e3)
+    parts = dm.partition(F, 2)
+    files = []
+    for r, P in enumerate(parts):
+        files.append(str(tmp_path / f"e.dat{r:04d}"))
+        dm.write_database(files[-1], P, SpectralBasis(4), bkgrdmodel="prem_iso_light", solid_domain=[1] * 8 + [0, 1], dt=0.5)
+    out = {}
+    for tag, extra in (("dump", ["--strain-it", "50"]), ("nodump", [])):
+        pre = subprocess.run([os.path.join(root, "axisem_b200", "axisem_b200_precomp"), "--out", str(tmp_path / f"pre_{tag}"),
+                              "--src", "explosion", "--depth", "300", "--period", "250", "--niter", "400", "--seis-it", "4",
+                              "--receivers", "30,90,150"] + extra + files, capture_output=True, text=True)
+        assert pre.returncode == 0, pre.stderr
+        cont = [str(tmp_path / f"pre_{tag}.rank{r:04d}.axbp") for r in range(2)]
+        run = subprocess.run([oracle.build_host(), "--quiet", "--out", str(tmp_path / f"run_{tag}")] + cont, capture_output=True, text=True)
+        assert run.returncode == 0, run.stderr
+        out[tag] = str(tmp_path / f"{tag}.ncdir")
+        sch = nc_layout.write_database_native(out[tag], cont, str(tmp_path / f"run_{tag}"), background_model="prem_iso_light")
+        assert sch["attributes"]["background model"] == "prem_iso_light" and sch["attributes"]["source type"] == "explosion"
+    d = out["dump"]
+    S, Z = (nc_layout.read_variable(d, "Mesh", k) for k in ("mesh_S", "mesh_Z"))
+    npt = sum(P["nglob_solid"] + P["nglob_fluid"] for P in parts)
+    assert S.size == npt and np.hypot(S, Z).min() == 0.0 and np.hypot(S, Z).max() == pytest.approx(6371e3)
+    el = nc_layout.read_variable(d, "Mesh", "eltype")
+    assert np.bincount(el).tolist() == [F["eltype"].count(k) for k in ("curved", "linear", "semino", "semiso")]
+    sem, fem, mid = (nc_layout.read_variable(d, "Mesh", k) for k in ("sem_mesh", "fem_mesh", "midpoint_mesh"))
+    assert sem.shape == (F["nelem"], 5, 5) and sem.min() == 0 and sem.max() == npt - 1
+    assert np.array_equal(fem[:, 0], sem[:, 0, 0]) and np.array_equal(fem[:, 2], sem[:, 4, 4]) and np.array_equal(mid, sem[:, 2, 2])
+    assert np.allclose(nc_layout.read_variable(d, "Mesh", "mp_mesh_S"), S[mid])
+    # the corners of an element, through fem_mesh, are the corners the generator gave it (rank blocks in order)
+    corners = np.array([c for P in parts for c in P_corners(P, F)])
+    assert np.allclose(np.stack([S[fem], Z[fem]], axis=-1), corners, atol=1e-3)
+    vs = nc_layout.read_variable(d, "Mesh", "mesh_vs")
+    r = np.hypot(S, Z)
+    assert (vs[(r > 1221.5e3 + 1) & (r < 3480e3 - 1)] == 0).all() and (vs[r > 3480e3 + 1] > 3000).all()       # fluid outer core
+    ds = nc_layout.read_variable(d, "Snapshots", "disp_s")
+    assert ds.shape == (400 // 50 + 1, npt) and np.abs(ds).max() > 0
+    disp = nc_layout.read_variable(d, "Seismograms", "displacement")
+    assert disp.shape == (3, 3, 101) and np.array_equal(disp, nc_layout.read_variable(out["nodump"], "Seismograms", "displacement"))
+    assert not os.path.exists(os.path.join(out["nodump"], "Mesh", "mesh_S.bin"))
+
+
+def P_corners(P, F):
+    """corner coordinates (4, 2) per element of a rank, in the rank's element order"""
+    crd = P["crd"].reshape(-1, 8, 2)
+    return [crd[e, [0, 2, 4, 6]] for e in range(P["nelem"])]
