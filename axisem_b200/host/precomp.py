@@ -417,9 +417,11 @@ def sf_boundary_terms(mesh: LocalMesh, gs: Geometry, es: ElementSet) -> np.ndarr
 @dataclass
 class AttenuationModel:
     """What `prepare_attenuation` (attenuation.f90:682-1095) leaves behind for the loop.
-    The SLS fit itself (simulated annealing with an unseeded RNG, :1183-1339) is not
-    reproducible; `w_j`, `y_j` are therefore inputs here (defaults: a 5-SLS log-spaced
-    fit for 1 mHz - 1 Hz, in the reference's own output range)."""
+    The SLS fit (a random search with an unseeded RNG, :1183-1339) is not reproducible in the
+    reference; `w_j`, `y_j` are therefore inputs here.  Defaults: a rounded log-spaced 5-SLS set
+    for 1 mHz - 1 Hz whose Q is flat to 16 % (tests/test_sls_fit.py); `invert_linear_solids` below
+    is the reference's search with a seed (flat to 2 % over the upper two decades) and
+    `AttenuationModel.fitted(...)` the set it finds."""
     n_sls: int = 5
     w_j: np.ndarray = field(default_factory=lambda: 2 * np.pi * np.array(
         [0.0015, 0.0090, 0.052, 0.29, 1.55]))
@@ -430,6 +432,62 @@ class AttenuationModel:
     w_0: float = 1.0            # reference frequency of the background model [Hz]
     do_corr_lowq: bool = True
     coarse_grained: bool = True
+
+    @classmethod
+    def fitted(cls, n_sls: int = 5, f_min: float = 0.001, f_max: float = 1.0, seed: int = 0, max_it: int = 100000, **kw):
+        """The set the reference's search finds for this band (NR_LIN_SOLIDS, F_MIN, F_MAX, MAXINT_SA of inparam_advanced)."""
+        w_j, y_j, _ = invert_linear_solids(n_sls, f_min, f_max, seed=seed, max_it=max_it)
+        return cls(n_sls=n_sls, w_j=w_j, y_j=y_j, f_min=f_min, f_max=f_max, **kw)
+
+
+def q_linear_solid(y_j, w_j, w, exact: bool = False) -> np.ndarray:
+    """Q(w) of a set of standard linear solids (Emmerich & Korn eq. 21 inverted, or its linearisation eq. 22;
+    attenuation.f90:1099-1130)."""
+    y_j, w_j, w = (np.asarray(a, dtype=np.float64) for a in (y_j, w_j, w))
+    num = np.ones_like(w)
+    if exact:
+        num = num + (y_j[:, None] * w[None, :] ** 2 / (w[None, :] ** 2 + w_j[:, None] ** 2)).sum(axis=0)
+    den = (y_j[:, None] * w[None, :] * w_j[:, None] / (w[None, :] ** 2 + w_j[:, None] ** 2)).sum(axis=0)
+    return num / den
+
+
+def invert_linear_solids(n_sls: int = 5, f_min: float = 0.001, f_max: float = 1.0, *, Q: float = 1.0, nfsamp: int = 100,
+                         max_it: int = 100000, Tw: float = 0.1, Ty: float = 0.1, d: float = 0.99995, fixfreq: bool = False,
+                         freq_weight: bool = True, w_ref: float = 1.0, alpha: float = 0.0, exact: bool = False, seed: int = 0):
+    """The reference's fit of the SLS set to a constant (or power-law) Q: a random search that perturbs the
+    relaxation frequencies and amplitudes within a shrinking range and keeps what lowers the frequency-weighted
+    log-l2 misfit (invert_linear_solids + l2_error, attenuation.f90:1159-1339; the defaults are those of
+    inparam_advanced: NR_F_SAMPLE 100, MAXINT_SA 100000, TSTART_SR / TSTART_AMP 0.1, T_DECAY 0.99995, FREQ_WEIGHT
+    true).  The reference draws from an unseeded random_number; here the stream is seeded, so a fit can be
+    repeated.  Returns (w_j [rad/s], y_j for Q = 1 — the loop divides by Q —, misfit per iteration)."""
+    rng = np.random.default_rng(seed)
+    if n_sls > 1:
+        expo = (np.log10(f_max) - np.log10(f_min)) / (n_sls - 1.0)
+        w_j = 2 * np.pi * 10.0 ** (np.log10(f_min) + np.arange(n_sls) * expo)
+    else:
+        w_j = np.array([np.sqrt(f_max * f_min) * 2 * np.pi])
+    expo = (np.log10(f_max) - np.log10(f_min)) / (nfsamp - 1.0)
+    w = 2 * np.pi * 10.0 ** (np.log10(f_min) + np.arange(nfsamp) * expo)
+    q_target = Q * (w / w_ref) ** alpha
+    weights = w / w.sum() * nfsamp if freq_weight else np.ones(nfsamp)
+
+    def misfit(y, wj):
+        return np.sqrt((np.log(q_target / q_linear_solid(y, wj, w, exact)) ** 2 * weights).sum() / float(nfsamp))
+
+    y_j = np.full(n_sls, 1.0 / Q * 1.5)
+    chi = misfit(y_j, w_j)
+    chil = np.zeros(max_it)
+    r = rng.random((max_it, n_sls, 2))
+    for it in range(max_it):
+        w_t = w_j if fixfreq else w_j * (1.0 + (0.5 - r[it, :, 0]) * Tw)
+        y_t = y_j * (1.0 + (0.5 - r[it, :, 1]) * Ty)
+        c = misfit(y_t, w_t)
+        Tw *= d
+        Ty *= d
+        if c < chi:
+            y_j, w_j, chi = y_t, w_t, c
+        chil[it] = chi
+    return w_j, y_j, chil
 
 
 def fast_correct(y_j: np.ndarray) -> np.ndarray:

@@ -1043,6 +1043,54 @@ void precompute(std::vector<Modules> &ranks, const PrecompOptions &opt) {
     }
 }
 
+// ---- the SLS fit (invert_linear_solids + q_linear_solid + l2_error, attenuation.f90:1099-1339) ---------------------
+std::vector<double> q_linear_solid(const std::vector<double> &y_j, const std::vector<double> &w_j, const std::vector<double> &w) {
+    std::vector<double> q(w.size());
+    for (size_t k = 0; k < w.size(); k++) {
+        double den = 0.0;
+        for (size_t j = 0; j < y_j.size(); j++) den += y_j[j] * w[k] * w_j[j] / (w[k] * w[k] + w_j[j] * w_j[j]);
+        q[k] = 1.0 / den;
+    }
+    return q;
+}
+
+double fit_linear_solids(AttenuationOptions &A, int n_sls, double f_min, double f_max, uint64_t seed, int max_it) {
+    const int nfsamp = 100;
+    double Tw = 0.1, Ty = 0.1;
+    const double d = 0.99995;
+    std::vector<double> w_j(n_sls), y_j(n_sls, 1.5), w(nfsamp), weights(nfsamp);
+    if (n_sls > 1) {
+        const double expo = (std::log10(f_max) - std::log10(f_min)) / (n_sls - 1.0);
+        for (int j = 0; j < n_sls; j++) w_j[j] = 2 * PI * std::pow(10.0, std::log10(f_min) + j * expo);
+    } else w_j[0] = std::sqrt(f_max * f_min) * 2 * PI;
+    const double expo = (std::log10(f_max) - std::log10(f_min)) / (nfsamp - 1.0);
+    double wsum = 0.0;
+    for (int k = 0; k < nfsamp; k++) { w[k] = 2 * PI * std::pow(10.0, std::log10(f_min) + k * expo); wsum += w[k]; }
+    for (int k = 0; k < nfsamp; k++) weights[k] = w[k] / wsum * nfsamp;          // FREQ_WEIGHT true
+    auto misfit = [&](const std::vector<double> &y, const std::vector<double> &wj) {
+        const std::vector<double> q = q_linear_solid(y, wj, w);
+        double lse = 0.0;
+        for (int k = 0; k < nfsamp; k++) { const double l = std::log(1.0 / q[k]); lse += l * l * weights[k]; }    // Q_target = 1
+        return std::sqrt(lse / (double)nfsamp);
+    };
+    double chi = misfit(y_j, w_j);
+    // the reference draws from an unseeded random_number; a seeded 64-bit generator makes the fit repeatable
+    uint64_t s = seed * 6364136223846793005ULL + 1442695040888963407ULL;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (double)(s >> 11) / 9007199254740992.0; };
+    std::vector<double> wt(n_sls), yt(n_sls);
+    for (int it = 0; it < max_it; it++) {
+        for (int j = 0; j < n_sls; j++) {
+            wt[j] = w_j[j] * (1.0 + (0.5 - rnd()) * Tw);
+            yt[j] = y_j[j] * (1.0 + (0.5 - rnd()) * Ty);
+        }
+        const double c = misfit(yt, wt);
+        Tw *= d; Ty *= d;
+        if (c < chi) { y_j = yt; w_j = wt; chi = c; }
+    }
+    A.w_j = w_j; A.y_j = y_j; A.f_min = f_min; A.f_max = f_max;
+    return chi;
+}
+
 std::vector<std::vector<int>> receiver_indices(const std::vector<Modules> &ranks) {
     std::vector<std::vector<int>> out;
     for (const Modules &m : ranks) {

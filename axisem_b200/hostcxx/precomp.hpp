@@ -59,6 +59,12 @@ struct PrecompOptions {
     double xdmf_rmin = 0.0, xdmf_rmax = 7.0e6, xdmf_thetamin = 0.0, xdmf_thetamax = 3.14159265358979323846;
 };
 
+// The reference's fit of n_sls standard linear solids to constant Q over [f_min, f_max] Hz (invert_linear_solids,
+// attenuation.f90:1183-1339, with the defaults of inparam_advanced), seeded; fills A.w_j, A.y_j (for Q = 1), A.f_min,
+// A.f_max and returns the frequency-weighted log-l2 misfit
+double fit_linear_solids(AttenuationOptions &A, int n_sls, double f_min, double f_max, uint64_t seed = 0, int max_it = 100000);
+std::vector<double> q_linear_solid(const std::vector<double> &y_j, const std::vector<double> &w_j, const std::vector<double> &w);
+
 // loc2globrec / recfile_th of every rank after precompute (for receiver_pts.dat)
 std::vector<std::vector<int>> receiver_indices(const std::vector<Modules> &ranks);
 std::vector<std::vector<double>> receiver_colatitudes(const std::vector<Modules> &ranks);

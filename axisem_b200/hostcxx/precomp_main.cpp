@@ -151,6 +151,14 @@ int main(int argc, char **argv) {
             pre.xdmf_thetamax = std::atof(need()) * 3.14159265358979323846 / 180.0;
         }
         else if (a == "--attenuation") { pre.attenuation = true; pre.att.coarse_grained = std::string(need()) != "full"; }
+        else if (a == "--fit-sls") {          // N F_MIN F_MAX SEED: NR_LIN_SOLIDS, F_MIN, F_MAX of inparam_advanced
+            const int n = std::atoi(need());
+            const double f0 = std::atof(need()), f1 = std::atof(need());
+            const uint64_t seed = (uint64_t)std::atoll(need());
+            if (n < 1 || n > 8 || !(f0 > 0 && f1 > f0)) { std::fprintf(stderr, "--fit-sls N F_MIN F_MAX SEED: 1 <= N <= 8, 0 < F_MIN < F_MAX\n"); return 2; }
+            const double chi = axisem::fit_linear_solids(pre.att, n, f0, f1, seed);
+            std::printf("sls_misfit %.6e\n", chi);
+        }
         else if (a == "--receivers") {
             const std::string v = need();
             size_t pos = 0;
