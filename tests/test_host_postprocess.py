@@ -232,3 +232,40 @@ def test_run_directories_in_the_references_layout(exe, tmp_path, sys):
     (tmp_path / "MZZ" / "simulation.info").write_text(info)
     run = subprocess.run([exe, "--simdir", str(tmp_path / "MZZ"), "--out", str(out)], capture_output=True, text=True)
     assert run.returncode != 0 and "NetCDF" in run.stderr
+
+
+def test_solver_run_directory_through_the_post_processing(exe, tmp_path):
+    """End to end on the files alone: axisem_b200_solver --rundir (its CPU twin) leaves the reference's run
+    directory for a source off the pole and STATIONS in geographic coordinates; axisem_b200_postproc --simdir
+    reads it — source position from simulation.info, receiver names and solver-frame coordinates from Data/ —
+    and returns what it returns for the raw seismogram file of the same run with the rotated station list."""
+    from axisem_b200.host import SourceParams, build_problem, prem_mesh_spec
+    from axisem_b200.host.meshdb_io import write_meshdb
+    from oracle import oracle
+    spec = prem_mesh_spec(ntheta=16, nr_target=18)
+    prob = build_problem(spec, SourceParams(src_type2="mtr", t_0=3.0), niter=40, seis_it=2)
+    db = str(tmp_path / "meshdb.dat0000")
+    write_meshdb(prob.mesh, db, dt=prob.deltat)
+    st = tmp_path / "STATIONS"
+    st.write_text("AAA XX 10.0 20.0 0.0 0.0\nBBB XX -35.5 140.0 0.0 0.0\nCCC YY 62.0 -110.0 0.0 0.0\n")
+    run = subprocess.run([oracle.build_host(), "--quiet", "--out", str(tmp_path / "run"), "--rundir", str(tmp_path / "RUN"), "--src", "mtr",
+                          "--period", "3", "--niter", "40", "--seis-it", "2", "--stations", str(st), "--src-lat", "36.5", "--src-lon", "140.25", db],
+                         capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stderr
+    a = subprocess.run([exe, "--simdir", str(tmp_path / "RUN"), "--sys", "enz", "--out", str(tmp_path / "a.f32"), "--ascii-out", str(tmp_path / "POST")],
+                       capture_output=True, text=True)
+    assert a.returncode == 0, a.stderr
+    # the reference rotates with the coordinates of the grid points taken (receiver_pts.dat), not those asked for
+    pts = np.loadtxt(tmp_path / "RUN" / "Data" / "receiver_pts.dat")
+    (tmp_path / "pts.txt").write_text("".join(f"{c!r} {l!r}\n" for c, l in pts[:, :2].tolist()))
+    b = subprocess.run([exe, "--src", "mtr", "--seis", str(tmp_path / "run.rank0000.seis.f32"), "--stations", str(tmp_path / "pts.txt"),
+                        "--srccolat", repr(90.0 - 36.5), "--srclon", "140.25", "--sys", "enz", "--out", str(tmp_path / "b.f32")],
+                       capture_output=True, text=True)
+    assert b.returncode == 0, b.stderr
+    x, y = (np.fromfile(tmp_path / f, dtype=np.float32).reshape(3, 3, -1) for f in ("a.f32", "b.f32"))
+    assert x.shape == y.shape == (3, 3, 21) and np.abs(y).max() > 0
+    # (simulation.info holds the source position to seven decimals of a radian, the *_disp.dat files nine digits)
+    assert np.abs(x - y).max() <= 1e-5 * np.abs(y).max()
+    assert sorted(os.listdir(tmp_path / "POST" / "SEISMOGRAMS"))[:3] == ["AAA_XX_disp_post_mij_conv0000_E.dat",
+                                                                         "AAA_XX_disp_post_mij_conv0000_N.dat",
+                                                                         "AAA_XX_disp_post_mij_conv0000_Z.dat"]
