@@ -85,3 +85,12 @@ def test_bad_arguments_are_reported_like_the_reference_stops():
         loop.run(1)                                # beyond niter
     with pytest.raises(AxbError):
         loop.seismograms(first=0, n=99)            # beyond the recorded samples
+
+
+def test_integration_guide_binds_every_entry_point():
+    """INTEGRATION.md's iso_c_binding module declares an interface for every symbol of the header, no more."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    syms = set(re.findall(r"AXB\((\w+)\)\(", open(os.path.join(root, "include", "axisem_b200.h")).read()))
+    bound = set(re.findall(r"name='axb_(\w+)'", open(os.path.join(root, "INTEGRATION.md")).read()))
+    assert syms == bound, (sorted(syms - bound), sorted(bound - syms))
